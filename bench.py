@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- alerts/sec of the multimodal ConvNeXt scoring hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--precision bf16|fp32]
+
+Workload (BASELINE.json configs[2], "C3"): bulk scoring of synthetic alerts with mm_ConvNeXt / convnext_nano
+(random-init weights, 25 metadata columns), index-range sharded over ranks with NO collective on the data path.
+A "step" is one forward pass of every rank over one micro-batch of B alerts ([B,3,63,63] fp32 + [B,25] fp32,
+390 MB at B=8192 -> larger than the 126 MB L2, and consecutive steps rotate over distinct resident batches).
+
+  value    : alerts/s, inputs already resident in HBM, CUDA events around exactly K steps, max over ranks
+  e2e      : same metric through the public API from pinned HOST buffers: H2D copy of the HWC triplets + metadata,
+             K1 layout kernel, model forward, D2H of the logits -- all inside the timed region
+  roofline : dominant kernel (largest share of the step) timed per launch with CUDA events in an instrumented
+             replay of the same K steps right after the timed region (events perturb launches, so `value`
+             comes from the un-instrumented pass; `kernels` lists every kernel family for cross-checking)
+  cpu_baseline : the CPU oracle (port of the reference path: btsbot/architectures.py glue + restated timm trunk)
+             following inference_example.py:62-91 (batch 64, fp32, eval/no_grad) on a bounded sample
+
+`--impl reference` times that CPU port alone with all host threads (the reference itself cannot run offline:
+timm is not installable).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL_KIND = "convnext_nano.d1h_in1k"
+ALERT_IN_BYTES = 63 * 63 * 3 * 4 + 25 * 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192, help="alerts per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=8192, help="alerts in the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sust=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+def cpu_port(sample_alerts: int, cfg, sd_np, threads: int):
+    """inference_example.py:62-91 on the CPU oracle: float32, eval, no_grad, DataLoader(batch 64, shuffle=False).
+    Returns alerts/s over `sample_alerts` synthetic alerts (after one warm-up batch)."""
+    from btsbot_b200 import synth, utils
+    from oracle import convnext_oracle as O
+    from torch.utils.data import DataLoader
+    torch.set_num_threads(threads)
+    sd = synth.to_torch(sd_np)
+    trip = synth.make_triplets(sample_alerts, start=0)
+    meta = synth.make_metadata(sample_alerts, start=0)
+    img = torch.from_numpy(np.ascontiguousarray(np.transpose(trip.astype(np.float32), (0, 3, 1, 2))))
+    ds = utils.FlexibleDataset(images=img, metadata=torch.from_numpy(meta), labels=torch.zeros(sample_alerts, dtype=torch.long))
+    dl = DataLoader(ds, batch_size=64, shuffle=False, num_workers=0)
+    O.forward(sd, cfg, img[:64], torch.from_numpy(meta[:64]))       # warm-up
+    t0 = time.perf_counter()
+    n = 0
+    for ib, mb, _ in dl:
+        logits = O.forward(sd, cfg, ib, mb)
+        _ = torch.sigmoid(logits).round()
+        n += ib.shape[0]
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from btsbot_b200 import synth
+    cfg = synth.canonical_config("mm_ConvNeXt", MODEL_KIND)
+    sd = synth.make_state_dict(cfg, seed=2)
+    threads = os.cpu_count() or 1
+    per_step = 1024                                  # bounded sample of the workload per step
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_port(256, cfg, sd, threads)
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        rate, dt = cpu_port(per_step, cfg, sd, threads)
+        t_total += dt
+        n_total += per_step
+    value = n_total / t_total
+    line = {
+        "impl": "reference", "metric": "alerts/sec", "value": value, "unit": "alerts/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3 multimodal ConvNeXt-nano bulk scoring (CPU port of the reference path)",
+                   "model_kind": MODEL_KIND, "alerts_per_step": per_step, "batch": 64},
+        "cpu_baseline": {"value": value, "unit": "alerts/s", "cores": threads, "kind": "port",
+                         "sample": f"{per_step} synthetic alerts per step in batches of 64, torch {torch.__version__} CPU fp32, "
+                                   f"{threads} threads; reference itself not runnable offline (timm missing)"},
+        "e2e": {"value": value, "unit": "alerts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import btsbot_b200 as btsbot
+    from btsbot_b200 import synth, _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+
+    cfg = dict(synth.canonical_config("mm_ConvNeXt", MODEL_KIND), precision=args.precision)
+    sd_np = synth.make_state_dict(cfg, seed=2)
+    model = btsbot.mm_ConvNeXt(cfg)
+    model.load_state_dict(synth.to_torch(sd_np), strict=True)
+    model = model.to(dev).eval()
+
+    # ---- synthetic inputs: a pool of unique index-keyed alerts for this rank's shard, tiled on device ----------
+    pool = 2048
+    shard0 = rank * B                                        # this rank's index range starts here
+    trip_pool = synth.make_triplets(pool, start=shard0 % (1 << 20))
+    meta_pool = synth.make_metadata(pool, start=shard0 % (1 << 20))
+    nres = 2                                                 # distinct resident batches rotated across steps
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    res_img, res_meta, host_trip, host_meta = [], [], [], []
+    tp = torch.from_numpy(trip_pool).to(dev)
+    mp = torch.from_numpy(meta_pool).to(dev)
+    for r in range(nres):
+        idx = torch.randint(0, pool, (B,), generator=g).to(dev)
+        hwc = tp[idx].contiguous()                           # [B,63,63,3] fp32 HWC (what a user holds)
+        res_img.append(btsbot.alert_utils.triplets_to_model_input(hwc))          # K1 -> [B,3,63,63] resident
+        res_meta.append(mp[idx].contiguous())
+        host_trip.append(hwc.cpu().pin_memory())
+        host_meta.append(res_meta[-1].cpu().pin_memory())
+    del tp, mp
+    torch.cuda.synchronize()
+
+    def step(i):
+        with torch.no_grad():
+            return model(image_input=res_img[i % nres], metadata_input=res_meta[i % nres])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        out = step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region: exactly K steps, device-resident inputs -------------------------------------------------
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = step(i)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: public API from pinned host buffers, H2D + K1 + forward + D2H inside the timed region --------------
+    out_host = torch.empty((B, 1), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        with torch.no_grad():
+            t = host_trip[i % nres].to(dev, non_blocking=True)
+            m = host_meta[i % nres].to(dev, non_blocking=True)
+            x = btsbot.alert_utils.triplets_to_model_input(t)
+            lg = model(image_input=x, metadata_input=m)
+            out_host.copy_(lg, non_blocking=True)
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    # ---- instrumented replay of the same K steps: per-kernel CUDA-event timing ---------------------------------
+    prof = _lib.KernelProfiler()
+    _lib.profiler = prof
+    for i in range(args.steps):
+        step(i)
+    _lib.profiler = None
+    kern = prof.summary()
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    total_alerts = world * B * args.steps
+    value = total_alerts / (ms * 1e-3)
+    e2e_value = total_alerts / (ms_e2e * 1e-3)
+    kernels = {}
+    for name, a in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
+        per = a["ms"] / a["launches"]
+        kernels[name] = {"launches_per_step": a["launches"] / args.steps, "ms_per_launch": per,
+                         "gbs": a["bytes"] / a["launches"] / (per * 1e-3) / 1e9,
+                         "tflops": a["flops"] / a["launches"] / (per * 1e-3) / 1e12,
+                         "share": a["ms"] / sum(v["ms"] for v in kern.values())}
+    top = next(iter(kernels))
+    tk = kernels[top]
+    tensor_bound = top.startswith("gemm") and args.precision == "bf16"
+    if tensor_bound:
+        roof = {"kernel": top, "bound": "tensor", "achieved": tk["tflops"], "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": tk["tflops"] / pk["tf_sust"], "traffic": None,
+                "peak_source": pk["source"] + " (sustained bf16 cuBLAS: kernel timed inside a long step)"}
+    else:
+        roof = {"kernel": top, "bound": "hbm", "achieved": tk["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                "frac": tk["gbs"] / pk["hbm"], "traffic": None, "peak_source": pk["source"] + " (copy bandwidth)"}
+    roof["kernel_time_sum_ms_per_step"] = sum(v["ms"] for v in kern.values()) / args.steps
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, dt = cpu_port(args.cpu_sample, dict(cfg), sd_np, threads)
+        cpu = {"value": rate, "unit": "alerts/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_sample} synthetic alerts in batches of 64 ({dt:.1f} s), CPU oracle fp32, "
+                         f"torch {torch.__version__}, {threads} threads"}
+
+    line = {
+        "metric": "alerts/sec", "value": value, "unit": "alerts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "C3 multimodal ConvNeXt-nano bulk scoring, 63x63x3 triplet + 25 metadata per alert",
+                   "model_kind": MODEL_KIND, "alerts_per_gpu_per_step": B, "global_alerts_per_step": world * B,
+                   "sharding": "contiguous index ranges, no data-path collective",
+                   "l2_policy": f"inputs larger than L2 ({B * ALERT_IN_BYTES / 1e6:.0f} MB per step), "
+                                f"{nres} resident batches rotated"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "alerts/s", "h2d_bytes_per_step": world * B * ALERT_IN_BYTES,
+                "d2h_bytes_per_step": world * B * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "kernels": kernels,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

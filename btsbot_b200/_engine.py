@@ -1,0 +1,276 @@
+"""Host-side driver of the sm_100a kernels: weight packing and the kernel sequence of one forward pass.
+
+PyTorch is used here only for device memory (``torch.empty``), streams and one-off weight re-layout at
+load time; every arithmetic step of the hot path is a call into ``libbtsbot_b200.so`` through ctypes
+(``_lib``).  Nothing in this file can run without the CUDA library and an sm_100 device.
+
+Layout contract: API tensors are NCHW float32 like the reference's; between
+kernels activations are NHWC pixel rows ``[B*H*W, C]`` in the compute dtype (float32 or bfloat16).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .synth import convnext_arch
+
+BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by the reference (architectures.py:147)
+
+_DT = {"fp32": (L.F32, torch.float32), "bf16": (L.BF16, torch.bfloat16)}
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+class TrunkWeights:
+    """Kernel-ready copy of a timm-keyed ConvNeXt trunk (keys: SURVEY.md section 8b)."""
+
+    def __init__(self, sd: dict, prefix: str, arch: dict, precision: str):
+        code, wdt = _DT[precision]
+        self.precision, self.code, self.wdt = precision, code, wdt
+        self.dims, self.depths = tuple(arch["dims"]), tuple(arch["depths"])
+        g = lambda k: sd[prefix + k]
+        c0 = self.dims[0]
+        # stem.0 Conv2d weight [C0,3,4,4] -> [48, C0] with k = (ci*4+ky)*4+kx
+        self.stem_w = _f32c(g("stem.0.weight").reshape(c0, 48).t())
+        self.stem_b = _f32c(g("stem.0.bias"))
+        self.stem_ln_w, self.stem_ln_b = _f32c(g("stem.1.weight")), _f32c(g("stem.1.bias"))
+        self.stages = []
+        for i, (c, d) in enumerate(zip(self.dims, self.depths)):
+            st = {"blocks": []}
+            if i > 0:
+                cin = self.dims[i - 1]
+                q = f"stages.{i}.downsample."
+                st["ds_ln_w"], st["ds_ln_b"] = _f32c(g(q + "0.weight")), _f32c(g(q + "0.bias"))
+                # Conv2d [Cout,Cin,2,2] -> GEMM weight [Cout, (dy,dx,cin)] matching the lnpatch column order
+                st["ds_w"] = g(q + "1.weight").detach().permute(0, 2, 3, 1).reshape(c, 4 * cin).to(wdt).contiguous()
+                st["ds_b"] = _f32c(g(q + "1.bias"))
+            for j in range(d):
+                q = f"stages.{i}.blocks.{j}."
+                st["blocks"].append(dict(
+                    dw_w=_f32c(g(q + "conv_dw.weight").reshape(c, 49).t()),      # [49, C], k = ky*7+kx
+                    dw_b=_f32c(g(q + "conv_dw.bias")),
+                    ln_w=_f32c(g(q + "norm.weight")), ln_b=_f32c(g(q + "norm.bias")),
+                    fc1_w=g(q + "mlp.fc1.weight").detach().reshape(4 * c, c).to(wdt).contiguous(),
+                    fc1_b=_f32c(g(q + "mlp.fc1.bias")),
+                    fc2_w=g(q + "mlp.fc2.weight").detach().reshape(c, 4 * c).to(wdt).contiguous(),
+                    fc2_b=_f32c(g(q + "mlp.fc2.bias")),
+                    gamma=_f32c(g(q + "gamma")),
+                ))
+            self.stages.append(st)
+
+
+def _gemm(name, a, wt, bias, gamma, res, out, code, epi, st):
+    """out = epi(a @ wt^T + bias); algorithmic work: 2MNK flops; bytes = A + W + out (+ residual)."""
+    M, K = a.shape
+    N = wt.shape[0]
+    es = a.element_size()
+    nbytes = es * (M * K + N * K + M * N + (M * N if res is not None else 0)) + 4.0 * N
+    L.launch(name, L.lib().btsb_gemm_fwd, _p(a), _p(wt), _p(bias), _p(gamma), _p(res), _p(out), M, N, K, code, epi, st,
+             flops=2.0 * M * N * K, nbytes=nbytes)
+
+
+def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None):
+    """timm ``forward_features`` on the GPU kernels.  ``x``: [B,3,H,W] float32 CUDA.
+    Returns ``(rows [B*h*w, C_last] in the compute dtype, h, w)``."""
+    lib = L.lib()
+    L.require_cuda(x, "image input")
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"expected image batch [B,3,H,W], got {tuple(x.shape)}")
+    x = x.to(torch.float32).contiguous()
+    B, _, H, W = x.shape
+    if H < 4 or W < 4:
+        raise ValueError("image smaller than the 4x4 patch stem")
+    dev, st = x.device, L.stream_ptr()
+    code, adt = w.code, w.wdt
+    h, wd = (H - 4) // 4 + 1, (W - 4) // 4 + 1
+    c = w.dims[0]
+    cur = torch.empty((B * h * wd, c), device=dev, dtype=adt)
+    es = cur.element_size()
+    L.launch("stem", lib.btsb_convnext_stem_fwd, _p(x), B, H, W, _p(w.stem_w), _p(w.stem_b), _p(w.stem_ln_w),
+             _p(w.stem_ln_b), c, _p(cur), code, st,
+             flops=2.0 * 48 * c * B * h * wd, nbytes=4.0 * x.numel() + es * cur.numel())
+    if capture is not None:
+        capture["stem"] = (cur, h, wd)
+    for i, stg in enumerate(w.stages):
+        c = w.dims[i]
+        if i > 0:
+            cin = w.dims[i - 1]
+            if h < 2 or wd < 2:
+                raise ValueError("feature map too small for the 2x2/s2 downsample")
+            ho, wo = (h - 2) // 2 + 1, (wd - 2) // 2 + 1
+            patches = torch.empty((B * ho * wo, 4 * cin), device=dev, dtype=adt)
+            L.launch("lnpatch", lib.btsb_convnext_lnpatch_fwd, _p(cur), code, B, h, wd, cin, _p(stg["ds_ln_w"]),
+                     _p(stg["ds_ln_b"]), _p(patches), st, flops=8.0 * patches.numel(),
+                     nbytes=es * (cur.numel() + patches.numel()))
+            h, wd = ho, wo
+            cur = torch.empty((B * h * wd, c), device=dev, dtype=adt)
+            _gemm("gemm_down", patches, stg["ds_w"], stg["ds_b"], None, None, cur, code, L.EPI_BIAS, st)
+            if capture is not None:
+                capture[f"down{i}"] = (cur, h, wd)
+        M = B * h * wd
+        y = torch.empty((M, c), device=dev, dtype=adt)
+        hid = torch.empty((M, 4 * c), device=dev, dtype=adt)
+        for j, blk in enumerate(stg["blocks"]):
+            L.launch(f"dwln_{wd}x{c}", lib.btsb_convnext_dwln_fwd, _p(cur), code, B, h, wd, c, _p(blk["dw_w"]),
+                     _p(blk["dw_b"]), _p(blk["ln_w"]), _p(blk["ln_b"]), _p(y), st,
+                     flops=2.0 * 49 * M * c + 8.0 * M * c, nbytes=2.0 * es * M * c)
+            if capture is not None:
+                capture[f"s{i}b{j}.dwln"] = (y.clone(), h, wd)
+            _gemm(f"gemm_fc1_{c}", y, blk["fc1_w"], blk["fc1_b"], None, None, hid, code, L.EPI_BIAS_GELU, st)
+            nxt = torch.empty((M, c), device=dev, dtype=adt)
+            _gemm(f"gemm_fc2_{c}", hid, blk["fc2_w"], blk["fc2_b"], blk["gamma"], cur, nxt, code,
+                  L.EPI_SCALE_RES, st)
+            cur = nxt
+            if capture is not None:
+                capture[f"s{i}b{j}"] = (cur, h, wd)
+    return cur, h, wd
+
+
+def pool_ln(rows: torch.Tensor, B: int, hw: int, ln_w, ln_b, code: int) -> torch.Tensor:
+    """global-avg-pool + LayerNorm2d + flatten -> [B,C] float32 (architectures.py:109-113,136-141)."""
+    lib = L.lib()
+    cdim = rows.shape[1]
+    out = torch.empty((B, cdim), device=rows.device, dtype=torch.float32)
+    L.launch("poolln", lib.btsb_convnext_poolln_fwd, _p(rows), code, B, hw, cdim, _p(ln_w), _p(ln_b), _p(out),
+             L.stream_ptr(), flops=8.0 * rows.numel(), nbytes=rows.element_size() * rows.numel() + 4.0 * out.numel())
+    return out
+
+
+class HeadWeights:
+    """Folded BatchNorm1d + transposed fp32 Linear weights for the fused metadata/head kernel."""
+
+    def __init__(self, sd: dict, *, meta_prefix=None, head_prefix=None, head_idx=(0, 2, 5), final_prefix=None,
+                 meta_act=L.ACT_GELU, meta_out_act=L.ACT_GELU, head_act=L.ACT_GELU):
+        t = lambda k: _f32c(sd[k].t())
+        self.meta_act, self.meta_out_act, self.head_act = meta_act, meta_out_act, head_act
+        self.Mm = self.m1 = self.m2 = self.c1 = self.c2 = 0
+        self.bn_scale = self.bn_shift = self.m1t = self.m1b = self.m2t = self.m2b = None
+        self.h0t = self.h0b = self.h1t = self.h1b = None
+        if meta_prefix is not None:
+            p = meta_prefix
+            var, mean = sd[p + "0.running_var"].float(), sd[p + "0.running_mean"].float()
+            scale = sd[p + "0.weight"].float() / torch.sqrt(var + BN_EPS)
+            self.bn_scale = scale.contiguous()
+            self.bn_shift = (sd[p + "0.bias"].float() - mean * scale).contiguous()
+            self.m1t, self.m1b = t(p + "1.weight"), _f32c(sd[p + "1.bias"])
+            self.m2t, self.m2b = t(p + "4.weight"), _f32c(sd[p + "4.bias"])
+            self.Mm, self.m1, self.m2 = self.m1t.shape[0], self.m1t.shape[1], self.m2t.shape[1]
+        if head_prefix is not None:
+            a, b, c = head_idx
+            self.h0t, self.h0b = t(f"{head_prefix}{a}.weight"), _f32c(sd[f"{head_prefix}{a}.bias"])
+            self.h1t, self.h1b = t(f"{head_prefix}{b}.weight"), _f32c(sd[f"{head_prefix}{b}.bias"])
+            self.c1, self.c2 = self.h0t.shape[1], self.h1t.shape[1]
+            final_prefix = f"{head_prefix}{c}."
+        self.h2 = _f32c(sd[final_prefix + "weight"].reshape(-1))
+        self.h2b = _f32c(sd[final_prefix + "bias"].reshape(-1))
+        self.in_features = self.h0t.shape[0] if self.h0t is not None else self.m2
+
+
+def head_forward(hw: HeadWeights, feat: torch.Tensor | None, meta: torch.Tensor | None, B: int) -> torch.Tensor:
+    lib = L.lib()
+    p = L.HeadParams()
+    dev = (feat if feat is not None else meta).device
+    F = 0
+    if feat is not None:
+        feat = feat.contiguous()
+        F = feat.shape[1]
+        p.feat, p.F = feat.data_ptr(), F
+        p.feat_dtype = L.BF16 if feat.dtype == torch.bfloat16 else L.F32
+    if meta is not None:
+        L.require_cuda(meta, "metadata input")
+        meta = meta.to(torch.float32).contiguous()
+        if meta.dim() != 2 or meta.shape[1] != hw.Mm or meta.shape[0] != B:
+            raise ValueError(f"expected metadata [{B},{hw.Mm}], got {tuple(meta.shape)}")
+        p.meta, p.Mm = meta.data_ptr(), hw.Mm
+        p.bn_scale, p.bn_shift = hw.bn_scale.data_ptr(), hw.bn_shift.data_ptr()
+        p.m1t, p.m1b, p.m1 = hw.m1t.data_ptr(), hw.m1b.data_ptr(), hw.m1
+        p.m2t, p.m2b, p.m2 = hw.m2t.data_ptr(), hw.m2b.data_ptr(), hw.m2
+    p.meta_act, p.meta_out_act, p.head_act = hw.meta_act, hw.meta_out_act, hw.head_act
+    if hw.c1 > 0:
+        if F + (hw.m2 if meta is not None else 0) != hw.in_features:
+            # the reference fails the same way inside nn.Linear when the trunk map is not 1x1 (architectures.py:142-143)
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied: head expects {hw.in_features} "
+                               f"input features, got {F + (hw.m2 if meta is not None else 0)}")
+        p.h0t, p.h0b, p.c1 = hw.h0t.data_ptr(), hw.h0b.data_ptr(), hw.c1
+        p.h1t, p.h1b, p.c2 = hw.h1t.data_ptr(), hw.h1b.data_ptr(), hw.c2
+    p.h2, p.h2b = hw.h2.data_ptr(), hw.h2b.data_ptr()
+    logits = torch.empty((B, 1), device=dev, dtype=torch.float32)
+    macs = hw.Mm * hw.m1 + hw.m1 * hw.m2 + hw.in_features * hw.c1 + hw.c1 * hw.c2 + max(hw.c2, 1)
+    L.launch("meta_head", lib.btsb_meta_head_fwd, C.byref(p), B, _p(logits), L.stream_ptr(), flops=2.0 * macs * B,
+             nbytes=B * (F * (feat.element_size() if feat is not None else 0) + 4.0 * hw.Mm + 4.0))
+    return logits
+
+
+class Scorer:
+    """Eval-mode forward of one reference model class on the B200 kernels.
+
+    ``sd`` is a reference/timm-keyed state dict whose tensors live on the target CUDA device (e.g.
+    ``module.state_dict()``).  Mirrors `btsbot/architectures.py` ``forward`` of mm_ConvNeXt (:166-171),
+    ConvNeXt (:121-122), um_nn (:292-293) and frozen_fusion (:366-372).
+    """
+
+    def __init__(self, config: dict, sd: dict, precision: str = "fp32"):
+        if precision not in _DT:
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        L.lib()
+        self.config, self.precision = config, precision
+        self.name = name = config["model_name"]
+        self.trunk = self.head = None
+        self.pool_ln = None
+        if name == "mm_ConvNeXt":
+            arch = convnext_arch(config.get("model_kind", "convnext_nano.d1h_in1k"))
+            self.trunk = TrunkWeights(sd, "convnext_backbone.", arch, precision)
+            if "LS" in config["train_data_version"]:
+                self.pool_ln = (_f32c(sd["convnext_backbone.head.1.weight"]), _f32c(sd["convnext_backbone.head.1.bias"]))
+            self.head = HeadWeights(sd, meta_prefix="metadata_branch.", head_prefix="combined_head.")
+        elif name == "ConvNeXt":
+            arch = convnext_arch(config.get("model_kind", "convnext_nano.d1h_in1k"))
+            self.trunk = TrunkWeights(sd, "convnext.", arch, precision)
+            self.pool_ln = (_f32c(sd["convnext.head.1.weight"]), _f32c(sd["convnext.head.1.bias"]))
+            self.head = HeadWeights(sd, head_prefix="convnext.head.", head_idx=(3, 5, 8))
+        elif name == "um_nn":
+            self.head = HeadWeights(sd, meta_prefix="network.", final_prefix="network.6.",
+                                    meta_act=L.ACT_RELU, meta_out_act=L.ACT_RELU)
+        elif name == "frozen_fusion":
+            icfg = config["image_model_config"]
+            if icfg["model_name"] != "ConvNeXt" or config["meta_model_config"]["model_name"] != "um_nn":
+                raise ValueError("B200 frozen_fusion path: ConvNeXt image branch + um_nn metadata branch only")
+            arch = convnext_arch(icfg.get("model_kind", "convnext_nano.d1h_in1k"))
+            self.trunk = TrunkWeights(sd, "image_branch.convnext.", arch, precision)
+            self.pool_ln = (_f32c(sd["image_branch.convnext.head.1.weight"]),
+                            _f32c(sd["image_branch.convnext.head.1.bias"]))
+            self.head = HeadWeights(sd, meta_prefix="meta_branch.network.", head_prefix="combined_head.",
+                                    meta_act=L.ACT_RELU, meta_out_act=L.ACT_NONE, head_act=L.ACT_RELU)
+        else:
+            raise ValueError(f"no B200 path for model_name {name!r}")
+
+    def features(self, image_input: torch.Tensor, capture: dict | None = None) -> torch.Tensor:
+        rows, h, w = trunk_forward(self.trunk, image_input, capture)
+        B = image_input.shape[0]
+        if self.pool_ln is not None:
+            return pool_ln(rows, B, h * w, self.pool_ln[0], self.pool_ln[1], self.trunk.code)
+        if h * w != 1:
+            # nn.Flatten(1) of [B,C,h,w] is channel-major; only reachable when the reference itself would
+            # fail in combined_head (in_features == C), so just build the tensor it would have built
+            return rows.view(B, h * w, -1).permute(0, 2, 1).reshape(B, -1).contiguous()
+        return rows
+
+    def __call__(self, image_input=None, metadata_input=None, capture: dict | None = None) -> torch.Tensor:
+        feat = None
+        if self.trunk is not None:
+            feat = self.features(image_input, capture)
+            B = image_input.shape[0]
+        else:
+            B = metadata_input.shape[0]
+        meta = metadata_input if self.head.Mm > 0 else None
+        if capture is not None and feat is not None:
+            capture["features"] = feat
+        return head_forward(self.head, feat, meta, B)

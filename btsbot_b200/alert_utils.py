@@ -1,0 +1,153 @@
+"""Array preparation of ZTF alert cutouts on the GPU -- drop-in names from `btsbot/alert_utils.py`.
+
+* :func:`crop_norm_cutout`, :func:`crop_triplets`  (alert_utils.py:54-107) -> kernel ``btsb_preprocess_crop_norm``
+* :func:`make_triplet` / :func:`make_triplets`     (alert_utils.py:110-196) -> host gunzip + FITS parse, then kernel
+  ``btsb_preprocess_pad_norm`` for the numeric tail (nan_to_num, L2 normalise, drop flags, pad with 1e-9)
+* :func:`triplets_to_model_input`  -- the cast + NHWC->NCHW step every reference caller does next
+  (inference_example.py:62-64, train.py:139-155, val.py:92-94), fused with crop/normalise, output left on the GPU.
+* :func:`extract_triplets` (alert_utils.py:199-226) host bookkeeping.
+
+All arithmetic runs in ``libbtsbot_b200.so``; there is no numpy fallback.  Differences from the reference that
+are deliberate: inputs are not mutated (the reference normalises the caller's array in place through a view,
+alert_utils.py:75-76), and values are rounded to float32 once (callers cast to float32 anyway).
+Plotting / Kowalski query helpers of the reference module are outside the hot path and not provided.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import io
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("btsbot_b200.alert_utils needs an sm_100a GPU (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def triplets_to_model_input(triplets, crop_to_size: int = 63, normalize: bool = False) -> torch.Tensor:
+    """``[N,63,63,3]`` HWC float32/float64 (numpy or torch, host or device) -> ``[N,3,s,s]`` float32 CUDA tensor.
+
+    ``normalize=False`` is exactly ``astype(float32)`` + ``transpose(0,3,1,2)``; ``normalize=True`` additionally
+    applies ``crop_triplets`` semantics (centre crop with margin ``(63-s)//2`` and per-cutout L2 normalisation)."""
+    return _crop(triplets, crop_to_size, normalize, out_hwc=False)
+
+
+def _crop(triplets, s, normalize, out_hwc):
+    lib = L.lib()
+    dev = _dev()
+    t = torch.from_numpy(np.ascontiguousarray(triplets)) if isinstance(triplets, np.ndarray) else triplets
+    if t.dim() != 4 or tuple(t.shape[1:]) != (63, 63, 3):
+        raise ValueError(f"expected triplets of shape [N,63,63,3], got {tuple(t.shape)}")
+    if t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float64)
+    t = t.to(dev, non_blocking=True).contiguous()
+    n = t.shape[0]
+    shape = (n, s, s, 3) if out_hwc else (n, 3, s, s)
+    out = torch.empty(shape, device=dev, dtype=torch.float32)
+    code = L.F32 if t.dtype == torch.float32 else L.F64
+    L.check(lib.btsb_preprocess_crop_norm(_p(t), code, n, int(s), int(bool(normalize)), int(bool(out_hwc)), _p(out),
+                                          L.stream_ptr()), "crop_norm")
+    return out
+
+
+def crop_triplets(triplets, crop_to_size):
+    """Crop every cutout to ``crop_to_size`` and re-normalise with the L2 norm (alert_utils.py:81-107).
+    Returns ``ndarray[N,s,s,3]`` float64 like the reference (values carry float32 precision)."""
+    out = _crop(np.asarray(triplets), int(crop_to_size), True, out_hwc=True)
+    return out.cpu().numpy().astype(np.float64)
+
+
+def crop_norm_cutout(cutout, crop_to_size):
+    """Single 63x63 cutout version (alert_utils.py:54-78)."""
+    c = np.asarray(cutout)
+    if c.shape != (63, 63):
+        raise ValueError(f"expected a 63x63 cutout, got {c.shape}")
+    trip = np.repeat(c[None, :, :, None], 3, axis=3)
+    return crop_triplets(trip, crop_to_size)[0, :, :, 0].astype(c.dtype if c.dtype.kind == "f" else np.float64)
+
+
+# ---- alert ingest: gz-FITS stamps -> triplets -------------------------------------------------------------
+def _parse_fits_image(raw: bytes) -> np.ndarray:
+    """Primary-HDU image of a FITS file as float32 (BITPIX -32/-64/16/32 with BSCALE/BZERO), no astropy."""
+    kv, off, end = {}, 0, False
+    while not end:
+        block = raw[off:off + 2880]
+        if len(block) < 2880:
+            raise ValueError("truncated FITS header")
+        for i in range(0, 2880, 80):
+            card = block[i:i + 80].decode("ascii", "replace")
+            key = card[:8].strip()
+            if key == "END":
+                end = True
+                break
+            if card[8:10] == "= ":
+                kv[key] = card[10:].split("/")[0].strip().strip("'").strip()
+        off += 2880
+    bitpix, naxis = int(kv["BITPIX"]), int(kv["NAXIS"])
+    if naxis != 2:
+        raise ValueError(f"expected a 2-D FITS image, NAXIS={naxis}")
+    w, h = int(kv["NAXIS1"]), int(kv["NAXIS2"])
+    dt = {-32: ">f4", -64: ">f8", 16: ">i2", 32: ">i4", 8: "u1"}[bitpix]
+    data = np.frombuffer(raw, dtype=dt, count=w * h, offset=off).reshape(h, w)
+    if bitpix > 0:
+        data = data * float(kv.get("BSCALE", 1.0)) + float(kv.get("BZERO", 0.0))
+    return np.ascontiguousarray(data, dtype=np.float32)
+
+
+def _stamp(alert, which) -> np.ndarray:
+    blob = alert[f"cutout{which}"]["stampData"]
+    with gzip.open(io.BytesIO(bytes(blob)), "rb") as f:
+        return _parse_fits_image(f.read())
+
+
+def make_triplets(alerts, normalize: bool = True):
+    """Batched :func:`make_triplet`: ``(ndarray[N,63,63,3] float64, ndarray[N] bool)``; one kernel launch."""
+    lib = L.lib()
+    dev = _dev()
+    n = len(alerts)
+    stamps = np.zeros((n, 3, 63 * 63), dtype=np.float32)
+    hw = np.zeros((n, 3, 2), dtype=np.int32)
+    for i, alert in enumerate(alerts):
+        for c, which in enumerate(("Science", "Template", "Difference")):
+            d = _stamp(alert, which)
+            h, w = d.shape
+            if h < 1 or w < 1 or h > 63 or w > 63:
+                raise ValueError(f"cutout {which} of alert {i} has shape {d.shape}; expected at most 63x63")
+            stamps[i, c, :h * w] = d.reshape(-1)
+            hw[i, c] = (h, w)
+    s_d = torch.from_numpy(stamps).to(dev)
+    hw_d = torch.from_numpy(hw).to(dev)
+    out = torch.empty((n, 63, 63, 3), device=dev, dtype=torch.float64)
+    drop = torch.empty((n,), device=dev, dtype=torch.uint8)
+    L.check(lib.btsb_preprocess_pad_norm(_p(s_d), _p(hw_d), n, int(bool(normalize)), _p(out), L.F64, _p(drop),
+                                         L.stream_ptr()), "pad_norm")
+    return out.cpu().numpy(), drop.cpu().numpy().astype(bool)
+
+
+def make_triplet(alert, normalize: bool = True):
+    """Unpack the three gzipped FITS stamps of one alert and pre-process them (alert_utils.py:110-196).
+    Returns ``(triplet[63,63,3] float64, drop)``."""
+    trip, drop = make_triplets([alert], normalize)
+    return trip[0], bool(drop[0])
+
+
+def extract_triplets(alerts):
+    """Separate ``alert['triplet']`` from the alert dicts (alert_utils.py:199-226)."""
+    triplets = np.empty((len(alerts), 63, 63, 3))
+    for i, alert in enumerate(alerts):
+        triplets[i] = alert["triplet"]
+        alert.pop("triplet")
+        alert.pop("cutoutScience")
+        alert.pop("cutoutTemplate")
+        alert.pop("cutoutDifference")
+    return alerts, triplets

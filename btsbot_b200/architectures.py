@@ -1,0 +1,316 @@
+"""Model classes with the reference's names, constructor config keys, forward keywords and state-dict keys
+(`btsbot/architectures.py:25-372`), running on hand-written sm_100a kernels.
+
+The ``nn.Module`` tree below exists to *hold parameters under timm's / the reference's key names* so that
+``state_dict()`` / ``load_state_dict(strict=True)`` / ``.to()`` / ``.parameters()`` / ``DataParallel(...).module``
+behave exactly like the reference's models.  None of the sub-modules' own ``forward`` methods is ever used:
+``forward`` hands the whole batch to :class:`btsbot_b200._engine.Scorer`, i.e. to ``libbtsbot_b200.so``.
+There is no CPU / eager fallback -- calling a model on CPU tensors raises.
+
+Extra (opt-in) config key: ``precision`` = ``"fp32"`` (default, reference numerics: logits within 1e-4) or
+``"bf16"`` (tcgen05 tensor cores, logits within 2e-2).
+"""
+from __future__ import annotations
+
+import json
+import os.path as path
+import re
+import warnings
+
+import torch
+import torch.nn as nn
+
+from . import _engine
+from .synth import convnext_arch
+
+
+def get_model_image_size(model_kind: str) -> int:
+    """Image size encoded in a MaxViT model name, else 224 (architectures.py:10-22)."""
+    if "maxvit" in model_kind.lower():
+        m = re.search(r"_(\d+)\.", model_kind)
+        if m:
+            return int(m.group(1))
+    return 224
+
+
+# ---------------------------------------------------------------------------------------------------------
+# parameter containers mirroring timm's ConvNeXt module tree
+# ---------------------------------------------------------------------------------------------------------
+class _KernelOnly(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError("btsbot_b200: sub-modules are parameter containers; call the model, which runs the "
+                           "fused sm_100a kernels")
+
+
+class LayerNorm2d(_KernelOnly):
+    def __init__(self, c: int, eps: float = 1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.normalized_shape = (c,)
+        self.eps = eps
+
+
+class _ConvParams(_KernelOnly):
+    """Conv2d weight/bias holder (same parameter names and shapes as ``nn.Conv2d``)."""
+
+    def __init__(self, cin, cout, k, groups=1):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin // groups, k, k))
+        self.bias = nn.Parameter(torch.zeros(cout))
+        self.in_channels, self.out_channels, self.kernel_size, self.groups = cin, cout, (k, k), groups
+        nn.init.trunc_normal_(self.weight, std=0.02)       # timm ConvNeXt _init_weights
+
+
+class _Mlp(_KernelOnly):
+    def __init__(self, c):
+        super().__init__()
+        self.fc1 = _ConvParams(c, 4 * c, 1)
+        self.fc2 = _ConvParams(4 * c, c, 1)
+
+
+class _Block(_KernelOnly):
+    def __init__(self, c, ls_init_value=1e-6):
+        super().__init__()
+        self.conv_dw = _ConvParams(c, c, 7, groups=c)
+        self.norm = LayerNorm2d(c)
+        self.mlp = _Mlp(c)
+        self.gamma = nn.Parameter(ls_init_value * torch.ones(c))
+
+
+class _Stage(_KernelOnly):
+    def __init__(self, cin, c, depth, first):
+        super().__init__()
+        if first:
+            self.downsample = nn.Identity()
+        else:
+            self.downsample = nn.Sequential(LayerNorm2d(cin), _ConvParams(cin, c, 2))
+        self.blocks = nn.Sequential(*[_Block(c) for _ in range(depth)])
+
+
+class _TimmHead(_KernelOnly):
+    """Attribute surface of timm's ``NormMlpClassifierHead`` that the reference reads
+    (architectures.py:109-113,134-143)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.global_pool = nn.AdaptiveAvgPool2d(1)
+        self.norm = LayerNorm2d(c)
+        self.flatten = nn.Flatten(1)
+        self.in_features = c
+
+
+class ConvNeXtTrunk(nn.Module):
+    """Stand-in for ``timm.create_model('convnext_nano|pico...')``: same parameter tree, no arithmetic."""
+
+    def __init__(self, model_kind: str, pretrained: bool = False):
+        super().__init__()
+        arch = convnext_arch(model_kind)
+        self.model_kind, self.arch = model_kind, arch
+        if pretrained:
+            warnings.warn("btsbot_b200: pretrained timm weights need the network; the trunk is random-initialised "
+                          "-- load a checkpoint with load_state_dict()", stacklevel=3)
+        dims, depths = arch["dims"], arch["depths"]
+        self.stem = nn.Sequential(_ConvParams(3, dims[0], 4), LayerNorm2d(dims[0]))
+        self.stages = nn.Sequential(*[
+            _Stage(dims[i - 1] if i else dims[0], dims[i], depths[i], first=(i == 0)) for i in range(4)])
+        self.norm_pre = nn.Identity()
+        self.head = _TimmHead(dims[-1])
+        self.num_features = dims[-1]
+
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError("btsbot_b200: the trunk runs inside the model's fused forward")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# shared forward machinery
+# ---------------------------------------------------------------------------------------------------------
+class _B200Model(nn.Module):
+    """Caches a packed :class:`_engine.Scorer` and rebuilds it when parameters change or move."""
+
+    def _init_runtime(self, config: dict):
+        self._config = dict(config)
+        self._precision = config.get("precision", "fp32")
+        self._scorer = None
+        self._scorer_key = None
+
+    def _state_key(self):
+        ver, dev = 0, None
+        for t in list(self.parameters()) + list(self.buffers()):
+            ver += t._version
+            dev = t.device
+        return (ver, str(dev), self._precision, len(list(self.parameters())))
+
+    def set_precision(self, precision: str):
+        """``"fp32"`` or ``"bf16"``; takes effect on the next forward."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError(precision)
+        self._precision = precision
+        return self
+
+    def scorer(self) -> _engine.Scorer:
+        key = self._state_key()
+        if self._scorer is None or key != self._scorer_key:
+            self._scorer = _engine.Scorer(self._config, self.state_dict(), self._precision)
+            self._scorer_key = key
+        return self._scorer
+
+    def _run(self, image_input=None, metadata_input=None):
+        if self.training and torch.is_grad_enabled():
+            from . import _autograd
+            return _autograd.training_forward(self, image_input, metadata_input)
+        return self.scorer()(image_input=image_input, metadata_input=metadata_input)
+
+
+def _metadata_branch(n, cfg, act):
+    # architectures.py:146-153 (GELU) / :205-212, :282-289 (ReLU)
+    return [nn.BatchNorm1d(n), nn.Linear(n, cfg["meta_fc1_neurons"]), act(), nn.Dropout(cfg["meta_dropout"]),
+            nn.Linear(cfg["meta_fc1_neurons"], cfg["meta_fc2_neurons"]), act()]
+
+
+def _combined_head(nin, cfg, act):
+    # architectures.py:157-164 / :357-365
+    return nn.Sequential(nn.Linear(nin, cfg["comb_fc1_neurons"]), act(),
+                         nn.Linear(cfg["comb_fc1_neurons"], cfg["comb_fc2_neurons"]), act(),
+                         nn.Dropout(cfg["comb_dropout"]), nn.Linear(cfg["comb_fc2_neurons"], 1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference model classes
+# ---------------------------------------------------------------------------------------------------------
+class ConvNeXt(_B200Model):
+    """Image-only ConvNeXt (architectures.py:104-122): trunk -> pool -> LN2d -> flatten -> 3-layer head."""
+
+    def __init__(self, config):
+        super().__init__()
+        model_kind = config.get("model_kind", "convnext_nano.d1h_in1k")
+        self.convnext = ConvNeXtTrunk(model_kind, pretrained=config.get("pretrained", True))
+        h = self.convnext.head
+        self.convnext.head = nn.Sequential(
+            h.global_pool, h.norm, h.flatten,
+            nn.Linear(h.in_features, config["fc1_neurons"]), nn.GELU(),
+            nn.Linear(config["fc1_neurons"], config["fc2_neurons"]), nn.GELU(),
+            nn.Dropout(config["dropout"]), nn.Linear(config["fc2_neurons"], 1))
+        self._init_runtime(dict(config, model_name="ConvNeXt"))
+
+    def forward(self, input_data: torch.Tensor) -> torch.Tensor:
+        return self._run(image_input=input_data)
+
+
+class mm_ConvNeXt(_B200Model):
+    """Multimodal ConvNeXt (architectures.py:125-171)."""
+
+    def __init__(self, config):
+        super().__init__()
+        model_kind = config.get("model_kind", "convnext_nano.d1h_in1k")
+        n_meta = len(config.get("metadata_cols", []))
+        self.convnext_backbone = ConvNeXtTrunk(model_kind, pretrained=config.get("pretrained", True))
+        self.convnext_feature_dim = self.convnext_backbone.head.in_features
+        h = self.convnext_backbone.head
+        if "LS" in config["train_data_version"]:
+            self.convnext_backbone.head = nn.Sequential(h.global_pool, h.norm, h.flatten)
+        else:
+            self.convnext_backbone.head = h.flatten
+        self.metadata_branch = nn.Sequential(*_metadata_branch(n_meta, config, nn.GELU))
+        self.combined_head = _combined_head(self.convnext_feature_dim + config["meta_fc2_neurons"], config, nn.GELU)
+        self._init_runtime(dict(config, model_name="mm_ConvNeXt"))
+
+    def forward(self, image_input: torch.Tensor, metadata_input: torch.Tensor) -> torch.Tensor:
+        return self._run(image_input=image_input, metadata_input=metadata_input)
+
+
+class um_nn(_B200Model):
+    """Metadata-only MLP (architectures.py:277-293); runs in the fused metadata/head kernel."""
+
+    def __init__(self, config):
+        super().__init__()
+        n_meta = len(config.get("metadata_cols", []))
+        self.network = nn.Sequential(*_metadata_branch(n_meta, config, nn.ReLU),
+                                     nn.Linear(config["meta_fc2_neurons"], 1))
+        self._init_runtime(dict(config, model_name="um_nn"))
+
+    def forward(self, input_data: torch.Tensor) -> torch.Tensor:
+        return self._run(metadata_input=input_data)
+
+
+class frozen_fusion(_B200Model):
+    """Late fusion of a trained image branch and metadata branch (architectures.py:296-372) -- what the
+    published HF "-metadata" checkpoints are (`to_HF.py:143`)."""
+
+    @staticmethod
+    def remove_branch_head(model, model_name):
+        if model_name == "um_nn":
+            model.network = nn.Sequential(*list(model.network.children())[:-2])
+            emb_dim = model.network[-1].out_features
+        elif model_name == "ConvNeXt":
+            model.convnext.head = nn.Sequential(*list(model.convnext.head.children())[0:3])
+            emb_dim = model.convnext.head[1].normalized_shape[0]
+        elif model_name == "MaxViT":
+            emb_dim = model.maxvit.head[1].in_features
+            model.maxvit.head = nn.Sequential(*list(model.maxvit.head.children())[0:1])
+        elif model_name == "um_cnn":
+            emb_dim = model.head[0].in_features
+            model.head = nn.Identity()
+        else:
+            raise ValueError(f"Model {model_name} not supported")
+        return model, emb_dim
+
+    @staticmethod
+    def load_BTSbot_model(model_dir, train_config=None, skip_load_state=False):
+        if train_config is None:
+            with open(path.join(model_dir, "report.json"), "r") as f:
+                train_config = json.load(f)["train_config"]
+        try:
+            model_type = globals()[train_config["model_name"]]
+        except KeyError:
+            print(f"Could not find model of name {train_config['model_name']}")
+            exit(0)
+        model = model_type(train_config)
+        if not skip_load_state:
+            model.load_state_dict(torch.load(path.join(model_dir, "best_model.pth")))
+        return frozen_fusion.remove_branch_head(model, train_config["model_name"])
+
+    def __init__(self, config):
+        super().__init__()
+        skip = config.get("skip_load_state", False)
+        self.image_branch, img_dim = frozen_fusion.load_BTSbot_model(
+            config["image_model_dir"], train_config=config.get("image_model_config", None), skip_load_state=skip)
+        self.meta_branch, meta_dim = frozen_fusion.load_BTSbot_model(
+            config["meta_model_dir"], train_config=config.get("meta_model_config", None), skip_load_state=skip)
+        self.combined_head = _combined_head(img_dim + meta_dim, config, nn.ReLU)
+        cfg = dict(config, model_name="frozen_fusion")
+        cfg["image_model_config"] = dict(self.image_branch._config)
+        cfg["meta_model_config"] = dict(self.meta_branch._config)
+        self._init_runtime(cfg)
+
+    def forward(self, image_input: torch.Tensor, metadata_input: torch.Tensor) -> torch.Tensor:
+        return self._run(image_input=image_input, metadata_input=metadata_input)
+
+
+class _NotOnB200(nn.Module):
+    _why = ""
+
+    def __init__(self, config):
+        super().__init__()
+        raise NotImplementedError(f"btsbot_b200: {type(self).__name__} {self._why}")
+
+
+class MaxViT(_NotOnB200):
+    """architectures.py:25-51 -- MaxViT trunk kernels (bilinear stem, MBConv, window/grid attention) are the
+    next hot-path row; not built yet, and there is no eager fallback."""
+    _why = "has no sm_100a kernels yet (SURVEY.md section 8 row a7); no eager fallback is provided"
+
+
+class mm_MaxViT(_NotOnB200):
+    """architectures.py:54-101 -- see :class:`MaxViT`."""
+    _why = "has no sm_100a kernels yet (SURVEY.md section 8 row a7); no eager fallback is provided"
+
+
+class mm_cnn(_NotOnB200):
+    """architectures.py:174-229 -- legacy 2-block CNN, outside the north-star hot path."""
+    _why = "is a legacy model outside the B200 hot path (SURVEY.md section 8 row a8)"
+
+
+class um_cnn(_NotOnB200):
+    """architectures.py:232-274 -- legacy 2-block CNN, outside the north-star hot path."""
+    _why = "is a legacy model outside the B200 hot path (SURVEY.md section 8 row a8)"

@@ -1,0 +1,288 @@
+// K4 / K5b (bf16 mode): out[M,N] = epi(A[M,K] . Wt[N,K]^T + bias) on the 5th-generation tensor cores.
+//
+//   * operands: TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 4-stage shared-memory ring
+//   * math:     tcgen05.mma cta_group::1 kind::f16 (bf16 x bf16 -> fp32), M=128 x N=BN x K=16 per instruction,
+//               issued by one thread; accumulators in TMEM, double buffered (2 x 256 columns)
+//   * epilogue: 8 warps, tcgen05.ld 32x32b (thread = output row), bias / GELU / gamma*acc+residual in registers,
+//               bf16 rows written straight to global (32 B per thread per 16 columns)
+//   * persistent: grid = min(#tiles, #SMs); tiles walk N fastest so concurrent CTAs share A rows in L2
+//
+// Replaces timm mlp.fc1 (+GELU), mlp.fc2 (*gamma + shortcut) and downsample.1 (see include/btsbot_b200.h).
+#include "tc_common.cuh"
+
+namespace btsb {
+
+namespace {
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kMaxBN = 256;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = 512;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kABytes = BM * BK * 2;              // 16 KB
+constexpr int kBBytes = kMaxBN * BK * 2;          // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+}  // namespace
+
+template <int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const float* __restrict__ bias, const float* __restrict__ gamma,
+               const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out, int M, int N, int K, int BN) {
+  using namespace tc;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  // barrier map (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem address slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccStages + s); };
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem_al + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccStages));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32((const void*)tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t tx_bytes = (uint32_t)(BM + BN) * BK * 2;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), tx_bytes);
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+        tma_load_2d(sa + kABytes, &tmB, full_bar(stage), kb * BK, n0);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    // ===================== MMA issuer (single thread) =====================
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    const uint32_t idesc = idesc_bf16_f32(BM, BN);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(as), aphase ^ 1u);          // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * kMaxBN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * kStageBytes;
+        const uint64_t adesc = smem_desc_sw128(sa);
+        const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
+        const int kmax = min(BK, K - kb * BK) / 16;    // K tail: TMA zero-fills, but skip the useless MMAs
+        for (int kk = 0; kk < kmax; ++kk) {
+          // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));                  // frees this smem stage when the MMAs retire
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(as));                       // accumulator complete -> epilogue
+      if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                       // TMEM lanes this warp may touch: 32*(warp%4) ..
+    const int half = ew >> 2;                           // column half handled by this warp
+    int as = 0; uint32_t aphase = 0;
+    const int chunks = BN / 16;
+    const int c_lo = half == 0 ? 0 : (chunks + 1) / 2;
+    const int c_hi = half == 0 ? (chunks + 1) / 2 : chunks;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kMaxBN);
+      if (c_lo >= c_hi) {                               // narrow tile: this warp has no columns, release at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
+      for (int ch = c_lo; ch < c_hi; ++ch) {
+        uint32_t r[16];
+        tmem_ld16(taddr + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+        if (ch == c_hi - 1) {                           // last TMEM read of this warp for this tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        const int n = n0 + ch * 16;
+        if (row < M && n < N) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));
+            v[i] = __uint_as_float(r[i]) + b4.x; v[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
+            v[i + 2] = __uint_as_float(r[i + 2]) + b4.z; v[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
+          }
+          if (EPI == BTSB_EPI_BIAS_GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+          }
+          if (EPI == BTSB_EPI_SCALE_RES) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * N + n);
+            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
+              v[i] = fmaf(g4.x, v[i], bf16_lo(rr[i / 2]));
+              v[i + 1] = fmaf(g4.y, v[i + 1], bf16_hi(rr[i / 2]));
+              v[i + 2] = fmaf(g4.z, v[i + 2], bf16_lo(rr[i / 2 + 1]));
+              v[i + 3] = fmaf(g4.w, v[i + 3], bf16_hi(rr[i / 2 + 1]));
+            }
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * N + n);
+          op[0] = o0; op[1] = o1;
+        }
+      }
+      if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return BTSB_ECUDA; }
+  BTSB_REQUIRE(((uintptr_t)base % 16) == 0 && (cols * 2) % 16 == 0, "tensor map: base/pitch must be 16-byte aligned");
+  BTSB_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u not in [1,256]", box_rows);
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return BTSB_ECUDA; }
+  return BTSB_OK;
+}
+
+static int pick_bn(int N) {
+  for (int bn = kMaxBN; bn >= 16; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 16;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res, void* out,
+              int64_t M, int N, int K, int epilogue, cudaStream_t st) {
+  BTSB_REQUIRE(N % 16 == 0 && K % 16 == 0, "gemm bf16: N=%d and K=%d must be multiples of 16", N, K);
+  BTSB_REQUIRE(M < (1ll << 31), "gemm bf16: M too large");
+  BTSB_REQUIRE(((uintptr_t)out % 16) == 0 && ((uintptr_t)bias % 16) == 0, "gemm bf16: out/bias must be 16-byte aligned");
+  if (epilogue == BTSB_EPI_SCALE_RES)
+    BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)gamma % 16) == 0, "gemm bf16: res/gamma must be 16-byte aligned");
+  const int BN = pick_bn(N);
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM)) return e;
+  if (int e = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint32_t)BN)) return e;
+  const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
+  const int grid = min(m_tiles * n_tiles, num_sms());
+  static bool attr_done = false;
+  if (!attr_done) {
+    BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+    BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+    BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_SCALE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+    attr_done = true;
+  }
+  const __nv_bfloat16* r = (const __nv_bfloat16*)res;
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  if (epilogue == BTSB_EPI_BIAS)
+    gemm_tc_kernel<BTSB_EPI_BIAS><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, r, o, (int)M, N, K, BN);
+  else if (epilogue == BTSB_EPI_BIAS_GELU)
+    gemm_tc_kernel<BTSB_EPI_BIAS_GELU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, r, o, (int)M, N, K, BN);
+  else
+    gemm_tc_kernel<BTSB_EPI_SCALE_RES><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, r, o, (int)M, N, K, BN);
+  return launch_done("gemm_bf16");
+}
+
+int gemm_f32(const float* A, const float* Wt, const float* bias, const float* gamma, const float* res, float* out,
+             int64_t M, int N, int K, int epilogue, cudaStream_t st);
+
+}  // namespace btsb
+
+using namespace btsb;
+
+extern "C" int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res,
+                             void* out, int64_t M, int N, int K, int dtype, int epilogue, void* stream) {
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(M >= 0 && N >= 1 && K >= 1, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  BTSB_REQUIRE(dtype == BTSB_F32 || dtype == BTSB_BF16, "gemm: dtype must be F32 or BF16");
+  BTSB_REQUIRE(epilogue >= BTSB_EPI_BIAS && epilogue <= BTSB_EPI_SCALE_RES, "gemm: unknown epilogue %d", epilogue);
+  if (M == 0) return BTSB_OK;
+  BTSB_REQUIRE(A && Wt && bias && out, "gemm: null pointer");
+  if (epilogue == BTSB_EPI_SCALE_RES) BTSB_REQUIRE(gamma && res, "gemm: SCALE_RES needs gamma and res");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == BTSB_F32)
+    return gemm_f32((const float*)A, (const float*)Wt, bias, gamma, (const float*)res, (float*)out, M, N, K, epilogue, st);
+  return gemm_bf16(A, Wt, bias, gamma, res, out, M, N, K, epilogue, st);
+}

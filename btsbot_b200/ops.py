@@ -1,0 +1,85 @@
+"""Per-kernel Python entry points (torch CUDA tensors in/out) over the C ABI -- used by the unit tests, the
+training path and anyone who wants a single fused op.  Shapes/dtypes: see ``include/btsbot_b200.h``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_CODE = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float64: L.F64}
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is not None:
+            L.require_cuda(t, "tensor")
+            if not t.is_contiguous():
+                raise ValueError("btsbot_b200.ops: tensors must be contiguous")
+
+
+def stem(x, w48, bias, ln_w, ln_b, out_dtype=torch.float32):
+    """x [B,3,H,W] f32; w48 [48,C0] f32 -> rows [B*h*w, C0]."""
+    _chk(x, w48, bias, ln_w, ln_b)
+    B, _, H, W = x.shape
+    c0 = w48.shape[1]
+    h, w = (H - 4) // 4 + 1, (W - 4) // 4 + 1
+    out = torch.empty((B * h * w, c0), device=x.device, dtype=out_dtype)
+    L.check(L.lib().btsb_convnext_stem_fwd(_p(x), B, H, W, _p(w48), _p(bias), _p(ln_w), _p(ln_b), c0, _p(out),
+                                           _CODE[out_dtype], L.stream_ptr()), "stem")
+    return out
+
+
+def dwln(x, B, H, W, w49, bias, ln_w, ln_b):
+    """x rows [B*H*W, C] (f32|bf16); w49 [49,C] f32 -> same shape/dtype."""
+    _chk(x, w49, bias, ln_w, ln_b)
+    out = torch.empty_like(x)
+    L.check(L.lib().btsb_convnext_dwln_fwd(_p(x), _CODE[x.dtype], B, H, W, x.shape[1], _p(w49), _p(bias), _p(ln_w),
+                                           _p(ln_b), _p(out), L.stream_ptr()), "dwln")
+    return out
+
+
+def lnpatch(x, B, H, W, ln_w, ln_b):
+    _chk(x, ln_w, ln_b)
+    c = x.shape[1]
+    ho, wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
+    out = torch.empty((B * ho * wo, 4 * c), device=x.device, dtype=x.dtype)
+    L.check(L.lib().btsb_convnext_lnpatch_fwd(_p(x), _CODE[x.dtype], B, H, W, c, _p(ln_w), _p(ln_b), _p(out),
+                                              L.stream_ptr()), "lnpatch")
+    return out
+
+
+def poolln(x, B, HW, ln_w=None, ln_b=None):
+    _chk(x, ln_w, ln_b)
+    out = torch.empty((B, x.shape[1]), device=x.device, dtype=torch.float32)
+    L.check(L.lib().btsb_convnext_poolln_fwd(_p(x), _CODE[x.dtype], B, HW, x.shape[1], _p(ln_w), _p(ln_b), _p(out),
+                                             L.stream_ptr()), "poolln")
+    return out
+
+
+def gemm(a, wt, bias, epilogue=L.EPI_BIAS, gamma=None, res=None):
+    """out[M,N] = epi(a[M,K] @ wt[N,K]^T + bias); a/wt/res share dtype (f32 -> CUDA cores, bf16 -> tcgen05)."""
+    _chk(a, wt, bias, gamma, res)
+    if a.dtype != wt.dtype or (res is not None and res.dtype != a.dtype):
+        raise ValueError("gemm: a, wt and res must share one dtype")
+    M, K = a.shape
+    N = wt.shape[0]
+    out = torch.empty((M, N), device=a.device, dtype=a.dtype)
+    L.check(L.lib().btsb_gemm_fwd(_p(a), _p(wt), _p(bias), _p(gamma), _p(res), _p(out), M, N, K, _CODE[a.dtype],
+                                  epilogue, L.stream_ptr()), "gemm")
+    return out
+
+
+def score(logits):
+    """sigmoid + 0.5 threshold on device -> (scores f32, labels uint8)."""
+    _chk(logits)
+    flat = logits.reshape(-1)
+    s = torch.empty_like(flat)
+    lab = torch.empty(flat.shape, device=flat.device, dtype=torch.uint8)
+    L.check(L.lib().btsb_score_epilogue(_p(flat), flat.numel(), _p(s), _p(lab), L.stream_ptr()), "score")
+    return s.view_as(logits), lab.view_as(logits)

@@ -1,0 +1,153 @@
+/*
+ * btsbot_b200 -- C ABI of the B200 (sm_100a) alert-scoring hot path.
+ *
+ * The reference (nabeelre/BTSbot) has no FFI: its seam is Python (`btsbot/architectures.py`
+ * classes calling `timm.create_model`, `btsbot/alert_utils.py` numpy helpers).  Each entry point
+ * below names the reference code whose arithmetic it replaces (file:line under /root/reference).
+ * The Python package `btsbot_b200` binds these with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; every pointer is DEVICE memory owned by the caller
+ *    unless a parameter is documented as host memory;
+ *  - the library never allocates or frees device memory, never synchronises the device and keeps no
+ *    pointer after the call returns; work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *  - activations between kernels are NHWC "pixel rows": a [B,H,W,C] map is the row-major matrix
+ *    [B*H*W, C]; API-facing images stay NCHW float32 like the reference's tensors;
+ *  - return value: BTSB_OK (0) or a negative BTSB_E* code; btsb_last_error_string() describes the
+ *    last failure on the calling thread.  No exceptions or abort() cross this boundary;
+ *  - dtype codes: BTSB_F32 / BTSB_BF16 / BTSB_F64 (arithmetic always accumulates in fp32, the
+ *    preprocessing norms in fp64);
+ *  - there is no CPU path: on a device that is not compute capability 10.x every compute entry
+ *    returns BTSB_EARCH.
+ */
+#ifndef BTSBOT_B200_H
+#define BTSBOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BTSB_OK 0
+#define BTSB_EINVAL (-1)  /* bad shape / dtype / alignment / null pointer */
+#define BTSB_EARCH (-2)   /* device is not sm_100 */
+#define BTSB_ECUDA (-3)   /* CUDA runtime / driver error, see btsb_last_error_string */
+
+#define BTSB_F32 0
+#define BTSB_BF16 1
+#define BTSB_F64 2
+
+/* activation codes (metadata branch / heads) */
+#define BTSB_ACT_NONE 0
+#define BTSB_ACT_GELU 1 /* exact erf GELU (torch.nn.GELU default) */
+#define BTSB_ACT_RELU 2
+
+/* GEMM epilogues */
+#define BTSB_EPI_BIAS 0      /* out = acc + bias[n] */
+#define BTSB_EPI_BIAS_GELU 1 /* out = gelu(acc + bias[n]) */
+#define BTSB_EPI_SCALE_RES 2 /* out = res[m,n] + gamma[n] * (acc + bias[n]) */
+
+int btsb_version(void);
+const char* btsb_last_error_string(void);
+/* 0 when the current device can run the library (compute capability 10.x), else BTSB_EARCH. */
+int btsb_device_ok(void);
+/* number of kernels this library has launched in this process (all threads); bench.py's gpu_launches. */
+uint64_t btsb_launch_count(void);
+
+/* ---- K1: array preparation -------------------------------------------------------------------
+ * crop_norm: replaces alert_utils.crop_triplets / crop_norm_cutout (alert_utils.py:54-107) fused with the
+ * cast + NHWC->NCHW transpose every caller performs next (inference_example.py:62-64, train.py:139-155,
+ * val.py:92-94).  in: [n,63,63,3] HWC, in_dtype F32 or F64.  out: [n,3,s,s] NCHW float32.
+ * margin = (63-s)/2 (floor).  normalize!=0: each cutout is divided by the L2 norm of its cropped window
+ * (norm accumulated in fp64; for F64 input the quotient is formed in fp64 and rounded once to fp32, which
+ * is what `.astype(np.float32)` does to the reference's float64 result).  normalize==0: crop/cast/transpose only.
+ * out_hwc!=0 keeps the reference's [n,s,s,3] HWC layout (the drop-in return value of crop_triplets).
+ */
+int btsb_preprocess_crop_norm(const void* in, int in_dtype, int64_t n, int crop_to_size, int normalize,
+                              int out_hwc, float* out, void* stream);
+
+/* pad_norm: numeric tail of alert_utils.make_triplet (alert_utils.py:147-193) for n alerts.
+ * stamps: [n,3,63*63] float32, stamp (a,c) stored densely row-major with its own width at the start of its
+ * slot; hw: [n,3,2] int32 (rows, cols), each in [1,63].  Per cutout, in order science/template/difference:
+ * nanmedian==+-inf -> drop; NaN->0, +-inf->+-FLT_MAX; if normalize and not yet dropped divide by the L2 norm
+ * (float32 like numpy: an overflowing norm is +inf, a zero norm yields NaN as in the reference); all-zero
+ * -> drop; pad bottom/right to 63x63 with float32(1e-9) AFTER normalisation.
+ * out: [n,63,63,3] HWC, out_dtype F64 (reference's storage type) or F32.  drop: [n] uint8.
+ */
+int btsb_preprocess_pad_norm(const float* stamps, const int32_t* hw, int64_t n, int normalize,
+                             void* out, int out_dtype, uint8_t* drop, void* stream);
+
+/* ---- K2a: ConvNeXt stem -- timm stem.0 Conv2d(3,C0,k4,s4)+bias and stem.1 LayerNorm2d(eps 1e-6)
+ * (called at architectures.py:108,132).  x: [B,3,H,W] NCHW float32.  w: [48,C0] float32 with
+ * k = (ci*4+ky)*4+kx (transposed conv weight), bias/ln_w/ln_b: [C0] float32.
+ * out: [B*h*w, C0] (h=(H-4)/4+1, w likewise), out_dtype F32 or BF16.  C0 <= 128.
+ */
+int btsb_convnext_stem_fwd(const float* x, int64_t B, int H, int W, const float* w, const float* bias,
+                           const float* ln_w, const float* ln_b, int C0, void* out, int out_dtype, void* stream);
+
+/* ---- K3: depthwise 7x7 (pad 3) + bias + LayerNorm2d -- timm blocks.j.conv_dw + blocks.j.norm.
+ * x, out: [B*H*W, C] dtype F32|BF16 (same for both).  w: [49,C] float32 (k = ky*7+kx), bias/ln_w/ln_b [C].
+ */
+int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* w,
+                           const float* bias, const float* ln_w, const float* ln_b, void* out, void* stream);
+
+/* ---- K5a: downsample prologue -- timm stages.i.downsample.0 LayerNorm2d, emitted directly as the
+ * 2x2/s2 patch matrix the conv (downsample.1) consumes as a GEMM.  x: [B*H*W, C]; out: [B*Ho*Wo, 4C] with
+ * column (dy*2+dx)*C + c, Ho=(H-2)/2+1 (floor: last odd row/col dropped, as Conv2d does).
+ */
+int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* ln_w,
+                              const float* ln_b, void* out, void* stream);
+
+/* ---- head prologue: global average pool + LayerNorm2d + flatten (architectures.py:109-113,136-141,
+ * 309-313).  x: [B*HW, C] dtype F32|BF16 -> out [B, C] float32.  ln_w==NULL: pool only.
+ */
+int btsb_convnext_poolln_fwd(const void* x, int dtype, int64_t B, int HW, int C, const float* ln_w,
+                             const float* ln_b, float* out, void* stream);
+
+/* ---- K4 / K5b: pointwise GEMM with fused epilogue -- timm mlp.fc1 (+GELU), mlp.fc2 (*gamma + shortcut),
+ * downsample.1.  out[M,N] = epi(A[M,K] . Wt[N,K]^T + bias).  dtype F32: CUDA-core fp32 (the 1e-4 path);
+ * dtype BF16: tcgen05/TMEM tensor cores with TMA operand staging, fp32 accumulate, A/Wt/res/out bf16.
+ * bias/gamma: [N] float32.  res: [M,N] in `dtype` (EPI_SCALE_RES only).  F32: K % 4 == 0.  BF16: K % 16 == 0,
+ * N % 16 == 0, all pointers 16-byte aligned.
+ */
+int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res,
+                  void* out, int64_t M, int N, int K, int dtype, int epilogue, void* stream);
+
+/* ---- K6: metadata branch + fusion head in one kernel (architectures.py:146-164,168-170; um_nn 282-290;
+ * image-only heads 109-119; frozen_fusion 357-365).
+ * feat: [B,F] (feat_dtype F32|BF16) or NULL (F=0); meta: [B,Mm] float32 or NULL (Mm=0).
+ * BatchNorm1d is passed folded: bn_scale = w/sqrt(var+eps), bn_shift = b - mean*bn_scale.
+ * Weights are float32 and TRANSPOSED ([in,out], out contiguous): m1t [Mm,m1], m2t [m1,m2],
+ * h0t [F+m2 (or F, or m2), c1], h1t [c1,c2], h2 [c2].  meta_act after m1; meta_out_act after m2
+ * (GELU for mm_*, NONE for frozen_fusion, RELU for um_nn); head_act after h0 and h1.
+ * When Mm>0 and c1==0 the head is just `h2` applied to the meta embedding (um_nn: Linear(m2,1)).
+ * logits: [B] float32.
+ */
+typedef struct {
+  const void* feat; int feat_dtype; int F;
+  const float* meta; int Mm;
+  const float *bn_scale, *bn_shift;
+  const float *m1t, *m1b; int m1;
+  const float *m2t, *m2b; int m2;
+  int meta_act, meta_out_act;
+  const float *h0t, *h0b; int c1;
+  const float *h1t, *h1b; int c2;
+  const float *h2, *h2b;
+  int head_act;
+} btsb_head_params;
+int btsb_meta_head_fwd(const btsb_head_params* p, int64_t B, float* logits, void* stream);
+
+/* ---- scoring epilogue (train.py:530-538, val.py:153,168, inference_example.py:91):
+ * score = sigmoid(logit), label = score > 0.5.  scores/labels may be NULL. */
+int btsb_score_epilogue(const float* logits, int64_t B, float* scores, uint8_t* labels, void* stream);
+
+/* dtype helpers used by the weight packer: float32 -> bf16 (round-to-nearest-even) and back. */
+int btsb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
+int btsb_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BTSBOT_B200_H */

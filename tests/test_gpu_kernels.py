@@ -1,0 +1,163 @@
+"""GPU: every C-ABI kernel against a plain PyTorch fp32 reference of the same op (run on the CPU)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rows_to_nchw(rows, B, H, W):
+    return rows.float().view(B, H, W, -1).permute(0, 3, 1, 2).contiguous()
+
+
+def _nchw_to_rows(x):
+    B, C, H, W = x.shape
+    return x.permute(0, 2, 3, 1).reshape(B * H * W, C).contiguous()
+
+
+def _ln2d(x, w, b):
+    return F.layer_norm(x.permute(0, 2, 3, 1), (x.shape[1],), w, b, 1e-6).permute(0, 3, 1, 2)
+
+
+def _report(name, got, ref):
+    err = (got - ref).abs().max().item()
+    print(f"[parity] {name}: max|err|={err:.3e} ref_absmax={ref.abs().max().item():.3e}")
+    return err
+
+
+@pytest.mark.parametrize("C0,H,W,B", [(80, 63, 63, 5), (64, 63, 63, 3), (80, 64, 37, 2), (128, 16, 16, 9)])
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_stem(cuda_dev, C0, H, W, B, odt):
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 3, H, W, generator=g) * 0.02 + 0.016
+    w = torch.randn(C0, 3, 4, 4, generator=g) / 7
+    b, lw, lb = torch.randn(C0, generator=g) * 0.1, torch.rand(C0, generator=g) + 0.5, torch.randn(C0, generator=g) * 0.1
+    ref = _ln2d(F.conv2d(x, w, b, stride=4), lw, lb)
+    got = ops.stem(x.to(cuda_dev), w.reshape(C0, 48).t().contiguous().to(cuda_dev), b.to(cuda_dev), lw.to(cuda_dev),
+                   lb.to(cuda_dev), odt)
+    h, wd = ref.shape[2:]
+    err = _report(f"stem C0={C0} {H}x{W} {odt}", _rows_to_nchw(got.cpu(), B, h, wd), ref)
+    assert err < (2e-5 if odt == torch.float32 else 3e-2)
+
+
+@pytest.mark.parametrize("C,H,W,B", [(80, 15, 15, 7), (160, 7, 7, 33), (320, 3, 3, 70), (640, 1, 1, 130),
+                                     (64, 15, 15, 3), (128, 7, 7, 5), (256, 3, 3, 5), (512, 1, 1, 5),
+                                     (64, 9, 11, 4), (96, 5, 2, 3)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_dwln(cuda_dev, C, H, W, B, dt):
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, C, H, W, generator=g)
+    if dt == torch.bfloat16:
+        x = x.bfloat16().float()
+    w = torch.randn(C, 1, 7, 7, generator=g) / 7
+    b, lw, lb = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    ref = _ln2d(F.conv2d(x, w, b, padding=3, groups=C), lw, lb)
+    got = ops.dwln(_nchw_to_rows(x).to(dt).to(cuda_dev), B, H, W, w.reshape(C, 49).t().contiguous().to(cuda_dev),
+                   b.to(cuda_dev), lw.to(cuda_dev), lb.to(cuda_dev))
+    err = _report(f"dwln C={C} {H}x{W} {dt}", _rows_to_nchw(got.cpu(), B, H, W), ref)
+    assert err < (3e-5 if dt == torch.float32 else 4e-2)
+
+
+@pytest.mark.parametrize("C,H,W,B", [(80, 15, 15, 5), (160, 7, 7, 9), (320, 3, 3, 11), (64, 15, 15, 2), (256, 4, 6, 3)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_lnpatch_then_gemm_is_downsample(cuda_dev, C, H, W, B, dt):
+    from btsbot_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, H, W, generator=g)
+    if dt == torch.bfloat16:
+        x = x.bfloat16().float()
+    lw, lb = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    cout = 2 * C
+    w = torch.randn(cout, C, 2, 2, generator=g) / (2 * C ** 0.5)
+    if dt == torch.bfloat16:
+        w = w.bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(_ln2d(x, lw, lb), w, b, stride=2)
+    patches = ops.lnpatch(_nchw_to_rows(x).to(dt).to(cuda_dev), B, H, W, lw.to(cuda_dev), lb.to(cuda_dev))
+    ho, wo = ref.shape[2:]
+    assert patches.shape == (B * ho * wo, 4 * C)
+    wt = w.permute(0, 2, 3, 1).reshape(cout, 4 * C).contiguous().to(dt).to(cuda_dev)
+    got = ops.gemm(patches, wt, b.to(cuda_dev), L.EPI_BIAS)
+    err = _report(f"downsample C={C} {H}x{W} {dt}", _rows_to_nchw(got.cpu(), B, ho, wo), ref)
+    assert err < (3e-5 if dt == torch.float32 else 5e-2)
+
+
+@pytest.mark.parametrize("C,HW,B,ln", [(640, 1, 70, True), (512, 9, 5, True), (80, 4, 3, False)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_poolln(cuda_dev, C, HW, B, ln, dt):
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B * HW, C, generator=g).to(dt)
+    lw, lb = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    pooled = x.float().view(B, HW, C).mean(1)
+    ref = F.layer_norm(pooled, (C,), lw, lb, 1e-6) if ln else pooled
+    got = ops.poolln(x.to(cuda_dev), B, HW, lw.to(cuda_dev) if ln else None, lb.to(cuda_dev) if ln else None)
+    assert _report(f"poolln C={C} HW={HW} {dt}", got.cpu(), ref) < 2e-5
+
+
+GEMM_SHAPES = [(1000, 320, 80), (1000, 80, 320), (300, 640, 160), (513, 2560, 640), (128, 16, 16), (5000, 256, 1024),
+               (77, 160, 640), (1, 640, 2560), (257, 512, 2048), (1125, 64, 256)]
+
+
+def _gemm_ref(a, w, bias, epi, gamma, res):
+    from btsbot_b200 import _lib as L
+    v = a.double() @ w.double().t() + bias.double()
+    if epi == L.EPI_BIAS_GELU:
+        v = F.gelu(v)
+    if epi == L.EPI_SCALE_RES:
+        v = res.double() + gamma.double() * v
+    return v.float()
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_gemm_f32(cuda_dev, M, N, K, epi):
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5
+    bias, gamma, res = torch.randn(N, generator=g) * 0.1, torch.rand(N, generator=g) + 0.5, torch.randn(M, N, generator=g)
+    ref = _gemm_ref(a, w, bias, epi, gamma, res)
+    got = ops.gemm(a.to(cuda_dev), w.to(cuda_dev), bias.to(cuda_dev), epi,
+                   gamma.to(cuda_dev) if epi == 2 else None, res.to(cuda_dev) if epi == 2 else None)
+    assert _report(f"gemm f32 {M}x{N}x{K} epi{epi}", got.cpu(), ref) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2])
+def test_gemm_bf16_tcgen05(cuda_dev, M, N, K, epi):
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    bias, gamma = torch.randn(N, generator=g) * 0.1, torch.rand(N, generator=g) + 0.5
+    res = torch.randn(M, N, generator=g).bfloat16()
+    ref = _gemm_ref(a.float(), w.float(), bias, epi, gamma, res.float())
+    got = ops.gemm(a.to(cuda_dev), w.to(cuda_dev), bias.to(cuda_dev), epi,
+                   gamma.to(cuda_dev) if epi == 2 else None, res.to(cuda_dev) if epi == 2 else None)
+    torch.cuda.synchronize()
+    got = got.float().cpu()
+    err = _report(f"gemm bf16 {M}x{N}x{K} epi{epi}", got, ref)
+    # exact fp32-accumulated product rounded once to bf16: half an ulp of |value| <= ~8
+    assert err < 3.2e-2 and (got - ref).abs().mean().item() < 4e-3
+
+
+def test_gemm_rejects_bad_arguments(cuda_dev):
+    from btsbot_b200 import ops
+    a = torch.zeros(8, 24, device=cuda_dev, dtype=torch.bfloat16)
+    w = torch.zeros(16, 24, device=cuda_dev, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="multiples of 16"):
+        ops.gemm(a, w, torch.zeros(16, device=cuda_dev))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gemm(a.cpu(), w.cpu(), torch.zeros(16))
+
+
+def test_score_epilogue(cuda_dev):
+    from btsbot_b200 import ops
+    lg = torch.linspace(-8, 8, 1001).view(-1, 1)
+    s, lab = ops.score(lg.to(cuda_dev))
+    assert (s.cpu() - torch.sigmoid(lg)).abs().max() < 1e-6
+    ref_lab = (torch.sigmoid(lg) > 0.5).to(torch.uint8)
+    assert torch.equal(lab.cpu(), ref_lab)

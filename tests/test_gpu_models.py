@@ -1,0 +1,147 @@
+"""GPU: whole-model parity of the drop-in classes against the CPU oracle and the reference-made goldens.
+
+Tolerances are the north star's: fp32 logits within 1e-4 abs, bf16 within 2e-2 abs, identical labels at the
+0.5 threshold (asserted where |oracle logit| exceeds the tolerance; the excluded count is printed)."""
+import numpy as np
+import pytest
+import torch
+
+import btsbot_b200 as btsbot
+from btsbot_b200 import synth
+from cases import MODEL_CASES, case_state_dict
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _build(case, golden_logits, dev, precision):
+    cfg, sd = case_state_dict(case, golden_logits)
+    cfg = dict(cfg, precision=precision)
+    model = getattr(btsbot, cfg["model_name"])(cfg)
+    model.load_state_dict(synth.to_torch(sd), strict=True)
+    return cfg, sd, model.to(dev).eval()
+
+
+def _call(model, cfg, img, meta):
+    with torch.no_grad():
+        if cfg["model_name"] in ("mm_ConvNeXt", "frozen_fusion"):
+            return model(image_input=img, metadata_input=meta)
+        if cfg["model_name"] == "um_nn":
+            return model(input_data=meta)
+        return model(input_data=img)
+
+
+@pytest.mark.parametrize("case", list(MODEL_CASES))
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_logits_match_reference(cuda_dev, golden_logits, golden_batch, case, precision):
+    from oracle import convnext_oracle as O
+    img, meta = golden_batch
+    cfg, sd, model = _build(case, golden_logits, cuda_dev, precision)
+    got = _call(model, cfg, torch.from_numpy(img).to(cuda_dev), torch.from_numpy(meta).to(cuda_dev))
+    torch.cuda.synchronize()
+    assert got.shape == (img.shape[0], 1) and got.dtype == torch.float32 and got.is_cuda
+    got = got.cpu().numpy()
+    ref = golden_logits[case]                                   # reference architectures.py executed verbatim
+    orc = O.forward(synth.to_torch(sd), cfg, torch.from_numpy(img), torch.from_numpy(meta)).numpy()
+    e_ref, e_orc = np.abs(got - ref).max(), np.abs(got - orc).max()
+    tol = TOL[precision]
+    sure = np.abs(orc) > tol
+    print(f"[parity] {case} {precision}: max|logit-ref|={e_ref:.3e} max|logit-oracle|={e_orc:.3e} "
+          f"labels compared {int(sure.sum())}/{sure.size}")
+    assert e_orc < tol and e_ref < tol + 5e-5
+    assert np.array_equal((got > 0)[sure], (orc > 0)[sure])
+    assert 0.3 < (orc > 0).mean() < 0.7                         # labels are not vacuous
+
+
+@pytest.mark.parametrize("kind", ["convnext_nano.d1h_in1k", "convnext_pico.d1_in1k"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_trunk_intermediates(cuda_dev, kind, precision):
+    """Per-block tensors, not only logits: every dw+LN output and block output."""
+    from oracle import convnext_oracle as O
+    from btsbot_b200 import _engine
+    cfg = dict(synth.canonical_config("mm_ConvNeXt", kind), precision=precision)
+    sd = synth.to_torch(synth.make_state_dict(cfg, seed=5))
+    B = 6
+    img = torch.from_numpy(np.ascontiguousarray(synth.make_triplets(B, start=40).transpose(0, 3, 1, 2)))
+    meta = torch.from_numpy(synth.make_metadata(B, start=40))
+    cap_o, cap_g = {}, {}
+    O.forward(sd, cfg, img, meta, capture=cap_o)
+    scorer = _engine.Scorer(cfg, {k: v.to(cuda_dev) for k, v in sd.items()}, precision)
+    scorer(image_input=img.to(cuda_dev), metadata_input=meta.to(cuda_dev), capture=cap_g)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for name, ref in cap_o.items():
+        if name in ("features", "meta"):
+            continue
+        rows, h, w = cap_g[name]
+        got = rows.float().cpu().view(B, h, w, -1).permute(0, 3, 1, 2)
+        assert got.shape == ref.shape, name
+        rel = ((got - ref).abs().max() / ref.abs().max()).item()
+        worst = max(worst, rel)
+        assert rel < (2e-5 if precision == "fp32" else 3e-2), (name, rel)
+    print(f"[parity] intermediates {kind} {precision}: worst relative error {worst:.3e} over {len(cap_o)} tensors")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_batch_and_shard_invariance(cuda_dev, golden_logits, precision):
+    """Per-alert results do not depend on batch composition: scoring [0,N) at once == scoring index-range shards
+    (the multi-GPU partitioning of SURVEY.md 8e) -- bitwise."""
+    cfg, sd, model = _build("mm_nano", golden_logits, cuda_dev, precision)
+    n = 777
+    img = torch.from_numpy(np.ascontiguousarray(synth.make_triplets(n, start=0).transpose(0, 3, 1, 2))).to(cuda_dev)
+    meta = torch.from_numpy(synth.make_metadata(n, start=0)).to(cuda_dev)
+    whole = _call(model, cfg, img, meta)
+    parts = torch.cat([_call(model, cfg, img[a:b], meta[a:b]) for a, b in ((0, 1), (1, 130), (130, 389), (389, n))])
+    assert torch.equal(whole, parts)
+    assert torch.isfinite(whole).all()
+
+
+def test_large_batch_against_oracle_sample(cuda_dev, golden_logits):
+    """BASELINE config-2/3-sized batch through the bf16 path; a strided sample is checked against the oracle."""
+    from oracle import convnext_oracle as O
+    cfg, sd, model = _build("mm_nano", golden_logits, cuda_dev, "bf16")
+    n = 4096
+    trip = synth.make_triplets(n, start=0)
+    meta = synth.make_metadata(n, start=0)
+    img = torch.from_numpy(np.ascontiguousarray(trip.transpose(0, 3, 1, 2)))
+    got = _call(model, cfg, img.to(cuda_dev), torch.from_numpy(meta).to(cuda_dev)).cpu().numpy()
+    idx = np.arange(0, n, 64)
+    orc = O.forward(synth.to_torch(sd), cfg, img[idx], torch.from_numpy(meta[idx])).numpy()
+    err = np.abs(got[idx] - orc).max()
+    print(f"[parity] large batch bf16: max|err|={err:.3e} on {idx.size} sampled alerts; logits std {got.std():.3f}")
+    assert err < TOL["bf16"]
+
+
+def test_error_behaviour(cuda_dev, golden_logits):
+    cfg, sd, model = _build("mm_pico", golden_logits, cuda_dev, "fp32")
+    img = torch.zeros(2, 3, 63, 63, device=cuda_dev)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(image_input=img.cpu(), metadata_input=torch.zeros(2, 25))
+    with pytest.raises(ValueError):
+        model(image_input=img, metadata_input=torch.zeros(2, 24, device=cuda_dev))
+    with pytest.raises(TypeError):
+        model(img, torch.zeros(2, 25, device=cuda_dev), None)
+    with pytest.raises(RuntimeError):          # 127x127 leaves a 3x3 map: the reference's Flatten head fails too
+        model(image_input=torch.zeros(2, 3, 127, 127, device=cuda_dev), metadata_input=torch.zeros(2, 25, device=cuda_dev))
+    assert model(image_input=img[:0], metadata_input=torch.zeros(0, 25, device=cuda_dev)).shape == (0, 1)
+
+
+def test_load_HF_model_from_local_dir(cuda_dev, golden_logits, golden_batch, tmp_path, monkeypatch):
+    """`btsbot.load_HF_model` from a local models/ directory (from_HF.py:59-81): the published multimodal
+    checkpoints are frozen_fusion/pico (to_HF.py:143), so that is what the fixture synthesises."""
+    import json
+    cfg, sd = case_state_dict("ff_pico", golden_logits)
+    mdir = tmp_path / "models" / "BTSbot-convnext-pico-randinit-metadata"
+    mdir.mkdir(parents=True)
+    (mdir / "train_config.json").write_text(json.dumps(cfg))
+    torch.save(synth.to_torch(sd), mdir / "pytorch_model.bin")
+    monkeypatch.chdir(tmp_path)
+    model = btsbot.load_HF_model("convnext", True, "randinit").eval()
+    img, meta = golden_batch
+    with torch.no_grad():
+        got = model(image_input=torch.from_numpy(img[:39]).cuda(), metadata_input=torch.from_numpy(meta[:39]).cuda())
+    raw_preds = torch.sigmoid(got).round().squeeze().cpu().numpy().astype(int)     # inference_example.py:91
+    ref = golden_logits["ff_pico"][:39]
+    assert np.abs(got.cpu().numpy() - ref).max() < 1.5e-4
+    assert np.array_equal(raw_preds[np.abs(ref[:, 0]) > 1e-4], (ref[:, 0] > 0).astype(int)[np.abs(ref[:, 0]) > 1e-4])

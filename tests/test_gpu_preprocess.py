@@ -1,0 +1,102 @@
+"""GPU: K1 array preparation against the golden vectors made by the reference's own alert_utils.py and the
+numpy oracle.  Indexing must be bit-exact; values within 1 ulp(fp32) of the reference quotient."""
+import gzip
+
+import numpy as np
+import pytest
+import torch
+
+from btsbot_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ulp_diff(a, b):
+    a = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, np.int64(-2 ** 31) - a, a)
+    b = np.where(b < 0, np.int64(-2 ** 31) - b, b)
+    return np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("s", [63, 49, 32, 31])
+@pytest.mark.parametrize("dt", ["f64", "f32"])
+def test_crop_triplets_matches_reference(cuda_dev, golden_pre, s, dt):
+    from btsbot_b200 import alert_utils as au
+    t = synth.make_triplets(2, start=5000, dtype=np.float64) * 37.5
+    if dt == "f32":
+        t = t.astype(np.float32)
+    keep = t.copy()
+    got = au.crop_triplets(t, s)
+    ref = golden_pre[f"crop{s}_{dt}"]
+    assert got.shape == ref.shape == (2, s, s, 3) and got.dtype == np.float64
+    assert np.array_equal(t, keep)                       # input not mutated
+    d = _ulp_diff(got, ref.astype(np.float32))
+    print(f"[parity] crop s={s} {dt}: max ulp diff {d}")
+    assert d <= (1 if dt == "f64" else 2)
+    # fused model-input form: same values, NCHW float32, left on the device
+    x = au.triplets_to_model_input(keep, s, normalize=True)
+    assert x.is_cuda and x.dtype == torch.float32 and tuple(x.shape) == (2, 3, s, s)
+    assert np.array_equal(x.cpu().numpy(), got.astype(np.float32).transpose(0, 3, 1, 2))
+
+
+def test_cast_transpose_is_bit_exact(cuda_dev, example_inputs):
+    from btsbot_b200 import alert_utils as au
+    from oracle import preprocess_oracle as P
+    trip64 = example_inputs["triplets"].astype(np.float64)          # the shipped .npy is float64
+    ref = P.to_model_layout(trip64)
+    for src in (trip64, trip64.astype(np.float32), torch.from_numpy(trip64)):
+        got = au.triplets_to_model_input(src, 63, normalize=False)
+        assert np.array_equal(got.cpu().numpy(), ref)
+    assert au.triplets_to_model_input(trip64[:0]).shape == (0, 3, 63, 63)
+    with pytest.raises(ValueError):
+        au.triplets_to_model_input(np.zeros((2, 3, 63, 63)))
+
+
+def test_crop_large_batch_properties(cuda_dev):
+    """Full-size property checks: unit L2 norm per cutout, idempotence at s=63, index-range sharding invariance."""
+    from btsbot_b200 import alert_utils as au
+    n = 4096
+    t = torch.from_numpy(synth.make_triplets(n, start=0)).to(cuda_dev) * 3.0
+    x = au.triplets_to_model_input(t, 49, normalize=True)
+    nrm = x.double().pow(2).sum(dim=(2, 3)).sqrt()
+    assert (nrm - 1).abs().max().item() < 2e-6
+    a = au.triplets_to_model_input(t, 63, normalize=True)
+    again = au.triplets_to_model_input(a.permute(0, 2, 3, 1).contiguous(), 63, normalize=True)
+    assert (a - again).abs().max().item() < 1e-7
+    parts = torch.cat([au.triplets_to_model_input(t[:1000], 49, True), au.triplets_to_model_input(t[1000:], 49, True)])
+    assert torch.equal(parts, x)
+
+
+def _fits_gz(arr):
+    cards = [f"SIMPLE  = {'T':>20}", f"BITPIX  = {-32:>20}", f"NAXIS   = {2:>20}",
+             f"NAXIS1  = {arr.shape[1]:>20}", f"NAXIS2  = {arr.shape[0]:>20}", "END"]
+    hdr = "".join(c.ljust(80) for c in cards).ljust(2880).encode("ascii")
+    data = arr.astype(">f4").tobytes()
+    return gzip.compress(hdr + data + b"\0" * (-len(data) % 2880))
+
+
+def test_make_triplet_tail_matches_reference(cuda_dev, golden_pre):
+    from btsbot_b200 import alert_utils as au
+    from oracle.make_golden import adversarial_stamps
+    alerts = []
+    for i, stamps in enumerate(adversarial_stamps()):
+        alert = {"candidate": {"candid": i}}
+        for nm, st in zip(("Science", "Template", "Difference"), stamps):
+            alert["cutout" + nm] = {"stampData": _fits_gz(st)}
+        alerts.append(alert)
+    trips, drops = au.make_triplets(alerts, normalize=True)
+    for i in range(len(alerts)):
+        ref = golden_pre[f"tail{i}"]
+        assert np.array_equal(np.isnan(trips[i]), np.isnan(ref)), i
+        got32, ref32 = np.nan_to_num(trips[i]).astype(np.float32), np.nan_to_num(ref).astype(np.float32)
+        d = _ulp_diff(got32, ref32)
+        print(f"[parity] make_triplet tail {i}: max ulp diff {d}, drop {drops[i]}")
+        assert d <= 2, i
+        assert bool(drops[i]) == bool(golden_pre[f"tail{i}_drop"]), i
+        pad = ref == np.float64(np.float32(1e-9))
+        assert np.array_equal(trips[i][pad], ref[pad])          # pad region exact, not rescaled
+    one, drop = au.make_triplet(alerts[1], normalize=True)
+    assert np.array_equal(np.nan_to_num(one), np.nan_to_num(trips[1])) and drop == bool(drops[1])
+    raw, _ = au.make_triplets(alerts[:1], normalize=False)
+    assert np.array_equal(raw[0, :, :, 0], adversarial_stamps()[0][0].astype(np.float64))
