@@ -18,6 +18,9 @@ from .synth import convnext_arch
 
 BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by the reference (architectures.py:147)
 
+#: use the fused fc1->GELU->fc2 kernel where it applies (bf16, C <= 160); tests flip this to cover both paths
+FUSE_MLP = True
+
 _DT = {"fp32": (L.F32, torch.float32), "bf16": (L.BF16, torch.bfloat16)}
 
 
@@ -117,17 +120,24 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
                 capture[f"down{i}"] = (cur, h, wd)
         M = B * h * wd
         y = torch.empty((M, c), device=dev, dtype=adt)
-        hid = torch.empty((M, 4 * c), device=dev, dtype=adt)
+        fused = FUSE_MLP and code == L.BF16 and c % 16 == 0 and 64 <= c <= 160
+        hid = None if fused else torch.empty((M, 4 * c), device=dev, dtype=adt)
         for j, blk in enumerate(stg["blocks"]):
             L.launch(f"dwln_{wd}x{c}", lib.btsb_convnext_dwln_fwd, _p(cur), code, B, h, wd, c, _p(blk["dw_w"]),
                      _p(blk["dw_b"]), _p(blk["ln_w"]), _p(blk["ln_b"]), _p(y), st,
                      flops=2.0 * 49 * M * c + 8.0 * M * c, nbytes=2.0 * es * M * c)
             if capture is not None:
                 capture[f"s{i}b{j}.dwln"] = (y.clone(), h, wd)
-            _gemm(f"gemm_fc1_{c}", y, blk["fc1_w"], blk["fc1_b"], None, None, hid, code, L.EPI_BIAS_GELU, st)
             nxt = torch.empty((M, c), device=dev, dtype=adt)
-            _gemm(f"gemm_fc2_{c}", hid, blk["fc2_w"], blk["fc2_b"], blk["gamma"], cur, nxt, code,
-                  L.EPI_SCALE_RES, st)
+            if fused:
+                # fc1 -> GELU -> fc2 -> *gamma -> +shortcut in one kernel; bytes: y + res + out (+ L2-resident weights)
+                L.launch(f"mlp_fused_{c}", lib.btsb_convnext_mlp_fused_fwd, _p(y), _p(cur), _p(blk["fc1_w"]),
+                         _p(blk["fc1_b"]), _p(blk["fc2_w"]), _p(blk["fc2_b"]), _p(blk["gamma"]), _p(nxt), M, c, st,
+                         flops=16.0 * M * c * c, nbytes=es * (3.0 * M * c + 8.0 * c * c))
+            else:
+                _gemm(f"gemm_fc1_{c}", y, blk["fc1_w"], blk["fc1_b"], None, None, hid, code, L.EPI_BIAS_GELU, st)
+                _gemm(f"gemm_fc2_{c}", hid, blk["fc2_w"], blk["fc2_b"], blk["gamma"], cur, nxt, code,
+                      L.EPI_SCALE_RES, st)
             cur = nxt
             if capture is not None:
                 capture[f"s{i}b{j}"] = (cur, h, wd)
@@ -266,11 +276,16 @@ class Scorer:
     def __call__(self, image_input=None, metadata_input=None, capture: dict | None = None) -> torch.Tensor:
         feat = None
         if self.trunk is not None:
-            feat = self.features(image_input, capture)
             B = image_input.shape[0]
+            if B > 0:
+                feat = self.features(image_input, capture)
         else:
+            L.require_cuda(metadata_input, "metadata input")
             B = metadata_input.shape[0]
         meta = metadata_input if self.head.Mm > 0 else None
+        if B == 0:
+            dev = (image_input if image_input is not None else metadata_input).device
+            return torch.empty((0, 1), device=dev, dtype=torch.float32)
         if capture is not None and feat is not None:
             capture["features"] = feat
         return head_forward(self.head, feat, meta, B)

@@ -115,6 +115,15 @@ int btsb_convnext_poolln_fwd(const void* x, int dtype, int64_t B, int HW, int C,
 int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res,
                   void* out, int64_t M, int N, int K, int dtype, int epilogue, void* stream);
 
+/* ---- K4 fused: ONE kernel for fc1 -> GELU -> fc2 -> *gamma -> +shortcut; the 4C hidden activation stays in
+ * TMEM / shared memory (timm blocks.j.mlp + gamma + residual).  BF16 only; C a multiple of 16 in [64,160]
+ * (ConvNeXt nano/pico stages 0-1, where the hidden tensor would be 4x the activation traffic).
+ * y: dw+LN output [M,C]; res: block input [M,C]; W1 [4C,C], W2 [C,4C] bf16 row-major; b1 [4C], b2/gamma [C] f32.
+ */
+int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const void* W1, const float* b1,
+                                const void* W2, const float* b2, const float* gamma, void* out, int64_t M,
+                                int C, void* stream);
+
 /* ---- K6: metadata branch + fusion head in one kernel (architectures.py:146-164,168-170; um_nn 282-290;
  * image-only heads 109-119; frozen_fusion 357-365).
  * feat: [B,F] (feat_dtype F32|BF16) or NULL (F=0); meta: [B,Mm] float32 or NULL (Mm=0).

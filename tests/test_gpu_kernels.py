@@ -144,6 +144,28 @@ def test_gemm_bf16_tcgen05(cuda_dev, M, N, K, epi):
     assert err < 3.2e-2 and (got - ref).abs().mean().item() < 4e-3
 
 
+@pytest.mark.parametrize("C,M", [(80, 1000), (160, 777), (64, 4096), (128, 129), (80, 128 * 300 + 5), (96, 50)])
+def test_mlp_fused_tcgen05(cuda_dev, C, M):
+    """fused fc1->GELU->fc2->*gamma->+res vs fp32 math on the same bf16 operands (hidden rounded to bf16 as the
+    kernel does before the second GEMM)."""
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    y = torch.randn(M, C, generator=g).bfloat16()
+    res = torch.randn(M, C, generator=g).bfloat16()
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).bfloat16()
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).bfloat16()
+    b1, b2 = torch.randn(4 * C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    gamma = torch.rand(C, generator=g) + 0.5
+    hid = F.gelu(y.double() @ w1.double().t() + b1.double()).float().bfloat16()
+    ref = (res.double() + gamma.double() * (hid.double() @ w2.double().t() + b2.double())).float()
+    got = ops.mlp_fused(y.to(cuda_dev), res.to(cuda_dev), w1.to(cuda_dev), b1.to(cuda_dev), w2.to(cuda_dev),
+                        b2.to(cuda_dev), gamma.to(cuda_dev))
+    torch.cuda.synchronize()
+    got = got.float().cpu()
+    err = _report(f"mlp_fused C={C} M={M}", got, ref)
+    assert err < 4e-2 and (got - ref).abs().mean().item() < 5e-3
+
+
 def test_gemm_rejects_bad_arguments(cuda_dev):
     from btsbot_b200 import ops
     a = torch.zeros(8, 24, device=cuda_dev, dtype=torch.bfloat16)

@@ -1,0 +1,124 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; the Python surface mirrors the reference's;
+the product refuses to run without an sm_100 GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import btsbot_b200 as btsbot
+from btsbot_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "btsbot_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(btsb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 15
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/btsbot_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.lib().btsb_version() >= 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU refusal path")
+def test_no_gpu_means_refusal_not_fallback():
+    lib = _lib.lib()
+    assert lib.btsb_device_ok() == -2
+    rc = lib.btsb_score_epilogue(None, 4, None, None, None)
+    assert rc == -2 and b"CUDA" in lib.btsb_last_error_string()
+    cfg = synth.canonical_config("mm_ConvNeXt", "convnext_pico.d1_in1k")
+    model = btsbot.mm_ConvNeXt(cfg).eval()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(image_input=torch.zeros(1, 3, 63, 63), metadata_input=torch.zeros(1, 25))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        btsbot.alert_utils.crop_triplets(np.zeros((1, 63, 63, 3)), 49)
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libbtsbot_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_package_surface_matches_reference_init():
+    # btsbot/__init__.py:28-46
+    for name in ["architectures", "utils", "alert_utils", "FlexibleDataset", "RandomRightAngleRotation", "make_report",
+                 "MaxViT", "ConvNeXt", "mm_MaxViT", "mm_ConvNeXt", "mm_cnn", "um_cnn", "um_nn", "frozen_fusion",
+                 "download_HF_model", "load_HF_model", "__version__"]:
+        assert hasattr(btsbot, name), name
+    for fn in ["crop_norm_cutout", "crop_triplets", "make_triplet", "extract_triplets"]:
+        assert callable(getattr(btsbot.alert_utils, fn))
+    assert btsbot.architectures.get_model_image_size("maxvit_tiny_rw_224.sw_in1k") == 224
+    assert btsbot.architectures.get_model_image_size("maxvit_large_tf_384.in1k") == 384
+    assert btsbot.architectures.get_model_image_size("convnext_nano.d1h_in1k") == 224
+
+
+def test_from_hf_name_mangling():
+    f = btsbot.from_HF
+    assert f.get_HF_model_link("convnext", True, "randinit") == "nabeelr/BTSbot-convnext-pico-randinit-metadata"
+    assert f.get_local_model_dir("maxvit", False, "imagenet") == os.path.join("models", "BTSbot-maxvit-tiny-in1k")
+    with pytest.raises(ValueError):
+        f.validate_model_params("resnet", False, "randinit")
+    with pytest.raises(ValueError):
+        f.validate_model_params("convnext", False, "laion")
+
+
+def test_timm_key_names_and_shapes():
+    """Trunk parameter names/shapes follow timm's ConvNeXt so reference checkpoints load."""
+    cfg = synth.canonical_config("mm_ConvNeXt", "convnext_nano.d1h_in1k")
+    sd = btsbot.mm_ConvNeXt(cfg).state_dict()
+    assert sd["convnext_backbone.stem.0.weight"].shape == (80, 3, 4, 4)
+    assert sd["convnext_backbone.stages.1.downsample.1.weight"].shape == (160, 80, 2, 2)
+    assert sd["convnext_backbone.stages.2.blocks.7.conv_dw.weight"].shape == (320, 1, 7, 7)
+    assert sd["convnext_backbone.stages.3.blocks.1.mlp.fc1.weight"].shape == (2560, 640, 1, 1)
+    assert sd["convnext_backbone.stages.0.blocks.0.gamma"].shape == (80,)
+    assert float(sd["convnext_backbone.stages.0.blocks.0.gamma"][0]) == pytest.approx(1e-6)
+    assert not any(k.startswith("convnext_backbone.head") for k in sd)      # non-LS: head is a bare Flatten
+    assert not any("stages.0.downsample" in k for k in sd)
+    n = sum(v.numel() for k, v in sd.items() if "num_batches" not in k and "running" not in k)
+    assert n == 15070643                                                    # 15.071 M params
+    pico = btsbot.ConvNeXt(synth.canonical_config("ConvNeXt", "convnext_pico.d1_in1k")).state_dict()
+    assert pico["convnext.head.8.weight"].shape == (1, 8) and pico["convnext.head.1.weight"].shape == (512,)
+
+
+def test_frozen_fusion_surgery():
+    cfg = synth.canonical_config("frozen_fusion", "convnext_pico.d1_in1k")
+    m = btsbot.frozen_fusion(cfg)
+    keys = set(m.state_dict())
+    assert "image_branch.convnext.head.1.weight" in keys and "image_branch.convnext.head.3.weight" not in keys
+    assert "meta_branch.network.4.weight" in keys and "meta_branch.network.6.weight" not in keys
+    assert m.combined_head[0].in_features == 512 + 128
+
+
+def test_unsupported_models_fail_loudly():
+    for cls in (btsbot.MaxViT, btsbot.mm_MaxViT, btsbot.mm_cnn, btsbot.um_cnn):
+        with pytest.raises(NotImplementedError):
+            cls({})
+    with pytest.raises(ValueError):
+        btsbot.ConvNeXt(dict(synth.canonical_config("ConvNeXt"), model_kind="convnext_base"))
+
+
+def test_flexible_dataset_and_rotation():
+    img = torch.arange(2 * 3 * 5 * 5, dtype=torch.float32).view(2, 3, 5, 5)
+    meta, lab = torch.ones(2, 4), torch.tensor([0, 1])
+    assert len(btsbot.FlexibleDataset(img, meta, lab)[1]) == 3
+    assert len(btsbot.FlexibleDataset(images=img, labels=lab)[0]) == 2
+    assert btsbot.FlexibleDataset(metadata=meta, labels=lab)[1][0].shape == (4,)
+    np.random.seed(2)
+    angles = [int(np.random.choice([0, 90, 180, 270])) for _ in range(8)]
+    np.random.seed(2)
+    rot = btsbot.RandomRightAngleRotation()
+    import torchvision.transforms.v2.functional as TF
+    for a in angles:
+        assert torch.equal(rot(img[0]), TF.rotate(img[0], a))               # exact permutation, same RNG stream
