@@ -1,6 +1,8 @@
 // CUDA-core kernels of the ConvNeXt path: stem conv+LN (K2a), depthwise 7x7+LN (K3), LN+2x2 patch gather (K5a),
 // pool+LN head prologue, fp32 GEMM with fused epilogues (the 1e-4 "correctness" mode of K4/K5b), scoring epilogue.
 // Activations are NHWC pixel rows [B*H*W, C]; see include/btsbot_b200.h for the contracts and reference citations.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace btsb {
@@ -221,6 +223,58 @@ lnpatch_kernel(const T* __restrict__ x, int64_t B, int H, int W, int C, int Ho, 
   }
 }
 
+// bf16 specialisation: a lane owns channel PAIRS (32-bit loads/stores), C <= 640, C even.
+__global__ void __launch_bounds__(256)
+lnpatch_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int W, int C, int Ho, int Wo,
+                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int Hu = 2 * Ho, Wu = 2 * Wo, C2 = C >> 1;
+  const int64_t total = B * (int64_t)Hu * Wu;
+  constexpr int MAXJ = 10;
+  float2 gw[MAXJ], gb[MAXJ];
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    const int k2 = lane + 32 * j;
+    gw[j] = k2 < C2 ? __ldg(reinterpret_cast<const float2*>(ln_w) + k2) : make_float2(0.f, 0.f);
+    gb[j] = k2 < C2 ? __ldg(reinterpret_cast<const float2*>(ln_b) + k2) : make_float2(0.f, 0.f);
+  }
+  for (int64_t p = warp; p < total; p += nwarps) {
+    const int ix = (int)(p % Wu);
+    const int64_t t = p / Wu;
+    const int iy = (int)(t % Hu);
+    const int64_t b = t / Hu;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + ((b * H + iy) * (int64_t)W + ix) * C);
+    float2 v[MAXJ];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int k2 = lane + 32 * j;
+      const uint32_t u = k2 < C2 ? __ldg(src + k2) : 0u;
+      v[j] = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+      s += v[j].x + v[j].y;
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j)
+      if (lane + 32 * j < C2) { const float d0 = v[j].x - mean, d1 = v[j].y - mean; q += d0 * d0 + d1 * d1; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + kLnEps);
+    const int oy = iy >> 1, dy = iy & 1, ox = ix >> 1, dx = ix & 1;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((b * Ho + oy) * (int64_t)Wo + ox) * (4 * (int64_t)C) + (dy * 2 + dx) * C);
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int k2 = lane + 32 * j;
+      if (k2 < C2) {
+        __nv_bfloat162 o = __floats2bfloat162_rn((v[j].x - mean) * rstd * gw[j].x + gb[j].x,
+                                                 (v[j].y - mean) * rstd * gw[j].y + gb[j].y);
+        dst[k2] = *reinterpret_cast<uint32_t*>(&o);
+      }
+    }
+  }
+}
+
 // =====================================================================================================
 // head prologue: global average pool over HW + optional LayerNorm -> [B,C] fp32; one warp per image.
 // =====================================================================================================
@@ -426,6 +480,10 @@ static int dispatch_dwln(const void* x, int64_t B, int H, int W, int C, const fl
   return launch_dwln<T, 8>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
 }
 
+namespace btsb {
+int dwln_bf16_v2(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
+                 const float* ln_b, void* out, cudaStream_t st);
+}
 extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* w,
                                       const float* bias, const float* ln_w, const float* ln_b, void* out,
                                       void* stream) {
@@ -436,6 +494,11 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
   BTSB_REQUIRE(x && w && bias && ln_w && ln_b && out, "dwln: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == BTSB_F32) return dispatch_dwln<float>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  static const bool force_v1 = getenv("BTSB_DWLN_V1") != nullptr;     // debugging aid: generic kernel for bf16 too
+  if (!force_v1) {
+    const int rc = dwln_bf16_v2(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+    if (rc != 1) return rc;
+  }
   return dispatch_dwln<__nv_bfloat16>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
 }
 
@@ -452,6 +515,9 @@ extern "C" int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, in
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == BTSB_F32)
     lnpatch_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, H, W, C, Ho, Wo, ln_w, ln_b, (float*)out);
+  else if (C % 2 == 0 && ((uintptr_t)ln_w % 8) == 0 && ((uintptr_t)ln_b % 8) == 0)
+    lnpatch_bf16x2_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, H, W, C, Ho, Wo, ln_w, ln_b,
+                                                (__nv_bfloat16*)out);
   else
     lnpatch_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, H, W, C, Ho, Wo, ln_w, ln_b,
                                                         (__nv_bfloat16*)out);

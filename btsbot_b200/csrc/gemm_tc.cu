@@ -3,7 +3,7 @@
 //   * operands: TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 4-stage shared-memory ring
 //   * math:     tcgen05.mma cta_group::1 kind::f16 (bf16 x bf16 -> fp32), M=128 x N=BN x K=16 per instruction,
 //               issued by one thread; accumulators in TMEM, double buffered (2 x 256 columns)
-//   * epilogue: 8 warps, tcgen05.ld 32x32b (thread = output row), bias / GELU / gamma*acc+residual in registers,
+//   * epilogue: 16 warps, tcgen05.ld 32x32b (thread = output row), bias / GELU / gamma*acc+residual in registers,
 //               bf16 rows written straight to global (32 B per thread per 16 columns)
 //   * persistent: grid = min(#tiles, #SMs); tiles walk N fastest so concurrent CTAs share A rows in L2
 //
@@ -19,7 +19,7 @@ constexpr int kStages = 4;
 constexpr int kMaxBN = 256;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + kEpiWarps * 32;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int kABytes = BM * BK * 2;              // 16 KB
 constexpr int kBBytes = kMaxBN * BK * 2;          // 32 KB
@@ -111,11 +111,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue warps =====================
     const int ew = warp - 2;
     const int quarter = warp & 3;                       // TMEM lanes this warp may touch: 32*(warp%4) ..
-    const int half = ew >> 2;                           // column half handled by this warp
+    const int part = ew >> 2;                           // column slice handled by this warp (kEpiWarps/4 slices)
+    constexpr int kParts = kEpiWarps / 4;
     int as = 0; uint32_t aphase = 0;
     const int chunks = BN / 16;
-    const int c_lo = half == 0 ? 0 : (chunks + 1) / 2;
-    const int c_hi = half == 0 ? (chunks + 1) / 2 : chunks;
+    const int c_lo = (chunks * part) / kParts;
+    const int c_hi = (chunks * (part + 1)) / kParts;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       mbar_wait(tfull_bar(as), aphase);
