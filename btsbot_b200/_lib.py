@@ -54,6 +54,24 @@ SIGNATURES = {
     "btsb_convnext_mlp_fused_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]),
     "btsb_meta_head_fwd": (i32, [C.POINTER(HeadParams), i64, vp, vp]),
     "btsb_score_epilogue": (i32, [vp, i64, vp, vp, vp]),
+    "btsb_gemm_f32_strided": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, i32, vp]),
+    "btsb_colsum_f32": (i32, [vp, vp, vp, i64, i32, i32, vp]),
+    "btsb_act_f32": (i32, [vp, vp, vp, i64, i32, vp]),
+    "btsb_colscale_f32": (i32, [vp, vp, vp, vp, i64, i32, vp]),
+    "btsb_bias_add_f32": (i32, [vp, vp, i64, i32, vp]),
+    "btsb_layernorm_fwd_f32": (i32, [vp, vp, vp, vp, i64, i32, C.c_float, vp]),
+    "btsb_layernorm_bwd_f32": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, C.c_float, vp]),
+    "btsb_dwconv7_f32": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "btsb_dwconv7_wgrad_f32": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "btsb_stem_im2col_f32": (i32, [vp, vp, i64, i32, i32, vp]),
+    "btsb_patch2x2_f32": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
+    "btsb_pool_f32": (i32, [vp, vp, i64, i32, i32, i32, vp]),
+    "btsb_bn1d_train_fwd_f32": (i32, [vp, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp, i64, i32, vp]),
+    "btsb_bn1d_bwd_f32": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]),
+    "btsb_dropout_f32": (i32, [vp, vp, vp, i64, C.c_float, C.c_uint64, i32, vp]),
+    "btsb_bce_logits_f32": (i32, [vp, vp, C.c_float, vp, vp, i64, C.c_float, vp]),
+    "btsb_adamw_f32": (i32, [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64,
+                             C.c_float, vp]),
     "btsb_cast_f32_to_bf16": (i32, [vp, vp, i64, vp]),
     "btsb_cast_bf16_to_f32": (i32, [vp, vp, i64, vp]),
 }

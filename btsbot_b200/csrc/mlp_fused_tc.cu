@@ -28,19 +28,20 @@ struct FusedLayout {
   int ny;             // y tile buffers (1 or 2)
   int w_stage_bytes;  // kb1 * 8 KB + C * 128 B
   int y_bytes;        // kb1 * 16 KB
-  int off_w, off_h, off_bar, total;
+  int off_w, off_h, off_bar, off_b1, total;
 };
 __host__ __device__ inline FusedLayout fused_layout(int C) {
   FusedLayout L;
   L.kb1 = (C + 63) / 64;
   L.w_stage_bytes = L.kb1 * (NH * 128) + ((C * 128 + 1023) / 1024) * 1024;
   L.y_bytes = L.kb1 * kYBlockBytes;
-  const int fixed = kWStages * L.w_stage_bytes + 2 * kHBytes + 1024 + 512;
+  const int fixed = kWStages * L.w_stage_bytes + 2 * kHBytes + 1024 + 512 + 4 * C * 4;
   L.ny = (fixed + 2 * L.y_bytes <= 227 * 1024) ? 2 : 1;
   L.off_w = L.ny * L.y_bytes;
   L.off_h = L.off_w + kWStages * L.w_stage_bytes;
   L.off_bar = L.off_h + 2 * kHBytes;
-  L.total = L.off_bar + 512 + 1024;
+  L.off_b1 = L.off_bar + 512;
+  L.total = L.off_b1 + 4 * C * 4 + 1024;
   return L;
 }
 }  // namespace
@@ -84,6 +85,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
+  float* b1s = reinterpret_cast<float*>(sal + L.off_b1);            // fc1 bias staged once per CTA
+  for (int i = threadIdx.x; i < 4 * C; i += kThreadsF) b1s[i] = __ldg(b1 + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -168,6 +171,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     uint32_t ccount = 0, tcount = 0;
     const int groups2 = C / 16;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+      // residual rows for this warp's D2 column groups: issued now, consumed after the last chunk (latency hidden)
+      const int row = tile * FM + r_in_tile;
+      uint4 rpre[3][2];
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int gi = s + 4 * u;
+        if (gi < groups2 && row < M) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + gi * 16);
+          rpre[u][0] = __ldg(rp); rpre[u][1] = __ldg(rp + 1);
+        } else {
+          rpre[u][0] = make_uint4(0, 0, 0, 0); rpre[u][1] = make_uint4(0, 0, 0, 0);
+        }
+      }
       for (int j = 0; j < NJ; ++j) {
         const int b = ccount & 1; const uint32_t bph = (ccount >> 1) & 1u; ++ccount;
         mbar_wait(d1_full(b), bph);
@@ -182,7 +198,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(b1 + hcol + i));
+          const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
           v[i] = gelu_fast(__uint_as_float(r[i]) + b4.x);
           v[i + 1] = gelu_fast(__uint_as_float(r[i + 1]) + b4.y);
           v[i + 2] = gelu_fast(__uint_as_float(r[i + 2]) + b4.z);
@@ -204,8 +220,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
       // ---- final epilogue of the tile: D2 -> out
       mbar_wait(d2_full, tcount & 1u);
       tc_fence_after();
-      const int row = tile * FM + r_in_tile;
-      for (int gi = s; gi < groups2; gi += 4) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const int gi = s + 4 * u;
+        if (gi >= groups2) break;
         uint32_t r[16];
         tmem_ld16(lane_addr + (uint32_t)(kD2Col + gi * 16), r);
         tmem_ld_wait();
@@ -216,8 +234,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
         }
         if (row < M) {
           const int n = gi * 16;
-          const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + n);
-          const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          const uint4 r0 = rpre[u][0], r1 = rpre[u][1];
           const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
           float v[16];
 #pragma unroll

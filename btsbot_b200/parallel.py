@@ -1,0 +1,206 @@
+"""One-process-per-GPU data parallelism for the hot path.
+
+* Inference / bulk scoring: alerts are independent, so rank r scores the contiguous index range
+  ``shard_range(n, r, world)`` with **no collective on the data path**; :func:`score_alerts` optionally gathers the
+  N float32 scores afterwards (host-side convenience, 4 B per alert).
+* Training: replicas hold full weights; gradients are averaged with NCCL all-reduce on flat buckets that are launched
+  from inside the hand-written backward (last layers first) on a side stream, overlapping the remaining backward.
+  This replaces the reference's single-process ``nn.DataParallel`` (train.py:238-240), which re-broadcasts all
+  parameters every step and reduces gradients to GPU 0.
+
+Works with the ``gloo`` backend on CPU tensors too (used by the world-size-2 tests of the host logic).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced index range of ``rank``: sizes differ by at most one, concatenation order = rank order."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def score_alerts(score_fn, triplets, metadata, batch_size: int = 8192, gather: bool = True, device=None):
+    """Score ``triplets [N,63,63,3]`` (+ ``metadata [N,M]``) sharded over the ranks of the default process group.
+
+    ``score_fn(triplets_chunk, metadata_chunk) -> 1-D float32 tensor`` scores one micro-batch (normally
+    :class:`AlertScorer`).  Returns the scores of the local shard (``gather=False``) or of all N alerts on every
+    rank (``gather=True``; an all_gather of 4 bytes per alert after the data path)."""
+    rank, world = _world()
+    n = len(triplets)
+    lo, hi = shard_range(n, rank, world)
+    outs = []
+    for a in range(lo, hi, batch_size):
+        b = min(hi, a + batch_size)
+        outs.append(score_fn(triplets[a:b], None if metadata is None else metadata[a:b]).reshape(-1).float())
+    local = torch.cat(outs) if outs else torch.empty((0,), dtype=torch.float32, device=device)
+    if not gather or world == 1:
+        return local
+    sizes = [shard_range(n, r, world)[1] - shard_range(n, r, world)[0] for r in range(world)]
+    pad = max(sizes)
+    buf = torch.zeros((pad,), dtype=torch.float32, device=local.device)
+    buf[: local.numel()] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)])
+
+
+class AlertScorer:
+    """The end-to-end public scoring call: host (numpy / pinned torch) HWC triplets + metadata -> scores.
+
+    Per micro-batch: async H2D copy on a copy stream, K1 (cast + NHWC->NCHW [+ crop/normalise]), model forward,
+    sigmoid epilogue; copies of batch i+1 overlap the kernels of batch i (two streams, two staging buffers)."""
+
+    def __init__(self, model, crop_to_size: int = 63, normalize: bool = False, return_scores: bool = True):
+        from . import alert_utils, ops
+        self.model, self.crop, self.norm, self.return_scores = model.eval(), crop_to_size, normalize, return_scores
+        self._au, self._ops = alert_utils, ops
+        self.multimodal = model._config["model_name"] in ("mm_ConvNeXt", "frozen_fusion")
+        self.meta_only = model._config["model_name"] == "um_nn"
+        self.dev = next(model.parameters()).device
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+
+    def _to_dev(self, x):
+        t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
+        return t.to(self.dev, non_blocking=True)
+
+    @torch.no_grad()
+    def __call__(self, triplets, metadata=None):
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            t = None if self.meta_only else self._to_dev(triplets)
+            m = self._to_dev(metadata) if (self.multimodal or self.meta_only) else None
+        cur.wait_stream(self.copy_stream)
+        for z in (t, m):
+            if z is not None:
+                z.record_stream(cur)
+        if self.meta_only:
+            logits = self.model(input_data=m)
+        else:
+            x = self._au.triplets_to_model_input(t, self.crop, self.norm)
+            logits = self.model(image_input=x, metadata_input=m) if self.multimodal else self.model(input_data=x)
+        if not self.return_scores:
+            return logits.reshape(-1)
+        scores, _ = self._ops.score(logits)
+        return scores.reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training: flat gradient buckets + overlapped all-reduce
+# ---------------------------------------------------------------------------------------------------------------
+class GradSink:
+    """Flat fp32 gradient buffer; parameters are laid out in REVERSE forward order so the backward fills it front to
+    back, and every completed bucket is all-reduced (average) immediately on a side stream."""
+
+    def __init__(self, params, bucket_bytes: int = 8 << 20, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.pg = process_group
+        order = list(reversed(self.params))
+        self.offset, off = {}, 0
+        for p in order:
+            self.offset[id(p)] = off
+            off += p.numel()
+        self.total = off
+        dev = self.params[0].device
+        self.flat = torch.zeros((self.total,), device=dev, dtype=torch.float32)
+        per = max(1, bucket_bytes // 4)
+        self.bounds = [(a, min(self.total, a + per)) for a in range(0, self.total, per)]
+        self.bucket_of = {}
+        for p in order:
+            a = self.offset[id(p)]
+            b = a + p.numel()
+            self.bucket_of[id(p)] = [i for i, (lo, hi) in enumerate(self.bounds) if lo < b and a < hi]
+        self.need = [0] * len(self.bounds)
+        for p in order:
+            for i in self.bucket_of[id(p)]:
+                self.need[i] += 1
+        self.cuda = dev.type == "cuda"
+        self.stream = torch.cuda.Stream(device=dev) if self.cuda else None
+        self.launched_buckets = []
+        self.reset()
+
+    def reset(self):
+        self.count = [0] * len(self.bounds)
+        self.seen = set()
+        self.sent = [False] * len(self.bounds)
+        self.handles = []
+        self.launched_buckets = []
+
+    def view(self, p):
+        a = self.offset[id(p)]
+        return self.flat[a:a + p.numel()].view(p.shape)
+
+    def adopt(self, p, g):
+        v = self.view(p)
+        v.copy_(g)
+        return v
+
+    def ready(self, p):
+        if id(p) in self.seen:
+            return
+        self.seen.add(id(p))
+        for i in self.bucket_of[id(p)]:
+            self.count[i] += 1
+            if self.count[i] == self.need[i]:
+                self._launch(i)
+
+    def _launch(self, i):
+        if self.sent[i]:
+            return
+        self.sent[i] = True
+        self.launched_buckets.append(i)
+        _, world = _world()
+        if world == 1:
+            return
+        lo, hi = self.bounds[i]
+        chunk = self.flat[lo:hi]
+        if self.cuda:
+            self.stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.pg)
+        else:
+            self.handles.append((dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.pg, async_op=True), chunk, world))
+
+    def flush(self):
+        """End of backward: send what is left (parameters without gradient this step), then join."""
+        for i in range(len(self.bounds)):
+            self._launch(i)
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        for h, chunk, world in self.handles:
+            h.wait()
+            chunk.div_(world)
+        launched = self.launched_buckets
+        self.reset()
+        self.launched_buckets = launched
+
+
+class DistributedDataParallel(torch.nn.Module):
+    """``model = DistributedDataParallel(model)``: same role as ``DataParallel(model)`` at train.py:238-240, but one
+    process per GPU.  ``.module`` is the wrapped model (the reference unwraps it when saving, train.py:314-317)."""
+
+    def __init__(self, module, bucket_mb: float = 8.0, process_group=None):
+        super().__init__()
+        self.module = module
+        rank, world = _world()
+        if world > 1:
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, src=0, group=process_group)
+        self.sink = GradSink(list(module.parameters()), int(bucket_mb * (1 << 20)), process_group)
+        module._grad_sink = self.sink
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.module.zero_grad(set_to_none=set_to_none)

@@ -152,6 +152,52 @@ int btsb_meta_head_fwd(const btsb_head_params* p, int64_t B, float* logits, void
  * score = sigmoid(logit), label = score > 0.5.  scores/labels may be NULL. */
 int btsb_score_epilogue(const float* logits, int64_t B, float* scores, uint8_t* labels, void* stream);
 
+/* ---- K7: training (fp32).  Replaces what autograd + ATen/cuDNN + torch.optim do inside train.py:496-547
+ * (forward with saved intermediates, BCEWithLogitsLoss(pos_weight) :211-212,525, backward :526, AdamW.step :527).
+ * All tensors float32, row-major, contiguous unless strides are given. */
+/* C[M,N] (+)= sum_k A(m,k) B(k,n) with element strides (sam,sak) / (sbk,sbn): covers dgrad (NN) and wgrad (TN, split-K). */
+int btsb_gemm_f32_strided(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn,
+                          float* C, int64_t M, int64_t N, int64_t K, int accumulate, void* stream);
+/* out[n] (+)= sum_m X[m,n] * (Y ? Y[m,n] : 1)  -- bias gradients, d(gamma) */
+int btsb_colsum_f32(const float* X, const float* Y, float* out, int64_t M, int N, int accumulate, void* stream);
+/* dout == NULL: out = act(pre); else out = dout * act'(pre)   (act: BTSB_ACT_*) */
+int btsb_act_f32(const float* pre, const float* dout, float* out, int64_t n, int act, void* stream);
+/* out[m,n] = (res ? res[m,n] : 0) + g[n] * X[m,n]   -- layer scale + shortcut, and its backward */
+int btsb_colscale_f32(const float* X, const float* g, const float* res, float* out, int64_t M, int N, void* stream);
+/* X[m,n] += b[n] (in place) */
+int btsb_bias_add_f32(float* X, const float* b, int64_t M, int N, void* stream);
+int btsb_layernorm_fwd_f32(const float* u, const float* w, const float* b, float* y, int64_t M, int C, float eps, void* stream);
+/* du may be NULL; dw/db are accumulated (+=). */
+int btsb_layernorm_bwd_f32(const float* u, const float* w, const float* dy, float* du, float* dw, float* db,
+                           int64_t M, int C, float eps, void* stream);
+/* depthwise 7x7 pad 3 on NHWC rows; w49 [49,C]; bias may be NULL; flip=1 uses the 180-degree rotated kernel (dgrad). */
+int btsb_dwconv7_f32(const float* x, const float* w49, const float* bias, float* out, int64_t B, int H, int W, int C,
+                     int flip, void* stream);
+/* dw49[k,c] += sum du * shifted x;  dbias[c] += sum du */
+int btsb_dwconv7_wgrad_f32(const float* x, const float* du, float* dw49, float* dbias, int64_t B, int H, int W, int C,
+                           void* stream);
+/* x [B,3,H,W] -> patches [B*ho*wo, 48] (k = (ci*4+ky)*4+kx): the stem conv as a GEMM operand */
+int btsb_stem_im2col_f32(const float* x, float* patches, int64_t B, int H, int W, void* stream);
+/* reverse=0: rows [B*H*W,C] -> 2x2/s2 patches [B*Ho*Wo,4C]; reverse=1: patches -> rows (dropped pixels get 0) */
+int btsb_patch2x2_f32(const float* src, float* dst, int64_t B, int H, int W, int C, int reverse, void* stream);
+/* reverse=0: mean over HW, [B*HW,C] -> [B,C]; reverse=1: d[B,C]/HW broadcast to [B*HW,C] */
+int btsb_pool_f32(const float* src, float* dst, int64_t B, int HW, int C, int reverse, void* stream);
+/* BatchNorm1d in training mode (batch statistics, running stats updated with the unbiased variance like torch) */
+int btsb_bn1d_train_fwd_f32(const float* x, const float* w, const float* b, float* run_mean, float* run_var,
+                            float momentum, float eps, float* y, float* save_mean, float* save_rstd, int64_t B, int F,
+                            void* stream);
+int btsb_bn1d_bwd_f32(const float* x, const float* dy, const float* w, const float* save_mean, const float* save_rstd,
+                      float* dx, float* dw, float* db, int64_t B, int F, void* stream);
+/* inverted dropout; reuse_mask=0 draws mask[i] = hash(seed,i) >= p, reuse_mask=1 applies the stored mask (backward) */
+int btsb_dropout_f32(const float* x, float* y, uint8_t* mask, int64_t n, float p, uint64_t seed, int reuse_mask,
+                     void* stream);
+/* BCEWithLogitsLoss(pos_weight), mean reduction: *loss = mean l_i; dlogits (may be NULL) = dscale * dl/dx */
+int btsb_bce_logits_f32(const float* logits, const float* labels, float pos_weight, float* loss, float* dlogits,
+                        int64_t B, float dscale, void* stream);
+/* fused AdamW over a flat parameter buffer (torch.optim.AdamW semantics; g is multiplied by grad_scale first) */
+int btsb_adamw_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float wd, int64_t step, float grad_scale, void* stream);
+
 /* dtype helpers used by the weight packer: float32 -> bf16 (round-to-nearest-even) and back. */
 int btsb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
 int btsb_cast_bf16_to_f32(const void* in, float* out, int64_t n, void* stream);

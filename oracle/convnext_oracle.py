@@ -72,7 +72,12 @@ def pool_norm_flatten(sd, p, x):
     return x.flatten(1)
 
 
+_TRAIN = False     # set by forward_train(): BatchNorm1d uses batch statistics (dropout must be 0 for parity)
+
+
 def bn1d_eval(sd, p, x):
+    if _TRAIN:
+        return F.batch_norm(x, None, None, sd[p + "weight"], sd[p + "bias"], True, 0.1, BN_EPS)
     return (x - sd[p + "running_mean"]) / torch.sqrt(sd[p + "running_var"] + BN_EPS) * sd[p + "weight"] + sd[p + "bias"]
 
 
@@ -94,9 +99,24 @@ def head3(sd, p, idx, x, act):
     return lin(sd, f"{p}{idx[2]}.", x)
 
 
-@torch.no_grad()
 def forward(sd: dict, config: dict, image_input=None, metadata_input=None, capture: dict | None = None):
     """Eval-mode logits ``[B,1]`` for ``config['model_name']`` (reference forward kwargs)."""
+    with torch.no_grad():
+        return _forward(sd, config, image_input, metadata_input, capture)
+
+
+def forward_train(sd: dict, config: dict, image_input=None, metadata_input=None):
+    """Training-mode forward WITH autograd (BatchNorm1d batch statistics; dropout layers are identity, so parity
+    tests set the dropout probabilities to 0).  ``sd`` tensors that require grad receive gradients."""
+    global _TRAIN
+    _TRAIN = True
+    try:
+        return _forward(sd, config, image_input, metadata_input, None)
+    finally:
+        _TRAIN = False
+
+
+def _forward(sd, config, image_input, metadata_input, capture):
     name = config["model_name"]
     if name == "mm_ConvNeXt":
         arch = arch_of(config.get("model_kind", "convnext_nano.d1h_in1k"))
