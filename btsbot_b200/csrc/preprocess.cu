@@ -174,9 +174,44 @@ pad_norm_kernel(const float* __restrict__ stamps, const int32_t* __restrict__ hw
   if (tid == 0) drop_out[a] = (uint8_t)s_drop;
 }
 
+// ---- training-time augmentation fused with the batch gather (utils.py:44-48, train.py:178-199) ----------------------
+// out[b] = rot90^k( vflip?( hflip?( images[idx[b]] ))) -- pure index permutations, bit-exact.
+// flags[b]: bit0 = horizontal flip, bit1 = vertical flip, bits 2-3 = k (counter-clockwise quarter turns).
+__global__ void __launch_bounds__(256)
+augment_gather_kernel(const float* __restrict__ images, const int64_t* __restrict__ idx, const uint8_t* __restrict__ flags,
+                      float* __restrict__ out, int S) {
+  const int64_t b = blockIdx.x;
+  const int64_t src_img = idx[b];
+  const int f = flags ? flags[b] : 0;
+  const int hf = f & 1, vf = (f >> 1) & 1, k = (f >> 2) & 3;
+  const int plane = S * S;
+  const float* src = images + src_img * 3 * plane;
+  float* dst = out + b * 3 * plane;
+  for (int e = threadIdx.x; e < 3 * plane; e += 256) {
+    const int c = e / plane, r = e - c * plane;
+    const int i = r / S, j = r - i * S;
+    int a, bb;
+    if (k == 0) { a = i; bb = j; } else if (k == 1) { a = j; bb = S - 1 - i; }
+    else if (k == 2) { a = S - 1 - i; bb = S - 1 - j; } else { a = S - 1 - j; bb = i; }
+    if (vf) a = S - 1 - a;
+    if (hf) bb = S - 1 - bb;
+    dst[e] = __ldg(src + c * plane + a * S + bb);
+  }
+}
+
 }  // namespace btsb
 
 using namespace btsb;
+
+extern "C" int btsb_augment_gather_f32(const float* images, const int64_t* idx, const uint8_t* flags, int64_t B, int S,
+                                       float* out, void* stream) {
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(B >= 0 && S >= 1, "augment_gather: bad shape");
+  if (B == 0) return BTSB_OK;
+  BTSB_REQUIRE(images && idx && out, "augment_gather: null pointer");
+  augment_gather_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(images, idx, flags, out, S);
+  return launch_done("augment_gather");
+}
 
 extern "C" int btsb_preprocess_crop_norm(const void* in, int in_dtype, int64_t n, int crop_to_size, int normalize,
                                          int out_hwc, float* out, void* stream) {

@@ -126,7 +126,7 @@ class GradSink:
                 self.need[i] += 1
         self.cuda = dev.type == "cuda"
         self.stream = torch.cuda.Stream(device=dev) if self.cuda else None
-        self.launched_buckets = []
+        self.last_order, self.last_early = [], 0     # bucket launch order / #buckets sent before flush() (last step)
         self.reset()
 
     def reset(self):
@@ -135,6 +135,8 @@ class GradSink:
         self.sent = [False] * len(self.bounds)
         self.handles = []
         self.launched_buckets = []
+        self.in_flush = False
+        self.early = 0
 
     def view(self, p):
         a = self.offset[id(p)]
@@ -159,6 +161,8 @@ class GradSink:
             return
         self.sent[i] = True
         self.launched_buckets.append(i)
+        if not self.in_flush:
+            self.early += 1
         _, world = _world()
         if world == 1:
             return
@@ -173,6 +177,7 @@ class GradSink:
 
     def flush(self):
         """End of backward: send what is left (parameters without gradient this step), then join."""
+        self.in_flush = True
         for i in range(len(self.bounds)):
             self._launch(i)
         if self.cuda:
@@ -180,9 +185,8 @@ class GradSink:
         for h, chunk, world in self.handles:
             h.wait()
             chunk.div_(world)
-        launched = self.launched_buckets
+        self.last_order, self.last_early = self.launched_buckets, self.early
         self.reset()
-        self.launched_buckets = launched
 
 
 class DistributedDataParallel(torch.nn.Module):

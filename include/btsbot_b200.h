@@ -79,6 +79,12 @@ int btsb_preprocess_crop_norm(const void* in, int in_dtype, int64_t n, int crop_
 int btsb_preprocess_pad_norm(const float* stamps, const int32_t* hw, int64_t n, int normalize,
                              void* out, int out_dtype, uint8_t* drop, void* stream);
 
+/* training-time batch gather + augmentation (utils.py:44-48, train.py:178-199 RandomHorizontalFlip /
+ * RandomVerticalFlip / RandomRightAngleRotation): out[b] = rot90^k(vflip(hflip(images[idx[b]]))), square [3,S,S] fp32
+ * images; flags[b] bit0 = hflip, bit1 = vflip, bits2-3 = k counter-clockwise quarter turns (flags NULL = no aug). */
+int btsb_augment_gather_f32(const float* images, const int64_t* idx, const uint8_t* flags, int64_t B, int S,
+                            float* out, void* stream);
+
 /* ---- K2a: ConvNeXt stem -- timm stem.0 Conv2d(3,C0,k4,s4)+bias and stem.1 LayerNorm2d(eps 1e-6)
  * (called at architectures.py:108,132).  x: [B,3,H,W] NCHW float32.  w: [48,C0] float32 with
  * k = (ci*4+ky)*4+kx (transposed conv weight), bias/ln_w/ln_b: [C0] float32.

@@ -61,7 +61,7 @@ def _worker(rank, world, port, n, out):
         sink.flush()
         for i, p in enumerate(params):
             assert torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1)))        # mean over ranks 1,2
-        assert sink.launched_buckets == sorted(sink.launched_buckets) and len(sink.launched_buckets) == len(sink.bounds)
+        assert sorted(sink.last_order) == list(range(len(sink.bounds))) and sink.last_early == len(sink.bounds)
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
