@@ -20,6 +20,8 @@ BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by the reference (architectu
 
 #: use the fused fc1->GELU->fc2 kernel where it applies (bf16, C <= 160); tests flip this to cover both paths
 FUSE_MLP = True
+#: bf16 stem as im2col + tcgen05 GEMM with the LayerNorm in the epilogue (else the CUDA-core stem kernel)
+TC_STEM = True
 
 _DT = {"fp32": (L.F32, torch.float32), "bf16": (L.BF16, torch.bfloat16)}
 
@@ -45,6 +47,12 @@ class TrunkWeights:
         self.stem_w = _f32c(g("stem.0.weight").reshape(c0, 48).t())
         self.stem_b = _f32c(g("stem.0.bias"))
         self.stem_ln_w, self.stem_ln_b = _f32c(g("stem.1.weight")), _f32c(g("stem.1.bias"))
+        # tensor-core stem (bf16): [C0, 64] with the 48 taps zero-padded to one 64-wide k-block
+        self.stem_w_tc = None
+        if code == L.BF16 and c0 % 16 == 0 and c0 <= 128:
+            wt = torch.zeros((c0, 64), device=self.stem_b.device, dtype=torch.bfloat16)
+            wt[:, :48] = g("stem.0.weight").detach().reshape(c0, 48).to(torch.bfloat16)
+            self.stem_w_tc = wt.contiguous()
         self.stages = []
         for i, (c, d) in enumerate(zip(self.dims, self.depths)):
             st = {"blocks": []}
@@ -97,9 +105,17 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
     c = w.dims[0]
     cur = torch.empty((B * h * wd, c), device=dev, dtype=adt)
     es = cur.element_size()
-    L.launch("stem", lib.btsb_convnext_stem_fwd, _p(x), B, H, W, _p(w.stem_w), _p(w.stem_b), _p(w.stem_ln_w),
-             _p(w.stem_ln_b), c, _p(cur), code, st,
-             flops=2.0 * 48 * c * B * h * wd, nbytes=4.0 * x.numel() + es * cur.numel())
+    if TC_STEM and w.stem_w_tc is not None:
+        patches = torch.empty((B * h * wd, 64), device=dev, dtype=torch.bfloat16)
+        L.launch("stem_im2col", lib.btsb_stem_im2col_bf16, _p(x), _p(patches), B, H, W, st,
+                 nbytes=4.0 * x.numel() + 2.0 * patches.numel())
+        L.launch("stem_gemm_ln", lib.btsb_gemm_ln_fwd, _p(patches), _p(w.stem_w_tc), _p(w.stem_b), _p(w.stem_ln_w),
+                 _p(w.stem_ln_b), _p(cur), B * h * wd, c, 64, st, flops=2.0 * 48 * c * B * h * wd,
+                 nbytes=2.0 * patches.numel() + es * cur.numel())
+    else:
+      L.launch("stem", lib.btsb_convnext_stem_fwd, _p(x), B, H, W, _p(w.stem_w), _p(w.stem_b), _p(w.stem_ln_w),
+               _p(w.stem_ln_b), c, _p(cur), code, st,
+               flops=2.0 * 48 * c * B * h * wd, nbytes=4.0 * x.numel() + es * cur.numel())
     if capture is not None:
         capture["stem"] = (cur, h, wd)
     for i, stg in enumerate(w.stages):

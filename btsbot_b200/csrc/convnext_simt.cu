@@ -223,7 +223,8 @@ lnpatch_kernel(const T* __restrict__ x, int64_t B, int H, int W, int C, int Ho, 
   }
 }
 
-// bf16 specialisation: a lane owns channel PAIRS (32-bit loads/stores), C <= 640, C even.
+// bf16 specialisation: a lane owns channel PAIRS (32-bit loads/stores); MAXJ = ceil(C/64) pairs per lane.
+template <int MAXJ>
 __global__ void __launch_bounds__(256)
 lnpatch_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int W, int C, int Ho, int Wo,
                       const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
@@ -232,7 +233,6 @@ lnpatch_bf16x2_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int Hu = 2 * Ho, Wu = 2 * Wo, C2 = C >> 1;
   const int64_t total = B * (int64_t)Hu * Wu;
-  constexpr int MAXJ = 10;
   float2 gw[MAXJ], gb[MAXJ];
 #pragma unroll
   for (int j = 0; j < MAXJ; ++j) {
@@ -515,10 +515,14 @@ extern "C" int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, in
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == BTSB_F32)
     lnpatch_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, H, W, C, Ho, Wo, ln_w, ln_b, (float*)out);
-  else if (C % 2 == 0 && ((uintptr_t)ln_w % 8) == 0 && ((uintptr_t)ln_b % 8) == 0)
-    lnpatch_bf16x2_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, H, W, C, Ho, Wo, ln_w, ln_b,
-                                                (__nv_bfloat16*)out);
-  else
+  else if (C % 2 == 0 && ((uintptr_t)ln_w % 8) == 0 && ((uintptr_t)ln_b % 8) == 0) {
+    const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
+    __nv_bfloat16* xo = (__nv_bfloat16*)out;
+    if (C <= 128) lnpatch_bf16x2_kernel<2><<<grid, 256, 0, st>>>(xi, B, H, W, C, Ho, Wo, ln_w, ln_b, xo);
+    else if (C <= 192) lnpatch_bf16x2_kernel<3><<<grid, 256, 0, st>>>(xi, B, H, W, C, Ho, Wo, ln_w, ln_b, xo);
+    else if (C <= 320) lnpatch_bf16x2_kernel<5><<<grid, 256, 0, st>>>(xi, B, H, W, C, Ho, Wo, ln_w, ln_b, xo);
+    else lnpatch_bf16x2_kernel<10><<<grid, 256, 0, st>>>(xi, B, H, W, C, Ho, Wo, ln_w, ln_b, xo);
+  } else
     lnpatch_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, H, W, C, Ho, Wo, ln_w, ln_b,
                                                         (__nv_bfloat16*)out);
   return launch_done("lnpatch");

@@ -108,36 +108,25 @@ dwln2_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C, int G, const
     }
     __syncthreads();
 
-    // LayerNorm over channels: one warp per pixel, two-pass, bf16x2 stores
+    // LayerNorm over channels: one warp per pixel, two-pass over the staged fp32 row (re-read from shared memory, so
+    // no per-lane register array sized for the widest C), bf16x2 stores
     const int npix = cnt * HW;
-    constexpr int KMAX = 10;                                  // C <= 640 -> at most 10 channel pairs per lane
+    const float invC = 1.0f / (float)C;
     for (int p = wid; p < npix; p += nw) {
-      const float* v = conv + (size_t)p * C;
-      float2 val[KMAX];
+      const float2* v = reinterpret_cast<const float2*>(conv + (size_t)p * C);
       float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        const int k2 = lane + 32 * j;
-        val[j] = k2 < C2 ? *reinterpret_cast<const float2*>(v + 2 * k2) : make_float2(0.f, 0.f);
-        s += val[j].x + val[j].y;
-      }
-      const float mean = warp_sum(s) / (float)C;
+      for (int k2 = lane; k2 < C2; k2 += 32) { const float2 t = v[k2]; s += t.x + t.y; }
+      const float mean = warp_sum(s) * invC;
       float q = 0.f;
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j)
-        if (lane + 32 * j < C2) { const float d0 = val[j].x - mean, d1 = val[j].y - mean; q += d0 * d0 + d1 * d1; }
-      const float rstd = rsqrtf(warp_sum(q) / (float)C + kLnEps);
+      for (int k2 = lane; k2 < C2; k2 += 32) { const float2 t = v[k2]; const float d0 = t.x - mean, d1 = t.y - mean; q += d0 * d0 + d1 * d1; }
+      const float rstd = rsqrtf(warp_sum(q) * invC + kLnEps);
       uint32_t* dst = reinterpret_cast<uint32_t*>(out + (b0 * HW + p) * (int64_t)C);
-#pragma unroll
-      for (int j = 0; j < KMAX; ++j) {
-        const int k2 = lane + 32 * j;
-        if (k2 < C2) {
-          const float2 gw = *reinterpret_cast<const float2*>(gsm + 2 * k2);
-          const float2 gb = *reinterpret_cast<const float2*>(hsm + 2 * k2);
-          __nv_bfloat162 o = __floats2bfloat162_rn((val[j].x - mean) * rstd * gw.x + gb.x,
-                                                   (val[j].y - mean) * rstd * gw.y + gb.y);
-          dst[k2] = *reinterpret_cast<uint32_t*>(&o);
-        }
+      for (int k2 = lane; k2 < C2; k2 += 32) {
+        const float2 t = v[k2];
+        const float2 gw = *reinterpret_cast<const float2*>(gsm + 2 * k2);
+        const float2 gb = *reinterpret_cast<const float2*>(hsm + 2 * k2);
+        __nv_bfloat162 o = __floats2bfloat162_rn((t.x - mean) * rstd * gw.x + gb.x, (t.y - mean) * rstd * gw.y + gb.y);
+        dst[k2] = *reinterpret_cast<uint32_t*>(&o);
       }
     }
     // the next iteration's top-of-loop __syncthreads orders these conv reads before the next conv writes

@@ -27,12 +27,18 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 }  // namespace
 
+constexpr int EPI_LN = 3;   // internal: out = LayerNorm(acc + bias) * gamma(ln_w) + aux(ln_b), whole rows per thread
+
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float* __restrict__ bias, const float* __restrict__ gamma,
+               const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ aux,
                const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out, int M, int N, int K, int BN) {
   using namespace tc;
+  // LN mode: rows must stay in one thread, so 4 warps (one per TMEM lane quarter) own a whole tile; the 16 epilogue
+  // warps form 4 such groups working on 4 accumulator stages of 128 columns (BN = N <= 128).
+  constexpr int kAcc = (EPI == EPI_LN) ? 4 : kAccStages;
+  constexpr int kAccCols = (EPI == EPI_LN) ? 128 : kMaxBN;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -41,9 +47,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAccStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAcc + s); };
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem_al + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAccStages));
+      reinterpret_cast<volatile uint32_t*>(smem_al + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAcc));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
@@ -54,7 +60,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
+    for (int s = 0; s < kAcc; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == EPI_LN ? 4 : kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -89,7 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(as), aphase ^ 1u);          // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * kMaxBN);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccCols);
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
@@ -105,7 +111,76 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(tfull_bar(as));                       // accumulator complete -> epilogue
-      if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+      if (++as == kAcc) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp >= 2 && EPI == EPI_LN) {
+    // ===================== epilogue, LayerNorm mode: thread = one full output row =====================
+    const int group = (warp - 2) >> 2, quarter = warp & 3;
+    const int chunks = BN / 16;
+    const float invN = 1.0f / (float)N;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 3) != group) continue;
+      const int as = group; const uint32_t aphase = (uint32_t)(lt >> 2) & 1u;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int row = tile * BM + quarter * 32 + lane;         // n_tiles == 1 in this mode
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccCols);
+      uint32_t r[16];
+      float s = 0.f;
+      for (int ch = 0; ch < chunks; ++ch) {
+        tmem_ld16(taddr + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 16 + i));
+          s += (__uint_as_float(r[i]) + b4.x) + (__uint_as_float(r[i + 1]) + b4.y) + (__uint_as_float(r[i + 2]) + b4.z) +
+               (__uint_as_float(r[i + 3]) + b4.w);
+        }
+      }
+      const float mean = s * invN;
+      float q = 0.f;
+      for (int ch = 0; ch < chunks; ++ch) {
+        tmem_ld16(taddr + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 16 + i));
+          const float d0 = __uint_as_float(r[i]) + b4.x - mean, d1 = __uint_as_float(r[i + 1]) + b4.y - mean;
+          const float d2 = __uint_as_float(r[i + 2]) + b4.z - mean, d3 = __uint_as_float(r[i + 3]) + b4.w - mean;
+          q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+      }
+      const float rstd = rsqrtf(q * invN + kLnEps);
+      for (int ch = 0; ch < chunks; ++ch) {
+        tmem_ld16(taddr + (uint32_t)(ch * 16), r);
+        tmem_ld_wait();
+        if (ch == chunks - 1) {                               // accumulator fully consumed by this warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        if (row < M) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 16 + i));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 16 + i));
+            const float4 h4 = __ldg(reinterpret_cast<const float4*>(aux + ch * 16 + i));
+            v[i] = (__uint_as_float(r[i]) + b4.x - mean) * rstd * g4.x + h4.x;
+            v[i + 1] = (__uint_as_float(r[i + 1]) + b4.y - mean) * rstd * g4.y + h4.y;
+            v[i + 2] = (__uint_as_float(r[i + 2]) + b4.z - mean) * rstd * g4.z + h4.z;
+            v[i + 3] = (__uint_as_float(r[i + 3]) + b4.w - mean) * rstd * g4.w + h4.w;
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * N + ch * 16);
+          op[0] = o0; op[1] = o1;
+        }
+      }
     }
   } else if (warp >= 2) {
     // ===================== epilogue warps =====================
@@ -122,17 +197,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kMaxBN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccCols);
       if (c_lo >= c_hi) {                               // narrow tile: this warp has no columns, release at once
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      for (int ch = c_lo; ch < c_hi; ++ch) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)(ch * 16), r);
+      // chunks of 16 columns, software-pipelined: the TMEM load of chunk ch+1 is in flight during the math of chunk ch
+      uint32_t ra[16], rb[16];
+      auto process = [&](int ch, uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
         tmem_ld_wait();
-        if (ch == c_hi - 1) {                           // last TMEM read of this warp for this tile
+        if (ch + 1 < c_hi) {
+          tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), nxt);
+        } else {                                          // last TMEM read of this warp for this tile
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(as));
@@ -143,8 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));
-            v[i] = __uint_as_float(r[i]) + b4.x; v[i + 1] = __uint_as_float(r[i + 1]) + b4.y;
-            v[i + 2] = __uint_as_float(r[i + 2]) + b4.z; v[i + 3] = __uint_as_float(r[i + 3]) + b4.w;
+            v[i] = __uint_as_float(cur[i]) + b4.x; v[i + 1] = __uint_as_float(cur[i + 1]) + b4.y;
+            v[i + 2] = __uint_as_float(cur[i + 2]) + b4.z; v[i + 3] = __uint_as_float(cur[i + 3]) + b4.w;
           }
           if (EPI == BTSB_EPI_BIAS_GELU) {
 #pragma unroll
@@ -153,14 +230,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (EPI == BTSB_EPI_SCALE_RES) {
             const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * N + n);
             const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const uint32_t rcur[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
-              v[i] = fmaf(g4.x, v[i], bf16_lo(rr[i / 2]));
-              v[i + 1] = fmaf(g4.y, v[i + 1], bf16_hi(rr[i / 2]));
-              v[i + 2] = fmaf(g4.z, v[i + 2], bf16_lo(rr[i / 2 + 1]));
-              v[i + 3] = fmaf(g4.w, v[i + 3], bf16_hi(rr[i / 2 + 1]));
+              v[i] = fmaf(g4.x, v[i], bf16_lo(rcur[i / 2]));
+              v[i + 1] = fmaf(g4.y, v[i + 1], bf16_hi(rcur[i / 2]));
+              v[i + 2] = fmaf(g4.z, v[i + 2], bf16_lo(rcur[i / 2 + 1]));
+              v[i + 3] = fmaf(g4.w, v[i + 3], bf16_hi(rcur[i / 2 + 1]));
             }
           }
           uint4 o0, o1;
@@ -171,8 +248,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * N + n);
           op[0] = o0; op[1] = o1;
         }
+      };
+      if (c_lo < c_hi) tmem_ld16(taddr + (uint32_t)(c_lo * 16), ra);
+      for (int ch = c_lo; ch < c_hi; ch += 2) {
+        process(ch, ra, rb);
+        if (ch + 1 < c_hi) process(ch + 1, rb, ra);
       }
-      if (++as == kAccStages) { as = 0; aphase ^= 1u; }
+      if (++as == kAcc) { as = 0; aphase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -258,20 +340,85 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
   const __nv_bfloat16* r = (const __nv_bfloat16*)res;
   __nv_bfloat16* o = (__nv_bfloat16*)out;
   if (epilogue == BTSB_EPI_BIAS)
-    gemm_tc_kernel<BTSB_EPI_BIAS><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, r, o, (int)M, N, K, BN);
+    gemm_tc_kernel<BTSB_EPI_BIAS><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
   else if (epilogue == BTSB_EPI_BIAS_GELU)
-    gemm_tc_kernel<BTSB_EPI_BIAS_GELU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, r, o, (int)M, N, K, BN);
+    gemm_tc_kernel<BTSB_EPI_BIAS_GELU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
   else
-    gemm_tc_kernel<BTSB_EPI_SCALE_RES><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, r, o, (int)M, N, K, BN);
+    gemm_tc_kernel<BTSB_EPI_SCALE_RES><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
   return launch_done("gemm_bf16");
 }
 
 int gemm_f32(const float* A, const float* Wt, const float* bias, const float* gamma, const float* res, float* out,
              int64_t M, int N, int K, int epilogue, cudaStream_t st);
 
+// out = LayerNorm_rows(A . Wt^T + bias) * ln_w + ln_b   (bf16 operands, N <= 128)
+int gemm_ln_bf16(const void* A, const void* Wt, const float* bias, const float* ln_w, const float* ln_b, void* out,
+                 int64_t M, int N, int K, cudaStream_t st) {
+  BTSB_REQUIRE(N % 16 == 0 && N <= 128 && K % 16 == 0, "gemm_ln: need N %% 16 == 0, N <= 128, K %% 16 == 0 (N=%d K=%d)", N, K);
+  BTSB_REQUIRE(M < (1ll << 31), "gemm_ln: M too large");
+  BTSB_REQUIRE(((uintptr_t)out % 16) == 0 && ((uintptr_t)bias % 16) == 0 && ((uintptr_t)ln_w % 16) == 0 &&
+                   ((uintptr_t)ln_b % 16) == 0, "gemm_ln: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM)) return e;
+  if (int e = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint32_t)N)) return e;
+  const int m_tiles = (int)((M + BM - 1) / BM);
+  const int grid = min(m_tiles, num_sms());
+  static bool attr_done = false;
+  if (!attr_done) {
+    BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm_ln attr");
+    attr_done = true;
+  }
+  gemm_tc_kernel<EPI_LN><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, ln_w, ln_b, nullptr, (__nv_bfloat16*)out,
+                                                             (int)M, N, K, N);
+  return launch_done("gemm_ln_bf16");
+}
+
+// stem im2col for the tensor-core path: x [B,3,H,W] fp32 -> patches [B*ho*wo, 64] bf16, k = (ci*4+ky)*4+kx, 48..63 = 0
+__global__ void __launch_bounds__(256)
+stem_im2col_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ p, int64_t B, int H, int W, int ho, int wo) {
+  const int64_t total = B * ho * wo * 8;                      // one thread = 8 consecutive k (16 bytes)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    int64_t t = i >> 3;
+    const int ox = (int)(t % wo); t /= wo;
+    const int oy = (int)(t % ho);
+    const int64_t b = t / ho;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (j < 6) {
+      const int ci = j >> 1, ky0 = (j & 1) * 2;
+      const float* r0 = x + ((b * 3 + ci) * H + oy * 4 + ky0) * (int64_t)W + ox * 4;
+      const float* r1 = r0 + W;
+      o.x = tc::pack_bf16x2(__ldg(r0), __ldg(r0 + 1)); o.y = tc::pack_bf16x2(__ldg(r0 + 2), __ldg(r0 + 3));
+      o.z = tc::pack_bf16x2(__ldg(r1), __ldg(r1 + 1)); o.w = tc::pack_bf16x2(__ldg(r1 + 2), __ldg(r1 + 3));
+    }
+    reinterpret_cast<uint4*>(p)[i] = o;
+  }
+}
+
 }  // namespace btsb
 
 using namespace btsb;
+
+extern "C" int btsb_gemm_ln_fwd(const void* A, const void* Wt, const float* bias, const float* ln_w, const float* ln_b,
+                                void* out, int64_t M, int N, int K, void* stream) {
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(M >= 0 && N >= 1 && K >= 1, "gemm_ln: bad shape");
+  if (M == 0) return BTSB_OK;
+  BTSB_REQUIRE(A && Wt && bias && ln_w && ln_b && out, "gemm_ln: null pointer");
+  return gemm_ln_bf16(A, Wt, bias, ln_w, ln_b, out, M, N, K, (cudaStream_t)stream);
+}
+
+extern "C" int btsb_stem_im2col_bf16(const float* x, void* patches, int64_t B, int H, int W, void* stream) {
+  if (int e = check_device()) return e;
+  if (B <= 0) return BTSB_OK;
+  BTSB_REQUIRE(x && patches && H >= 4 && W >= 4 && ((uintptr_t)patches % 16) == 0, "im2col bf16: bad arguments");
+  const int ho = (H - 4) / 4 + 1, wo = (W - 4) / 4 + 1;
+  const int64_t total = B * ho * wo * 8;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  stem_im2col_bf16_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)patches, B, H, W, ho, wo);
+  return launch_done("im2col_bf16");
+}
 
 extern "C" int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res,
                              void* out, int64_t M, int N, int K, int dtype, int epilogue, void* stream) {

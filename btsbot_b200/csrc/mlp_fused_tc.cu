@@ -78,8 +78,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     for (int i = 0; i < 2; ++i) { mbar_init(y_full(i), 1); mbar_init(y_empty(i), 1); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(d1_full(i), 1); mbar_init(d1_empty(i), kEpiWarpsF);
-      mbar_init(h_full(i), kEpiWarpsF); mbar_init(h_empty(i), 1);
+      mbar_init(d1_full(i), 1); mbar_init(d1_empty(i), kEpiWarpsF / 2);
+      mbar_init(h_full(i), kEpiWarpsF / 2); mbar_init(h_empty(i), 1);
     }
     mbar_init(d2_full, 1); mbar_init(d2_empty, kEpiWarpsF);
     fence_barrier_init();
@@ -169,6 +169,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t ccount = 0, tcount = 0;
+    const int grp = (warp - 2) >> 3;        // epilogue warp group (8 warps): owns D1/H buffer `grp`
+    const int half = ((warp - 2) >> 2) & 1; // 32-column half of a 64-column chunk
     const int groups2 = C / 16;
     for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       // residual rows for this warp's D2 column groups: issued now, consumed after the last chunk (latency hidden)
@@ -184,35 +186,44 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           rpre[u][0] = make_uint4(0, 0, 0, 0); rpre[u][1] = make_uint4(0, 0, 0, 0);
         }
       }
-      for (int j = 0; j < NJ; ++j) {
-        const int b = ccount & 1; const uint32_t bph = (ccount >> 1) & 1u; ++ccount;
+      // D1 chunks: the two warp groups take alternate chunks (global chunk parity == group), so one group's barrier
+      // round trips (d1_full wait, TMEM load, h_full hand-off) overlap the other group's GELU arithmetic.
+      for (int j = 0; j < NJ; ++j, ++ccount) {
+        if ((int)(ccount & 1u) != grp) continue;
+        const int b = grp; const uint32_t bph = (ccount >> 1) & 1u;
         mbar_wait(d1_full(b), bph);
         tc_fence_after();
-        uint32_t r[16];
-        tmem_ld16(lane_addr + (uint32_t)(b * NH + s * 16), r);
+        uint32_t ra[16], rb[16];
+        tmem_ld16(lane_addr + (uint32_t)(b * NH + half * 32), ra);
+        tmem_ld16(lane_addr + (uint32_t)(b * NH + half * 32 + 16), rb);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(d1_empty(b));
-        const int hcol = j * NH + s * 16;
-        float v[16];
+        if (lane == 0) mbar_arrive(d1_empty(b));         // D1[b] may be overwritten by G1 of chunk j+2
+        const int hcol = j * NH + half * 32;
+        uint4 o[4];
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
-          v[i] = gelu_fast(__uint_as_float(r[i]) + b4.x);
-          v[i + 1] = gelu_fast(__uint_as_float(r[i + 1]) + b4.y);
-          v[i + 2] = gelu_fast(__uint_as_float(r[i + 2]) + b4.z);
-          v[i + 3] = gelu_fast(__uint_as_float(r[i + 3]) + b4.w);
+        for (int hh = 0; hh < 2; ++hh) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + hh * 16 + i);
+            const uint32_t* r = hh == 0 ? ra : rb;
+            v[i] = gelu_fast(__uint_as_float(r[i]) + b4.x);
+            v[i + 1] = gelu_fast(__uint_as_float(r[i + 1]) + b4.y);
+            v[i + 2] = gelu_fast(__uint_as_float(r[i + 2]) + b4.z);
+            v[i + 3] = gelu_fast(__uint_as_float(r[i + 3]) + b4.w);
+          }
+          o[2 * hh].x = pack_bf16x2(v[0], v[1]); o[2 * hh].y = pack_bf16x2(v[2], v[3]);
+          o[2 * hh].z = pack_bf16x2(v[4], v[5]); o[2 * hh].w = pack_bf16x2(v[6], v[7]);
+          o[2 * hh + 1].x = pack_bf16x2(v[8], v[9]); o[2 * hh + 1].y = pack_bf16x2(v[10], v[11]);
+          o[2 * hh + 1].z = pack_bf16x2(v[12], v[13]); o[2 * hh + 1].w = pack_bf16x2(v[14], v[15]);
         }
-        uint4 o0, o1;
-        o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-        o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-        o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-        o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
         mbar_wait(h_empty(b), bph ^ 1u);                 // G2 of chunk j-2 has finished reading H[b]
         unsigned char* hb = sal + L.off_h + b * kHBytes;
-        *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, s * 16)) = o0;
-        *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, s * 16 + 8)) = o1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, half * 32 + u * 8)) = o[u];
         fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(h_full(b));

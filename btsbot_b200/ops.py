@@ -85,6 +85,21 @@ def mlp_fused(y, res, w1, b1, w2, b2, gamma):
     return out
 
 
+def stem_tc(x, w_pad, bias, ln_w, ln_b):
+    """bf16 tensor-core stem: im2col (K padded 48->64) + tcgen05 GEMM with bias+LayerNorm epilogue.
+    x [B,3,H,W] f32; w_pad [C0,64] bf16 -> rows [B*h*w, C0] bf16."""
+    _chk(x, w_pad, bias, ln_w, ln_b)
+    B, _, H, W = x.shape
+    h, w = (H - 4) // 4 + 1, (W - 4) // 4 + 1
+    c0 = w_pad.shape[0]
+    patches = torch.empty((B * h * w, 64), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().btsb_stem_im2col_bf16(_p(x), _p(patches), B, H, W, L.stream_ptr()), "im2col")
+    out = torch.empty((B * h * w, c0), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().btsb_gemm_ln_fwd(_p(patches), _p(w_pad), _p(bias), _p(ln_w), _p(ln_b), _p(out), B * h * w, c0, 64,
+                                     L.stream_ptr()), "gemm_ln")
+    return out, patches
+
+
 def score(logits):
     """sigmoid + 0.5 threshold on device -> (scores f32, labels uint8)."""
     _chk(logits)

@@ -121,6 +121,14 @@ int btsb_convnext_poolln_fwd(const void* x, int dtype, int64_t B, int HW, int C,
 int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res,
                   void* out, int64_t M, int N, int K, int dtype, int epilogue, void* stream);
 
+/* ---- K2a on tensor cores (bf16): the patch stem as im2col + tcgen05 GEMM whose epilogue applies bias and the
+ * LayerNorm2d over the C0 output channels (thread = output row, three passes over the TMEM accumulator).
+ * im2col: x [B,3,H,W] fp32 -> patches [B*h*w, 64] bf16 (k = (ci*4+ky)*4+kx, columns 48..63 zero).
+ * gemm_ln: out[M,N] = LayerNorm_rows(A[M,K] . Wt[N,K]^T + bias) * ln_w + ln_b, bf16 operands/output, N <= 128. */
+int btsb_stem_im2col_bf16(const float* x, void* patches, int64_t B, int H, int W, void* stream);
+int btsb_gemm_ln_fwd(const void* A, const void* Wt, const float* bias, const float* ln_w, const float* ln_b,
+                     void* out, int64_t M, int N, int K, void* stream);
+
 /* ---- K4 fused: ONE kernel for fc1 -> GELU -> fc2 -> *gamma -> +shortcut; the 4C hidden activation stays in
  * TMEM / shared memory (timm blocks.j.mlp + gamma + residual).  BF16 only; C a multiple of 16 in [64,160]
  * (ConvNeXt nano/pico stages 0-1, where the hidden tensor would be 4x the activation traffic).

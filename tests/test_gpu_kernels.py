@@ -166,6 +166,27 @@ def test_mlp_fused_tcgen05(cuda_dev, C, M):
     assert err < 4e-2 and (got - ref).abs().mean().item() < 5e-3
 
 
+@pytest.mark.parametrize("C0,H,W,B", [(80, 63, 63, 37), (64, 63, 63, 5), (128, 20, 36, 3), (16, 8, 8, 700)])
+def test_stem_tcgen05(cuda_dev, C0, H, W, B):
+    """tensor-core stem (im2col + GEMM with bias+LayerNorm epilogue) vs fp32 conv+LN on the bf16-rounded operands."""
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(B, 3, H, W, generator=g) * 0.02 + 0.016).bfloat16().float()
+    w = (torch.randn(C0, 3, 4, 4, generator=g) / 7).bfloat16().float()
+    b, lw, lb = torch.randn(C0, generator=g) * 0.1, torch.rand(C0, generator=g) + 0.5, torch.randn(C0, generator=g) * 0.1
+    ref = _ln2d(F.conv2d(x, w, b, stride=4), lw, lb)
+    wp = torch.zeros(C0, 64)
+    wp[:, :48] = w.reshape(C0, 48)
+    got, patches = ops.stem_tc(x.to(cuda_dev), wp.bfloat16().to(cuda_dev), b.to(cuda_dev), lw.to(cuda_dev), lb.to(cuda_dev))
+    torch.cuda.synchronize()
+    h, wd = ref.shape[2:]
+    # im2col is exact (inputs are bf16-representable): patch (b,oy,ox) row k=(ci,ky,kx)
+    unf = F.unfold(x, kernel_size=4, stride=4).transpose(1, 2).reshape(B * h * wd, 48)
+    assert torch.equal(patches[:, :48].float().cpu(), unf) and patches[:, 48:].abs().max().item() == 0
+    err = _report(f"stem tcgen05 C0={C0} {H}x{W}", _rows_to_nchw(got.cpu(), B, h, wd), ref)
+    assert err < 3e-2
+
+
 def test_gemm_rejects_bad_arguments(cuda_dev):
     from btsbot_b200 import ops
     a = torch.zeros(8, 24, device=cuda_dev, dtype=torch.bfloat16)
