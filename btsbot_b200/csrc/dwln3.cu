@@ -1,0 +1,228 @@
+// K3 v3 (bf16 activations, square maps 15/7/3/1): depthwise 7x7 + bias + LayerNorm2d with the LayerNorm statistics
+// reduced straight from the convolution registers -- no fp32 staging buffer, no second pass over the map.
+//
+//   * persistent CTA, one image per iteration, next image prefetched with cp.async
+//   * thread = (output row, channel pair); the S outputs of the row live in registers (compile-time tap pruning)
+//   * channel pairs of a row are spread over A full warps (32 pairs each) plus, when C/2 is not a multiple of 32,
+//     aligned segments of REM = 8 or 16 lanes inside "tail" warps, so every cross-channel reduction is an aligned
+//     power-of-two shuffle tree
+//   * per-pixel sum / sum-of-squares: recursive-halving shuffle reduction (31 shuffles for 30 values instead of 150),
+//     partial results of the A+1 contributors meet in a 4 KB shared-memory table; each thread then normalises its own
+//     registers and writes bf16x2 (coalesced 128 B per warp)
+#include "common.cuh"
+
+namespace btsb {
+
+constexpr int kDw3MaxThreads = 608;
+
+__device__ __forceinline__ void cp_async16_v3(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// Sum 32 per-lane values across an aligned group of WIDTH lanes; afterwards v[0 .. 32/WIDTH) of lane l hold the group
+// totals of value indices (l % WIDTH) * (32/WIDTH) + i.
+template <int WIDTH>
+__device__ __forceinline__ void seg_reduce32(float (&v)[32], int lane) {
+  int n = 32;
+#pragma unroll
+  for (int off = WIDTH / 2; off >= 1; off >>= 1) {
+    n >>= 1;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n) {
+        const float lo = v[i], hi = v[i + n];
+        const float send = up ? lo : hi;
+        const float keep = up ? hi : lo;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kDw3MaxThreads, 1)
+dwln3_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C, int A, int REM, const float* __restrict__ wt,
+             const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+             __nv_bfloat16* __restrict__ out) {
+  constexpr int R = S > 3 ? 3 : S - 1;
+  constexpr int NT = 2 * R + 1;
+  constexpr int HW = S * S;
+  static_assert(2 * S <= 32, "row statistics must fit the 32-value reduction");
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* wsm = reinterpret_cast<float*>(sm);                 // [NT*NT][C] reachable taps
+  float* bsm = wsm + NT * NT * C;                            // conv bias
+  float* gsm = bsm + C;                                      // LN weight
+  float* hsm = gsm + C;                                      // LN bias
+  const int ncontrib = A + (REM > 0 ? 1 : 0);
+  float* part = hsm + C;                                     // [S rows][32 values][ncontrib]
+  __nv_bfloat16* tin = reinterpret_cast<__nv_bfloat16*>(part + S * 32 * ncontrib);   // [2][HW*C]
+
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int img_elems = HW * C;
+  const int C2 = C >> 1;
+
+  // ---- thread -> (row, channel pair, contributor slot) -------------------------------------------------------------
+  const int main_warps = S * A;
+  int row, c2, contrib, width;
+  bool active = true;
+  if (warp < main_warps) {
+    row = warp / A; contrib = warp - row * A; c2 = contrib * 32 + lane; width = 32;
+  } else {
+    const int per = 32 / REM;                                // rows per tail warp (REM > 0 here)
+    row = (warp - main_warps) * per + lane / REM;
+    c2 = A * 32 + lane % REM; contrib = A; width = REM;
+    active = row < S;
+    if (!active) row = S - 1;                                // keep shuffles convergent; results discarded
+  }
+
+  auto issue = [&](int64_t img, int buf) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + img * img_elems);
+    uint4* dst = reinterpret_cast<uint4*>(tin + (size_t)buf * img_elems);
+    for (int i = tid; i < img_elems / 8; i += T) cp_async16_v3(dst + i, src + i);
+  };
+  if ((int64_t)blockIdx.x < B) issue(blockIdx.x, 0);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int i = tid; i < NT * NT * C; i += T) {
+    const int t = i / C, c = i - t * C;
+    const int ty = t / NT, tx = t - ty * NT;
+    wsm[i] = __ldg(wt + ((ty + 3 - R) * 7 + (tx + 3 - R)) * C + c);
+  }
+  for (int i = tid; i < C; i += T) { bsm[i] = __ldg(bias + i); gsm[i] = __ldg(ln_w + i); hsm[i] = __ldg(ln_b + i); }
+
+  const float invC = 1.0f / (float)C;
+  int it = 0;
+  for (int64_t img = blockIdx.x; img < B; img += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int64_t nxt = img + gridDim.x;
+    if (nxt < B) issue(nxt, buf ^ 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                                          // input landed; previous iteration's `part` reads are done
+
+    // ---- depthwise conv of one output row, two channels ------------------------------------------------------------
+    float acc0[S], acc1[S];
+    {
+      const float2 bv = *reinterpret_cast<const float2*>(bsm + 2 * c2);
+#pragma unroll
+      for (int t = 0; t < S; ++t) { acc0[t] = bv.x; acc1[t] = bv.y; }
+      const __nv_bfloat16* im = tin + (size_t)buf * img_elems + 2 * c2;
+#pragma unroll
+      for (int dy = -R; dy <= R; ++dy) {
+        const int iy = row + dy;
+        if (iy < 0 || iy >= S) continue;
+        float2 wv[NT];
+#pragma unroll
+        for (int kx = 0; kx < NT; ++kx) wv[kx] = *reinterpret_cast<const float2*>(wsm + ((dy + R) * NT + kx) * C + 2 * c2);
+#pragma unroll
+        for (int ix = 0; ix < S; ++ix) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(im + (size_t)(iy * S + ix) * C);
+          const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+#pragma unroll
+          for (int kx = 0; kx < NT; ++kx) {
+            const int t = ix - (kx - R);
+            if (t >= 0 && t < S) { acc0[t] = fmaf(wv[kx].x, lo, acc0[t]); acc1[t] = fmaf(wv[kx].y, hi, acc1[t]); }
+          }
+        }
+      }
+    }
+
+    // ---- per-pixel channel statistics: values [0,S) = sums, [16,16+S) = sums of squares -----------------------------
+    float red[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) red[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < S; ++t) {
+      red[t] = acc0[t] + acc1[t];
+      red[16 + t] = fmaf(acc0[t], acc0[t], acc1[t] * acc1[t]);
+    }
+    if (width == 32) {
+      seg_reduce32<32>(red, lane);
+      if (lane < S || (lane >= 16 && lane < 16 + S)) part[(row * 32 + lane) * ncontrib + contrib] = red[0];
+    } else if (width == 16) {
+      seg_reduce32<16>(red, lane);
+      const int base = (lane & 15) * 2;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int idx = base + i;
+        if (active && (idx < S || (idx >= 16 && idx < 16 + S))) part[(row * 32 + idx) * ncontrib + contrib] = red[i];
+      }
+    } else {
+      seg_reduce32<8>(red, lane);
+      const int base = (lane & 7) * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = base + i;
+        if (active && (idx < S || (idx >= 16 && idx < 16 + S))) part[(row * 32 + idx) * ncontrib + contrib] = red[i];
+      }
+    }
+    __syncthreads();
+
+    // ---- normalise the registers and store bf16x2 -------------------------------------------------------------------
+    if (active) {
+      const float2 gw = *reinterpret_cast<const float2*>(gsm + 2 * c2);
+      const float2 gb = *reinterpret_cast<const float2*>(hsm + 2 * c2);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(out + (img * HW + row * S) * (int64_t)C) + c2;
+#pragma unroll
+      for (int t = 0; t < S; ++t) {
+        float s = 0.f, q = 0.f;
+        for (int k = 0; k < ncontrib; ++k) {
+          s += part[(row * 32 + t) * ncontrib + k];
+          q += part[(row * 32 + 16 + t) * ncontrib + k];
+        }
+        const float mean = s * invC;
+        const float var = fmaxf(q * invC - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + kLnEps);
+        __nv_bfloat162 o = __floats2bfloat162_rn((acc0[t] - mean) * rstd * gw.x + gb.x, (acc1[t] - mean) * rstd * gw.y + gb.y);
+        dst[(size_t)t * C2] = *reinterpret_cast<uint32_t*>(&o);
+      }
+    }
+    // the next iteration's first __syncthreads orders these `part` reads before the next writes
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+int num_sms();
+
+template <int S>
+static int launch_dwln3(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
+                        const float* ln_b, void* out, cudaStream_t st) {
+  constexpr int R = S > 3 ? 3 : S - 1;
+  constexpr int NT = 2 * R + 1;
+  constexpr int HW = S * S;
+  const int C2 = C / 2, A = C2 / 32, REM = C2 % 32;
+  if (!(REM == 0 || REM == 8 || REM == 16)) return 1;
+  const int tail_warps = REM ? (S * REM + 31) / 32 : 0;
+  const int warps = S * A + tail_warps;
+  if (warps * 32 > kDw3MaxThreads || warps < 1) return 1;
+  const int ncontrib = A + (REM ? 1 : 0);
+  const size_t smem = (size_t)(NT * NT + 3) * C * 4 + (size_t)S * 32 * ncontrib * 4 + 2 * (size_t)HW * C * 2;
+  if (smem > 227 * 1024) return 1;
+  auto kern = dwln3_kernel<S>;
+  BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "dwln3 attr");
+  const int sms = num_sms();
+  // small maps: several CTAs per SM are possible (few warps, little shared memory)
+  int per_sm = 1;
+  if (warps * 32 <= 304 && smem <= 100 * 1024) per_sm = 2;
+  const int64_t cap = (int64_t)sms * per_sm;
+  const int grid = (int)(B < cap ? B : cap);
+  kern<<<grid, warps * 32, smem, st>>>((const __nv_bfloat16*)x, B, C, A, REM, w, bias, ln_w, ln_b, (__nv_bfloat16*)out);
+  return launch_done("dwln3");
+}
+
+// returns 1 if the shape is not handled here (caller falls back to dwln2 / the generic kernel)
+int dwln_bf16_v3(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
+                 const float* ln_b, void* out, cudaStream_t st) {
+  if (H != W || C % 16 != 0 || C > 640) return 1;
+  if (((uintptr_t)x % 16) != 0 || ((uintptr_t)out % 4) != 0) return 1;
+  switch (H) {
+    case 15: return launch_dwln3<15>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    case 7: return launch_dwln3<7>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    // 3x3 and 1x1 maps: one image per CTA iteration is too little work per barrier; dwln2 (several images per
+    // iteration) is faster there (measured: 0.078 vs 0.106 ms and 0.020 vs 0.050 ms at B = 8192)
+    default: return 1;
+  }
+}
+
+}  // namespace btsb

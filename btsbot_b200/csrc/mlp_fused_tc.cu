@@ -68,9 +68,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
   auto d1_empty = [&](int i) { return bar0 + 8u * (6 + 2 * kWStages + i); };
   auto h_full = [&](int i) { return bar0 + 8u * (8 + 2 * kWStages + i); };
   auto h_empty = [&](int i) { return bar0 + 8u * (10 + 2 * kWStages + i); };
-  const uint32_t d2_full = bar0 + 8u * (12 + 2 * kWStages);
-  const uint32_t d2_empty = bar0 + 8u * (13 + 2 * kWStages);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + L.off_bar + 8 * (14 + 2 * kWStages));
+  auto d2_full = [&](int i) { return bar0 + 8u * (12 + 2 * kWStages + i); };
+  auto d2_empty = [&](int i) { return bar0 + 8u * (14 + 2 * kWStages + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + L.off_bar + 8 * (16 + 2 * kWStages));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -78,10 +78,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     for (int i = 0; i < 2; ++i) { mbar_init(y_full(i), 1); mbar_init(y_empty(i), 1); }
     for (int i = 0; i < kWStages; ++i) { mbar_init(w_full(i), 1); mbar_init(w_empty(i), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(d1_full(i), 1); mbar_init(d1_empty(i), kEpiWarpsF / 2);
-      mbar_init(h_full(i), kEpiWarpsF / 2); mbar_init(h_empty(i), 1);
+      mbar_init(d1_full(i), 1); mbar_init(d1_empty(i), kEpiWarpsF);
+      mbar_init(h_full(i), kEpiWarpsF); mbar_init(h_empty(i), 1);
+      mbar_init(d2_full(i), 1); mbar_init(d2_empty(i), kEpiWarpsF);
     }
-    mbar_init(d2_full, 1); mbar_init(d2_empty, kEpiWarpsF);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
@@ -112,70 +112,72 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
     }
   } else if (threadIdx.x == 32) {
     // ============================== MMA issuer ==============================
-    uint32_t ycount = 0, wcount = 0, g1count = 0, g2count = 0, tcount = 0;
+    // One global chunk sequence over all tiles of this CTA: G1 of chunk g is issued before G2 of chunk g-1, also across
+    // tile boundaries (D2 is double buffered), so the tensor pipe never idles behind the epilogue's last chunk.
+    uint32_t nt = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) ++nt;
+    const uint32_t total = nt * (uint32_t)NJ;
     const uint32_t idesc1 = idesc_bf16_f32(FM, NH);
     const uint32_t idesc2 = idesc_bf16_f32(FM, C);
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-      const int yb = ycount % L.ny; const uint32_t yph = (ycount / L.ny) & 1u; ++ycount;
-      mbar_wait(y_full(yb), yph);
+    auto do_g1 = [&](uint32_t g) {
+      const uint32_t ti = g / (uint32_t)NJ; const int j = (int)(g - ti * NJ);
+      const int yb = (int)(ti % (uint32_t)L.ny); const uint32_t yph = (ti / (uint32_t)L.ny) & 1u;
+      if (j == 0) mbar_wait(y_full(yb), yph);
+      const int ws = (int)(g % kWStages); const uint32_t wph = (g / kWStages) & 1u;
+      const int b = (int)(g & 1u); const uint32_t bph = (g >> 1) & 1u;
+      mbar_wait(w_full(ws), wph);
+      mbar_wait(d1_empty(b), bph ^ 1u);
       tc_fence_after();
       const uint32_t ybase = sbase + yb * L.y_bytes;
-      uint32_t wstage_of_g2 = wcount;     // weight-stage counter of the chunk G2 will consume next
-      for (int step = 0; step <= NJ; ++step) {
-        if (step < NJ) {
-          // ---- G1_j : D1[b] = y . W1_j^T
-          const int ws = wcount % kWStages; const uint32_t wph = (wcount / kWStages) & 1u; ++wcount;
-          const int b = g1count & 1; const uint32_t bph = (g1count >> 1) & 1u; ++g1count;
-          mbar_wait(w_full(ws), wph);
-          mbar_wait(d1_empty(b), bph ^ 1u);
-          tc_fence_after();
-          const uint32_t wb = sbase + L.off_w + ws * L.w_stage_bytes;
-          for (int kb = 0; kb < L.kb1; ++kb) {
-            const uint64_t ad = smem_desc_sw128(ybase + kb * kYBlockBytes);
-            const uint64_t bd = smem_desc_sw128(wb + kb * (NH * 128));
-            const int kmax = min(64, C - kb * 64) / 16;
-            for (int kk = 0; kk < kmax; ++kk)
-              umma_bf16(tmem_base + (uint32_t)(b * NH), ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc1,
-                        (kb | kk) != 0 ? 1u : 0u);
-          }
-          umma_commit(d1_full(b));
-          if (step == NJ - 1) umma_commit(y_empty(yb));        // y tile no longer needed once these retire
-        }
-        if (step >= 1) {
-          // ---- G2_j (j = step-1): D2 += H[b] . W2_j^T
-          const int j = step - 1;
-          const int ws = wstage_of_g2 % kWStages; ++wstage_of_g2;
-          const int b = g2count & 1; const uint32_t bph = (g2count >> 1) & 1u; ++g2count;
-          mbar_wait(h_full(b), bph);
-          if (j == 0) mbar_wait(d2_empty, (tcount & 1u) ^ 1u);
-          tc_fence_after();
-          const uint32_t wb = sbase + L.off_w + ws * L.w_stage_bytes + L.kb1 * (NH * 128);
-          const uint64_t ad = smem_desc_sw128(sbase + L.off_h + b * kHBytes);
-          const uint64_t bd = smem_desc_sw128(wb);
-          for (int kk = 0; kk < NH / 16; ++kk)
-            umma_bf16(tmem_base + (uint32_t)kD2Col, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc2,
-                      (j | kk) != 0 ? 1u : 0u);
-          umma_commit(h_empty(b));
-          umma_commit(w_empty(ws));
-          if (j == NJ - 1) umma_commit(d2_full);
-        }
+      const uint32_t wb = sbase + L.off_w + ws * L.w_stage_bytes;
+      for (int kb = 0; kb < L.kb1; ++kb) {
+        const uint64_t ad = smem_desc_sw128(ybase + kb * kYBlockBytes);
+        const uint64_t bd = smem_desc_sw128(wb + kb * (NH * 128));
+        const int kmax = min(64, C - kb * 64) / 16;
+        for (int kk = 0; kk < kmax; ++kk)
+          umma_bf16(tmem_base + (uint32_t)(b * NH), ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc1,
+                    (kb | kk) != 0 ? 1u : 0u);
       }
-      ++tcount;
+      umma_commit(d1_full(b));
+      if (j == NJ - 1) umma_commit(y_empty(yb));               // y tile no longer needed once these retire
+    };
+    auto do_g2 = [&](uint32_t g) {
+      const uint32_t ti = g / (uint32_t)NJ; const int j = (int)(g - ti * NJ);
+      const int tb = (int)(ti & 1u); const uint32_t tph = (ti >> 1) & 1u;
+      const int ws = (int)(g % kWStages);
+      const int b = (int)(g & 1u); const uint32_t bph = (g >> 1) & 1u;
+      mbar_wait(h_full(b), bph);
+      if (j == 0) mbar_wait(d2_empty(tb), tph ^ 1u);
+      tc_fence_after();
+      const uint32_t wb = sbase + L.off_w + ws * L.w_stage_bytes + L.kb1 * (NH * 128);
+      const uint64_t ad = smem_desc_sw128(sbase + L.off_h + b * kHBytes);
+      const uint64_t bd = smem_desc_sw128(wb);
+      for (int kk = 0; kk < NH / 16; ++kk)
+        umma_bf16(tmem_base + (uint32_t)(kD2Col + tb * C), ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc2,
+                  (j | kk) != 0 ? 1u : 0u);
+      umma_commit(h_empty(b));
+      umma_commit(w_empty(ws));
+      if (j == NJ - 1) umma_commit(d2_full(tb));
+    };
+    for (uint32_t g = 0; g <= total; ++g) {
+      const bool g1 = g < total, g2 = g >= 1;
+      // with a single y buffer the next tile's y load only starts after this tile's last G1 retires: do not let
+      // the wait for it delay G2 of the previous chunk
+      if (g1 && g2 && L.ny == 1 && (g % (uint32_t)NJ) == 0) { do_g2(g - 1); do_g1(g); }
+      else { if (g1) do_g1(g); if (g2) do_g2(g - 1); }
     }
   } else if (warp >= 2) {
     // ============================== epilogue warps ==============================
     const int q = warp & 3;                 // TMEM lane quarter
-    const int s = (warp - 2) >> 2;          // 16-column slice of a 64-column chunk, 0..3
+    const int s = (warp - 2) >> 2;          // 16-column slice of a 64-column chunk / D2 column-group stride, 0..3
     const int r_in_tile = q * 32 + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t ccount = 0, tcount = 0;
-    const int grp = (warp - 2) >> 3;        // epilogue warp group (8 warps): owns D1/H buffer `grp`
-    const int half = ((warp - 2) >> 2) & 1; // 32-column half of a 64-column chunk
     const int groups2 = C / 16;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
-      // residual rows for this warp's D2 column groups: issued now, consumed after the last chunk (latency hidden)
+    uint32_t ccount = 0, ti = 0;
+    uint4 rpre[3][2];                       // residual rows of the tile whose D2 epilogue is pending
+
+    auto prefetch_res = [&](int tile) {
       const int row = tile * FM + r_in_tile;
-      uint4 rpre[3][2];
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
         const int gi = s + 4 * u;
@@ -186,62 +188,24 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           rpre[u][0] = make_uint4(0, 0, 0, 0); rpre[u][1] = make_uint4(0, 0, 0, 0);
         }
       }
-      // D1 chunks: the two warp groups take alternate chunks (global chunk parity == group), so one group's barrier
-      // round trips (d1_full wait, TMEM load, h_full hand-off) overlap the other group's GELU arithmetic.
-      for (int j = 0; j < NJ; ++j, ++ccount) {
-        if ((int)(ccount & 1u) != grp) continue;
-        const int b = grp; const uint32_t bph = (ccount >> 1) & 1u;
-        mbar_wait(d1_full(b), bph);
-        tc_fence_after();
-        uint32_t ra[16], rb[16];
-        tmem_ld16(lane_addr + (uint32_t)(b * NH + half * 32), ra);
-        tmem_ld16(lane_addr + (uint32_t)(b * NH + half * 32 + 16), rb);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(d1_empty(b));         // D1[b] may be overwritten by G1 of chunk j+2
-        const int hcol = j * NH + half * 32;
-        uint4 o[4];
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          float v[16];
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + hh * 16 + i);
-            const uint32_t* r = hh == 0 ? ra : rb;
-            v[i] = gelu_fast(__uint_as_float(r[i]) + b4.x);
-            v[i + 1] = gelu_fast(__uint_as_float(r[i + 1]) + b4.y);
-            v[i + 2] = gelu_fast(__uint_as_float(r[i + 2]) + b4.z);
-            v[i + 3] = gelu_fast(__uint_as_float(r[i + 3]) + b4.w);
-          }
-          o[2 * hh].x = pack_bf16x2(v[0], v[1]); o[2 * hh].y = pack_bf16x2(v[2], v[3]);
-          o[2 * hh].z = pack_bf16x2(v[4], v[5]); o[2 * hh].w = pack_bf16x2(v[6], v[7]);
-          o[2 * hh + 1].x = pack_bf16x2(v[8], v[9]); o[2 * hh + 1].y = pack_bf16x2(v[10], v[11]);
-          o[2 * hh + 1].z = pack_bf16x2(v[12], v[13]); o[2 * hh + 1].w = pack_bf16x2(v[14], v[15]);
-        }
-        mbar_wait(h_empty(b), bph ^ 1u);                 // G2 of chunk j-2 has finished reading H[b]
-        unsigned char* hb = sal + L.off_h + b * kHBytes;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, half * 32 + u * 8)) = o[u];
-        fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h_full(b));
-      }
-      // ---- final epilogue of the tile: D2 -> out
-      mbar_wait(d2_full, tcount & 1u);
+    };
+    // D2 -> +b2 -> *gamma + res -> bf16 rows of tile `tile` (local index tl)
+    auto d2_epilogue = [&](int tile, uint32_t tl) {
+      const int tb = (int)(tl & 1u);
+      mbar_wait(d2_full(tb), (tl >> 1) & 1u);
       tc_fence_after();
+      const int row = tile * FM + r_in_tile;
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
         const int gi = s + 4 * u;
         if (gi >= groups2) break;
         uint32_t r[16];
-        tmem_ld16(lane_addr + (uint32_t)(kD2Col + gi * 16), r);
+        tmem_ld16(lane_addr + (uint32_t)(kD2Col + tb * C + gi * 16), r);
         tmem_ld_wait();
         if (gi + 4 >= groups2) {                         // last D2 read of this warp for this tile
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(d2_empty);
+          if (lane == 0) mbar_arrive(d2_empty(tb));
         }
         if (row < M) {
           const int n = gi * 16;
@@ -266,12 +230,52 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
           op[0] = o0; op[1] = o1;
         }
       }
-      if (s >= groups2) {                                // (C < 64) this warp owns no D2 columns
+    };
+
+    int prev_tile = -1;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++ti) {
+      // the previous tile's D2 epilogue is deferred until after this tile's first chunk, so the tail latency
+      // (last H hand-off -> G2 -> commit) is hidden behind GELU work; its residual rows are fetched now
+      if (prev_tile >= 0) prefetch_res(prev_tile);
+      for (int j = 0; j < NJ; ++j, ++ccount) {
+        const int b = (int)(ccount & 1u); const uint32_t bph = (ccount >> 1) & 1u;
+        mbar_wait(d1_full(b), bph);
+        tc_fence_after();
+        uint32_t r[16];
+        tmem_ld16(lane_addr + (uint32_t)(b * NH + s * 16), r);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(d2_empty);
+        if (lane == 0) mbar_arrive(d1_empty(b));         // D1[b] may be overwritten by G1 of chunk j+2
+        const int hcol = j * NH + s * 16;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
+          v[i] = gelu_fast(__uint_as_float(r[i]) + b4.x);
+          v[i + 1] = gelu_fast(__uint_as_float(r[i + 1]) + b4.y);
+          v[i + 2] = gelu_fast(__uint_as_float(r[i + 2]) + b4.z);
+          v[i + 3] = gelu_fast(__uint_as_float(r[i + 3]) + b4.w);
+        }
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+        o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+        o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+        o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+        mbar_wait(h_empty(b), bph ^ 1u);                 // G2 of chunk j-2 has finished reading H[b]
+        unsigned char* hb = sal + L.off_h + b * kHBytes;
+        *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, s * 16)) = o0;
+        *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, s * 16 + 8)) = o1;
+        fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_full(b));
+        if (j == 0 && prev_tile >= 0) d2_epilogue(prev_tile, ti - 1);
       }
-      ++tcount;
+      prev_tile = tile;
+    }
+    if (prev_tile >= 0) {
+      prefetch_res(prev_tile);
+      d2_epilogue(prev_tile, ti - 1);
     }
   }
   tc_fence_before();

@@ -36,8 +36,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);                        // back off: polling warps must not steal issue slots from the math warps
     if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
       printf("btsbot_b200: mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
@@ -122,13 +124,14 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
 // form: max |error| = 2.5e-5, i.e. far below half a bf16 ulp wherever |gelu| > 0.01.  One ex2 + one rcp + 6 FMA-pipe
 // ops instead of ~17 for an A&S erf.  The fp32 path keeps erff() (common.cuh gelu_erf).
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);          // the quintic is only monotone on |x| < 11
-  const float x2 = xc * xc;
+  // the quintic is only monotone on |x| < 11: clamp x^2 (one op); beyond |x| = 8 the slope is frozen at p(8)/8 > 0, so
+  // the sigmoid still saturates to 0 / 1 (ex2 -> 0 or +inf, rcp(+inf) = 0)
+  const float x2 = fminf(x * x, 64.0f);
   // -2*log2(e) * {a, b, c}
   float p = fmaf(x2, 1.01426306e-3f, -0.10677572f);
   p = fmaf(x2, p, -2.3011213f);
   float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * xc));   // exp(-2 p(x))
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * x));    // exp(-2 p(x))
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
