@@ -240,7 +240,7 @@ class Scorer:
 
     ``sd`` is a reference/timm-keyed state dict whose tensors live on the target CUDA device (e.g.
     ``module.state_dict()``).  Mirrors `btsbot/architectures.py` ``forward`` of mm_ConvNeXt (:166-171),
-    ConvNeXt (:121-122), um_nn (:292-293) and frozen_fusion (:366-372).
+    ConvNeXt (:121-122), um_nn (:292-293), frozen_fusion (:366-372), MaxViT (:42-51) and mm_MaxViT (:88-101).
     """
 
     def __init__(self, config: dict, sd: dict, precision: str = "fp32"):
@@ -249,7 +249,7 @@ class Scorer:
         L.lib()
         self.config, self.precision = config, precision
         self.name = name = config["model_name"]
-        self.trunk = self.head = None
+        self.trunk = self.head = self.maxvit = None
         self.pool_ln = None
         if name == "mm_ConvNeXt":
             arch = convnext_arch(config.get("model_kind", "convnext_nano.d1h_in1k"))
@@ -262,6 +262,14 @@ class Scorer:
             self.trunk = TrunkWeights(sd, "convnext.", arch, precision)
             self.pool_ln = (_f32c(sd["convnext.head.1.weight"]), _f32c(sd["convnext.head.1.bias"]))
             self.head = HeadWeights(sd, head_prefix="convnext.head.", head_idx=(3, 5, 8))
+        elif name == "mm_MaxViT":
+            from . import _maxvit
+            self.maxvit = _maxvit.MaxVitWeights(sd, "maxvit_backbone.", _maxvit.arch_for(config), precision)
+            self.head = HeadWeights(sd, meta_prefix="metadata_branch.", head_prefix="combined_head.")
+        elif name == "MaxViT":
+            from . import _maxvit
+            self.maxvit = _maxvit.MaxVitWeights(sd, "maxvit.", _maxvit.arch_for(config), precision)
+            self.head = HeadWeights(sd, head_prefix="maxvit.head.", head_idx=(1, 3, 6))
         elif name == "um_nn":
             self.head = HeadWeights(sd, meta_prefix="network.", final_prefix="network.6.",
                                     meta_act=L.ACT_RELU, meta_out_act=L.ACT_RELU)
@@ -279,6 +287,9 @@ class Scorer:
             raise ValueError(f"no B200 path for model_name {name!r}")
 
     def features(self, image_input: torch.Tensor, capture: dict | None = None) -> torch.Tensor:
+        if self.maxvit is not None:
+            from . import _maxvit
+            return _maxvit.maxvit_features(self.maxvit, image_input, capture)
         rows, h, w = trunk_forward(self.trunk, image_input, capture)
         B = image_input.shape[0]
         if self.pool_ln is not None:
@@ -291,7 +302,7 @@ class Scorer:
 
     def __call__(self, image_input=None, metadata_input=None, capture: dict | None = None) -> torch.Tensor:
         feat = None
-        if self.trunk is not None:
+        if self.trunk is not None or self.maxvit is not None:
             B = image_input.shape[0]
             if B > 0:
                 feat = self.features(image_input, capture)

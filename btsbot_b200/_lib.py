@@ -11,7 +11,7 @@ import threading
 
 F32, BF16, F64 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
-EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES = 0, 1, 2
+EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES, EPI_BIAS_SILU = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbtsbot_b200.so")
@@ -75,6 +75,15 @@ SIGNATURES = {
     "btsb_bce_logits_f32": (i32, [vp, vp, C.c_float, vp, vp, i64, C.c_float, vp]),
     "btsb_adamw_f32": (i32, [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64,
                              C.c_float, vp]),
+    "btsb_maxvit_stem1_fwd": (i32, [vp, i64, i32, i32, i32, vp, vp, i32, vp, i32, vp]),
+    "btsb_maxvit_im2col3_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
+    "btsb_maxvit_avgpool2_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
+    "btsb_maxvit_dw3_fwd": (i32, [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
+    "btsb_maxvit_se_fwd": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "btsb_maxvit_scale_fwd": (i32, [vp, vp, i64, i32, i32, i32, vp]),
+    "btsb_layernorm_rows_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
+    "btsb_maxvit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp, i32, vp]),
+    "btsb_maxvit_lnpool_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "btsb_cast_f32_to_bf16": (i32, [vp, vp, i64, vp]),
     "btsb_cast_bf16_to_f32": (i32, [vp, vp, i64, vp]),
 }

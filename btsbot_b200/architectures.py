@@ -295,15 +295,160 @@ class _NotOnB200(nn.Module):
         raise NotImplementedError(f"btsbot_b200: {type(self).__name__} {self._why}")
 
 
-class MaxViT(_NotOnB200):
-    """architectures.py:25-51 -- MaxViT trunk kernels (bilinear stem, MBConv, window/grid attention) are the
-    next hot-path row; not built yet, and there is no eager fallback."""
-    _why = "has no sm_100a kernels yet (SURVEY.md section 8 row a7); no eager fallback is provided"
+# ---------------------------------------------------------------------------------------------------------
+# parameter containers mirroring timm's MaxxVit module tree; forward never used
+# ---------------------------------------------------------------------------------------------------------
+class _RelPosBias(_KernelOnly):
+    def __init__(self, win, heads):
+        super().__init__()
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * win - 1) ** 2, heads))
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=0.02)
 
 
-class mm_MaxViT(_NotOnB200):
-    """architectures.py:54-101 -- see :class:`MaxViT`."""
-    _why = "has no sm_100a kernels yet (SURVEY.md section 8 row a7); no eager fallback is provided"
+class _AttentionCl(_KernelOnly):
+    def __init__(self, c, arch):
+        super().__init__()
+        self.qkv = nn.Linear(c, 3 * c)
+        self.rel_pos = _RelPosBias(arch["window"], c // arch["dim_head"])
+        self.proj = nn.Linear(c, c)
+
+
+class _TokenMlp(_KernelOnly):
+    def __init__(self, c):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(c, 4 * c), nn.Linear(4 * c, c)
+
+
+class _PartitionAttention(_KernelOnly):
+    def __init__(self, c, arch):
+        super().__init__()
+        self.norm1, self.attn = nn.LayerNorm(c, eps=1e-6), _AttentionCl(c, arch)
+        self.norm2, self.mlp = nn.LayerNorm(c, eps=1e-6), _TokenMlp(c)
+
+
+class _SE(_KernelOnly):
+    def __init__(self, c, rd):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Conv2d(c, rd, 1), nn.Conv2d(rd, c, 1)
+
+
+class _ShortcutParams(_KernelOnly):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.expand = nn.Conv2d(cin, cout, 1, bias=False) if cin != cout else nn.Identity()
+
+
+class _MbConv(_KernelOnly):
+    def __init__(self, cin, cout, stride, arch):
+        super().__init__()
+        mid = arch["expand"] * cin
+        self.shortcut = _ShortcutParams(cin, cout) if stride == 2 else nn.Identity()
+        self.pre_norm = nn.BatchNorm2d(cin, eps=1e-5)
+        self.conv1_1x1 = nn.Conv2d(cin, mid, 1, bias=False)
+        self.norm1 = nn.BatchNorm2d(mid, eps=1e-5)
+        self.conv2_kxk = nn.Conv2d(mid, mid, 3, stride=stride, padding=1, groups=mid, bias=False)
+        self.norm2 = nn.BatchNorm2d(mid, eps=1e-5)
+        self.se = _SE(mid, mid // arch["se_div"])
+        self.conv3_1x1 = nn.Conv2d(mid, cout, 1, bias=False)
+
+
+class _MaxVitBlock(_KernelOnly):
+    def __init__(self, cin, cout, stride, arch):
+        super().__init__()
+        self.conv = _MbConv(cin, cout, stride, arch)
+        self.attn_block = _PartitionAttention(cout, arch)
+        self.attn_grid = _PartitionAttention(cout, arch)
+
+
+class _MaxVitStage(_KernelOnly):
+    def __init__(self, cin, cout, depth, arch):
+        super().__init__()
+        self.blocks = nn.Sequential(*[_MaxVitBlock(cin if j == 0 else cout, cout, 2 if j == 0 else 1, arch)
+                                      for j in range(depth)])
+
+
+class _MaxVitStem(_KernelOnly):
+    def __init__(self, widths):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, widths[0], 3, stride=2, padding=1, bias=False)
+        self.norm1 = nn.BatchNorm2d(widths[0], eps=1e-5)
+        self.conv2 = nn.Conv2d(widths[0], widths[1], 3, stride=1, padding=1, bias=False)
+
+
+class _GlobalPool(_KernelOnly):
+    """Stands in for timm's ``SelectAdaptivePool2d('avg', flatten=True)`` (parameter-free)."""
+
+
+class _MaxVitHead(_KernelOnly):
+    """Attribute surface of timm's ``ClassifierHead`` that the reference reads (architectures.py:33-34,64-65)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.global_pool = _GlobalPool()
+        self.in_features = c
+
+
+class MaxVitTrunk(nn.Module):
+    """Stand-in for ``timm.create_model('maxvit_tiny_rw_224...')``: same parameter tree, no arithmetic."""
+
+    def __init__(self, model_kind: str, pretrained: bool = False):
+        super().__init__()
+        from .synth import maxvit_arch
+        arch = maxvit_arch(model_kind)
+        self.model_kind, self.arch = model_kind, arch
+        if pretrained:
+            warnings.warn("btsbot_b200: pretrained timm weights need the network; the trunk is random-initialised "
+                          "-- load a checkpoint with load_state_dict()", stacklevel=3)
+        dims = arch["embed_dim"]
+        self.stem = _MaxVitStem(arch["stem_width"])
+        cins = (arch["stem_width"][1],) + tuple(dims[:-1])
+        self.stages = nn.Sequential(*[_MaxVitStage(cins[i], dims[i], arch["depths"][i], arch) for i in range(4)])
+        self.norm = LayerNorm2d(dims[-1])
+        self.head = _MaxVitHead(dims[-1])
+        self.num_features = dims[-1]
+
+    def forward(self, *a, **k):  # pragma: no cover - guard
+        raise RuntimeError("btsbot_b200: the trunk runs inside the model's fused forward")
+
+
+class MaxViT(_B200Model):
+    """Image-only MaxViT (architectures.py:25-51): bilinear resize to the model's image size, trunk, head =
+    pool -> Linear -> GELU -> Linear -> GELU -> Dropout -> Linear."""
+
+    def __init__(self, config):
+        super().__init__()
+        model_kind = config.get("model_kind", "maxvit_tiny_rw_224.sw_in1k")
+        self.image_size = get_model_image_size(model_kind)
+        self.maxvit = MaxVitTrunk(model_kind, pretrained=config.get("pretrained", True))
+        h = self.maxvit.head
+        self.maxvit.head = nn.Sequential(
+            h.global_pool,
+            nn.Linear(h.in_features, config["fc1_neurons"]), nn.GELU(),
+            nn.Linear(config["fc1_neurons"], config["fc2_neurons"]), nn.GELU(),
+            nn.Dropout(config["dropout"]), nn.Linear(config["fc2_neurons"], 1))
+        self._init_runtime(dict(config, model_name="MaxViT"))
+
+    def forward(self, input_data: torch.Tensor) -> torch.Tensor:
+        return self._run(image_input=input_data)
+
+
+class mm_MaxViT(_B200Model):
+    """Multimodal MaxViT (architectures.py:54-101)."""
+
+    def __init__(self, config):
+        super().__init__()
+        model_kind = config.get("model_kind", "maxvit_tiny_rw_224.sw_in1k")
+        self.image_size = get_model_image_size(model_kind)
+        n_meta = len(config.get("metadata_cols", []))
+        self.maxvit_backbone = MaxVitTrunk(model_kind, pretrained=config.get("pretrained", True))
+        self.maxvit_feature_dim = self.maxvit_backbone.head.in_features
+        self.maxvit_backbone.head = self.maxvit_backbone.head.global_pool
+        self.metadata_branch = nn.Sequential(*_metadata_branch(n_meta, config, nn.GELU))
+        self.combined_head = _combined_head(self.maxvit_feature_dim + config["meta_fc2_neurons"], config, nn.GELU)
+        self._init_runtime(dict(config, model_name="mm_MaxViT"))
+
+    def forward(self, image_input: torch.Tensor, metadata_input: torch.Tensor) -> torch.Tensor:
+        return self._run(image_input=image_input, metadata_input=metadata_input)
 
 
 class mm_cnn(_NotOnB200):

@@ -383,6 +383,7 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Wt, const fl
       if (gn >= N) continue;
       float v = acc[i][j] + bias[gn];
       if (EPI == BTSB_EPI_BIAS_GELU) v = gelu_erf(v);
+      if (EPI == BTSB_EPI_BIAS_SILU) v = v / (1.0f + expf(-v));
       if (EPI == BTSB_EPI_SCALE_RES) v = res[gm * N + gn] + gamma[gn] * v;
       out[gm * N + gn] = v;
     }
@@ -561,6 +562,8 @@ int gemm_f32(const float* A, const float* Wt, const float* bias, const float* ga
     sgemm_kernel<BTSB_EPI_BIAS><<<grid, 256, 0, st>>>(A, Wt, bias, gamma, res, out, M, N, K);
   else if (epilogue == BTSB_EPI_BIAS_GELU)
     sgemm_kernel<BTSB_EPI_BIAS_GELU><<<grid, 256, 0, st>>>(A, Wt, bias, gamma, res, out, M, N, K);
+  else if (epilogue == BTSB_EPI_BIAS_SILU)
+    sgemm_kernel<BTSB_EPI_BIAS_SILU><<<grid, 256, 0, st>>>(A, Wt, bias, gamma, res, out, M, N, K);
   else
     sgemm_kernel<BTSB_EPI_SCALE_RES><<<grid, 256, 0, st>>>(A, Wt, bias, gamma, res, out, M, N, K);
   return launch_done("gemm_f32");

@@ -27,7 +27,7 @@ constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 }  // namespace
 
-constexpr int EPI_LN = 3;   // internal: out = LayerNorm(acc + bias) * gamma(ln_w) + aux(ln_b), whole rows per thread
+constexpr int EPI_LN = 100;   // internal: out = LayerNorm(acc + bias) * gamma(ln_w) + aux(ln_b), whole rows per thread
 
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -227,6 +227,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
           }
+          if (EPI == BTSB_EPI_BIAS_SILU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = silu_fast(v[i]);
+          }
           if (EPI == BTSB_EPI_SCALE_RES) {
             const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * N + n);
             const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
@@ -335,6 +339,7 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_SCALE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+    BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     attr_done = true;
   }
   const __nv_bfloat16* r = (const __nv_bfloat16*)res;
@@ -343,6 +348,8 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
     gemm_tc_kernel<BTSB_EPI_BIAS><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
   else if (epilogue == BTSB_EPI_BIAS_GELU)
     gemm_tc_kernel<BTSB_EPI_BIAS_GELU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
+  else if (epilogue == BTSB_EPI_BIAS_SILU)
+    gemm_tc_kernel<BTSB_EPI_BIAS_SILU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
   else
     gemm_tc_kernel<BTSB_EPI_SCALE_RES><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
   return launch_done("gemm_bf16");
@@ -425,7 +432,7 @@ extern "C" int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, c
   if (int e = check_device()) return e;
   BTSB_REQUIRE(M >= 0 && N >= 1 && K >= 1, "gemm: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
   BTSB_REQUIRE(dtype == BTSB_F32 || dtype == BTSB_BF16, "gemm: dtype must be F32 or BF16");
-  BTSB_REQUIRE(epilogue >= BTSB_EPI_BIAS && epilogue <= BTSB_EPI_SCALE_RES, "gemm: unknown epilogue %d", epilogue);
+  BTSB_REQUIRE(epilogue >= BTSB_EPI_BIAS && epilogue <= BTSB_EPI_BIAS_SILU, "gemm: unknown epilogue %d", epilogue);
   if (M == 0) return BTSB_OK;
   BTSB_REQUIRE(A && Wt && bias && out, "gemm: null pointer");
   if (epilogue == BTSB_EPI_SCALE_RES) BTSB_REQUIRE(gamma && res, "gemm: SCALE_RES needs gamma and res");

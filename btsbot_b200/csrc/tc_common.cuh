@@ -137,6 +137,15 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return x * r;
 }
 
+// SiLU x * sigmoid(x) for bf16 outputs: one ex2 + one rcp (relative error ~1e-6, far below bf16 rounding)
+__device__ __forceinline__ float silu_fast(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -149,6 +149,22 @@ def convnext_arch(model_kind: str) -> dict:
                      f"(supported: {sorted(CONVNEXT_KINDS)})")
 
 
+MAXVIT_KINDS = {
+    # timm maxvit_tiny_rw_224
+    "maxvit_tiny_rw": dict(embed_dim=(64, 128, 256, 512), depths=(2, 2, 5, 2), stem_width=(32, 64), dim_head=32,
+                           window=7, expand=4, se_div=16, img=224),
+}
+
+
+def maxvit_arch(model_kind: str) -> dict:
+    """Map a timm model name (``maxvit_tiny_rw_224.sw_in1k`` ...) to its MaxViT configuration."""
+    k = model_kind.lower()
+    for name, arch in MAXVIT_KINDS.items():
+        if name in k:
+            return dict(arch, name=name)
+    raise ValueError(f"unsupported MaxViT kind for the B200 path: {model_kind!r} (supported: {sorted(MAXVIT_KINDS)})")
+
+
 class _W:
     """numpy weight factory; ``perturb=False`` reproduces timm/torch default init statistics."""
 
@@ -198,10 +214,15 @@ def _convnext_trunk_sd(w: _W, prefix: str, arch: dict, sd: dict, gamma_base: flo
             sd[p + "mlp.fc2.bias"] = w.bias(c)
 
 
-def _bn_sd(w: _W, prefix: str, n: int, sd: dict):
+def _bn_sd(w: _W, prefix: str, n: int, sd: dict, data_std: float | None = None):
     sd[prefix + "weight"] = w.scale(n)
     sd[prefix + "bias"] = w.bias(n)
-    if w.perturb and n == len(METADATA_COLS):
+    if w.perturb and data_std is not None:
+        # running statistics at the scale of the layer's actual input (a trained net's would be): L2-normalised
+        # cutouts have pixel values ~1/63, so a unit-variance BatchNorm would drown the image in its own bias
+        sd[prefix + "running_mean"] = (data_std * w.g.standard_normal(n)).astype(np.float32)
+        sd[prefix + "running_var"] = (data_std ** 2 * w.g.uniform(0.7, 1.3, n)).astype(np.float32)
+    elif w.perturb and n == len(METADATA_COLS):
         # running stats near the column moments so normalised metadata is O(1) and logits straddle 0
         mu, sdv = METADATA_MOMENTS[:, 0], METADATA_MOMENTS[:, 1]
         sd[prefix + "running_mean"] = (mu + 0.1 * sdv * w.g.standard_normal(n)).astype(np.float32)
@@ -215,6 +236,51 @@ def _bn_sd(w: _W, prefix: str, n: int, sd: dict):
     sd[prefix + "num_batches_tracked"] = np.array(0 if not w.perturb else 17, dtype=np.int64)
 
 
+def _maxvit_trunk_sd(w: _W, prefix: str, arch: dict, sd: dict, branch_gain: float):
+    """timm MaxxVit ('maxvit_tiny_rw_224') parameter tree.  The net has no layer scale, so the last linear map of each
+    residual branch (conv3_1x1, attn.proj, mlp.fc2) is damped by ``branch_gain`` to keep the residual stream O(1)."""
+    sw = arch["stem_width"]
+    sd[f"{prefix}stem.conv1.weight"] = w.dense(sw[0], 3, 3, 3, fan_in=27)
+    _bn_sd(w, f"{prefix}stem.norm1.", sw[0], sd, data_std=0.01)
+    sd[f"{prefix}stem.conv2.weight"] = w.dense(sw[1], sw[0], 3, 3, fan_in=9 * sw[0])
+    cin = sw[1]
+    g = branch_gain if w.perturb else 1.0
+    for i, (c, d) in enumerate(zip(arch["embed_dim"], arch["depths"])):
+        heads = c // arch["dim_head"]
+        for j in range(d):
+            p = f"{prefix}stages.{i}.blocks.{j}."
+            mid, rd = arch["expand"] * cin, arch["expand"] * cin // arch["se_div"]
+            q = p + "conv."
+            if j == 0 and cin != c:
+                sd[q + "shortcut.expand.weight"] = w.dense(c, cin, 1, 1, fan_in=cin)
+            _bn_sd(w, q + "pre_norm.", cin, sd)
+            sd[q + "conv1_1x1.weight"] = w.dense(mid, cin, 1, 1, fan_in=cin)
+            _bn_sd(w, q + "norm1.", mid, sd)
+            sd[q + "conv2_kxk.weight"] = w.dense(mid, 1, 3, 3, fan_in=9)
+            _bn_sd(w, q + "norm2.", mid, sd)
+            sd[q + "se.fc1.weight"] = w.dense(rd, mid, 1, 1, fan_in=mid)
+            sd[q + "se.fc1.bias"] = w.bias(rd)
+            sd[q + "se.fc2.weight"] = w.dense(mid, rd, 1, 1, fan_in=rd)
+            sd[q + "se.fc2.bias"] = w.bias(mid)
+            sd[q + "conv3_1x1.weight"] = w.dense(c, mid, 1, 1, fan_in=mid) * np.float32(g)
+            cin = c
+            for part in ("attn_block.", "attn_grid."):
+                q = p + part
+                sd[q + "norm1.weight"], sd[q + "norm1.bias"] = w.scale(c), w.bias(c)
+                _linear_sd(w, q + "attn.qkv.", 3 * c, c, sd)
+                n_rel = (2 * arch["window"] - 1) ** 2
+                sd[q + "attn.rel_pos.relative_position_bias_table"] = \
+                    (w.g.standard_normal((n_rel, heads)) * (0.5 if w.perturb else 0.02)).astype(np.float32)
+                _linear_sd(w, q + "attn.proj.", c, c, sd)
+                sd[q + "attn.proj.weight"] *= np.float32(g)
+                sd[q + "norm2.weight"], sd[q + "norm2.bias"] = w.scale(c), w.bias(c)
+                _linear_sd(w, q + "mlp.fc1.", 4 * c, c, sd)
+                _linear_sd(w, q + "mlp.fc2.", c, 4 * c, sd)
+                sd[q + "mlp.fc2.weight"] *= np.float32(g)
+    sd[f"{prefix}norm.weight"] = w.scale(arch["embed_dim"][-1])
+    sd[f"{prefix}norm.bias"] = w.bias(arch["embed_dim"][-1])
+
+
 def _linear_sd(w: _W, prefix: str, nout: int, nin: int, sd: dict):
     sd[prefix + "weight"] = w.dense(nout, nin, fan_in=nin)
     sd[prefix + "bias"] = w.bias(nout)
@@ -222,7 +288,7 @@ def _linear_sd(w: _W, prefix: str, nout: int, nin: int, sd: dict):
 
 def make_state_dict(config: dict, seed: int = 2, perturb: bool = True, gamma_base: float = 0.5) -> dict:
     """State dict (numpy arrays, timm/reference key names) for ``config['model_name']`` in
-    {mm_ConvNeXt, ConvNeXt, um_nn, frozen_fusion}.  Keys follow `btsbot/architectures.py:104-171,277-372`
+    {mm_ConvNeXt, ConvNeXt, um_nn, frozen_fusion, mm_MaxViT, MaxViT}.  Keys follow `btsbot/architectures.py:104-171,277-372`
     and timm's ConvNeXt."""
     w = _W(seed, perturb)
     sd: dict = {}
@@ -250,6 +316,23 @@ def make_state_dict(config: dict, seed: int = 2, perturb: bool = True, gamma_bas
         _linear_sd(w, "convnext.head.3.", config["fc1_neurons"], feat, sd)
         _linear_sd(w, "convnext.head.5.", config["fc2_neurons"], config["fc1_neurons"], sd)
         _linear_sd(w, "convnext.head.8.", 1, config["fc2_neurons"], sd)
+    elif name == "mm_MaxViT":
+        arch = maxvit_arch(config.get("model_kind", "maxvit_tiny_rw_224.sw_in1k"))
+        _maxvit_trunk_sd(w, "maxvit_backbone.", arch, sd, gamma_base)
+        feat = arch["embed_dim"][-1]
+        _bn_sd(w, "metadata_branch.0.", nmeta, sd)
+        _linear_sd(w, "metadata_branch.1.", config["meta_fc1_neurons"], nmeta, sd)
+        _linear_sd(w, "metadata_branch.4.", config["meta_fc2_neurons"], config["meta_fc1_neurons"], sd)
+        _linear_sd(w, "combined_head.0.", config["comb_fc1_neurons"], feat + config["meta_fc2_neurons"], sd)
+        _linear_sd(w, "combined_head.2.", config["comb_fc2_neurons"], config["comb_fc1_neurons"], sd)
+        _linear_sd(w, "combined_head.5.", 1, config["comb_fc2_neurons"], sd)
+    elif name == "MaxViT":
+        arch = maxvit_arch(config.get("model_kind", "maxvit_tiny_rw_224.sw_in1k"))
+        _maxvit_trunk_sd(w, "maxvit.", arch, sd, gamma_base)
+        feat = arch["embed_dim"][-1]
+        _linear_sd(w, "maxvit.head.1.", config["fc1_neurons"], feat, sd)
+        _linear_sd(w, "maxvit.head.3.", config["fc2_neurons"], config["fc1_neurons"], sd)
+        _linear_sd(w, "maxvit.head.6.", 1, config["fc2_neurons"], sd)
     elif name == "um_nn":
         _bn_sd(w, "network.0.", nmeta, sd)
         _linear_sd(w, "network.1.", config["meta_fc1_neurons"], nmeta, sd)
@@ -278,7 +361,8 @@ def make_state_dict(config: dict, seed: int = 2, perturb: bool = True, gamma_bas
 
 
 FINAL_LAYER = {"mm_ConvNeXt": "combined_head.5.", "frozen_fusion": "combined_head.5.",
-               "ConvNeXt": "convnext.head.8.", "um_nn": "network.6."}
+               "ConvNeXt": "convnext.head.8.", "um_nn": "network.6.",
+               "mm_MaxViT": "combined_head.5.", "MaxViT": "maxvit.head.6."}
 
 
 def apply_calibration(sd: dict, config: dict, scale: float, shift: float) -> dict:

@@ -48,6 +48,7 @@ extern "C" {
 #define BTSB_EPI_BIAS 0      /* out = acc + bias[n] */
 #define BTSB_EPI_BIAS_GELU 1 /* out = gelu(acc + bias[n]) */
 #define BTSB_EPI_SCALE_RES 2 /* out = res[m,n] + gamma[n] * (acc + bias[n]) */
+#define BTSB_EPI_BIAS_SILU 3 /* out = silu(acc + bias[n])   (MaxViT MBConv: 1x1 conv + folded BatchNorm + SiLU) */
 
 int btsb_version(void);
 const char* btsb_last_error_string(void);
@@ -211,6 +212,44 @@ int btsb_bce_logits_f32(const float* logits, const float* labels, float pos_weig
 /* fused AdamW over a flat parameter buffer (torch.optim.AdamW semantics; g is multiplied by grad_scale first) */
 int btsb_adamw_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float wd, int64_t step, float grad_scale, void* stream);
+
+/* ---- MaxViT (timm maxvit_tiny_rw_224 behind btsbot/architectures.py:25-101) -------------
+ * The 1x1 convolutions / Linear layers of the MBConv, attention and MLP blocks are btsb_gemm_fwd calls (tcgen05 in
+ * bf16) with BatchNorm folded into the weights; the kernels below are everything between those GEMMs.  Activations
+ * are NHWC pixel rows [B*H*W, C] in `dtype` (F32 | BF16), math in fp32.  At most 65535 images per call.
+ *
+ * stem1: F.interpolate(x, (S,S), bilinear, align_corners=False) (architectures.py:44-50,90-96) fused into stem.conv1
+ *   (3x3, stride 2, pad 1, no bias) + stem.norm1 (BatchNorm, folded) + SiLU.  x [B,3,Hin,Win] fp32 NCHW ->
+ *   out [B*(S/2)*(S/2), C1]; w [27][C1] fp32 (k = (ci*3+ky)*3+kx, BN scale folded in), shift [C1].  S == Hin skips
+ *   nothing: the interpolation weights degenerate to the identity, as torch's do.
+ * im2col3: 3x3 / stride 1 / pad 1 patch matrix [B*H*W, 9C], column (ky*3+kx)*C + c, for stem.conv2 as a GEMM.
+ * avgpool2: MBConv shortcut AvgPool2d(2).
+ * dw3: conv2_kxk depthwise 3x3 (stride 1|2, pad 1, no bias) + norm2 (folded) + SiLU; also writes the SE squeeze
+ *   pooled[b,c] = mean_{h,w} out (fixed summation order).  w [9][C] fp32 (BN scale folded), shift [C].
+ * se: gate[b,c] = sigmoid(W2 . silu(W1 . pooled[b] + b1) + b2);  w1 [R][C], w2 [C][R] fp32.
+ * scale: x[b,p,c] *= gate[b,c] in place (SE excite, ahead of the conv3_1x1 GEMM).
+ * layernorm_rows: LayerNorm(eps 1e-6) over C for every row (PartitionAttentionCl.norm1 / norm2); C % 64 == 0, <= 512.
+ * attn: AttentionCl over 7x7 windows (grid_mode 0, 'block') or the 7x7 dilated grid (grid_mode 1): qkv rows
+ *   [B*H*W, 3C] in image order, head h = columns [96h, 96h+96) = q|k|v (head_first); out rows [B*H*W, C];
+ *   softmax(q k^T / sqrt(32) + table[rel_pos_index(i,j), h]) v;  table [169, C/32] fp32.  The window / grid partition
+ *   and its reverse are index arithmetic inside the kernel.
+ * lnpool: final LayerNorm2d(C) then global average pool -> out [B, C] fp32.
+ */
+int btsb_maxvit_stem1_fwd(const float* x, int64_t B, int Hin, int Win, int S, const float* w, const float* shift,
+                          int C1, void* out, int dtype, void* stream);
+int btsb_maxvit_im2col3_fwd(const void* x, void* out, int64_t B, int H, int W, int C, int dtype, void* stream);
+int btsb_maxvit_avgpool2_fwd(const void* x, void* out, int64_t B, int H, int W, int C, int dtype, void* stream);
+int btsb_maxvit_dw3_fwd(const void* x, int64_t B, int H, int W, int C, int stride, const float* w, const float* shift,
+                        void* out, float* pooled, int dtype, void* stream);
+int btsb_maxvit_se_fwd(const float* pooled, int64_t B, int C, int R, const float* w1, const float* b1, const float* w2,
+                       const float* b2, float* gate, void* stream);
+int btsb_maxvit_scale_fwd(void* x, const float* gate, int64_t B, int HW, int C, int dtype, void* stream);
+int btsb_layernorm_rows_fwd(const void* x, const float* ln_w, const float* ln_b, void* out, int64_t M, int C, int dtype,
+                            void* stream);
+int btsb_maxvit_attn_fwd(const void* qkv, void* out, int64_t B, int H, int W, int C, int grid_mode, const float* table,
+                         int dtype, void* stream);
+int btsb_maxvit_lnpool_fwd(const void* x, const float* ln_w, const float* ln_b, float* out, int64_t B, int HW, int C,
+                           int dtype, void* stream);
 
 /* dtype helpers used by the weight packer: float32 -> bf16 (round-to-nearest-even) and back. */
 int btsb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);

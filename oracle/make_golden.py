@@ -196,5 +196,59 @@ def main():
     print("wrote", os.listdir(GOLD))
 
 
+MAXVIT_CASES = {
+    "mm_maxvit": ("mm_MaxViT", "maxvit_tiny_rw_224.sw_in1k", {}),
+    "img_maxvit": ("MaxViT", "maxvit_tiny_rw_224.sw_in1k", {}),
+}
+#: MaxViT is ~40x the FLOPs of ConvNeXt-nano: goldens on 8 shipped example alerts + 8 synthetic ones
+MAXVIT_EXAMPLE, MAXVIT_SYN = 8, 8
+
+
+def maxvit_batch():
+    trip = np.load(os.path.join(REF, "example_data/usage_triplets.npy")).astype(np.float32)
+    import pandas as pd
+    cand = pd.read_csv(os.path.join(REF, "example_data/usage_candidates.csv"))
+    meta = cand[synth.METADATA_COLS].values.astype(np.float32)
+    sel = np.linspace(0, len(trip) - 1, MAXVIT_EXAMPLE).round().astype(int)       # spans both labels
+    t = np.concatenate([trip[sel], synth.make_triplets(MAXVIT_SYN, start=2000)])
+    m = np.concatenate([meta[sel], synth.make_metadata(MAXVIT_SYN, start=2000)])
+    return sel, np.ascontiguousarray(t.transpose(0, 3, 1, 2)), m
+
+
+def main_maxvit():
+    """Goldens for `architectures.py:25-101` (MaxViT / mm_MaxViT) executed verbatim on the module-based MaxViT twin
+    of the timm shim: pins the reference-owned wrapper (bilinear resize, head surgery, metadata branch, fusion head)."""
+    arch = ref_architectures()
+    sel, img, met = maxvit_batch()
+    img, met = torch.from_numpy(img), torch.from_numpy(met)
+    out = {"example_idx": sel, "nsyn": MAXVIT_SYN}
+    torch.set_num_threads(8)
+    for case, (name, kind, extra) in MAXVIT_CASES.items():
+        cfg = synth.canonical_config(name, kind)
+        cfg.update(extra)
+        model = getattr(arch, name)(cfg)
+        sd = synth.make_state_dict(cfg, seed=2)
+        timm_shim.load_timm_keys(model, sd)
+        model.eval()
+
+        def run(model):
+            with torch.no_grad():
+                return model(image_input=img, metadata_input=met) if name == "mm_MaxViT" else model(input_data=img)
+        raw = run(model).numpy().astype(np.float64)
+        shift, scale = float(np.median(raw)), float(min(10.0, 0.5 / raw.std()))
+        sd = synth.apply_calibration(sd, cfg, scale, shift)
+        timm_shim.load_timm_keys(model, sd)
+        logits = run(model)
+        out[case + "_cal"] = np.array([scale, shift], dtype=np.float64)
+        out[case] = logits.numpy().astype(np.float32)
+        print(case, tuple(logits.shape), float(logits.min()), float(logits.max()), "pos frac",
+              float((logits > 0).float().mean()), "gain", scale)
+        out[case + "_keys"] = np.array(sorted(k for k in model.state_dict() if ".head.fc." not in k))
+    np.savez_compressed(os.path.join(GOLD, "maxvit_logits.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--maxvit" in sys.argv:
+        main_maxvit()
+    else:
+        main()
