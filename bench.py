@@ -2,6 +2,7 @@
 """bench.py -- alerts/sec of the multimodal ConvNeXt scoring hot path (BASELINE.json metric) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--precision bf16|fp32]
+                    [--workload c3|c4]
 
 Workload (BASELINE.json configs[2], "C3"): bulk scoring of synthetic alerts with mm_ConvNeXt / convnext_nano
 (random-init weights, 25 metadata columns), index-range sharded over ranks with NO collective on the data path.
@@ -16,6 +17,9 @@ A "step" is one forward pass of every rank over one micro-batch of B alerts ([B,
              comes from the un-instrumented pass; `kernels` lists every kernel family for cross-checking)
   cpu_baseline : the CPU oracle (port of the reference path: btsbot/architectures.py glue + restated timm trunk)
              following inference_example.py:62-91 (batch 64, fp32, eval/no_grad) on a bounded sample
+
+`--workload c4` runs BASELINE.json configs[3] instead (multimodal MaxViT-tiny-rw-224, batch 4096 per GPU per step, bf16);
+the default (and what the driver measures) is C3.
 
 `--impl reference` times that CPU port alone with all host threads (the reference itself cannot run offline:
 timm is not installable).
@@ -36,6 +40,13 @@ sys.path.insert(0, ROOT)
 
 MODEL_KIND = "convnext_nano.d1h_in1k"
 ALERT_IN_BYTES = 63 * 63 * 3 * 4 + 25 * 4
+WORKLOADS = {
+    "c3": dict(model="mm_ConvNeXt", kind="convnext_nano.d1h_in1k", batch=8192, cpu_sample=8192, cpu_batch=64,
+               label="C3 multimodal ConvNeXt-nano bulk scoring, 63x63x3 triplet + 25 metadata per alert"),
+    "c4": dict(model="mm_MaxViT", kind="maxvit_tiny_rw_224.sw_in1k", batch=4096, cpu_sample=64, cpu_batch=64,
+               label="C4 multimodal MaxViT-tiny-rw-224 scoring (bilinear 63->224, MBConv, window+grid attention), "
+                     "63x63x3 triplet + 25 metadata per alert"),
+}
 
 
 def parse():
@@ -44,11 +55,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8192, help="alerts per GPU per step")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="alerts per GPU per step (default: the workload's)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-sample", type=int, default=8192, help="alerts in the cpu_baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=None, help="alerts in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.batch = args.batch or wl["batch"]
+    args.cpu_sample = args.cpu_sample or wl["cpu_sample"]
+    return args
 
 
 def peaks():
@@ -110,7 +126,10 @@ def cpu_port(sample_alerts: int, cfg, sd_np, threads: int):
     """inference_example.py:62-91 on the CPU oracle: float32, eval, no_grad, DataLoader(batch 64, shuffle=False).
     Returns alerts/s over `sample_alerts` synthetic alerts (after one warm-up batch)."""
     from btsbot_b200 import synth, utils
-    from oracle import convnext_oracle as O
+    if "MaxViT" in cfg["model_name"]:
+        from oracle import maxvit_oracle as O
+    else:
+        from oracle import convnext_oracle as O
     from torch.utils.data import DataLoader
     torch.set_num_threads(threads)
     sd = synth.to_torch(sd_np)
@@ -119,7 +138,8 @@ def cpu_port(sample_alerts: int, cfg, sd_np, threads: int):
     img = torch.from_numpy(np.ascontiguousarray(np.transpose(trip.astype(np.float32), (0, 3, 1, 2))))
     ds = utils.FlexibleDataset(images=img, metadata=torch.from_numpy(meta), labels=torch.zeros(sample_alerts, dtype=torch.long))
     dl = DataLoader(ds, batch_size=64, shuffle=False, num_workers=0)
-    O.forward(sd, cfg, img[:64], torch.from_numpy(meta[:64]))       # warm-up
+    nw = 8 if "MaxViT" in cfg["model_name"] else 64
+    O.forward(sd, cfg, img[:nw], torch.from_numpy(meta[:nw]))       # warm-up
     t0 = time.perf_counter()
     n = 0
     for ib, mb, _ in dl:
@@ -134,12 +154,13 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from btsbot_b200 import synth
-    cfg = synth.canonical_config("mm_ConvNeXt", MODEL_KIND)
+    wl = WORKLOADS[args.workload]
+    cfg = synth.canonical_config(wl["model"], wl["kind"])
     sd = synth.make_state_dict(cfg, seed=2)
     threads = os.cpu_count() or 1
-    per_step = 1024                                  # bounded sample of the workload per step
+    per_step = 1024 if args.workload == "c3" else 64      # bounded sample of the workload per step
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_port(256, cfg, sd, threads)
+        cpu_port(per_step // 4, cfg, sd, threads)
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
         rate, dt = cpu_port(per_step, cfg, sd, threads)
@@ -150,8 +171,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "alerts/sec", "value": value, "unit": "alerts/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3 multimodal ConvNeXt-nano bulk scoring (CPU port of the reference path)",
-                   "model_kind": MODEL_KIND, "alerts_per_step": per_step, "batch": 64},
+        "config": {"workload": wl["label"] + " (CPU port of the reference path)",
+                   "model_kind": wl["kind"], "alerts_per_step": per_step, "batch": 64},
         "cpu_baseline": {"value": value, "unit": "alerts/s", "cores": threads, "kind": "port",
                          "sample": f"{per_step} synthetic alerts per step in batches of 64, torch {torch.__version__} CPU fp32, "
                                    f"{threads} threads; reference itself not runnable offline (timm missing)"},
@@ -181,9 +202,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
 
-    cfg = dict(synth.canonical_config("mm_ConvNeXt", MODEL_KIND), precision=args.precision)
+    wl = WORKLOADS[args.workload]
+    cfg = dict(synth.canonical_config(wl["model"], wl["kind"]), precision=args.precision)
     sd_np = synth.make_state_dict(cfg, seed=2)
-    model = btsbot.mm_ConvNeXt(cfg)
+    model = getattr(btsbot, wl["model"])(cfg)
     model.load_state_dict(synth.to_torch(sd_np), strict=True)
     model = model.to(dev).eval()
 
@@ -287,7 +309,8 @@ def main():
                          "share": a["ms"] / sum(v["ms"] for v in kern.values())}
     top = next(iter(kernels))
     tk = kernels[top]
-    tensor_bound = top.startswith("gemm") and args.precision == "bf16"
+    tensor_bound = args.precision == "bf16" and any(t in top for t in ("gemm", "mv_expand", "mv_project", "mv_qkv", "mv_proj",
+                                                                       "mv_fc", "mv_stem2", "mv_shortcut"))
     if tensor_bound:
         roof = {"kernel": top, "bound": "tensor", "achieved": tk["tflops"], "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": tk["tflops"] / pk["tf_sust"], "traffic": None,
@@ -309,8 +332,8 @@ def main():
         "metric": "alerts/sec", "value": value, "unit": "alerts/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "C3 multimodal ConvNeXt-nano bulk scoring, 63x63x3 triplet + 25 metadata per alert",
-                   "model_kind": MODEL_KIND, "alerts_per_gpu_per_step": B, "global_alerts_per_step": world * B,
+        "config": {"workload": wl["label"],
+                   "model_kind": wl["kind"], "alerts_per_gpu_per_step": B, "global_alerts_per_step": world * B,
                    "sharding": "contiguous index ranges, no data-path collective",
                    "l2_policy": f"inputs larger than L2 ({B * ALERT_IN_BYTES / 1e6:.0f} MB per step), "
                                 f"{nres} resident batches rotated"},

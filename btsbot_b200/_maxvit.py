@@ -24,7 +24,7 @@ from .synth import maxvit_arch
 BN2D_EPS = 1e-5     # timm conv_cfg.norm_eps for the 'rw' MaxViT variants
 
 #: images per pass through the trunk (bounds the largest activation: chunk x 112 x 112 x 256 elements)
-CHUNK = {"fp32": 128, "bf16": 256}
+CHUNK = {"fp32": 128, "bf16": 1024}
 #: use the fused fc1->GELU->fc2 kernel in the attention MLPs where it applies (bf16, C <= 160)
 FUSE_MLP = True
 
@@ -77,7 +77,7 @@ class MaxVitWeights:
                 blk["dw_shift"] = tn2.contiguous()
                 blk["se_w1"] = _f32c(g(m + "se.fc1.weight").reshape(-1, blk["mid"]))
                 blk["se_b1"] = _f32c(g(m + "se.fc1.bias"))
-                blk["se_w2"] = _f32c(g(m + "se.fc2.weight").reshape(blk["mid"], -1))
+                blk["se_w2"] = _f32c(g(m + "se.fc2.weight").reshape(blk["mid"], -1).t())          # [R, mid]
                 blk["se_b2"] = _f32c(g(m + "se.fc2.bias"))
                 blk["w3"] = g(m + "conv3_1x1.weight").reshape(c, blk["mid"]).to(wdt).contiguous()
                 blk["sc_w"] = None

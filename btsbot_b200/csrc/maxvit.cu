@@ -210,7 +210,7 @@ mv_dw3_kernel(const T* __restrict__ x, int H, int W, int C, int stride, int Ho, 
 
 // =====================================================================================================
 // M4  SE gate: g[b,c] = sigmoid(W2 . silu(W1 . pooled[b] + b1) + b2), one CTA per image.
-//   w1 [R][C], w2 [C][R] fp32; R <= 128.
+//   w1 [R][C], w2 TRANSPOSED to [R][C] fp32 (so both phases read coalesced); R <= 128.
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
 mv_se_kernel(const float* __restrict__ pooled, int C, int R, const float* __restrict__ w1, const float* __restrict__ b1,
@@ -231,7 +231,7 @@ mv_se_kernel(const float* __restrict__ pooled, int C, int R, const float* __rest
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = b2[c];
-    for (int r = 0; r < R; ++r) s = fmaf(w2[(int64_t)c * R + r], hid[r], s);
+    for (int r = 0; r < R; ++r) s = fmaf(w2[(int64_t)r * C + c], hid[r], s);      // w2 is [R][C]: coalesced over c
     gate[b * C + c] = 1.0f / (1.0f + expf(-s));
   }
 }
@@ -417,6 +417,15 @@ mv_lnpool_kernel(const T* __restrict__ x, const float* __restrict__ g, const flo
 }  // namespace
 }  // namespace btsb
 
+namespace btsb {
+int maxvit_dw3_bf16(const void* x, int64_t B, int H, int W, int C, int stride, int Ho, int Wo, const float* w,
+                    const float* shift, void* out, float* pooled, cudaStream_t st);
+int maxvit_ln_bf16(const void* x, const float* g, const float* b, void* out, int64_t M, int C, cudaStream_t st);
+int maxvit_scale_bf16(void* x, const float* gate, int64_t B, int HW, int C, cudaStream_t st);
+int maxvit_avgpool2_bf16(const void* x, void* out, int64_t B, int H, int W, int C, cudaStream_t st);
+int maxvit_attn_bf16_mma(const void* qkv, void* out, int64_t B, int H, int W, int C, int grid_mode, const float* table,
+                         cudaStream_t st);
+}
 using namespace btsb;
 
 #define MV_DISPATCH(dtype, CALL_F32, CALL_BF16) \
@@ -475,6 +484,7 @@ extern "C" int btsb_maxvit_avgpool2_fwd(const void* x, void* out, int64_t B, int
   const int64_t total = B * (H / 2) * (W / 2) * (C / 2);
   const int grid = grid_for(total, 256 * 4);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == BTSB_BF16) { const int r = maxvit_avgpool2_bf16(x, out, B, H, W, C, st); if (r != 1) return r; }
   MV_DISPATCH(dtype, (mv_avgpool2_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (float*)out, B, H, W, C)),
               (mv_avgpool2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, B, H, W, C)));
   return launch_done("maxvit_avgpool2");
@@ -491,6 +501,7 @@ extern "C" int btsb_maxvit_dw3_fwd(const void* x, int64_t B, int H, int W, int C
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   dim3 grid((C + 63) / 64, (unsigned)B);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == BTSB_BF16) { const int r = maxvit_dw3_bf16(x, B, H, W, C, stride, Ho, Wo, w, shift, out, pooled, st); if (r != 1) return r; }
   MV_DISPATCH(dtype,
               (mv_dw3_kernel<float><<<grid, kDwWarps * 32, 0, st>>>((const float*)x, H, W, C, stride, Ho, Wo, w, shift, (float*)out, pooled)),
               (mv_dw3_kernel<__nv_bfloat16><<<grid, kDwWarps * 32, 0, st>>>((const __nv_bfloat16*)x, H, W, C, stride, Ho, Wo, w, shift,
@@ -516,6 +527,7 @@ extern "C" int btsb_maxvit_scale_fwd(void* x, const float* gate, int64_t B, int 
   BTSB_REQUIRE(x && gate, "maxvit scale: null pointer");
   const int grid = grid_for(B * HW * (C / 2), 256 * 4);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == BTSB_BF16) { const int r = maxvit_scale_bf16(x, gate, B, HW, C, st); if (r != 1) return r; }
   MV_DISPATCH(dtype, (mv_scale_kernel<float><<<grid, 256, 0, st>>>((float*)x, gate, B, HW, C)),
               (mv_scale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)x, gate, B, HW, C)));
   return launch_done("maxvit_scale");
@@ -530,6 +542,7 @@ extern "C" int btsb_layernorm_rows_fwd(const void* x, const float* ln_w, const f
   BTSB_REQUIRE(x && ln_w && ln_b && out, "layernorm rows: null pointer");
   const int grid = grid_for(M, 8 * 4);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == BTSB_BF16) { const int r = maxvit_ln_bf16(x, ln_w, ln_b, out, M, C, st); if (r != 1) return r; }
   MV_DISPATCH(dtype, (mv_ln_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ln_w, ln_b, (float*)out, M, C)),
               (mv_ln_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ln_w, ln_b, (__nv_bfloat16*)out, M, C)));
   return launch_done("layernorm_rows");
@@ -545,9 +558,10 @@ extern "C" int btsb_maxvit_attn_fwd(const void* qkv, void* out, int64_t B, int H
   BTSB_REQUIRE(qkv && out && table, "maxvit attn: null pointer");
   const int64_t nwin = B * (H / kWin) * (W / kWin);
   BTSB_REQUIRE(nwin < (1ll << 31), "maxvit attn: too many windows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == BTSB_BF16) return maxvit_attn_bf16_mma(qkv, out, B, H, W, C, grid_mode, table, st);   // tensor cores
   dim3 grid((unsigned)nwin, C / kDh);
   const float scale = 0.17677669529663687f;   // dim_head ** -0.5
-  cudaStream_t st = (cudaStream_t)stream;
   MV_DISPATCH(dtype,
               (mv_attn_kernel<float><<<grid, 64, 0, st>>>((const float*)qkv, (float*)out, H, W, C, C / kDh, grid_mode, table, scale)),
               (mv_attn_kernel<__nv_bfloat16><<<grid, 64, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, H, W, C, C / kDh,

@@ -226,7 +226,7 @@ int btsb_adamw_f32(float* p, const float* g, float* m, float* v, int64_t n, floa
  * avgpool2: MBConv shortcut AvgPool2d(2).
  * dw3: conv2_kxk depthwise 3x3 (stride 1|2, pad 1, no bias) + norm2 (folded) + SiLU; also writes the SE squeeze
  *   pooled[b,c] = mean_{h,w} out (fixed summation order).  w [9][C] fp32 (BN scale folded), shift [C].
- * se: gate[b,c] = sigmoid(W2 . silu(W1 . pooled[b] + b1) + b2);  w1 [R][C], w2 [C][R] fp32.
+ * se: gate[b,c] = sigmoid(W2 . silu(W1 . pooled[b] + b1) + b2);  w1 [R][C] and w2t = W2^T [R][C], fp32.
  * scale: x[b,p,c] *= gate[b,c] in place (SE excite, ahead of the conv3_1x1 GEMM).
  * layernorm_rows: LayerNorm(eps 1e-6) over C for every row (PartitionAttentionCl.norm1 / norm2); C % 64 == 0, <= 512.
  * attn: AttentionCl over 7x7 windows (grid_mode 0, 'block') or the 7x7 dilated grid (grid_mode 1): qkv rows
@@ -241,7 +241,7 @@ int btsb_maxvit_im2col3_fwd(const void* x, void* out, int64_t B, int H, int W, i
 int btsb_maxvit_avgpool2_fwd(const void* x, void* out, int64_t B, int H, int W, int C, int dtype, void* stream);
 int btsb_maxvit_dw3_fwd(const void* x, int64_t B, int H, int W, int C, int stride, const float* w, const float* shift,
                         void* out, float* pooled, int dtype, void* stream);
-int btsb_maxvit_se_fwd(const float* pooled, int64_t B, int C, int R, const float* w1, const float* b1, const float* w2,
+int btsb_maxvit_se_fwd(const float* pooled, int64_t B, int C, int R, const float* w1, const float* b1, const float* w2t,
                        const float* b2, float* gate, void* stream);
 int btsb_maxvit_scale_fwd(void* x, const float* gate, int64_t B, int HW, int C, int dtype, void* stream);
 int btsb_layernorm_rows_fwd(const void* x, const float* ln_w, const float* ln_b, void* out, int64_t M, int C, int dtype,

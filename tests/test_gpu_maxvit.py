@@ -101,7 +101,7 @@ def test_se_gate_and_scale(cuda_dev):
     w2, b2 = torch.randn(Cc, R, generator=g) / 4, torch.randn(Cc, generator=g) * 0.1
     ref = torch.sigmoid(F.linear(F.silu(F.linear(pooled, w1, b1)), w2, b2))
     gate = torch.empty((B, Cc), device=cuda_dev)
-    dv = [t.contiguous().to(cuda_dev) for t in (pooled, w1, b1, w2, b2)]
+    dv = [t.contiguous().to(cuda_dev) for t in (pooled, w1, b1, w2.t(), b2)]
     L.check(L.lib().btsb_maxvit_se_fwd(p(dv[0]), B, Cc, R, p(dv[1]), p(dv[2]), p(dv[3]), p(dv[4]), p(gate),
                                        L.stream_ptr()), "se")
     assert relerr(gate.cpu(), ref) < 1e-5
