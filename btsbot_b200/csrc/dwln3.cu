@@ -41,15 +41,21 @@ __device__ __forceinline__ void seg_reduce32(float (&v)[32], int lane) {
   }
 }
 
-template <int S>
+// CT > 0: channel count known at compile time (nano 80/160, pico 64/128) -- every shared-memory address becomes an
+// immediate offset, which removes ~1/3 of the issued instructions (integer address arithmetic; profiles/r01c);
+// CT == 0: generic runtime C.
+template <int S, int CT>
 __global__ void __launch_bounds__(kDw3MaxThreads, 1)
-dwln3_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C, int A, int REM, const float* __restrict__ wt,
+dwln3_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C_rt, int A_rt, int REM_rt, const float* __restrict__ wt,
              const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
              __nv_bfloat16* __restrict__ out) {
   constexpr int R = S > 3 ? 3 : S - 1;
   constexpr int NT = 2 * R + 1;
   constexpr int HW = S * S;
   static_assert(2 * S <= 32, "row statistics must fit the 32-value reduction");
+  const int C = CT > 0 ? CT : C_rt;
+  const int A = CT > 0 ? (CT / 2) / 32 : A_rt;
+  const int REM = CT > 0 ? (CT / 2) % 32 : REM_rt;
   extern __shared__ __align__(16) unsigned char sm[];
   float* wsm = reinterpret_cast<float*>(sm);                 // [NT*NT][C] reachable taps
   float* bsm = wsm + NT * NT * C;                            // conv bias
@@ -185,7 +191,7 @@ dwln3_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C, int A, int R
 
 int num_sms();
 
-template <int S>
+template <int S, int CT>
 static int launch_dwln3(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
   constexpr int R = S > 3 ? 3 : S - 1;
@@ -199,7 +205,7 @@ static int launch_dwln3(const void* x, int64_t B, int C, const float* w, const f
   const int ncontrib = A + (REM ? 1 : 0);
   const size_t smem = (size_t)(NT * NT + 3) * C * 4 + (size_t)S * 32 * ncontrib * 4 + 2 * (size_t)HW * C * 2;
   if (smem > 227 * 1024) return 1;
-  auto kern = dwln3_kernel<S>;
+  auto kern = dwln3_kernel<S, CT>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "dwln3 attr");
   const int sms = num_sms();
   // small maps: several CTAs per SM are possible (few warps, little shared memory)
@@ -217,8 +223,14 @@ int dwln_bf16_v3(const void* x, int64_t B, int H, int W, int C, const float* w, 
   if (H != W || C % 16 != 0 || C > 640) return 1;
   if (((uintptr_t)x % 16) != 0 || ((uintptr_t)out % 4) != 0) return 1;
   switch (H) {
-    case 15: return launch_dwln3<15>(x, B, C, w, bias, ln_w, ln_b, out, st);
-    case 7: return launch_dwln3<7>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    case 15:
+      if (C == 80) return launch_dwln3<15, 80>(x, B, C, w, bias, ln_w, ln_b, out, st);
+      if (C == 64) return launch_dwln3<15, 64>(x, B, C, w, bias, ln_w, ln_b, out, st);
+      return launch_dwln3<15, 0>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    case 7:
+      if (C == 160) return launch_dwln3<7, 160>(x, B, C, w, bias, ln_w, ln_b, out, st);
+      if (C == 128) return launch_dwln3<7, 128>(x, B, C, w, bias, ln_w, ln_b, out, st);
+      return launch_dwln3<7, 0>(x, B, C, w, bias, ln_w, ln_b, out, st);
     // 3x3 and 1x1 maps: one image per CTA iteration is too little work per barrier; dwln2 (several images per
     // iteration) is faster there (measured: 0.078 vs 0.106 ms and 0.020 vs 0.050 ms at B = 8192)
     default: return 1;

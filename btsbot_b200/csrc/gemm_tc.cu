@@ -24,7 +24,10 @@ constexpr int kThreads = 64 + kEpiWarps * 32;     // warp0 TMA, warp1 MMA, warps
 constexpr int kABytes = BM * BK * 2;              // 16 KB
 constexpr int kBBytes = kMaxBN * BK * 2;          // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kMaxNBias = 4096;                  // bias (and LN weight/bias) staged in shared memory once per CTA
+constexpr int kMaxNGamma = 4096;                 // layer-scale vector of the SCALE_RES epilogue
+constexpr int kVecBytes = (kMaxNBias + kMaxNGamma) * 4;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kVecBytes;
 }  // namespace
 
 constexpr int EPI_LN = 100;   // internal: out = LayerNorm(acc + bias) * gamma(ln_w) + aux(ln_b), whole rows per thread
@@ -51,10 +54,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   volatile uint32_t* tmem_slot =
       reinterpret_cast<volatile uint32_t*>(smem_al + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAcc));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index made provably warp-uniform: the TMA / MMA roles below run converged and elect one issuing lane
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + BK - 1) / BK;
+
+  // per-column vectors -> shared memory (the epilogue re-reads them for every tile; a global load per 16-column chunk
+  // was the top stall of the GELU epilogue: profiles/r01c)
+  float* bias_s = reinterpret_cast<float*>(smem_al + kStages * kStageBytes + 256);
+  float* gamma_s = bias_s + kMaxNBias;
+  for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = __ldg(bias + i);
+  if (EPI == BTSB_EPI_SCALE_RES)
+    for (int i = threadIdx.x; i < N; i += kThreads) gamma_s[i] = __ldg(gamma + i);
+  if (EPI == EPI_LN)
+    for (int i = threadIdx.x; i < N; i += kThreads) { gamma_s[i] = __ldg(gamma + i); gamma_s[kMaxNGamma / 2 + i] = __ldg(aux + i); }
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -72,45 +87,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (threadIdx.x == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0) {
+    // ===================== TMA producer (converged warp, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     const uint32_t tx_bytes = (uint32_t)(BM + BN) * BK * 2;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx(full_bar(stage), tx_bytes);
-        const uint32_t sa = smem_base + stage * kStageBytes;
-        tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
-        tma_load_2d(sa + kABytes, &tmB, full_bar(stage), kb * BK, n0);
+        mbar_wait_spin(empty_bar(stage), phase ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), tx_bytes);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sa + kABytes, &tmB, full_bar(stage), kb * BK, n0);
+        }
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (threadIdx.x == 32) {
-    // ===================== MMA issuer (single thread) =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
     const uint32_t idesc = idesc_bf16_f32(BM, BN);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(tempty_bar(as), aphase ^ 1u);          // epilogue has drained this accumulator
+      mbar_wait_spin(tempty_bar(as), aphase ^ 1u);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccCols);
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait_spin(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * kStageBytes;
-        const uint64_t adesc = smem_desc_sw128(sa);
-        const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
-        const int kmax = min(BK, K - kb * BK) / 16;    // K tail: TMA zero-fills, but skip the useless MMAs
-        for (int kk = 0; kk < kmax; ++kk) {
-          // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+        if (elect_one()) {
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint64_t adesc = smem_desc_sw128(sa);
+          const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
+          const int kmax = min(BK, K - kb * BK) / 16;    // K tail: TMA zero-fills, but skip the useless MMAs
+          if (kmax == 4) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+          } else {
+            for (int kk = 0; kk < kmax; ++kk)
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                  // frees this smem stage when the MMAs retire
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(as));   // accumulator complete -> epilogue
         }
-        umma_commit(empty_bar(stage));                  // frees this smem stage when the MMAs retire
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tfull_bar(as));                       // accumulator complete -> epilogue
       if (++as == kAcc) { as = 0; aphase ^= 1u; }
     }
   } else if (warp >= 2 && EPI == EPI_LN) {
@@ -122,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       if ((lt & 3) != group) continue;
       const int as = group; const uint32_t aphase = (uint32_t)(lt >> 2) & 1u;
-      mbar_wait(tfull_bar(as), aphase);
+      mbar_wait_spin(tfull_bar(as), aphase);
       tc_fence_after();
       const int row = tile * BM + quarter * 32 + lane;         // n_tiles == 1 in this mode
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccCols);
@@ -133,7 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 16 + i));
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch * 16 + i);
           s += (__uint_as_float(r[i]) + b4.x) + (__uint_as_float(r[i + 1]) + b4.y) + (__uint_as_float(r[i + 2]) + b4.z) +
                (__uint_as_float(r[i + 3]) + b4.w);
         }
@@ -145,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 16 + i));
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch * 16 + i);
           const float d0 = __uint_as_float(r[i]) + b4.x - mean, d1 = __uint_as_float(r[i + 1]) + b4.y - mean;
           const float d2 = __uint_as_float(r[i + 2]) + b4.z - mean, d3 = __uint_as_float(r[i + 3]) + b4.w - mean;
           q += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
@@ -164,9 +190,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ch * 16 + i));
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + ch * 16 + i));
-            const float4 h4 = __ldg(reinterpret_cast<const float4*>(aux + ch * 16 + i));
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + ch * 16 + i);
+            const float4 g4 = *reinterpret_cast<const float4*>(gamma_s + ch * 16 + i);
+            const float4 h4 = *reinterpret_cast<const float4*>(gamma_s + kMaxNGamma / 2 + ch * 16 + i);
             v[i] = (__uint_as_float(r[i]) + b4.x - mean) * rstd * g4.x + h4.x;
             v[i + 1] = (__uint_as_float(r[i + 1]) + b4.y - mean) * rstd * g4.y + h4.y;
             v[i + 2] = (__uint_as_float(r[i + 2]) + b4.z - mean) * rstd * g4.z + h4.z;
@@ -194,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c_hi = (chunks * (part + 1)) / kParts;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-      mbar_wait(tfull_bar(as), aphase);
+      mbar_wait_spin(tfull_bar(as), aphase);
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccCols);
@@ -203,12 +229,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
-      // chunks of 16 columns, software-pipelined: the TMEM load of chunk ch+1 is in flight during the math of chunk ch
+      // chunks of 16 columns, software-pipelined: the TMEM load (and the residual load) of chunk ch+1 is in flight
+      // during the math of chunk ch
       uint32_t ra[16], rb[16];
-      auto process = [&](int ch, uint32_t (&cur)[16], uint32_t (&nxt)[16]) {
+      uint4 qa[2], qb[2];
+      auto load_res = [&](int ch, uint4 (&q)[2]) {
+        if (EPI == BTSB_EPI_SCALE_RES) {
+          const int n = n0 + ch * 16;
+          if (row < M && n < N) {
+            const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * N + n);
+            q[0] = __ldg(rp); q[1] = __ldg(rp + 1);
+          }
+        }
+      };
+      auto process = [&](int ch, uint32_t (&cur)[16], uint32_t (&nxt)[16], uint4 (&qcur)[2], uint4 (&qnxt)[2]) {
         tmem_ld_wait();
         if (ch + 1 < c_hi) {
           tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), nxt);
+          load_res(ch + 1, qnxt);
         } else {                                          // last TMEM read of this warp for this tile
           tc_fence_before();
           __syncwarp();
@@ -219,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n + i));
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + i);
             v[i] = __uint_as_float(cur[i]) + b4.x; v[i + 1] = __uint_as_float(cur[i + 1]) + b4.y;
             v[i + 2] = __uint_as_float(cur[i + 2]) + b4.z; v[i + 3] = __uint_as_float(cur[i + 3]) + b4.w;
           }
@@ -232,12 +270,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 16; ++i) v[i] = silu_fast(v[i]);
           }
           if (EPI == BTSB_EPI_SCALE_RES) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * N + n);
-            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const uint32_t rcur[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const uint32_t rcur[8] = {qcur[0].x, qcur[0].y, qcur[0].z, qcur[0].w, qcur[1].x, qcur[1].y, qcur[1].z, qcur[1].w};
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
-              const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
+              const float4 g4 = *reinterpret_cast<const float4*>(gamma_s + n + i);
               v[i] = fmaf(g4.x, v[i], bf16_lo(rcur[i / 2]));
               v[i + 1] = fmaf(g4.y, v[i + 1], bf16_hi(rcur[i / 2]));
               v[i + 2] = fmaf(g4.z, v[i + 2], bf16_lo(rcur[i / 2 + 1]));
@@ -253,10 +289,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           op[0] = o0; op[1] = o1;
         }
       };
-      if (c_lo < c_hi) tmem_ld16(taddr + (uint32_t)(c_lo * 16), ra);
+      if (c_lo < c_hi) { tmem_ld16(taddr + (uint32_t)(c_lo * 16), ra); load_res(c_lo, qa); }
       for (int ch = c_lo; ch < c_hi; ch += 2) {
-        process(ch, ra, rb);
-        if (ch + 1 < c_hi) process(ch + 1, rb, ra);
+        process(ch, ra, rb, qa, qb);
+        if (ch + 1 < c_hi) process(ch + 1, rb, ra, qb, qa);
       }
       if (++as == kAcc) { as = 0; aphase ^= 1u; }
     }
@@ -288,20 +324,31 @@ static EncodeTiledFn get_encoder() {
   return fn;
 }
 
-int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2-D bf16 row-major [rows, cols] tensor map with a [box_rows x box_cols] box whose rows are exactly one swizzle span
+// (box_cols * 2 == swizzle_bytes in {128, 64, 32})
+int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         uint32_t box_cols, int swizzle_bytes) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return BTSB_ECUDA; }
   BTSB_REQUIRE(((uintptr_t)base % 16) == 0 && (cols * 2) % 16 == 0, "tensor map: base/pitch must be 16-byte aligned");
   BTSB_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u not in [1,256]", box_rows);
+  BTSB_REQUIRE((int)box_cols * 2 == swizzle_bytes && (swizzle_bytes == 128 || swizzle_bytes == 64 || swizzle_bytes == 32),
+               "tensor map: box of %u columns does not match a %d-byte swizzle", box_cols, swizzle_bytes);
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return BTSB_ECUDA; }
   return BTSB_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  return make_tmap_bf16_2d_sw(out, base, rows, cols, box_rows, BK, 128);
 }
 
 static int pick_bn(int N) {
@@ -328,6 +375,8 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
   BTSB_REQUIRE(((uintptr_t)out % 16) == 0 && ((uintptr_t)bias % 16) == 0, "gemm bf16: out/bias must be 16-byte aligned");
   if (epilogue == BTSB_EPI_SCALE_RES)
     BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)gamma % 16) == 0, "gemm bf16: res/gamma must be 16-byte aligned");
+  BTSB_REQUIRE(N <= kMaxNBias && (epilogue != BTSB_EPI_SCALE_RES || N <= kMaxNGamma),
+               "gemm bf16: N=%d exceeds the staged-vector capacity (%d, %d with a layer scale)", N, kMaxNBias, kMaxNGamma);
   const int BN = pick_bn(N);
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM)) return e;

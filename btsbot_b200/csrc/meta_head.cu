@@ -10,30 +10,78 @@ constexpr int kTAp = 36;   // padded alert stride (16B-aligned rows)
 constexpr int kAT = 8;     // alerts per thread (register block)
 constexpr int kHeadThreads = 256;
 
+// One dense layer on the CTA's kTA alerts: out[n][a] = act(bias[n] + sum_k in[k][a] * Wt[k][n]).
+// Thread = NPT adjacent outputs x kAT alerts; the weight stream (L2-resident, coalesced) is prefetched one block of
+// kWU k-steps ahead into registers so its latency is hidden behind the kWU*NPT*kAT FMAs of the current block.
+constexpr int kWU = 8;
+
+template <int NPT>
+__device__ __forceinline__ void load_wblock(const float* __restrict__ wp, int N, int k0, int K, float (&w)[kWU][NPT]) {
+#pragma unroll
+  for (int u = 0; u < kWU; ++u) {
+    const int k = min(k0 + u, K - 1);                  // clamped: tail values are loaded but never used
+    if (NPT == 2) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(wp + (size_t)k * N));
+      w[u][0] = v.x; w[u][NPT - 1] = v.y;
+    } else {
+      w[u][0] = __ldg(wp + (size_t)k * N);
+    }
+  }
+}
+
+template <int NPT>
+__device__ __forceinline__ void dense_layer_t(const float* __restrict__ in, int K, const float* __restrict__ Wt,
+                                              const float* __restrict__ bias, int N, int act, float* __restrict__ out) {
+  const int groups = kTA / kAT;
+  const int NV = N / NPT;
+  for (int it = threadIdx.x; it < NV * groups; it += kHeadThreads) {
+    const int n = (it % NV) * NPT, ag = it / NV;
+    float acc[NPT][kAT];
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      const float bv = bias ? __ldg(bias + n + j) : 0.f;
+#pragma unroll
+      for (int a = 0; a < kAT; ++a) acc[j][a] = bv;
+    }
+    const float* src = in + ag * kAT;
+    const float* wp = Wt + n;
+    float wa[kWU][NPT], wb[kWU][NPT];
+    auto block = [&](int k0, const float (&w)[kWU][NPT]) {
+#pragma unroll
+      for (int u = 0; u < kWU; ++u) {
+        if (k0 + u < K) {
+          const float4 v0 = *reinterpret_cast<const float4*>(src + (k0 + u) * kTAp);
+          const float4 v1 = *reinterpret_cast<const float4*>(src + (k0 + u) * kTAp + 4);
+#pragma unroll
+          for (int j = 0; j < NPT; ++j) {
+            acc[j][0] = fmaf(w[u][j], v0.x, acc[j][0]); acc[j][1] = fmaf(w[u][j], v0.y, acc[j][1]);
+            acc[j][2] = fmaf(w[u][j], v0.z, acc[j][2]); acc[j][3] = fmaf(w[u][j], v0.w, acc[j][3]);
+            acc[j][4] = fmaf(w[u][j], v1.x, acc[j][4]); acc[j][5] = fmaf(w[u][j], v1.y, acc[j][5]);
+            acc[j][6] = fmaf(w[u][j], v1.z, acc[j][6]); acc[j][7] = fmaf(w[u][j], v1.w, acc[j][7]);
+          }
+        }
+      }
+    };
+    load_wblock<NPT>(wp, N, 0, K, wa);
+    for (int k0 = 0; k0 < K; k0 += 2 * kWU) {
+      if (k0 + kWU < K) load_wblock<NPT>(wp, N, k0 + kWU, K, wb);
+      block(k0, wa);
+      if (k0 + 2 * kWU < K) load_wblock<NPT>(wp, N, k0 + 2 * kWU, K, wa);
+      if (k0 + kWU < K) block(k0 + kWU, wb);
+    }
+#pragma unroll
+    for (int j = 0; j < NPT; ++j) {
+      float* dst = out + (n + j) * kTAp + ag * kAT;
+#pragma unroll
+      for (int a = 0; a < kAT; ++a) dst[a] = apply_act(acc[j][a], act);
+    }
+  }
+}
+
 __device__ __forceinline__ void dense_layer(const float* __restrict__ in, int K, const float* __restrict__ Wt,
                                             const float* __restrict__ bias, int N, int act, float* __restrict__ out) {
-  const int groups = kTA / kAT;
-  for (int it = threadIdx.x; it < N * groups; it += kHeadThreads) {
-    const int n = it % N, ag = it / N;
-    float acc[kAT];
-    const float bv = bias ? __ldg(bias + n) : 0.f;
-#pragma unroll
-    for (int a = 0; a < kAT; ++a) acc[a] = bv;
-    const float* src = in + ag * kAT;
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-      const float w = __ldg(Wt + (size_t)k * N + n);
-      const float4 v0 = *reinterpret_cast<const float4*>(src + k * kTAp);
-      const float4 v1 = *reinterpret_cast<const float4*>(src + k * kTAp + 4);
-      acc[0] = fmaf(w, v0.x, acc[0]); acc[1] = fmaf(w, v0.y, acc[1]);
-      acc[2] = fmaf(w, v0.z, acc[2]); acc[3] = fmaf(w, v0.w, acc[3]);
-      acc[4] = fmaf(w, v1.x, acc[4]); acc[5] = fmaf(w, v1.y, acc[5]);
-      acc[6] = fmaf(w, v1.z, acc[6]); acc[7] = fmaf(w, v1.w, acc[7]);
-    }
-    float* dst = out + n * kTAp + ag * kAT;
-#pragma unroll
-    for (int a = 0; a < kAT; ++a) dst[a] = apply_act(acc[a], act);
-  }
+  if ((N & 1) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 7) == 0) dense_layer_t<2>(in, K, Wt, bias, N, act, out);
+  else dense_layer_t<1>(in, K, Wt, bias, N, act, out);
 }
 
 __global__ void __launch_bounds__(kHeadThreads)

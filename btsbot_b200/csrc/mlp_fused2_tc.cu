@@ -1,0 +1,475 @@
+// K4 fused, second generation (bf16): out = res + gamma * (fc2(GELU(fc1(y) + b1)) + b2) in ONE kernel; the 4C-wide
+// hidden activation lives only in TMEM / shared memory.  Replaces timm blocks.j.mlp.fc1 -> act -> mlp.fc2 -> *gamma ->
+// +shortcut (and MaxViT's token MLPs) for C <= 160.
+//
+// What changed against mlp_fused_tc.cu (profiles/r01c: 20-28 % of all epilogue-warp samples sat on the D1 barrier
+// because the 3-stage weight ring gave the TMA producer only ~1 chunk of look-ahead against ~1 us of L2 latency):
+//   * weights RESIDENT in shared memory when they fit (C <= 96: W1 + W2 = 8 C^2 * 2 B <= 147 KB), loaded once per CTA;
+//     otherwise two independent rings (W1 slots are released as soon as G1 retires, W2 slots after G2) so both
+//     streams run 3-4 hidden chunks ahead of the tensor pipe
+//   * K is tiled as 64-column SW128 blocks plus compact 32-column (SW64) / 16-column (SW32) tail blocks instead of
+//     zero-padded 64-column blocks: C = 80 moves 20 KB per y tile instead of 32 KB
+//   * the 16 epilogue warps form two groups that own alternate hidden chunks (32 columns x 32 rows per warp and
+//     chunk): half as many barrier round trips / proxy fences per GELU, and the two groups run out of phase so
+//     the MUFU-bound part of one overlaps the TMEM-load / FMA / store part of the other
+//   * G1 of chunk g+2 is issued as soon as the epilogue has pulled chunk g out of TMEM (not after its GELU)
+//
+// Per CTA (persistent over 128-row tiles), hidden processed in chunks of 64 columns, global chunk index g:
+//   warp 0      TMA producer : y tiles, W1 chunk [64 x C], W2 chunk [C x 64]
+//   warp 1      MMA issuer   : G1_g: D1[g&1] = y . W1_g^T (M128 x N64, K = C);  G2_g: D2[tile&1] += H[g&1] . W2_g^T
+//   warps 2..17 epilogue     : group g&1: tcgen05.ld D1 -> +b1 -> GELU -> bf16 -> H[g&1] (SW128 K-major, what UMMA
+//                              reads); all 16 warps: D2 -> +b2 -> *gamma + res -> bf16 rows (deferred by one chunk)
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace btsb {
+namespace {
+constexpr int FM = 128;            // rows per tile
+constexpr int NH = 64;             // hidden chunk
+constexpr int kEpiWarps2 = 16;
+constexpr int kThreads2 = 64 + kEpiWarps2 * 32;
+constexpr int kHBytes = FM * 128;  // [128 x 64] bf16
+constexpr int kD2Col = 2 * NH;     // TMEM column of D2 (D1 buffers occupy [0,128))
+constexpr int kMaxSlots = 16;
+constexpr int kSmemMax = 227 * 1024;
+
+struct Plan2 {
+  int C = 0, NJ = 0;
+  int nfull = 0, t32 = 0, t16 = 0;   // K blocks: nfull x 64 columns (SW128) [+ 32 columns (SW64)] [+ 16 columns (SW32)]
+  int y_bytes = 0, w1_bytes = 0, w2_bytes = 0;
+  int ny = 0, n1 = 0, n2 = 0, resident = 0;
+  int off_w1 = 0, off_w2 = 0, off_h = 0, off_bar = 0, off_b1 = 0, total = 0;
+  bool ok = false;
+};
+__host__ __device__ constexpr Plan2 plan2_for(int C);
+
+__host__ __device__ constexpr int rup1k(int x) { return (x + 1023) & ~1023; }
+
+__host__ __device__ constexpr bool plan2_try(Plan2& P, int ny, int n1, int n2, int resident) {
+  P.ny = ny; P.n1 = n1; P.n2 = n2; P.resident = resident;
+  P.off_w1 = ny * P.y_bytes;
+  P.off_w2 = P.off_w1 + n1 * P.w1_bytes;
+  P.off_h = P.off_w2 + n2 * P.w2_bytes;
+  P.off_bar = P.off_h + 2 * kHBytes;
+  P.off_b1 = P.off_bar + 1024;
+  P.total = P.off_b1 + 4 * P.C * 4 + 1024 /*alignment slack*/;
+  return P.total <= kSmemMax && n1 <= kMaxSlots && n2 <= kMaxSlots;
+}
+
+__host__ __device__ constexpr bool make_plan2(Plan2& P, int C) {
+  P.C = C; P.NJ = (4 * C) / NH;
+  P.nfull = C / 64; P.t32 = (C % 64) >= 32 ? 1 : 0; P.t16 = (C % 32) >= 16 ? 1 : 0;
+  P.y_bytes = rup1k(FM * C * 2);
+  P.w1_bytes = rup1k(NH * C * 2);
+  P.w2_bytes = rup1k(C * 128);
+  if (plan2_try(P, 2, P.NJ, P.NJ, 1)) return true;      // everything resident, y double buffered
+  if (plan2_try(P, 2, 3, 4, 0)) return true;
+  if (plan2_try(P, 1, 3, 4, 0)) return true;
+  if (plan2_try(P, 1, 2, 3, 0)) return true;
+  return plan2_try(P, 1, 2, 2, 0);
+}
+
+__host__ __device__ constexpr Plan2 plan2_for(int C) {
+  Plan2 P;
+  P.ok = make_plan2(P, C);
+  return P;
+}
+
+// K-major operand tile descriptor for a block whose rows are `sw` bytes (128 / 64 / 32) with the matching swizzle
+__device__ __forceinline__ uint64_t smem_desc_k(uint32_t saddr, int sw) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * sw) >> 4) << 32;                 // stride byte offset: 8 rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(sw == 128 ? 2 : (sw == 64 ? 4 : 6)) << 61;
+  return d;
+}
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct Maps2 {
+  CUtensorMap y128, y64, y32;      // [M, C]   boxes [128 rows x 64|32|16 cols], swizzle 128|64|32 B
+  CUtensorMap a128, a64, a32;      // W1 [4C, C]: boxes [64 rows x 64|32|16 cols]
+  CUtensorMap w2;                  // W2 [C, 4C]: box [C rows x 64 cols], swizzle 128 B
+};
+}  // namespace
+
+template <int C>
+__global__ void __launch_bounds__(kThreads2, 1)   // 18 warps -> 5 on two SMSPs: 96 registers is the hardware ceiling
+mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
+                  const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
+                  __nv_bfloat16* __restrict__ out, int M) {
+  using namespace tc;
+  constexpr Plan2 P = plan2_for(C);
+  static_assert(P.ok, "no shared-memory plan for this C");
+  constexpr int NJ = P.NJ;
+  constexpr int nkb = P.nfull + P.t32 + P.t16;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sal = smem_dyn + (sbase - smem_u32(smem_dyn));
+  const int m_tiles = (M + FM - 1) / FM;
+  const uint32_t nt = blockIdx.x < (uint32_t)m_tiles ? (uint32_t)(m_tiles - 1 - blockIdx.x) / gridDim.x + 1u : 0u;
+  const uint32_t total = nt * (uint32_t)NJ;                      // hidden chunks this CTA processes
+
+  const uint32_t bar0 = sbase + P.off_bar;
+  auto y_full = [&](int i) { return bar0 + 8u * i; };                         // 2
+  auto y_empty = [&](int i) { return bar0 + 8u * (2 + i); };                  // 2
+  auto d1_full = [&](int i) { return bar0 + 8u * (4 + i); };                  // 2
+  auto d1_empty = [&](int i) { return bar0 + 8u * (6 + i); };                 // 2
+  auto h_full = [&](int i) { return bar0 + 8u * (8 + i); };                   // 2
+  auto h_empty = [&](int i) { return bar0 + 8u * (10 + i); };                 // 2
+  auto d2_full = [&](int i) { return bar0 + 8u * (12 + i); };                 // 2
+  auto d2_empty = [&](int i) { return bar0 + 8u * (14 + i); };                // 2
+  auto w1_full = [&](int i) { return bar0 + 8u * (16 + i); };                 // kMaxSlots
+  auto w1_empty = [&](int i) { return bar0 + 8u * (16 + kMaxSlots + i); };
+  auto w2_full = [&](int i) { return bar0 + 8u * (16 + 2 * kMaxSlots + i); };
+  auto w2_empty = [&](int i) { return bar0 + 8u * (16 + 3 * kMaxSlots + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + P.off_bar + 8 * (16 + 4 * kMaxSlots));
+
+  // warp index made provably warp-uniform so the role branches below are convergent (the single-thread roles then
+  // compile to predicated uniform-datapath instructions instead of per-lane serialisation loops)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm.y128); tma_prefetch_desc(&tm.a128); tma_prefetch_desc(&tm.w2);
+    if (P.t32) { tma_prefetch_desc(&tm.y64); tma_prefetch_desc(&tm.a64); }
+    if (P.t16) { tma_prefetch_desc(&tm.y32); tma_prefetch_desc(&tm.a32); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(y_full(i), 1); mbar_init(y_empty(i), 1);
+      mbar_init(d1_full(i), 1); mbar_init(d1_empty(i), kEpiWarps2 / 2);
+      mbar_init(h_full(i), kEpiWarps2 / 2); mbar_init(h_empty(i), 1);
+      mbar_init(d2_full(i), 1); mbar_init(d2_empty(i), kEpiWarps2);
+    }
+    for (int i = 0; i < kMaxSlots; ++i) {
+      mbar_init(w1_full(i), 1); mbar_init(w1_empty(i), 1); mbar_init(w2_full(i), 1); mbar_init(w2_empty(i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
+  float* b1s = reinterpret_cast<float*>(sal + P.off_b1);            // fc1 bias staged once per CTA
+  for (int i = threadIdx.x; i < 4 * C; i += kThreads2) b1s[i] = __ldg(b1 + i);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer (whole warp walks the schedule, one elected lane issues) ==============
+    // issue order == consumption order of the MMA warp: y_0, W1_0, W1_1, then per chunk g: W1_{g+2} (+ y of its tile), W2_g
+    int j1 = 0, s1 = 0, yb = 0; uint32_t ph1 = 0, yph = 0, t1 = 0;     // state of the G1-input stream
+    int j2 = 0, s2 = 0; uint32_t ph2 = 0, g2 = 0;                       // state of the W2 stream
+    auto load_g1_inputs = [&]() {
+      if (j1 == 0) {                                                    // first chunk of a tile: its y rows
+        const int tile = blockIdx.x + (int)t1 * gridDim.x;
+        mbar_wait_spin(y_empty(yb), yph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(y_full(yb), (uint32_t)(FM * C * 2));
+          uint32_t dst = sbase + yb * P.y_bytes;
+#pragma unroll
+          for (int kb = 0; kb < P.nfull; ++kb) tma_load_2d(dst + kb * FM * 128, &tm.y128, y_full(yb), kb * 64, tile * FM);
+          if (P.t32) tma_load_2d(dst + P.nfull * FM * 128, &tm.y64, y_full(yb), P.nfull * 64, tile * FM);
+          if (P.t16) tma_load_2d(dst + P.nfull * FM * 128 + P.t32 * FM * 64, &tm.y32, y_full(yb), P.nfull * 64 + P.t32 * 32, tile * FM);
+        }
+        __syncwarp();
+        if (P.ny == 2) { yb ^= 1; if (yb == 0) yph ^= 1u; } else { yph ^= 1u; }
+      }
+      if (!P.resident || t1 == 0) {
+        mbar_wait_spin(w1_empty(s1), ph1 ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(w1_full(s1), (uint32_t)(NH * C * 2));
+          const uint32_t dst = sbase + P.off_w1 + s1 * P.w1_bytes;
+#pragma unroll
+          for (int kb = 0; kb < P.nfull; ++kb) tma_load_2d(dst + kb * NH * 128, &tm.a128, w1_full(s1), kb * 64, j1 * NH);
+          if (P.t32) tma_load_2d(dst + P.nfull * NH * 128, &tm.a64, w1_full(s1), P.nfull * 64, j1 * NH);
+          if (P.t16) tma_load_2d(dst + P.nfull * NH * 128 + P.t32 * NH * 64, &tm.a32, w1_full(s1), P.nfull * 64 + P.t32 * 32, j1 * NH);
+        }
+        __syncwarp();
+      }
+      if (++s1 == P.n1) { s1 = 0; ph1 ^= 1u; }
+      if (++j1 == NJ) { j1 = 0; ++t1; if (P.resident) { s1 = 0; } }
+    };
+    auto load_w2 = [&]() {
+      if (!P.resident || g2 < (uint32_t)NJ) {
+        mbar_wait_spin(w2_empty(s2), ph2 ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(w2_full(s2), (uint32_t)(C * 128));
+          tma_load_2d(sbase + P.off_w2 + s2 * P.w2_bytes, &tm.w2, w2_full(s2), j2 * NH, 0);
+        }
+        __syncwarp();
+      }
+      if (++s2 == P.n2) { s2 = 0; ph2 ^= 1u; }
+      if (++j2 == NJ) { j2 = 0; if (P.resident) s2 = 0; }
+      ++g2;
+    };
+    if (total > 0) load_g1_inputs();
+    if (total > 1) load_g1_inputs();
+    for (uint32_t g = 0; g < total; ++g) {
+      if (g + 2 < total) load_g1_inputs();
+      load_w2();
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer (whole warp walks the schedule, one elected lane issues) ================
+    constexpr uint32_t idesc1 = idesc_bf16_f32(FM, NH);
+    constexpr uint32_t idesc2 = idesc_bf16_f32(FM, C);
+    // G1 stream state
+    int j1 = 0, s1 = 0, yb = 0, b1i = 0; uint32_t ph1 = 0, yph = 0, dph1 = 0, t1 = 0;
+    // G2 stream state
+    int j2 = 0, s2 = 0, b2i = 0, tb = 0; uint32_t ph2 = 0, hph = 0, d2ph = 0, t2 = 0;
+    auto do_g1 = [&]() {
+      if (j1 == 0) mbar_wait_spin(y_full(yb), yph);
+      if (!P.resident || t1 == 0) mbar_wait_spin(w1_full(s1), ph1);
+      mbar_wait_spin(d1_empty(b1i), dph1 ^ 1u);                      // the epilogue has pulled chunk g-2 out of D1[b]
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t ya = sbase + yb * P.y_bytes;
+        const uint32_t wa = sbase + P.off_w1 + s1 * P.w1_bytes;
+        const uint32_t dcol = tmem_base + (uint32_t)(b1i * NH);
+#pragma unroll
+        for (int kb = 0; kb < nkb; ++kb) {
+          constexpr int dummy = 0; (void)dummy;
+          const int sw = kb < P.nfull ? 128 : ((kb == P.nfull && P.t32) ? 64 : 32);
+          const int yoff = kb < P.nfull ? kb * FM * 128 : (P.nfull * FM * 128 + ((kb == P.nfull || !P.t32) ? 0 : FM * 64));
+          const int woff = kb < P.nfull ? kb * NH * 128 : (P.nfull * NH * 128 + ((kb == P.nfull || !P.t32) ? 0 : NH * 64));
+          const uint64_t ad = smem_desc_k(ya + yoff, sw), bd = smem_desc_k(wa + woff, sw);
+#pragma unroll
+          for (int kk = 0; kk < sw / 32; ++kk)
+            umma_bf16(dcol, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc1, (kb | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(d1_full(b1i));
+        if (!P.resident) umma_commit(w1_empty(s1));
+        if (j1 == NJ - 1) umma_commit(y_empty(yb));                // y tile no longer needed once these retire
+      }
+      __syncwarp();
+      b1i ^= 1; if (b1i == 0) dph1 ^= 1u;
+      if (++s1 == P.n1) { s1 = 0; ph1 ^= 1u; }
+      if (++j1 == NJ) {
+        j1 = 0; ++t1;
+        if (P.resident) s1 = 0;
+        if (P.ny == 2) { yb ^= 1; if (yb == 0) yph ^= 1u; } else { yph ^= 1u; }
+      }
+    };
+    auto do_g2 = [&]() {
+      if (!P.resident || t2 == 0) mbar_wait_spin(w2_full(s2), ph2);
+      if (j2 == 0) mbar_wait_spin(d2_empty(tb), d2ph ^ 1u);
+      mbar_wait_spin(h_full(b2i), hph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ad = smem_desc_sw128(sbase + P.off_h + b2i * kHBytes);
+        const uint64_t bd = smem_desc_sw128(sbase + P.off_w2 + s2 * P.w2_bytes);
+        const uint32_t dcol = tmem_base + (uint32_t)(kD2Col + tb * C);
+#pragma unroll
+        for (int kk = 0; kk < NH / 16; ++kk)
+          umma_bf16(dcol, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc2, (j2 | kk) != 0 ? 1u : 0u);
+        umma_commit(h_empty(b2i));
+        if (!P.resident) umma_commit(w2_empty(s2));
+        if (j2 == NJ - 1) umma_commit(d2_full(tb));
+      }
+      __syncwarp();
+      b2i ^= 1; if (b2i == 0) hph ^= 1u;
+      if (++s2 == P.n2) { s2 = 0; ph2 ^= 1u; }
+      if (++j2 == NJ) {
+        j2 = 0; ++t2;
+        if (P.resident) s2 = 0;
+        tb ^= 1; if (tb == 0) d2ph ^= 1u;
+      }
+    };
+    if (total > 0) do_g1();
+    if (total > 1) do_g1();
+    for (uint32_t g = 0; g < total; ++g) {
+      if (g + 2 < total) do_g1();
+      do_g2();
+    }
+  } else if (warp >= 2) {
+    // ============================== epilogue warps ==============================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+    const int k4 = (warp - 2) >> 2;         // 0..3
+    const int grp = k4 & 1;                 // owns hidden chunks g with (g & 1) == grp
+    const int half = k4 >> 1;               // 32-column half of the 64-column chunk
+    const int r_in_tile = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int groups2 = C / 16;
+    constexpr int NU = (groups2 + 3) / 4;   // 16-column groups of D2 per warp
+    uint4 rpre[NU][2];                       // residual rows of the tile whose D2 epilogue is pending
+
+    auto prefetch_res = [&](int tile) {
+      const int row = tile * FM + r_in_tile;
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int gi = k4 + 4 * u;
+        if (gi < groups2 && row < M) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + gi * 16);
+          rpre[u][0] = __ldg(rp); rpre[u][1] = __ldg(rp + 1);
+        } else {
+          rpre[u][0] = make_uint4(0, 0, 0, 0); rpre[u][1] = make_uint4(0, 0, 0, 0);
+        }
+      }
+    };
+    // D2 -> +b2 -> *gamma + res -> bf16 rows of tile `tile` (local index tl); column groups k4, k4+4, k4+8
+    auto d2_epilogue = [&](int tile, uint32_t tl) {
+      const int tb = (int)(tl & 1u);
+      mbar_wait_spin(d2_full(tb), (tl >> 1) & 1u);
+      tc_fence_after();
+      const int row = tile * FM + r_in_tile;
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int gi = k4 + 4 * u;
+        if (gi >= groups2) break;
+        uint32_t r[16];
+        tmem_ld16(lane_addr + (uint32_t)(kD2Col + tb * C + gi * 16), r);
+        tmem_ld_wait();
+        if (gi + 4 >= groups2) {                         // last D2 read of this warp for this tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d2_empty(tb));
+        }
+        if (row < M) {
+          const int n = gi * 16;
+          const uint4 r0 = rpre[u][0], r1 = rpre[u][1];
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
+            v[i] = fmaf(g4.x, __uint_as_float(r[i]) + b4.x, bf16_lo(rr[i / 2]));
+            v[i + 1] = fmaf(g4.y, __uint_as_float(r[i + 1]) + b4.y, bf16_hi(rr[i / 2]));
+            v[i + 2] = fmaf(g4.z, __uint_as_float(r[i + 2]) + b4.z, bf16_lo(rr[i / 2 + 1]));
+            v[i + 3] = fmaf(g4.w, __uint_as_float(r[i + 3]) + b4.w, bf16_hi(rr[i / 2 + 1]));
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * C + n);
+          op[0] = o0; op[1] = o1;
+        }
+      }
+    };
+
+    int pend_tl = -1;                       // local tile index whose D2 epilogue this warp still owes
+    uint32_t prev_tl = 0xffffffffu;
+    for (uint32_t g = (uint32_t)grp; g < total; g += 2) {
+      const uint32_t tl = g / (uint32_t)NJ; const int j = (int)(g - tl * NJ);
+      const uint32_t use = g >> 1;                       // per-buffer use count of D1[grp] / H[grp]
+      if (tl != prev_tl) {
+        // first chunk of this warp in a new tile: the previous tile's D2 epilogue is deferred until after this chunk's
+        // GELU so its tail latency (last H hand-off -> G2 -> commit) is hidden; fetch its residual rows now
+        if (prev_tl != 0xffffffffu) { pend_tl = (int)prev_tl; prefetch_res(blockIdx.x + pend_tl * gridDim.x); }
+        prev_tl = tl;
+      }
+      mbar_wait_spin(d1_full(grp), use & 1u);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(lane_addr + (uint32_t)(grp * NH + half * 32), r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d1_empty(grp));         // D1[grp] may be overwritten by G1 of chunk g+2
+      const int hcol = j * NH + half * 32;
+      uint32_t o[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
+        const float v0 = gelu_fast(__uint_as_float(r[i]) + b4.x);
+        const float v1 = gelu_fast(__uint_as_float(r[i + 1]) + b4.y);
+        const float v2 = gelu_fast(__uint_as_float(r[i + 2]) + b4.z);
+        const float v3 = gelu_fast(__uint_as_float(r[i + 3]) + b4.w);
+        o[i / 2] = pack_bf16x2(v0, v1);
+        o[i / 2 + 1] = pack_bf16x2(v2, v3);
+      }
+      mbar_wait_spin(h_empty(grp), (use & 1u) ^ 1u);         // G2 of chunk g-2 has finished reading H[grp]
+      unsigned char* hb = sal + P.off_h + grp * kHBytes;
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8)
+        *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, half * 32 + c8 * 8)) =
+            make_uint4(o[4 * c8], o[4 * c8 + 1], o[4 * c8 + 2], o[4 * c8 + 3]);
+      fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_full(grp));
+      if (pend_tl >= 0) { d2_epilogue(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl); pend_tl = -1; }
+    }
+    if (nt > 0) {
+      // every group has at least one chunk in every tile (NJ >= 4), so prev_tl is the CTA's last tile here
+      const int last = (int)nt - 1;
+      prefetch_res(blockIdx.x + last * gridDim.x);
+      d2_epilogue(blockIdx.x + last * gridDim.x, (uint32_t)last);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+int num_sms();
+int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         uint32_t box_cols, int swizzle_bytes);
+
+int mlp_fused2_supported(int C) {
+  return C % 16 == 0 && C >= 64 && C <= 160;
+}
+
+template <int C>
+static int launch2(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res, void* out,
+                   int64_t M, cudaStream_t st) {
+  constexpr Plan2 P = plan2_for(C);
+  auto kern = mlp_fused2_kernel<C>;
+  BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
+  const int m_tiles = (int)((M + FM - 1) / FM);
+  const int grid = min(m_tiles, num_sms());
+  kern<<<grid, kThreads2, P.total, st>>>(tm, b1, b2, gamma, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (int)M);
+  return launch_done("mlp_fused2");
+}
+
+int mlp_fused2_launch(const void* y, const void* res, const void* W1, const float* b1, const void* W2, const float* b2,
+                      const float* gamma, void* out, int64_t M, int C, cudaStream_t st) {
+  BTSB_REQUIRE(mlp_fused2_supported(C), "mlp_fused: C=%d unsupported", C);
+  const int t32 = (C % 64) >= 32, t16 = (C % 32) >= 16;
+  Maps2 tm;
+  memset(&tm, 0, sizeof(tm));
+  if (int e = make_tmap_bf16_2d_sw(&tm.y128, y, (uint64_t)M, (uint64_t)C, FM, 64, 128)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tm.a128, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 64, 128)) return e;
+  if (t32) {
+    if (int e = make_tmap_bf16_2d_sw(&tm.y64, y, (uint64_t)M, (uint64_t)C, FM, 32, 64)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.a64, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 32, 64)) return e;
+  }
+  if (t16) {
+    if (int e = make_tmap_bf16_2d_sw(&tm.y32, y, (uint64_t)M, (uint64_t)C, FM, 16, 32)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.a32, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 16, 32)) return e;
+  }
+  if (int e = make_tmap_bf16_2d_sw(&tm.w2, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)C, 64, 128)) return e;
+  switch (C) {
+    case 64: return launch2<64>(tm, b1, b2, gamma, res, out, M, st);
+    case 80: return launch2<80>(tm, b1, b2, gamma, res, out, M, st);
+    case 96: return launch2<96>(tm, b1, b2, gamma, res, out, M, st);
+    case 112: return launch2<112>(tm, b1, b2, gamma, res, out, M, st);
+    case 128: return launch2<128>(tm, b1, b2, gamma, res, out, M, st);
+    case 144: return launch2<144>(tm, b1, b2, gamma, res, out, M, st);
+    case 160: return launch2<160>(tm, b1, b2, gamma, res, out, M, st);
+  }
+  set_error("mlp_fused: C=%d unsupported", C);
+  return BTSB_EINVAL;
+}
+
+}  // namespace btsb

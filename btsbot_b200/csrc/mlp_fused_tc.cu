@@ -10,6 +10,8 @@
 //                              chunk behind G1 so the tensor pipe never waits for the GELU warps
 //   warps 2..17 epilogue     : D1 chunk: tcgen05.ld -> +b1 -> GELU -> bf16 -> H[j%2] in the SW128 K-major layout
 //                              UMMA reads; after the last chunk: D2 -> +b2 -> *gamma + res -> bf16 -> global
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace btsb {
@@ -284,6 +286,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant_
 }
 
 int num_sms();
+int mlp_fused2_supported(int C);
+int mlp_fused2_launch(const void* y, const void* res, const void* W1, const float* b1, const void* W2, const float* b2,
+                      const float* gamma, void* out, int64_t M, int C, cudaStream_t st);
+
+// BTSB_MLP_V1=1 selects the first-generation kernel in this file (kept for A/B timing against mlp_fused2_tc.cu)
+static bool use_v1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BTSB_MLP_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 
 }  // namespace btsb
 
@@ -300,6 +312,8 @@ extern "C" int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const
   BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)b1 % 16) == 0 &&
                    ((uintptr_t)b2 % 16) == 0 && ((uintptr_t)gamma % 16) == 0,
                "mlp_fused: pointers must be 16-byte aligned");
+  if (!use_v1() && mlp_fused2_supported(C))
+    return mlp_fused2_launch(y, res, W1, b1, W2, b2, gamma, out, M, C, (cudaStream_t)stream);
   CUtensorMap tmY, tmW1, tmW2;
   if (int e = make_tmap_bf16_2d(&tmY, y, (uint64_t)M, (uint64_t)C, FM)) return e;
   if (int e = make_tmap_bf16_2d(&tmW1, W1, (uint64_t)(4 * C), (uint64_t)C, NH)) return e;
