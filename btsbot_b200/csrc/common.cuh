@@ -69,6 +69,27 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Sum 32 per-lane values across an aligned group of WIDTH lanes; afterwards v[0 .. 32/WIDTH) of lane l hold the group
+// totals of value indices (l % WIDTH) * (32/WIDTH) + i.
+template <int WIDTH>
+__device__ __forceinline__ void seg_reduce32(float (&v)[32], int lane) {
+  int n = 32;
+#pragma unroll
+  for (int off = WIDTH / 2; off >= 1; off >>= 1) {
+    n >>= 1;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (i < n) {
+        const float lo = v[i], hi = v[i + n];
+        const float send = up ? lo : hi;
+        const float keep = up ? hi : lo;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+  }
+}
+
 constexpr float kLnEps = 1e-6f;  // timm LayerNorm2d eps for ConvNeXt
 
 }  // namespace btsb

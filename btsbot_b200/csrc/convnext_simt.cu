@@ -486,6 +486,8 @@ int dwln_bf16_v2(const void* x, int64_t B, int H, int W, int C, const float* w, 
                  const float* ln_b, void* out, cudaStream_t st);
 int dwln_bf16_v3(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
                  const float* ln_b, void* out, cudaStream_t st);
+int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
+                    const float* ln_b, void* out, cudaStream_t st);
 }
 extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* w,
                                       const float* bias, const float* ln_w, const float* ln_b, void* out,
@@ -497,8 +499,12 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
   BTSB_REQUIRE(x && w && bias && ln_w && ln_b && out, "dwln: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == BTSB_F32) return dispatch_dwln<float>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
-  // debugging aids: BTSB_DWLN=1 -> generic kernel, =2 -> v2 (smem-staged LayerNorm); default v3 -> v2 -> generic
+  // debugging aids: BTSB_DWLN=1 -> generic kernel, =2 -> v2 (smem-staged LayerNorm); default small/v3 -> v2 -> generic
   static const int force = getenv("BTSB_DWLN") ? atoi(getenv("BTSB_DWLN")) : 0;
+  if (force == 0) {
+    const int rc = dwln_bf16_small(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);   // 3x3 and 1x1 maps
+    if (rc != 1) return rc;
+  }
   if (force == 0 || force == 3) {
     const int rc = dwln_bf16_v3(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
     if (rc != 1) return rc;

@@ -20,27 +20,6 @@ __device__ __forceinline__ void cp_async16_v3(void* smem_dst, const void* gsrc) 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-// Sum 32 per-lane values across an aligned group of WIDTH lanes; afterwards v[0 .. 32/WIDTH) of lane l hold the group
-// totals of value indices (l % WIDTH) * (32/WIDTH) + i.
-template <int WIDTH>
-__device__ __forceinline__ void seg_reduce32(float (&v)[32], int lane) {
-  int n = 32;
-#pragma unroll
-  for (int off = WIDTH / 2; off >= 1; off >>= 1) {
-    n >>= 1;
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      if (i < n) {
-        const float lo = v[i], hi = v[i + n];
-        const float send = up ? lo : hi;
-        const float keep = up ? hi : lo;
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-      }
-    }
-  }
-}
-
 // CT > 0: channel count known at compile time (nano 80/160, pico 64/128) -- every shared-memory address becomes an
 // immediate offset, which removes ~1/3 of the issued instructions (integer address arithmetic; profiles/r01c);
 // CT == 0: generic runtime C.

@@ -1,0 +1,150 @@
+// K3 for the small maps (bf16 activations, 3x3 and 1x1): depthwise 7x7 + bias + LayerNorm2d, one image per CTA
+// iteration, everything in registers.
+//
+// On a 3x3 map every output pixel sees every input pixel (81 (out,in) pairs, 25 distinct reachable taps), so a thread
+// that owns a CHANNEL PAIR loads the image's 9 bf16x2 values straight from global memory (coalesced: a warp reads 128
+// contiguous bytes per pixel), runs the 162 FMAs, and the LayerNorm statistics of the 9 pixels are reduced over the
+// channel pairs with the 31-shuffle recursive-halving tree (common.cuh) + one shared-memory hop across the warps.
+// The previous path (dwln2: fp32 staging in shared memory + a second warp-per-pixel pass) ran at 1.2 TB/s on this
+// shape; the work is 94 MB of traffic and 0.2 GFMA per 8192 alerts, i.e. this kernel should sit on the HBM roofline.
+#include "common.cuh"
+
+namespace btsb {
+
+template <int S>
+__global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C, const float* __restrict__ wt,
+                                  const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                  const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
+  constexpr int R = S - 1;
+  constexpr int NT = 2 * R + 1;
+  constexpr int HW = S * S;
+  static_assert(HW <= 16, "statistics layout: sums in [0,16), sums of squares in [16,32)");
+  extern __shared__ __align__(16) unsigned char sm[];
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
+  float* wsm = reinterpret_cast<float*>(sm);                 // [NT*NT][C] reachable taps
+  float* part = wsm + NT * NT * C;                           // [2][nw][32]
+  float2* stat = reinterpret_cast<float2*>(part + 2 * nw * 32);   // [2][16] (mean, rstd)
+  const int C2 = C >> 1;
+  const bool active = tid < C2;
+  const int c2 = active ? tid : 0;
+
+  for (int i = tid; i < NT * NT * C; i += T) {
+    const int t = i / C, c = i - t * C;
+    const int ty = t / NT, tx = t - ty * NT;
+    wsm[i] = __ldg(wt + ((ty + 3 - R) * 7 + (tx + 3 - R)) * C + c);
+  }
+  const float2 bv = *reinterpret_cast<const float2*>(bias + 2 * c2);
+  const float2 gw = *reinterpret_cast<const float2*>(ln_w + 2 * c2);
+  const float2 gb = *reinterpret_cast<const float2*>(ln_b + 2 * c2);
+  __syncthreads();
+
+  uint32_t cur[HW], nxt[HW];
+  auto load_img = [&](int64_t img, uint32_t (&v)[HW]) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + img * (int64_t)HW * C) + c2;
+#pragma unroll
+    for (int p = 0; p < HW; ++p) v[p] = (active && img < B) ? __ldg(src + (size_t)p * C2) : 0u;
+  };
+  load_img(blockIdx.x, cur);
+  const float invC = 1.0f / (float)C;
+  int it = 0;
+  for (int64_t img = blockIdx.x; img < B; img += gridDim.x, ++it) {
+    load_img(img + gridDim.x, nxt);                          // prefetch: in flight during the math below
+    float a0[HW], a1[HW];
+#pragma unroll
+    for (int p = 0; p < HW; ++p) { a0[p] = bv.x; a1[p] = bv.y; }
+#pragma unroll
+    for (int ty = 0; ty < NT; ++ty) {
+#pragma unroll
+      for (int tx = 0; tx < NT; ++tx) {
+        const float2 w = *reinterpret_cast<const float2*>(wsm + (ty * NT + tx) * C + 2 * c2);
+        const int dy = ty - R, dx = tx - R;                  // input = output + (dy, dx)
+#pragma unroll
+        for (int oy = 0; oy < S; ++oy) {
+#pragma unroll
+          for (int ox = 0; ox < S; ++ox) {
+            const int iy = oy + dy, ix = ox + dx;
+            if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
+              const uint32_t v = cur[iy * S + ix];
+              a0[oy * S + ox] = fmaf(w.x, __uint_as_float(v << 16), a0[oy * S + ox]);
+              a1[oy * S + ox] = fmaf(w.y, __uint_as_float(v & 0xffff0000u), a1[oy * S + ox]);
+            }
+          }
+        }
+      }
+    }
+    // ---- per-pixel channel statistics ------------------------------------------------------------------------------
+    const int buf = it & 1;
+    float* pb = part + (buf * nw + warp) * 32;
+    if (HW == 1) {
+      const float s = warp_sum(active ? a0[0] + a1[0] : 0.f);
+      const float q = warp_sum(active ? fmaf(a0[0], a0[0], a1[0] * a1[0]) : 0.f);
+      if (lane == 0) { pb[0] = s; pb[16] = q; }
+    } else {
+      float red[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) red[i] = 0.f;
+      if (active) {
+#pragma unroll
+        for (int p = 0; p < HW; ++p) { red[p] = a0[p] + a1[p]; red[16 + p] = fmaf(a0[p], a0[p], a1[p] * a1[p]); }
+      }
+      seg_reduce32<32>(red, lane);
+      pb[lane] = red[0];
+    }
+    __syncthreads();
+    if (tid < HW) {
+      float s = 0.f, q = 0.f;
+      for (int w = 0; w < nw; ++w) { s += part[(buf * nw + w) * 32 + tid]; q += part[(buf * nw + w) * 32 + 16 + tid]; }
+      const float mean = s * invC;
+      const float var = fmaxf(q * invC - mean * mean, 0.f);
+      stat[buf * 16 + tid] = make_float2(mean, rsqrtf(var + kLnEps));
+    }
+    __syncthreads();
+    if (active) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(out + img * (int64_t)HW * C) + c2;
+#pragma unroll
+      for (int p = 0; p < HW; ++p) {
+        const float2 mr = stat[buf * 16 + p];
+        __nv_bfloat162 o = __floats2bfloat162_rn((a0[p] - mr.x) * mr.y * gw.x + gb.x, (a1[p] - mr.x) * mr.y * gw.y + gb.y);
+        dst[(size_t)p * C2] = *reinterpret_cast<uint32_t*>(&o);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < HW; ++p) cur[p] = nxt[p];
+  }
+}
+
+int num_sms();
+
+template <int S>
+static int launch_small(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
+                        const float* ln_b, void* out, cudaStream_t st) {
+  constexpr int NT = 2 * (S - 1) + 1;
+  const int threads = ((C / 2 + 31) / 32) * 32;
+  if (threads > 1024) return 1;
+  const int nw = threads / 32;
+  const size_t smem = (size_t)NT * NT * C * 4 + 2 * nw * 32 * 4 + 2 * 16 * 8;
+  if (smem > 200 * 1024) return 1;
+  auto kern = dwln_small_kernel<S>;
+  BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dwln_small attr");
+  int per_sm = 1;
+  BTSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem), "dwln_small occupancy");
+  if (per_sm < 1) per_sm = 1;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  const int grid = (int)(B < cap ? B : cap);
+  kern<<<grid, threads, smem, st>>>((const __nv_bfloat16*)x, B, C, w, bias, ln_w, ln_b, (__nv_bfloat16*)out);
+  return launch_done("dwln_small");
+}
+
+// returns 1 if the shape is not handled here
+int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
+                    const float* ln_b, void* out, cudaStream_t st) {
+  if (H != W || (C & 1) || C > 2048) return 1;
+  if (((uintptr_t)x % 4) != 0 || ((uintptr_t)out % 4) != 0 || ((uintptr_t)bias % 8) != 0 || ((uintptr_t)ln_w % 8) != 0 ||
+      ((uintptr_t)ln_b % 8) != 0)
+    return 1;
+  if (H == 3) return launch_small<3>(x, B, C, w, bias, ln_w, ln_b, out, st);
+  if (H == 1) return launch_small<1>(x, B, C, w, bias, ln_w, ln_b, out, st);
+  return 1;
+}
+
+}  // namespace btsb

@@ -75,7 +75,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < kAcc; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == EPI_LN ? 4 : kEpiWarps); }
+    for (int s = 0; s < kAcc; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == EPI_LN ? 4 : kEpiWarps / 2); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -210,15 +210,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 2) {
     // ===================== epilogue warps =====================
+    // Two groups of 8 warps own alternate tiles (= alternate accumulator stages): while one group is in the MUFU-bound
+    // middle of its tile the other is loading TMEM / storing rows, instead of all 16 warps hitting every phase together.
     const int ew = warp - 2;
     const int quarter = warp & 3;                       // TMEM lanes this warp may touch: 32*(warp%4) ..
-    const int part = ew >> 2;                           // column slice handled by this warp (kEpiWarps/4 slices)
-    constexpr int kParts = kEpiWarps / 4;
-    int as = 0; uint32_t aphase = 0;
+    const int grp = (ew >> 2) & 1;                      // accumulator stage / tile parity owned by this warp
+    const int part = ew >> 3;                           // column half handled by this warp
+    constexpr int kParts = 2;
+    const int as = grp;
     const int chunks = BN / 16;
     const int c_lo = (chunks * part) / kParts;
     const int c_hi = (chunks * (part + 1)) / kParts;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 1) != grp) continue;
+      const uint32_t aphase = (uint32_t)(lt >> 1) & 1u;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       mbar_wait_spin(tfull_bar(as), aphase);
       tc_fence_after();
@@ -294,7 +300,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         process(ch, ra, rb, qa, qb);
         if (ch + 1 < c_hi) process(ch + 1, rb, ra, qb, qa);
       }
-      if (++as == kAcc) { as = 0; aphase ^= 1u; }
     }
   }
   tc_fence_before();
