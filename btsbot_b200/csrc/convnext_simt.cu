@@ -516,6 +516,87 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
   return dispatch_dwln<__nv_bfloat16>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
 }
 
+// bf16 fast path for C = 8*NV*TPP (nano 80/160/320, pico 64/128/256): TPP threads per used input pixel, each thread keeps
+// its NV uint4 (8*NV channels, contiguous 16*NV bytes) in registers -- 128-bit loads/stores, thread-local two-pass
+// statistics, only log2(TPP) shuffles.  ~18 warp-instructions per pixel instead of ~200 for the warp-per-pixel kernels
+// above (which were issue-bound at 1.4-1.7 TB/s: profiles/r01c misc.summary).
+template <int NV, int TPP>
+__global__ void __launch_bounds__(256)
+lnpatch_tpp_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int W, int Ho, int Wo,
+                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
+  constexpr int CH = 8 * NV, C = CH * TPP;
+  __shared__ __align__(16) float gws[C], gbs[C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { gws[i] = __ldg(ln_w + i); gbs[i] = __ldg(ln_b + i); }
+  __syncthreads();
+  const int Hu = 2 * Ho, Wu = 2 * Wo;
+  const int64_t total = B * (int64_t)Hu * Wu * TPP;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int sub = (int)(i % TPP);
+    const int64_t p = i / TPP;
+    const int ix = (int)(p % Wu);
+    const int64_t t = p / Wu;
+    const int iy = (int)(t % Hu);
+    const int64_t b = t / Hu;
+    const uint4* src = reinterpret_cast<const uint4*>(x + ((b * H + iy) * (int64_t)W + ix) * C + sub * CH);
+    uint4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = __ldg(src + j);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += __uint_as_float(u[k] << 16) + __uint_as_float(u[k] & 0xffff0000u);
+    }
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / (float)C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float d0 = __uint_as_float(u[k] << 16) - mean, d1 = __uint_as_float(u[k] & 0xffff0000u) - mean;
+        q = fmaf(d0, d0, q); q = fmaf(d1, d1, q);
+      }
+    }
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / (float)C) + kLnEps);
+    const int oy = iy >> 1, dy = iy & 1, ox = ix >> 1, dx = ix & 1;
+    uint4* dst = reinterpret_cast<uint4*>(out + ((b * Ho + oy) * (int64_t)Wo + ox) * (4 * (int64_t)C) + (dy * 2 + dx) * C + sub * CH);
+    const float4* gw4 = reinterpret_cast<const float4*>(gws + sub * CH);
+    const float4* gb4 = reinterpret_cast<const float4*>(gbs + sub * CH);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+      const float4 w0 = gw4[2 * j], w1 = gw4[2 * j + 1], b0 = gb4[2 * j], b1 = gb4[2 * j + 1];
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float lo = (__uint_as_float(u[k] << 16) - mean) * rstd * wv[2 * k] + bb[2 * k];
+        const float hi = (__uint_as_float(u[k] & 0xffff0000u) - mean) * rstd * wv[2 * k + 1] + bb[2 * k + 1];
+        __nv_bfloat162 ob = __floats2bfloat162_rn(lo, hi);
+        o[k] = *reinterpret_cast<uint32_t*>(&ob);
+      }
+      dst[j] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <int NV, int TPP>
+static void launch_lnpatch_tpp(const __nv_bfloat16* xi, int64_t B, int H, int W, int Ho, int Wo, const float* ln_w,
+                               const float* ln_b, __nv_bfloat16* xo, cudaStream_t st) {
+  const int64_t total = B * 4 * (int64_t)Ho * Wo * TPP;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  lnpatch_tpp_kernel<NV, TPP><<<(unsigned)grid, 256, 0, st>>>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo);
+}
+
 extern "C" int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, int H, int W, int C,
                                          const float* ln_w, const float* ln_b, void* out, void* stream) {
   if (int e = check_device()) return e;
@@ -529,7 +610,19 @@ extern "C" int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, in
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == BTSB_F32)
     lnpatch_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, H, W, C, Ho, Wo, ln_w, ln_b, (float*)out);
-  else if (C % 2 == 0 && ((uintptr_t)ln_w % 8) == 0 && ((uintptr_t)ln_b % 8) == 0) {
+  else if ((C == 64 || C == 80 || C == 128 || C == 160 || C == 256 || C == 320) && ((uintptr_t)x % 16) == 0 &&
+           ((uintptr_t)out % 16) == 0 && !getenv("BTSB_LNPATCH_V1")) {
+    const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
+    __nv_bfloat16* xo = (__nv_bfloat16*)out;
+    switch (C) {
+      case 64: launch_lnpatch_tpp<8, 1>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
+      case 80: launch_lnpatch_tpp<10, 1>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
+      case 128: launch_lnpatch_tpp<8, 2>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
+      case 160: launch_lnpatch_tpp<10, 2>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
+      case 256: launch_lnpatch_tpp<8, 4>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
+      default: launch_lnpatch_tpp<10, 4>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
+    }
+  } else if (C % 2 == 0 && ((uintptr_t)ln_w % 8) == 0 && ((uintptr_t)ln_b % 8) == 0) {
     const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
     __nv_bfloat16* xo = (__nv_bfloat16*)out;
     if (C <= 128) lnpatch_bf16x2_kernel<2><<<grid, 256, 0, st>>>(xi, B, H, W, C, Ho, Wo, ln_w, ln_b, xo);

@@ -78,9 +78,89 @@ __device__ __forceinline__ void dense_layer_t(const float* __restrict__ in, int 
   }
 }
 
+// Weight-streaming variant: the [K][N] weight matrix is pulled through a 3-deep ring of kKT-row tiles in shared memory
+// with cp.async (two tiles = 64 k-steps in flight), so the L2 latency of the weight stream is fully hidden; threads
+// read their two weights with one conflict-free LDS.64 and the 8 alert activations with two broadcast LDS.128.
+// Needs N % 4 == 0 (16-byte cp.async granules) and a 16-byte aligned Wt.  ALL threads of the CTA must call it.
+constexpr int kKT = 32;           // k rows per tile
+constexpr int kWRing = 3;
+constexpr int kWTileMaxN = 128;   // ring sized for N <= 128 (3 * 32 * 128 * 4 B = 48 KB)
+
+__device__ __forceinline__ void cp_async16_h(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+__device__ __forceinline__ void dense_layer_ring(const float* __restrict__ in, int K, const float* __restrict__ Wt,
+                                                 const float* __restrict__ bias, int N, int act, float* __restrict__ out,
+                                                 float* __restrict__ ring) {
+  const int groups = kTA / kAT;
+  const int NV = N >> 1;
+  const int items = NV * groups;
+  const int ntiles = (K + kKT - 1) / kKT;
+  const int tile_floats = kKT * N;
+  auto issue = [&](int t) {
+    if (t < ntiles) {
+      const int rows = min(kKT, K - t * kKT);
+      const float4* src = reinterpret_cast<const float4*>(Wt + (size_t)t * kKT * N);
+      float4* dst = reinterpret_cast<float4*>(ring + (t % kWRing) * tile_floats);
+      for (int i = threadIdx.x; i < rows * N / 4; i += kHeadThreads) cp_async16_h(dst + i, src + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int pass = 0; pass < items; pass += kHeadThreads) {
+    const int it = pass + threadIdx.x;
+    const bool live = it < items;
+    const int n = live ? (it % NV) * 2 : 0, ag = live ? it / NV : 0;
+    float acc0[kAT], acc1[kAT];
+    {
+      const float b0 = bias ? __ldg(bias + n) : 0.f, b1 = bias ? __ldg(bias + n + 1) : 0.f;
+#pragma unroll
+      for (int a = 0; a < kAT; ++a) { acc0[a] = b0; acc1[a] = b1; }
+    }
+    const float* src = in + ag * kAT;
+    issue(0);
+    issue(1);
+    for (int t = 0; t < ntiles; ++t) {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");     // tile t has landed (tile t+1 may still be in flight)
+      __syncthreads();                                          // ... for every thread; tile t-1's buffer is free again
+      issue(t + 2);
+      const float* wt = ring + (t % kWRing) * tile_floats + n;
+      const int rows = min(kKT, K - t * kKT);
+      const float* sk = src + (size_t)t * kKT * kTAp;
+      if (live) {
+#pragma unroll 8
+        for (int k = 0; k < rows; ++k) {
+          const float2 w = *reinterpret_cast<const float2*>(wt + k * N);
+          const float4 v0 = *reinterpret_cast<const float4*>(sk + k * kTAp);
+          const float4 v1 = *reinterpret_cast<const float4*>(sk + k * kTAp + 4);
+          acc0[0] = fmaf(w.x, v0.x, acc0[0]); acc1[0] = fmaf(w.y, v0.x, acc1[0]);
+          acc0[1] = fmaf(w.x, v0.y, acc0[1]); acc1[1] = fmaf(w.y, v0.y, acc1[1]);
+          acc0[2] = fmaf(w.x, v0.z, acc0[2]); acc1[2] = fmaf(w.y, v0.z, acc1[2]);
+          acc0[3] = fmaf(w.x, v0.w, acc0[3]); acc1[3] = fmaf(w.y, v0.w, acc1[3]);
+          acc0[4] = fmaf(w.x, v1.x, acc0[4]); acc1[4] = fmaf(w.y, v1.x, acc1[4]);
+          acc0[5] = fmaf(w.x, v1.y, acc0[5]); acc1[5] = fmaf(w.y, v1.y, acc1[5]);
+          acc0[6] = fmaf(w.x, v1.z, acc0[6]); acc1[6] = fmaf(w.y, v1.z, acc1[6]);
+          acc0[7] = fmaf(w.x, v1.w, acc0[7]); acc1[7] = fmaf(w.y, v1.w, acc1[7]);
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                            // ring reusable by the next pass / layer
+    if (live) {
+      float* d0 = out + n * kTAp + ag * kAT;
+#pragma unroll
+      for (int a = 0; a < kAT; ++a) { d0[a] = apply_act(acc0[a], act); d0[kTAp + a] = apply_act(acc1[a], act); }
+    }
+  }
+}
+
 __device__ __forceinline__ void dense_layer(const float* __restrict__ in, int K, const float* __restrict__ Wt,
-                                            const float* __restrict__ bias, int N, int act, float* __restrict__ out) {
-  if ((N & 1) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 7) == 0) dense_layer_t<2>(in, K, Wt, bias, N, act, out);
+                                            const float* __restrict__ bias, int N, int act, float* __restrict__ out,
+                                            float* __restrict__ ring) {
+  if ((N & 3) == 0 && N <= kWTileMaxN && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0)
+    dense_layer_ring(in, K, Wt, bias, N, act, out, ring);
+  else if ((N & 1) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 7) == 0) dense_layer_t<2>(in, K, Wt, bias, N, act, out);
   else dense_layer_t<1>(in, K, Wt, bias, N, act, out);
 }
 
@@ -97,9 +177,12 @@ meta_head_kernel(btsb_head_params p, int64_t B, float* __restrict__ logits) {
   float* buf1 = bufM + (size_t)Mm * kTAp;            // [m1][kTAp]
   float* bufH0 = buf1 + (size_t)m1 * kTAp;           // [c1][kTAp]
   float* bufH1 = bufH0 + (size_t)c1 * kTAp;          // [c2][kTAp]
+  float* ring = bufH1 + (size_t)c2 * kTAp;           // [kWRing][kKT][<=128] weight tiles (16-byte aligned: kTAp % 4 == 0)
 
   // stage inputs (zero-fill alerts beyond the batch tail)
   if (F > 0) {
+    // a warp reads 32 consecutive features of one alert (coalesced) and scatters them down a column of `cat`
+    // (4-way bank conflict on the store: 640 warp-stores per CTA, negligible next to the 768-deep contraction)
     for (int i = tid; i < F * kTA; i += kHeadThreads) {
       const int a = i / F, k = i - a * F;
       float v = 0.f;
@@ -121,17 +204,17 @@ meta_head_kernel(btsb_head_params p, int64_t B, float* __restrict__ logits) {
   }
   __syncthreads();
   if (Mm > 0) {
-    dense_layer(bufM, Mm, p.m1t, p.m1b, m1, p.meta_act, buf1);
+    dense_layer(bufM, Mm, p.m1t, p.m1b, m1, p.meta_act, buf1, ring);
     __syncthreads();
-    dense_layer(buf1, m1, p.m2t, p.m2b, m2, p.meta_out_act, cat + (size_t)F * kTAp);
+    dense_layer(buf1, m1, p.m2t, p.m2b, m2, p.meta_out_act, cat + (size_t)F * kTAp, ring);
     __syncthreads();
   }
   const float* last = cat;
   int lastK = F + emb;
   if (c1 > 0) {
-    dense_layer(cat, F + emb, p.h0t, p.h0b, c1, p.head_act, bufH0);
+    dense_layer(cat, F + emb, p.h0t, p.h0b, c1, p.head_act, bufH0, ring);
     __syncthreads();
-    dense_layer(bufH0, c1, p.h1t, p.h1b, c2, p.head_act, bufH1);
+    dense_layer(bufH0, c1, p.h1t, p.h1b, c2, p.head_act, bufH1, ring);
     __syncthreads();
     last = bufH1;
     lastK = c2;
@@ -165,7 +248,8 @@ extern "C" int btsb_meta_head_fwd(const btsb_head_params* pp, int64_t B, float* 
   if (B == 0) return BTSB_OK;
   BTSB_REQUIRE(logits, "meta_head: null logits");
   const int emb = p.Mm > 0 ? p.m2 : 0;
-  const size_t smem = (size_t)(p.F + emb + p.Mm + (p.Mm > 0 ? p.m1 : 0) + p.c1 + p.c2) * kTAp * sizeof(float);
+  const size_t smem = (size_t)(p.F + emb + p.Mm + (p.Mm > 0 ? p.m1 : 0) + p.c1 + p.c2) * kTAp * sizeof(float) +
+                      (size_t)kWRing * kKT * kWTileMaxN * sizeof(float);
   BTSB_REQUIRE(smem <= 227 * 1024, "meta_head: layer widths need %zu B of shared memory (> 227 KB)", smem);
   BTSB_CUDA(cudaFuncSetAttribute(meta_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "meta_head attr");
   const int64_t grid = (B + kTA - 1) / kTA;
