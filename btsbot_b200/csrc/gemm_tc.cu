@@ -8,6 +8,9 @@
 //   * persistent: grid = min(#tiles, #SMs); tiles walk N fastest so concurrent CTAs share A rows in L2
 //
 // Replaces timm mlp.fc1 (+GELU), mlp.fc2 (*gamma + shortcut) and downsample.1 (see include/btsbot_b200.h).
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace btsb {
@@ -15,28 +18,45 @@ namespace btsb {
 namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kStages = 4;
+constexpr int kEpiWarps = 16;
+constexpr int kStages = 3;
 constexpr int kMaxBN = 256;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
-constexpr int kEpiWarps = 16;
 constexpr int kThreads = 64 + kEpiWarps * 32;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int kABytes = BM * BK * 2;              // 16 KB
 constexpr int kBBytes = kMaxBN * BK * 2;          // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kMaxNBias = 4096;                  // bias (and LN weight/bias) staged in shared memory once per CTA
-constexpr int kMaxNGamma = 4096;                 // layer-scale vector of the SCALE_RES epilogue
+constexpr int kMaxNBias = 2560;                  // bias (and LN weight/bias) staged in shared memory once per CTA
+constexpr int kMaxNGamma = 1920;                 // layer-scale vector of the SCALE_RES epilogue (read via __ldg beyond this)
 constexpr int kVecBytes = (kMaxNBias + kMaxNGamma) * 4;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kVecBytes;
+constexpr int kOffVec = kStages * kStageBytes + 256 /*barriers*/;
+constexpr int kOffStg = (kOffVec + kVecBytes + 1023) & ~1023;   // output staging: one 4 KB [32 rows x 128 B] slab per warp
+constexpr int kStgBytes = kEpiWarps * 4096;
+constexpr int kSmemBytes = kOffStg + kStgBytes + 1024 /*align slack*/;
+static_assert(kSmemBytes <= 227 * 1024, "shared-memory plan exceeds 227 KB");
 }  // namespace
+
+struct OutMaps {          // out [M, N] bf16: boxes of 32 rows x 64 | 32 | 16 columns (swizzle 128 | 64 | 32 B)
+  CUtensorMap o128, o64, o32;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 constexpr int EPI_LN = 100;   // internal: out = LayerNorm(acc + bias) * gamma(ln_w) + aux(ln_b), whole rows per thread
 
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ OutMaps tmO,
                const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ aux,
-               const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out, int M, int N, int K, int BN) {
+               const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out, int M, int N, int K, int BN, int dbg) {
   using namespace tc;
   // LN mode: rows must stay in one thread, so 4 warps (one per TMEM lane quarter) own a whole tile; the 16 epilogue
   // warps form 4 such groups working on 4 accumulator stages of 128 columns (BN = N <= 128).
@@ -63,10 +83,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // per-column vectors -> shared memory (the epilogue re-reads them for every tile; a global load per 16-column chunk
   // was the top stall of the GELU epilogue: profiles/r01c)
-  float* bias_s = reinterpret_cast<float*>(smem_al + kStages * kStageBytes + 256);
+  float* bias_s = reinterpret_cast<float*>(smem_al + kOffVec);
   float* gamma_s = bias_s + kMaxNBias;
   for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = __ldg(bias + i);
-  if (EPI == BTSB_EPI_SCALE_RES)
+  const bool gamma_staged = N <= kMaxNGamma;
+  if (EPI == BTSB_EPI_SCALE_RES && gamma_staged)
     for (int i = threadIdx.x; i < N; i += kThreads) gamma_s[i] = __ldg(gamma + i);
   if (EPI == EPI_LN)
     for (int i = threadIdx.x; i < N; i += kThreads) { gamma_s[i] = __ldg(gamma + i); gamma_s[kMaxNGamma / 2 + i] = __ldg(aux + i); }
@@ -218,6 +239,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int part = ew >> 3;                           // column half handled by this warp
     constexpr int kParts = 2;
     const int as = grp;
+    unsigned char* stg = smem_al + kOffStg + ew * 4096;
+    const uint32_t stg_addr = smem_base + kOffStg + ew * 4096;
     const int chunks = BN / 16;
     const int c_lo = (chunks * part) / kParts;
     const int c_hi = (chunks * (part + 1)) / kParts;
@@ -230,13 +253,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccCols);
+      if (dbg & 1) {                                    // timing experiment: main loop only, accumulator released unread
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        continue;
+      }
       if (c_lo >= c_hi) {                               // narrow tile: this warp has no columns, release at once
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(as));
+        continue;
       }
-      // chunks of 16 columns, software-pipelined: the TMEM load (and the residual load) of chunk ch+1 is in flight
-      // during the math of chunk ch
+      // The warp's columns are cut into slabs of 4 / 2 / 1 chunks (64 / 32 / 16 columns).  Each thread packs its row of
+      // the slab into the warp's private staging buffer in the swizzled layout of a [32 rows x 128|64|32 B] TMA box
+      // (conflict-free 16-byte stores), then one lane issues ONE bulk tensor store per slab.  Direct per-thread row
+      // stores (32 B to 32 different lines per warp instruction) kept the LSU busy for ~64 clk per chunk and made every
+      // small-K GEMM epilogue-bound: main loop alone 42 us, with stores 102 us at M=73728 N=1280 K=320 (profiles/r01g).
+      // TMEM load (and residual load) of chunk ch+1 is in flight during the math of chunk ch.
       uint32_t ra[16], rb[16];
       uint4 qa[2], qb[2];
       auto load_res = [&](int ch, uint4 (&q)[2]) {
@@ -248,7 +282,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       };
-      auto process = [&](int ch, uint32_t (&cur)[16], uint32_t (&nxt)[16], uint4 (&qcur)[2], uint4 (&qnxt)[2]) {
+      // sw = bytes per staged row (128 / 64 / 32), q0 = 16-byte column index of this chunk inside the slab row
+      auto process = [&](int ch, int sw, int q0, uint32_t (&cur)[16], uint32_t (&nxt)[16], uint4 (&qcur)[2], uint4 (&qnxt)[2]) {
         tmem_ld_wait();
         if (ch + 1 < c_hi) {
           tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), nxt);
@@ -259,48 +294,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
         const int n = n0 + ch * 16;
-        if (row < M && n < N) {
-          float v[16];
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + i);
+          v[i] = __uint_as_float(cur[i]) + b4.x; v[i + 1] = __uint_as_float(cur[i + 1]) + b4.y;
+          v[i + 2] = __uint_as_float(cur[i + 2]) + b4.z; v[i + 3] = __uint_as_float(cur[i + 3]) + b4.w;
+        }
+        if (EPI == BTSB_EPI_BIAS_GELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+        }
+        if (EPI == BTSB_EPI_BIAS_SILU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = silu_fast(v[i]);
+        }
+        if (EPI == BTSB_EPI_SCALE_RES) {
+          const uint32_t rcur[8] = {qcur[0].x, qcur[0].y, qcur[0].z, qcur[0].w, qcur[1].x, qcur[1].y, qcur[1].z, qcur[1].w};
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + i);
-            v[i] = __uint_as_float(cur[i]) + b4.x; v[i + 1] = __uint_as_float(cur[i + 1]) + b4.y;
-            v[i + 2] = __uint_as_float(cur[i + 2]) + b4.z; v[i + 3] = __uint_as_float(cur[i + 3]) + b4.w;
+            const float4 g4 = gamma_staged ? *reinterpret_cast<const float4*>(gamma_s + n + i)
+                                           : __ldg(reinterpret_cast<const float4*>(gamma + n + i));
+            v[i] = fmaf(g4.x, v[i], bf16_lo(rcur[i / 2]));
+            v[i + 1] = fmaf(g4.y, v[i + 1], bf16_hi(rcur[i / 2]));
+            v[i + 2] = fmaf(g4.z, v[i + 2], bf16_lo(rcur[i / 2 + 1]));
+            v[i + 3] = fmaf(g4.w, v[i + 3], bf16_hi(rcur[i / 2 + 1]));
           }
-          if (EPI == BTSB_EPI_BIAS_GELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
-          }
-          if (EPI == BTSB_EPI_BIAS_SILU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = silu_fast(v[i]);
-          }
-          if (EPI == BTSB_EPI_SCALE_RES) {
-            const uint32_t rcur[8] = {qcur[0].x, qcur[0].y, qcur[0].z, qcur[0].w, qcur[1].x, qcur[1].y, qcur[1].z, qcur[1].w};
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              const float4 g4 = *reinterpret_cast<const float4*>(gamma_s + n + i);
-              v[i] = fmaf(g4.x, v[i], bf16_lo(rcur[i / 2]));
-              v[i + 1] = fmaf(g4.y, v[i + 1], bf16_hi(rcur[i / 2]));
-              v[i + 2] = fmaf(g4.z, v[i + 2], bf16_lo(rcur[i / 2 + 1]));
-              v[i + 3] = fmaf(g4.w, v[i + 3], bf16_hi(rcur[i / 2 + 1]));
-            }
-          }
-          uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
-          uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * N + n);
-          op[0] = o0; op[1] = o1;
         }
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+        o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+        o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+        o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+        // swizzle of a [rows x sw bytes] box: 16-byte column index XOR (row / (128 / sw)) mod (sw / 16)
+        const int xr = sw == 128 ? (lane & 7) : (sw == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+        unsigned char* rowp = stg + lane * sw;
+        *reinterpret_cast<uint4*>(rowp + ((q0 ^ xr) << 4)) = o0;
+        *reinterpret_cast<uint4*>(rowp + (((q0 + 1) ^ xr) << 4)) = o1;
       };
-      if (c_lo < c_hi) { tmem_ld16(taddr + (uint32_t)(c_lo * 16), ra); load_res(c_lo, qa); }
-      for (int ch = c_lo; ch < c_hi; ch += 2) {
-        process(ch, ra, rb, qa, qb);
-        if (ch + 1 < c_hi) process(ch + 1, rb, ra, qb, qa);
+      tmem_ld16(taddr + (uint32_t)(c_lo * 16), ra);
+      load_res(c_lo, qa);
+      int par = 0;                                        // which register set holds the current chunk
+      for (int s0 = c_lo; s0 < c_hi;) {
+        const int left = c_hi - s0;
+        const int w = left >= 4 ? 4 : (left >= 2 ? 2 : 1);   // chunks in this slab
+        const int sw = w * 32;
+        if (lane == 0) tma_store_wait_read();               // the previous slab's bulk store has drained the buffer
+        __syncwarp();
+        for (int c = 0; c < w; ++c) {
+          if (par == 0) process(s0 + c, sw, 2 * c, ra, rb, qa, qb);
+          else process(s0 + c, sw, 2 * c, rb, ra, qb, qa);
+          par ^= 1;
+        }
+        fence_proxy_async();                                // generic-proxy smem writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          const CUtensorMap* mp = w == 4 ? &tmO.o128 : (w == 2 ? &tmO.o64 : &tmO.o32);
+          tma_store_2d(mp, stg_addr, n0 + s0 * 16, m0 + quarter * 32);
+          tma_store_commit();
+        }
+        s0 += w;
       }
     }
+    if (lane == 0) tma_store_wait_all();                  // smem must outlive the last bulk store's reads
   }
   tc_fence_before();
   __syncthreads();
@@ -380,12 +436,17 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
   BTSB_REQUIRE(((uintptr_t)out % 16) == 0 && ((uintptr_t)bias % 16) == 0, "gemm bf16: out/bias must be 16-byte aligned");
   if (epilogue == BTSB_EPI_SCALE_RES)
     BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)gamma % 16) == 0, "gemm bf16: res/gamma must be 16-byte aligned");
-  BTSB_REQUIRE(N <= kMaxNBias && (epilogue != BTSB_EPI_SCALE_RES || N <= kMaxNGamma),
-               "gemm bf16: N=%d exceeds the staged-vector capacity (%d, %d with a layer scale)", N, kMaxNBias, kMaxNGamma);
-  const int BN = pick_bn(N);
+  BTSB_REQUIRE(N <= kMaxNBias, "gemm bf16: N=%d exceeds the staged bias capacity (%d)", N, kMaxNBias);
+  static const int dbg = getenv("BTSB_GEMM_DBG") ? atoi(getenv("BTSB_GEMM_DBG")) : 0;   // timing experiments only
+  int BN = pick_bn(N);
+  if ((dbg & 2) && BN > 128 && N % 128 == 0) BN = 128;
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM)) return e;
   if (int e = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint32_t)BN)) return e;
+  OutMaps tmO;
+  if (int e = make_tmap_bf16_2d_sw(&tmO.o128, out, (uint64_t)M, (uint64_t)N, 32, 64, 128)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tmO.o64, out, (uint64_t)M, (uint64_t)N, 32, 32, 64)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tmO.o32, out, (uint64_t)M, (uint64_t)N, 32, 16, 32)) return e;
   const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
   const int grid = min(m_tiles * n_tiles, num_sms());
   static bool attr_done = false;
@@ -399,13 +460,13 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
   const __nv_bfloat16* r = (const __nv_bfloat16*)res;
   __nv_bfloat16* o = (__nv_bfloat16*)out;
   if (epilogue == BTSB_EPI_BIAS)
-    gemm_tc_kernel<BTSB_EPI_BIAS><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
+    gemm_tc_kernel<BTSB_EPI_BIAS><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, gamma, nullptr, r, o, (int)M, N, K, BN, dbg);
   else if (epilogue == BTSB_EPI_BIAS_GELU)
-    gemm_tc_kernel<BTSB_EPI_BIAS_GELU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
+    gemm_tc_kernel<BTSB_EPI_BIAS_GELU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, gamma, nullptr, r, o, (int)M, N, K, BN, dbg);
   else if (epilogue == BTSB_EPI_BIAS_SILU)
-    gemm_tc_kernel<BTSB_EPI_BIAS_SILU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
+    gemm_tc_kernel<BTSB_EPI_BIAS_SILU><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, gamma, nullptr, r, o, (int)M, N, K, BN, dbg);
   else
-    gemm_tc_kernel<BTSB_EPI_SCALE_RES><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, gamma, nullptr, r, o, (int)M, N, K, BN);
+    gemm_tc_kernel<BTSB_EPI_SCALE_RES><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, gamma, nullptr, r, o, (int)M, N, K, BN, dbg);
   return launch_done("gemm_bf16");
 }
 
@@ -429,8 +490,10 @@ int gemm_ln_bf16(const void* A, const void* Wt, const float* bias, const float* 
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm_ln attr");
     attr_done = true;
   }
-  gemm_tc_kernel<EPI_LN><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, bias, ln_w, ln_b, nullptr, (__nv_bfloat16*)out,
-                                                             (int)M, N, K, N);
+  OutMaps tmO;
+  memset(&tmO, 0, sizeof(tmO));                           // the LayerNorm epilogue writes rows directly
+  gemm_tc_kernel<EPI_LN><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, ln_w, ln_b, nullptr, (__nv_bfloat16*)out,
+                                                             (int)M, N, K, N, 0);
   return launch_done("gemm_ln_bf16");
 }
 

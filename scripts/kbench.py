@@ -54,6 +54,8 @@ def fc(C, HW):
     b1, b2, gm = rnd(4 * C, dtype=torch.float32, scale=0.1), rnd(C, dtype=torch.float32, scale=0.1), rnd(C, dtype=torch.float32)
     timeit(f"gemm fc1+gelu C={C} HW={HW}", lambda i: ops.gemm(ys[i], w1, b1, L.EPI_BIAS_GELU), 2,
            flops=8.0 * M * C * C, nbytes=2.0 * (M * C + 4 * M * C + 4 * C * C))
+    timeit(f"gemm fc1+bias C={C} HW={HW}", lambda i: ops.gemm(ys[i], w1, b1, L.EPI_BIAS), 2,
+           flops=8.0 * M * C * C, nbytes=2.0 * (M * C + 4 * M * C + 4 * C * C))
     timeit(f"gemm fc2+res C={C} HW={HW}", lambda i: ops.gemm(hid[i], w2, b2, L.EPI_SCALE_RES, gm, rs[i]), 2,
            flops=8.0 * M * C * C, nbytes=2.0 * (4 * M * C + 2 * M * C + 4 * C * C))
 
