@@ -19,18 +19,17 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kEpiWarps = 16;
-constexpr int kStages = 3;
+constexpr int kRingBytes = 3 * (128 * 64 * 2 + 256 * 64 * 2);   // 144 KB operand ring, cut into as many stages as fit
+constexpr int kMaxStages = 8;
 constexpr int kMaxBN = 256;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 64 + kEpiWarps * 32;     // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int kABytes = BM * BK * 2;              // 16 KB
-constexpr int kBBytes = kMaxBN * BK * 2;          // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kMaxNBias = 2560;                  // bias (and LN weight/bias) staged in shared memory once per CTA
 constexpr int kMaxNGamma = 1920;                 // layer-scale vector of the SCALE_RES epilogue (read via __ldg beyond this)
 constexpr int kVecBytes = (kMaxNBias + kMaxNGamma) * 4;
-constexpr int kOffVec = kStages * kStageBytes + 256 /*barriers*/;
+constexpr int kOffVec = kRingBytes + 256 /*barriers*/;
 constexpr int kOffStg = (kOffVec + kVecBytes + 1023) & ~1023;   // output staging: one 4 KB [32 rows x 128 B] slab per warp
 constexpr int kStgBytes = kEpiWarps * 4096;
 constexpr int kSmemBytes = kOffStg + kStgBytes + 1024 /*align slack*/;
@@ -65,14 +64,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
-  // barrier map (8 B each): full[kStages], empty[kStages], tfull[2], tempty[2], then tmem address slot
+  // ring geometry: a stage is the A box [128 x 64] plus the B box [BN x 64]; narrower B tiles buy deeper pipelines
+  const int kStageBytes = kABytes + ((BN * BK * 2 + 1023) & ~1023);
+  const int kStages = min(kMaxStages, kRingBytes / kStageBytes);
+  const uint32_t bar_base = smem_base + kRingBytes;
+  // barrier map (8 B each): full[kMaxStages], empty[kMaxStages], tfull[kAcc], tempty[kAcc], then tmem address slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + kAcc + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + kAcc + s); };
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem_al + kStages * kStageBytes + 8 * (2 * kStages + 2 * kAcc));
+      reinterpret_cast<volatile uint32_t*>(smem_al + kRingBytes + 8 * (2 * kMaxStages + 2 * kAcc));
 
   // warp index made provably warp-uniform: the TMA / MMA roles below run converged and elect one issuing lane
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -96,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < kAcc; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == EPI_LN ? 4 : kEpiWarps / 2); }
+    for (int s = 0; s < kAcc; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == EPI_LN ? 4 : kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -231,14 +233,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 2) {
     // ===================== epilogue warps =====================
-    // Two groups of 8 warps own alternate tiles (= alternate accumulator stages): while one group is in the MUFU-bound
-    // middle of its tile the other is loading TMEM / storing rows, instead of all 16 warps hitting every phase together.
+    // All 16 warps drain every tile (4 per TMEM lane quarter, 1/4 of the tile's columns each = one 64-column slab at
+    // BN = 256): with the bulk-store epilogue a tile is out of TMEM in about a quarter of its MMA time, so the two
+    // accumulator stages keep the tensor pipe fed (two 8-warp groups on alternate tiles drained each tile too slowly:
+    // 47 % of the samples of profiles/r01g/fc1_bias sat on the accumulator-full barrier while the MMA warp waited for
+    // an empty stage).
     const int ew = warp - 2;
     const int quarter = warp & 3;                       // TMEM lanes this warp may touch: 32*(warp%4) ..
-    const int grp = (ew >> 2) & 1;                      // accumulator stage / tile parity owned by this warp
-    const int part = ew >> 3;                           // column half handled by this warp
-    constexpr int kParts = 2;
-    const int as = grp;
+    const int part = ew >> 2;                           // column quarter handled by this warp
+    constexpr int kParts = 4;
     unsigned char* stg = smem_al + kOffStg + ew * 4096;
     const uint32_t stg_addr = smem_base + kOffStg + ew * 4096;
     const int chunks = BN / 16;
@@ -246,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c_hi = (chunks * (part + 1)) / kParts;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      if ((lt & 1) != grp) continue;
+      const int as = lt & 1;
       const uint32_t aphase = (uint32_t)(lt >> 1) & 1u;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
       mbar_wait_spin(tfull_bar(as), aphase);
