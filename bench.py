@@ -40,6 +40,14 @@ sys.path.insert(0, ROOT)
 
 MODEL_KIND = "convnext_nano.d1h_in1k"
 ALERT_IN_BYTES = 63 * 63 * 3 * 4 + 25 * 4
+#: DRAM bytes per launch (read + write) measured by ncu at 8192 alerts per launch; see profiles/r01f, r01g
+NCU_TRAFFIC_8192 = {
+    "mlp_fused_80": 590.3e6 + 266.1e6,
+    "dwln_15x80": 295.0e6 + 252.5e6,
+    "gemm_fc1_320": 48.0e6 + 132.8e6,
+    "gemm_fc2_320": 236.8e6 + 33.1e6,
+}
+
 WORKLOADS = {
     "c3": dict(model="mm_ConvNeXt", kind="convnext_nano.d1h_in1k", batch=8192, cpu_sample=8192, cpu_batch=64,
                label="C3 multimodal ConvNeXt-nano bulk scoring, 63x63x3 triplet + 25 metadata per alert"),
@@ -309,15 +317,24 @@ def main():
                          "share": a["ms"] / sum(v["ms"] for v in kern.values())}
     top = next(iter(kernels))
     tk = kernels[top]
-    tensor_bound = args.precision == "bf16" and any(t in top for t in ("gemm", "mv_expand", "mv_project", "mv_qkv", "mv_proj",
-                                                                       "mv_fc", "mv_stem2", "mv_shortcut"))
+    # dense contractions (K4/K5 GEMMs incl. the fused fc1-GELU-fc2 kernel, MaxViT 1x1 / Linear) are
+    # reported against the tensor roofline, everything else (dw conv + LN, LN, preprocessing ...) against HBM
+    tensor_bound = args.precision == "bf16" and any(t in top for t in ("gemm", "mlp_fused", "mv_expand", "mv_project", "mv_qkv",
+                                                                       "mv_proj", "mv_fc", "mv_stem2", "mv_shortcut"))
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures at 8192 alerts
+    # per launch (profiles/r01f/*.summary.txt, profiles/r01g/*.summary.txt), scaled to this run's batch
+    traffic = NCU_TRAFFIC_8192.get(top)
+    if traffic is not None:
+        traffic = traffic * B / 8192.0
     if tensor_bound:
         roof = {"kernel": top, "bound": "tensor", "achieved": tk["tflops"], "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": tk["tflops"] / pk["tf_sust"], "traffic": None,
-                "peak_source": pk["source"] + " (sustained bf16 cuBLAS: kernel timed inside a long step)"}
+                "frac": tk["tflops"] / pk["tf_sust"], "traffic": traffic,
+                "peak_source": pk["source"] + " (sustained bf16 cuBLAS: kernel timed inside a long step)",
+                "hbm_gbs": tk["gbs"], "hbm_frac": tk["gbs"] / pk["hbm"]}
     else:
         roof = {"kernel": top, "bound": "hbm", "achieved": tk["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                "frac": tk["gbs"] / pk["hbm"], "traffic": None, "peak_source": pk["source"] + " (copy bandwidth)"}
+                "frac": tk["gbs"] / pk["hbm"], "traffic": traffic, "peak_source": pk["source"] + " (copy bandwidth)"}
+    roof["algorithmic_bytes"] = tk["gbs"] * 1e9 * tk["ms_per_launch"] * 1e-3
     roof["kernel_time_sum_ms_per_step"] = sum(v["ms"] for v in kern.values()) / args.steps
 
     cpu = None

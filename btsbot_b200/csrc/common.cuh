@@ -90,6 +90,30 @@ __device__ __forceinline__ void seg_reduce32(float (&v)[32], int lane) {
   }
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2): one instruction = two FMAs.  The depthwise-conv kernels are instruction-issue
+// bound with FFMA at 57 % of their instruction mix (profiles/r01f/dwln15), and their natural unit is the channel PAIR
+// (bf16x2 input, float2 taps), so (acc_c, acc_c+1) += (w_c, w_c+1) * (x_c, x_c+1) is exactly one fma.rn.f32x2.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack_f32x2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(f32x2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+// bf16x2 word -> (float(lo half), float(hi half)) packed
+__device__ __forceinline__ f32x2_t bf16x2_to_f32x2(uint32_t v) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(v << 16), "r"(v & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ void fma_f32x2(f32x2_t& acc, f32x2_t a, f32x2_t b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 constexpr float kLnEps = 1e-6f;  // timm LayerNorm2d eps for ConvNeXt
 
 }  // namespace btsb

@@ -89,28 +89,30 @@ dwln3_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C_rt, int A_rt,
     // ---- depthwise conv of one output row, two channels ------------------------------------------------------------
     float acc0[S], acc1[S];
     {
-      const float2 bv = *reinterpret_cast<const float2*>(bsm + 2 * c2);
+      f32x2_t acc[S];
+      const f32x2_t bv = *reinterpret_cast<const f32x2_t*>(bsm + 2 * c2);
 #pragma unroll
-      for (int t = 0; t < S; ++t) { acc0[t] = bv.x; acc1[t] = bv.y; }
+      for (int t = 0; t < S; ++t) acc[t] = bv;
       const __nv_bfloat16* im = tin + (size_t)buf * img_elems + 2 * c2;
 #pragma unroll
       for (int dy = -R; dy <= R; ++dy) {
         const int iy = row + dy;
         if (iy < 0 || iy >= S) continue;
-        float2 wv[NT];
+        f32x2_t wv[NT];
 #pragma unroll
-        for (int kx = 0; kx < NT; ++kx) wv[kx] = *reinterpret_cast<const float2*>(wsm + ((dy + R) * NT + kx) * C + 2 * c2);
+        for (int kx = 0; kx < NT; ++kx) wv[kx] = *reinterpret_cast<const f32x2_t*>(wsm + ((dy + R) * NT + kx) * C + 2 * c2);
 #pragma unroll
         for (int ix = 0; ix < S; ++ix) {
-          const uint32_t v = *reinterpret_cast<const uint32_t*>(im + (size_t)(iy * S + ix) * C);
-          const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+          const f32x2_t xin = bf16x2_to_f32x2(*reinterpret_cast<const uint32_t*>(im + (size_t)(iy * S + ix) * C));
 #pragma unroll
           for (int kx = 0; kx < NT; ++kx) {
             const int t = ix - (kx - R);
-            if (t >= 0 && t < S) { acc0[t] = fmaf(wv[kx].x, lo, acc0[t]); acc1[t] = fmaf(wv[kx].y, hi, acc1[t]); }
+            if (t >= 0 && t < S) fma_f32x2(acc[t], wv[kx], xin);   // both channels of the pair in one FFMA2
           }
         }
       }
+#pragma unroll
+      for (int t = 0; t < S; ++t) { const float2 a = unpack_f32x2(acc[t]); acc0[t] = a.x; acc1[t] = a.y; }
     }
 
     // ---- per-pixel channel statistics: values [0,S) = sums, [16,16+S) = sums of squares -----------------------------

@@ -50,27 +50,29 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
   for (int64_t img = blockIdx.x; img < B; img += gridDim.x, ++it) {
     load_img(img + gridDim.x, nxt);                          // prefetch: in flight during the math below
     float a0[HW], a1[HW];
+    {
+      f32x2_t acc[HW], xin[HW];
+      const f32x2_t bvp = pack_f32x2(bv.x, bv.y);
 #pragma unroll
-    for (int p = 0; p < HW; ++p) { a0[p] = bv.x; a1[p] = bv.y; }
+      for (int p = 0; p < HW; ++p) { acc[p] = bvp; xin[p] = bf16x2_to_f32x2(cur[p]); }
 #pragma unroll
-    for (int ty = 0; ty < NT; ++ty) {
+      for (int ty = 0; ty < NT; ++ty) {
 #pragma unroll
-      for (int tx = 0; tx < NT; ++tx) {
-        const float2 w = *reinterpret_cast<const float2*>(wsm + (ty * NT + tx) * C + 2 * c2);
-        const int dy = ty - R, dx = tx - R;                  // input = output + (dy, dx)
+        for (int tx = 0; tx < NT; ++tx) {
+          const f32x2_t w = *reinterpret_cast<const f32x2_t*>(wsm + (ty * NT + tx) * C + 2 * c2);
+          const int dy = ty - R, dx = tx - R;                  // input = output + (dy, dx)
 #pragma unroll
-        for (int oy = 0; oy < S; ++oy) {
+          for (int oy = 0; oy < S; ++oy) {
 #pragma unroll
-          for (int ox = 0; ox < S; ++ox) {
-            const int iy = oy + dy, ix = ox + dx;
-            if (iy >= 0 && iy < S && ix >= 0 && ix < S) {
-              const uint32_t v = cur[iy * S + ix];
-              a0[oy * S + ox] = fmaf(w.x, __uint_as_float(v << 16), a0[oy * S + ox]);
-              a1[oy * S + ox] = fmaf(w.y, __uint_as_float(v & 0xffff0000u), a1[oy * S + ox]);
+            for (int ox = 0; ox < S; ++ox) {
+              const int iy = oy + dy, ix = ox + dx;
+              if (iy >= 0 && iy < S && ix >= 0 && ix < S) fma_f32x2(acc[oy * S + ox], w, xin[iy * S + ix]);
             }
           }
         }
       }
+#pragma unroll
+      for (int p = 0; p < HW; ++p) { const float2 a = unpack_f32x2(acc[p]); a0[p] = a.x; a1[p] = a.y; }
     }
     // ---- per-pixel channel statistics ------------------------------------------------------------------------------
     const int buf = it & 1;

@@ -19,6 +19,7 @@
 //   warp 1      MMA issuer   : G1_g: D1[g&1] = y . W1_g^T (M128 x N64, K = C);  G2_g: D2[tile&1] += H[g&1] . W2_g^T
 //   warps 2..17 epilogue     : group g&1: tcgen05.ld D1 -> +b1 -> GELU -> bf16 -> H[g&1] (SW128 K-major, what UMMA
 //                              reads); all 16 warps: D2 -> +b2 -> *gamma + res -> bf16 rows (deferred by one chunk)
+#include <stdlib.h>
 #include <string.h>
 
 #include "tc_common.cuh"
@@ -39,10 +40,11 @@ struct Plan2 {
   int nfull = 0, t32 = 0, t16 = 0;   // K blocks: nfull x 64 columns (SW128) [+ 32 columns (SW64)] [+ 16 columns (SW32)]
   int y_bytes = 0, w1_bytes = 0, w2_bytes = 0;
   int ny = 0, n1 = 0, n2 = 0, resident = 0;
-  int off_w1 = 0, off_w2 = 0, off_h = 0, off_bar = 0, off_b1 = 0, total = 0;
+  int off_w1 = 0, off_w2 = 0, off_h = 0, off_stg = 0, off_bar = 0, off_b1 = 0, total = 0;
+  int stg = 0;               // 1: residual / output rows move through a [128 x C] bf16 staging tile with bulk tensor copies
   bool ok = false;
 };
-__host__ __device__ constexpr Plan2 plan2_for(int C);
+__host__ __device__ constexpr Plan2 plan2_for(int C, bool te);
 
 __host__ __device__ constexpr int rup1k(int x) { return (x + 1023) & ~1023; }
 
@@ -51,14 +53,15 @@ __host__ __device__ constexpr bool plan2_try(Plan2& P, int ny, int n1, int n2, i
   P.off_w1 = ny * P.y_bytes;
   P.off_w2 = P.off_w1 + n1 * P.w1_bytes;
   P.off_h = P.off_w2 + n2 * P.w2_bytes;
-  P.off_bar = P.off_h + 2 * kHBytes;
+  P.off_stg = P.off_h + 2 * kHBytes;
+  P.off_bar = P.off_stg + (P.stg ? P.C * 256 : 0);
   P.off_b1 = P.off_bar + 1024;
   P.total = P.off_b1 + 4 * P.C * 4 + 1024 /*alignment slack*/;
   return P.total <= kSmemMax && n1 <= kMaxSlots && n2 <= kMaxSlots;
 }
 
-__host__ __device__ constexpr bool make_plan2(Plan2& P, int C) {
-  P.C = C; P.NJ = (4 * C) / NH;
+__host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te) {
+  P.C = C; P.NJ = (4 * C) / NH; P.stg = te ? 1 : 0;
   P.nfull = C / 64; P.t32 = (C % 64) >= 32 ? 1 : 0; P.t16 = (C % 32) >= 16 ? 1 : 0;
   P.y_bytes = rup1k(FM * C * 2);
   P.w1_bytes = rup1k(NH * C * 2);
@@ -70,9 +73,9 @@ __host__ __device__ constexpr bool make_plan2(Plan2& P, int C) {
   return plan2_try(P, 1, 2, 2, 0);
 }
 
-__host__ __device__ constexpr Plan2 plan2_for(int C) {
+__host__ __device__ constexpr Plan2 plan2_for(int C, bool te) {
   Plan2 P;
-  P.ok = make_plan2(P, C);
+  P.ok = make_plan2(P, C, te);
   return P;
 }
 
@@ -112,16 +115,18 @@ struct Maps2 {
   CUtensorMap y128, y64, y32;      // [M, C]   boxes [128 rows x 64|32|16 cols], swizzle 128|64|32 B
   CUtensorMap a128, a64, a32;      // W1 [4C, C]: boxes [64 rows x 64|32|16 cols]
   CUtensorMap w2;                  // W2 [C, 4C]: box [C rows x 64 cols], swizzle 128 B
+  CUtensorMap r128, r64, r32;      // res [M, C]: boxes [32 rows x 64|32|16 cols] (bulk loads into the staging tile)
+  CUtensorMap o128, o64, o32;      // out [M, C]: same boxes (bulk stores from the staging tile)
 };
 }  // namespace
 
-template <int C>
+template <int C, bool TE>
 __global__ void __launch_bounds__(kThreads2, 1)   // 18 warps -> 5 on two SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
                   __nv_bfloat16* __restrict__ out, int M) {
   using namespace tc;
-  constexpr Plan2 P = plan2_for(C);
+  constexpr Plan2 P = plan2_for(C, TE);
   static_assert(P.ok, "no shared-memory plan for this C");
   constexpr int NJ = P.NJ;
   constexpr int nkb = P.nfull + P.t32 + P.t16;
@@ -145,7 +150,8 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   auto w1_empty = [&](int i) { return bar0 + 8u * (16 + kMaxSlots + i); };
   auto w2_full = [&](int i) { return bar0 + 8u * (16 + 2 * kMaxSlots + i); };
   auto w2_empty = [&](int i) { return bar0 + 8u * (16 + 3 * kMaxSlots + i); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + P.off_bar + 8 * (16 + 4 * kMaxSlots));
+  auto res_bar = [&](int i) { return bar0 + 8u * (16 + 4 * kMaxSlots + i); };      // kEpiWarps2 (staging path only)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + P.off_bar + 8 * (16 + 4 * kMaxSlots + kEpiWarps2));
 
   // warp index made provably warp-uniform so the role branches below are convergent (the single-thread roles then
   // compile to predicated uniform-datapath instructions instead of per-lane serialisation loops)
@@ -164,6 +170,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(w1_full(i), 1); mbar_init(w1_empty(i), 1); mbar_init(w2_full(i), 1); mbar_init(w2_empty(i), 1);
     }
+    for (int i = 0; i < kEpiWarps2; ++i) mbar_init(res_bar(i), 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
@@ -385,6 +392,92 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       }
     };
 
+    // ---- staging path (TE): the warp owns the contiguous D2 column range [c_lo, c_hi) chunks of its 32 rows.  Residual
+    // rows arrive by bulk tensor loads into the warp's slab(s) of the staging tile (issued one hidden chunk ahead), are
+    // updated IN PLACE (thread = row: it reads and rewrites only its own 32 bytes per chunk) and leave by bulk tensor
+    // stores -- no per-thread scattered global access, and nothing for the per-chunk proxy fence (MEMBAR) to wait on.
+    const int ew = warp - 2;
+    const int c_lo = (groups2 * k4) / 4, c_hi = (groups2 * (k4 + 1)) / 4;
+    const uint32_t stg_addr = sbase + P.off_stg + (uint32_t)((q * groups2 + c_lo) * 1024);
+    unsigned char* stg = sal + P.off_stg + (q * groups2 + c_lo) * 1024;
+    uint32_t rph = 0;                        // phase of this warp's residual barrier
+    auto res_issue = [&](int tile) {
+      if (lane == 0 && c_lo < c_hi) {
+        tma_store_wait_read();                             // the previous tile's bulk stores have drained the slabs
+        mbar_expect_tx(res_bar(ew), (uint32_t)((c_hi - c_lo) * 1024));
+        uint32_t off = 0;
+        for (int s0 = c_lo; s0 < c_hi;) {
+          const int left = c_hi - s0;
+          const int w = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+          const CUtensorMap* mp = w == 4 ? &tm.r128 : (w == 2 ? &tm.r64 : &tm.r32);
+          tma_load_2d(stg_addr + off, mp, res_bar(ew), s0 * 16, tile * FM + q * 32);
+          off += (uint32_t)(w * 1024); s0 += w;
+        }
+      }
+      __syncwarp();
+    };
+    auto d2_epilogue_te = [&](int tile, uint32_t tl) {
+      const int tb = (int)(tl & 1u);
+      mbar_wait_spin(d2_full(tb), (tl >> 1) & 1u);
+      tc_fence_after();
+      if (c_lo >= c_hi) {                                  // (cannot happen for C >= 64: every warp owns >= 1 chunk)
+        tc_fence_before(); __syncwarp();
+        if (lane == 0) mbar_arrive(d2_empty(tb));
+        return;
+      }
+      mbar_wait_spin(res_bar(ew), rph); rph ^= 1u;
+      uint32_t off = 0;
+      for (int s0 = c_lo; s0 < c_hi;) {
+        const int left = c_hi - s0;
+        const int w = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+        const int sw = w * 32;
+        const int xr = sw == 128 ? (lane & 7) : (sw == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+        unsigned char* rowp = stg + off + lane * sw;
+        for (int c = 0; c < w; ++c) {
+          const int gi = s0 + c;
+          uint32_t r[16];
+          tmem_ld16(lane_addr + (uint32_t)(kD2Col + tb * C + gi * 16), r);
+          tmem_ld_wait();
+          if (gi + 1 == c_hi) {                            // last D2 read of this warp for this tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d2_empty(tb));
+          }
+          uint4* p0 = reinterpret_cast<uint4*>(rowp + (((2 * c) ^ xr) << 4));
+          uint4* p1 = reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ xr) << 4));
+          const uint4 r0 = *p0, r1 = *p1;
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          const int n = gi * 16;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
+            v[i] = fmaf(g4.x, __uint_as_float(r[i]) + b4.x, bf16_lo(rr[i / 2]));
+            v[i + 1] = fmaf(g4.y, __uint_as_float(r[i + 1]) + b4.y, bf16_hi(rr[i / 2]));
+            v[i + 2] = fmaf(g4.z, __uint_as_float(r[i + 2]) + b4.z, bf16_lo(rr[i / 2 + 1]));
+            v[i + 3] = fmaf(g4.w, __uint_as_float(r[i + 3]) + b4.w, bf16_hi(rr[i / 2 + 1]));
+          }
+          *p0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          *p1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        }
+        off += (uint32_t)(w * 1024); s0 += w;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        uint32_t o2 = 0;
+        for (int s0 = c_lo; s0 < c_hi;) {
+          const int left = c_hi - s0;
+          const int w = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+          const CUtensorMap* mp = w == 4 ? &tm.o128 : (w == 2 ? &tm.o64 : &tm.o32);
+          tma_store_2d(mp, stg_addr + o2, s0 * 16, tile * FM + q * 32);
+          o2 += (uint32_t)(w * 1024); s0 += w;
+        }
+        tma_store_commit();
+      }
+    };
+
     int pend_tl = -1;                       // local tile index whose D2 epilogue this warp still owes
     uint32_t prev_tl = 0xffffffffu;
     for (uint32_t g = (uint32_t)grp; g < total; g += 2) {
@@ -393,7 +486,10 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       if (tl != prev_tl) {
         // first chunk of this warp in a new tile: the previous tile's D2 epilogue is deferred until after this chunk's
         // GELU so its tail latency (last H hand-off -> G2 -> commit) is hidden; fetch its residual rows now
-        if (prev_tl != 0xffffffffu) { pend_tl = (int)prev_tl; prefetch_res(blockIdx.x + pend_tl * gridDim.x); }
+        if (prev_tl != 0xffffffffu) {
+          pend_tl = (int)prev_tl;
+          if (TE) res_issue(blockIdx.x + pend_tl * gridDim.x); else prefetch_res(blockIdx.x + pend_tl * gridDim.x);
+        }
         prev_tl = tl;
       }
       mbar_wait_spin(d1_full(grp), use & 1u);
@@ -425,13 +521,23 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(h_full(grp));
-      if (pend_tl >= 0) { d2_epilogue(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl); pend_tl = -1; }
+      if (pend_tl >= 0) {
+        if (TE) d2_epilogue_te(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl);
+        else d2_epilogue(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl);
+        pend_tl = -1;
+      }
     }
     if (nt > 0) {
       // every group has at least one chunk in every tile (NJ >= 4), so prev_tl is the CTA's last tile here
       const int last = (int)nt - 1;
-      prefetch_res(blockIdx.x + last * gridDim.x);
-      d2_epilogue(blockIdx.x + last * gridDim.x, (uint32_t)last);
+      if (TE) {
+        res_issue(blockIdx.x + last * gridDim.x);
+        d2_epilogue_te(blockIdx.x + last * gridDim.x, (uint32_t)last);
+        if (lane == 0) tma_store_wait_all();              // smem must outlive the last bulk store's reads
+      } else {
+        prefetch_res(blockIdx.x + last * gridDim.x);
+        d2_epilogue(blockIdx.x + last * gridDim.x, (uint32_t)last);
+      }
     }
   }
   tc_fence_before();
@@ -447,11 +553,11 @@ int mlp_fused2_supported(int C) {
   return C % 16 == 0 && C >= 64 && C <= 160;
 }
 
-template <int C>
+template <int C, bool TE>
 static int launch2(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res, void* out,
                    int64_t M, cudaStream_t st) {
-  constexpr Plan2 P = plan2_for(C);
-  auto kern = mlp_fused2_kernel<C>;
+  constexpr Plan2 P = plan2_for(C, TE);
+  auto kern = mlp_fused2_kernel<C, TE>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
@@ -476,14 +582,37 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
     if (int e = make_tmap_bf16_2d_sw(&tm.a32, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 16, 32)) return e;
   }
   if (int e = make_tmap_bf16_2d_sw(&tm.w2, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)C, 64, 128)) return e;
+  // residual / output rows through bulk tensor copies (staging tile) where the shared-memory plan has room for it
+  // without giving up weight look-ahead; BTSB_MLP_EPI=0|1 forces the choice (A/B timing)
+  static const int force = getenv("BTSB_MLP_EPI") ? atoi(getenv("BTSB_MLP_EPI")) : -1;
+  bool te = true;   // measured: 287 -> 253 us at C = 160, 207 -> 193 us at C = 128, neutral at C = 64 / 80 (profiles/r01h)
+  if (force == 0) te = false;
+  if (force == 1) te = true;
+  if (te) {
+    if (int e = make_tmap_bf16_2d_sw(&tm.r128, res, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.r64, res, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.r32, res, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
+    switch (C) {
+      case 64: return launch2<64, true>(tm, b1, b2, gamma, res, out, M, st);
+      case 80: return launch2<80, true>(tm, b1, b2, gamma, res, out, M, st);
+      case 96: return launch2<96, true>(tm, b1, b2, gamma, res, out, M, st);
+      case 112: return launch2<112, true>(tm, b1, b2, gamma, res, out, M, st);
+      case 128: return launch2<128, true>(tm, b1, b2, gamma, res, out, M, st);
+      case 144: return launch2<144, true>(tm, b1, b2, gamma, res, out, M, st);
+      case 160: return launch2<160, true>(tm, b1, b2, gamma, res, out, M, st);
+    }
+  }
   switch (C) {
-    case 64: return launch2<64>(tm, b1, b2, gamma, res, out, M, st);
-    case 80: return launch2<80>(tm, b1, b2, gamma, res, out, M, st);
-    case 96: return launch2<96>(tm, b1, b2, gamma, res, out, M, st);
-    case 112: return launch2<112>(tm, b1, b2, gamma, res, out, M, st);
-    case 128: return launch2<128>(tm, b1, b2, gamma, res, out, M, st);
-    case 144: return launch2<144>(tm, b1, b2, gamma, res, out, M, st);
-    case 160: return launch2<160>(tm, b1, b2, gamma, res, out, M, st);
+    case 64: return launch2<64, false>(tm, b1, b2, gamma, res, out, M, st);
+    case 80: return launch2<80, false>(tm, b1, b2, gamma, res, out, M, st);
+    case 96: return launch2<96, false>(tm, b1, b2, gamma, res, out, M, st);
+    case 112: return launch2<112, false>(tm, b1, b2, gamma, res, out, M, st);
+    case 128: return launch2<128, false>(tm, b1, b2, gamma, res, out, M, st);
+    case 144: return launch2<144, false>(tm, b1, b2, gamma, res, out, M, st);
+    case 160: return launch2<160, false>(tm, b1, b2, gamma, res, out, M, st);
   }
   set_error("mlp_fused: C=%d unsupported", C);
   return BTSB_EINVAL;
