@@ -10,8 +10,9 @@ A "step" is one forward pass of every rank over one micro-batch of B alerts ([B,
 390 MB at B=8192 -> larger than the 126 MB L2, and consecutive steps rotate over distinct resident batches).
 
   value    : alerts/s, inputs already resident in HBM, CUDA events around exactly K steps, max over ranks
-  e2e      : same metric through the public API from pinned HOST buffers: H2D copy of the HWC triplets + metadata,
-             K1 layout kernel, model forward, D2H of the logits -- all inside the timed region
+  e2e      : same metric through the public API (parallel.AlertScorer) from pinned HOST buffers: H2D copy of the HWC
+             triplets + metadata (copy stream, overlapping the previous micro-batch's kernels), K1 layout kernel, model
+             forward, D2H of the logits -- all inside the timed region
   roofline : dominant kernel (largest share of the step) timed per launch with CUDA events in an instrumented
              replay of the same K steps right after the timed region (events perturb launches, so `value`
              comes from the un-instrumented pass; `kernels` lists every kernel family for cross-checking)
@@ -86,47 +87,60 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML is polled from a
+    thread every 5 ms (a default run's timed region is ~0.1 s, too short for `nvidia-smi -lms`); falls back to one
+    nvidia-smi query when pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.sm, self.mask, self.stop_flag, self.t, self.h, self.nv = index, [], 0, False, None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # torch device index -> NVML handle (honours CUDA_VISIBLE_DEVICES through the PCI bus id)
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                        self.h = h
+            self.nv = pynvml
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 9:
-                continue
+        if self.nv is None:
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout.split(",")
+                return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1, "reasons": [],
+                        "note": "pynvml unavailable: one nvidia-smi query after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock query unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max,
+                "samples": len(self.sm), "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -269,13 +283,14 @@ def main():
     # ---- e2e: public API from pinned host buffers, H2D + K1 + forward + D2H inside the timed region --------------
     out_host = torch.empty((B, 1), dtype=torch.float32).pin_memory()
 
+    # the public bulk-scoring call (btsbot_b200.parallel.AlertScorer): pinned host arrays in, logits out; the H2D copy
+    # of micro-batch i+1 runs on a copy stream while the kernels of micro-batch i execute
+    from btsbot_b200.parallel import AlertScorer
+    scorer = AlertScorer(model, return_scores=False)
+
     def e2e_step(i):
-        with torch.no_grad():
-            t = host_trip[i % nres].to(dev, non_blocking=True)
-            m = host_meta[i % nres].to(dev, non_blocking=True)
-            x = btsbot.alert_utils.triplets_to_model_input(t)
-            lg = model(image_input=x, metadata_input=m)
-            out_host.copy_(lg, non_blocking=True)
+        lg = scorer(host_trip[i % nres], host_meta[i % nres])
+        out_host.copy_(lg.view(-1, 1), non_blocking=True)
     for i in range(2):
         e2e_step(i)
     barrier()

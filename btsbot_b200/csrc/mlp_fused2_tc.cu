@@ -42,9 +42,10 @@ struct Plan2 {
   int ny = 0, n1 = 0, n2 = 0, resident = 0;
   int off_w1 = 0, off_w2 = 0, off_h = 0, off_stg = 0, off_bar = 0, off_b1 = 0, total = 0;
   int stg = 0;               // 1: residual / output rows move through a [128 x C] bf16 staging tile with bulk tensor copies
+  int ht = 0;                // 1: the GELU'd hidden chunk H lives in TMEM (A operand of G2 from TMEM), no shared-memory H tiles
   bool ok = false;
 };
-__host__ __device__ constexpr Plan2 plan2_for(int C, bool te);
+__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht);
 
 __host__ __device__ constexpr int rup1k(int x) { return (x + 1023) & ~1023; }
 
@@ -53,15 +54,15 @@ __host__ __device__ constexpr bool plan2_try(Plan2& P, int ny, int n1, int n2, i
   P.off_w1 = ny * P.y_bytes;
   P.off_w2 = P.off_w1 + n1 * P.w1_bytes;
   P.off_h = P.off_w2 + n2 * P.w2_bytes;
-  P.off_stg = P.off_h + 2 * kHBytes;
+  P.off_stg = P.off_h + (P.ht ? 0 : 2 * kHBytes);
   P.off_bar = P.off_stg + (P.stg ? P.C * 256 : 0);
   P.off_b1 = P.off_bar + 1024;
   P.total = P.off_b1 + 4 * P.C * 4 + 1024 /*alignment slack*/;
   return P.total <= kSmemMax && n1 <= kMaxSlots && n2 <= kMaxSlots;
 }
 
-__host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te) {
-  P.C = C; P.NJ = (4 * C) / NH; P.stg = te ? 1 : 0;
+__host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht) {
+  P.C = C; P.NJ = (4 * C) / NH; P.stg = te ? 1 : 0; P.ht = ht ? 1 : 0;
   P.nfull = C / 64; P.t32 = (C % 64) >= 32 ? 1 : 0; P.t16 = (C % 32) >= 16 ? 1 : 0;
   P.y_bytes = rup1k(FM * C * 2);
   P.w1_bytes = rup1k(NH * C * 2);
@@ -73,9 +74,9 @@ __host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te) {
   return plan2_try(P, 1, 2, 2, 0);
 }
 
-__host__ __device__ constexpr Plan2 plan2_for(int C, bool te) {
+__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht) {
   Plan2 P;
-  P.ok = make_plan2(P, C, te);
+  P.ok = make_plan2(P, C, te, ht);
   return P;
 }
 
@@ -111,6 +112,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] . B[smem]^T : A (128 rows x 16 bf16) read from 8 TMEM columns (two K elements per 32-bit column)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 struct Maps2 {
   CUtensorMap y128, y64, y32;      // [M, C]   boxes [128 rows x 64|32|16 cols], swizzle 128|64|32 B
   CUtensorMap a128, a64, a32;      // W1 [4C, C]: boxes [64 rows x 64|32|16 cols]
@@ -120,14 +140,16 @@ struct Maps2 {
 };
 }  // namespace
 
-template <int C, bool TE>
+template <int C, bool TE, bool HT>
 __global__ void __launch_bounds__(kThreads2, 1)   // 18 warps -> 5 on two SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
                   __nv_bfloat16* __restrict__ out, int M) {
   using namespace tc;
-  constexpr Plan2 P = plan2_for(C, TE);
+  constexpr Plan2 P = plan2_for(C, TE, HT);
   static_assert(P.ok, "no shared-memory plan for this C");
+  constexpr int kHCol = kD2Col + 2 * C;                          // TMEM columns of H[0], H[1] (32 each) in HT mode
+  static_assert(!HT || kHCol + 64 <= 512, "TMEM column budget");
   constexpr int NJ = P.NJ;
   constexpr int nkb = P.nfull + P.t32 + P.t16;
   extern __shared__ unsigned char smem_dyn[];
@@ -289,12 +311,19 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
     auto do_g2 = [&]() {
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t ad = smem_desc_sw128(sbase + P.off_h + b2i * kHBytes);
         const uint64_t bd = smem_desc_sw128(sbase + P.off_w2 + s2 * P.w2_bytes);
         const uint32_t dcol = tmem_base + (uint32_t)(kD2Col + tb * C);
+        if (HT) {
+          const uint32_t acol = tmem_base + (uint32_t)(kHCol + b2i * 32);
 #pragma unroll
-        for (int kk = 0; kk < NH / 16; ++kk)
-          umma_bf16(dcol, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc2, (j2 | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < NH / 16; ++kk)
+            umma_bf16_ts(dcol, acol + (uint32_t)(8 * kk), bd + (uint64_t)(2 * kk), idesc2, (j2 | kk) != 0 ? 1u : 0u);
+        } else {
+          const uint64_t ad = smem_desc_sw128(sbase + P.off_h + b2i * kHBytes);
+#pragma unroll
+          for (int kk = 0; kk < NH / 16; ++kk)
+            umma_bf16(dcol, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc2, (j2 | kk) != 0 ? 1u : 0u);
+        }
         umma_commit(h_empty(b2i));
         if (!P.resident) umma_commit(w2_empty(s2));
         if (j2 == NJ - 1) umma_commit(d2_full(tb));
@@ -513,12 +542,20 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         o[i / 2 + 1] = pack_bf16x2(v2, v3);
       }
       mbar_wait_spin(h_empty(grp), (use & 1u) ^ 1u);         // G2 of chunk g-2 has finished reading H[grp]
-      unsigned char* hb = sal + P.off_h + grp * kHBytes;
+      if (HT) {
+        // H never touches shared memory: packed bf16 pairs go straight into the TMEM columns G2 reads its A operand
+        // from (thread = row / TMEM lane, 16 columns = this warp's 32 hidden values)
+        tmem_st16(lane_addr + (uint32_t)(kHCol + grp * 32 + half * 16), o);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
+        unsigned char* hb = sal + P.off_h + grp * kHBytes;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8)
-        *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, half * 32 + c8 * 8)) =
-            make_uint4(o[4 * c8], o[4 * c8 + 1], o[4 * c8 + 2], o[4 * c8 + 3]);
-      fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
+        for (int c8 = 0; c8 < 4; ++c8)
+          *reinterpret_cast<uint4*>(hb + sw128_offset(r_in_tile, half * 32 + c8 * 8)) =
+              make_uint4(o[4 * c8], o[4 * c8 + 1], o[4 * c8 + 2], o[4 * c8 + 3]);
+        fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(h_full(grp));
       if (pend_tl >= 0) {
@@ -553,11 +590,11 @@ int mlp_fused2_supported(int C) {
   return C % 16 == 0 && C >= 64 && C <= 160;
 }
 
-template <int C, bool TE>
+template <int C, bool TE, bool HT>
 static int launch2(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res, void* out,
                    int64_t M, cudaStream_t st) {
-  constexpr Plan2 P = plan2_for(C, TE);
-  auto kern = mlp_fused2_kernel<C, TE>;
+  constexpr Plan2 P = plan2_for(C, TE, HT);
+  auto kern = mlp_fused2_kernel<C, TE, HT>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
@@ -582,37 +619,33 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
     if (int e = make_tmap_bf16_2d_sw(&tm.a32, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 16, 32)) return e;
   }
   if (int e = make_tmap_bf16_2d_sw(&tm.w2, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)C, 64, 128)) return e;
-  // residual / output rows through bulk tensor copies (staging tile) where the shared-memory plan has room for it
-  // without giving up weight look-ahead; BTSB_MLP_EPI=0|1 forces the choice (A/B timing)
-  static const int force = getenv("BTSB_MLP_EPI") ? atoi(getenv("BTSB_MLP_EPI")) : -1;
-  bool te = true;   // measured: 287 -> 253 us at C = 160, 207 -> 193 us at C = 128, neutral at C = 64 / 80 (profiles/r01h)
-  if (force == 0) te = false;
-  if (force == 1) te = true;
-  if (te) {
-    if (int e = make_tmap_bf16_2d_sw(&tm.r128, res, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
-    if (int e = make_tmap_bf16_2d_sw(&tm.r64, res, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
-    if (int e = make_tmap_bf16_2d_sw(&tm.r32, res, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
-    if (int e = make_tmap_bf16_2d_sw(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
-    if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
-    if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
+  // BTSB_MLP_HSMEM=1 keeps the hidden chunk in shared memory (first version of this kernel) for A/B timing
+  static const int hsmem = getenv("BTSB_MLP_HSMEM") ? atoi(getenv("BTSB_MLP_HSMEM")) : 0;
+  if (int e = make_tmap_bf16_2d_sw(&tm.r128, res, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tm.r64, res, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tm.r32, res, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
+  if (hsmem) {
     switch (C) {
-      case 64: return launch2<64, true>(tm, b1, b2, gamma, res, out, M, st);
-      case 80: return launch2<80, true>(tm, b1, b2, gamma, res, out, M, st);
-      case 96: return launch2<96, true>(tm, b1, b2, gamma, res, out, M, st);
-      case 112: return launch2<112, true>(tm, b1, b2, gamma, res, out, M, st);
-      case 128: return launch2<128, true>(tm, b1, b2, gamma, res, out, M, st);
-      case 144: return launch2<144, true>(tm, b1, b2, gamma, res, out, M, st);
-      case 160: return launch2<160, true>(tm, b1, b2, gamma, res, out, M, st);
+      case 64: return launch2<64, true, false>(tm, b1, b2, gamma, res, out, M, st);
+      case 80: return launch2<80, true, false>(tm, b1, b2, gamma, res, out, M, st);
+      case 96: return launch2<96, true, false>(tm, b1, b2, gamma, res, out, M, st);
+      case 112: return launch2<112, true, false>(tm, b1, b2, gamma, res, out, M, st);
+      case 128: return launch2<128, true, false>(tm, b1, b2, gamma, res, out, M, st);
+      case 144: return launch2<144, true, false>(tm, b1, b2, gamma, res, out, M, st);
+      case 160: return launch2<160, true, false>(tm, b1, b2, gamma, res, out, M, st);
     }
   }
   switch (C) {
-    case 64: return launch2<64, false>(tm, b1, b2, gamma, res, out, M, st);
-    case 80: return launch2<80, false>(tm, b1, b2, gamma, res, out, M, st);
-    case 96: return launch2<96, false>(tm, b1, b2, gamma, res, out, M, st);
-    case 112: return launch2<112, false>(tm, b1, b2, gamma, res, out, M, st);
-    case 128: return launch2<128, false>(tm, b1, b2, gamma, res, out, M, st);
-    case 144: return launch2<144, false>(tm, b1, b2, gamma, res, out, M, st);
-    case 160: return launch2<160, false>(tm, b1, b2, gamma, res, out, M, st);
+    case 64: return launch2<64, true, true>(tm, b1, b2, gamma, res, out, M, st);
+    case 80: return launch2<80, true, true>(tm, b1, b2, gamma, res, out, M, st);
+    case 96: return launch2<96, true, true>(tm, b1, b2, gamma, res, out, M, st);
+    case 112: return launch2<112, true, true>(tm, b1, b2, gamma, res, out, M, st);
+    case 128: return launch2<128, true, true>(tm, b1, b2, gamma, res, out, M, st);
+    case 144: return launch2<144, true, true>(tm, b1, b2, gamma, res, out, M, st);
+    case 160: return launch2<160, true, true>(tm, b1, b2, gamma, res, out, M, st);
   }
   set_error("mlp_fused: C=%d unsupported", C);
   return BTSB_EINVAL;

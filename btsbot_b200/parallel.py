@@ -65,7 +65,7 @@ class AlertScorer:
         from . import alert_utils, ops
         self.model, self.crop, self.norm, self.return_scores = model.eval(), crop_to_size, normalize, return_scores
         self._au, self._ops = alert_utils, ops
-        self.multimodal = model._config["model_name"] in ("mm_ConvNeXt", "frozen_fusion")
+        self.multimodal = model._config["model_name"] in ("mm_ConvNeXt", "mm_MaxViT", "frozen_fusion")
         self.meta_only = model._config["model_name"] == "um_nn"
         self.dev = next(model.parameters()).device
         self.copy_stream = torch.cuda.Stream(device=self.dev)
