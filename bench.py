@@ -2,7 +2,7 @@
 """bench.py -- alerts/sec of the multimodal ConvNeXt scoring hot path (BASELINE.json metric) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--precision bf16|fp32]
-                    [--workload c3|c4]
+                    [--workload c3|c4|c5]
 
 Workload (BASELINE.json configs[2], "C3"): bulk scoring of synthetic alerts with mm_ConvNeXt / convnext_nano
 (random-init weights, 25 metadata columns), index-range sharded over ranks with NO collective on the data path.
@@ -20,7 +20,9 @@ A "step" is one forward pass of every rank over one micro-batch of B alerts ([B,
              following inference_example.py:62-91 (batch 64, fp32, eval/no_grad) on a bounded sample
 
 `--workload c4` runs BASELINE.json configs[3] instead (multimodal MaxViT-tiny-rw-224, batch 4096 per GPU per step, bf16);
-the default (and what the driver measures) is C3.
+`--workload c5` runs configs[4]: one TRAINING step (train.py:496-547: zero_grad, forward, BCE-with-logits, backward,
+AdamW) of the multimodal ConvNeXt-nano on 1024 alerts per GPU in mixed precision (tcgen05 bf16 GEMMs), gradients
+all-reduced over NCCL, overlapped with the backward, when N > 1.  The default (and what the driver measures) is C3.
 
 `--impl reference` times that CPU port alone with all host threads (the reference itself cannot run offline:
 timm is not installable).
@@ -55,6 +57,9 @@ WORKLOADS = {
     "c4": dict(model="mm_MaxViT", kind="maxvit_tiny_rw_224.sw_in1k", batch=4096, cpu_sample=64, cpu_batch=64,
                label="C4 multimodal MaxViT-tiny-rw-224 scoring (bilinear 63->224, MBConv, window+grid attention), "
                      "63x63x3 triplet + 25 metadata per alert"),
+    "c5": dict(model="mm_ConvNeXt", kind="convnext_nano.d1h_in1k", batch=1024, cpu_sample=128, cpu_batch=64,
+               label="C5 multimodal ConvNeXt-nano training step (forward + BCE + backward + AdamW, NCCL gradient "
+                     "all-reduce overlapped with backward), 63x63x3 triplet + 25 metadata per alert"),
 }
 
 
@@ -180,12 +185,13 @@ def run_reference(args, rank):
     cfg = synth.canonical_config(wl["model"], wl["kind"])
     sd = synth.make_state_dict(cfg, seed=2)
     threads = os.cpu_count() or 1
-    per_step = 1024 if args.workload == "c3" else 64      # bounded sample of the workload per step
+    per_step = {"c3": 1024, "c4": 64, "c5": 128}[args.workload]      # bounded sample of the workload per step
+    port = cpu_train_port if args.workload == "c5" else cpu_port
     for _ in range(max(1, min(args.warmup, 2))):
-        cpu_port(per_step // 4, cfg, sd, threads)
+        port(per_step // 4, cfg, sd, threads)
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
-        rate, dt = cpu_port(per_step, cfg, sd, threads)
+        rate, dt = port(per_step, cfg, sd, threads)
         t_total += dt
         n_total += per_step
     value = n_total / t_total
@@ -202,6 +208,183 @@ def run_reference(args, rank):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def cpu_train_port(sample_alerts: int, cfg, sd_np, threads: int, batch: int = 64):
+    """train.py:496-547 on the CPU oracle: torch autograd through the functional fp32 forward + torch.optim.AdamW."""
+    from btsbot_b200 import synth
+    from oracle import convnext_oracle as O
+    torch.set_num_threads(threads)
+    sd = {k: v.clone() for k, v in synth.to_torch(sd_np).items()}
+    params = []
+    for k, v in sd.items():
+        if v.is_floating_point() and "running" not in k:
+            v.requires_grad_(True)
+            params.append(v)
+    opt = torch.optim.AdamW(params, lr=1e-4, betas=(0.9, 0.999))
+    n = max(batch, sample_alerts // batch * batch)
+    img = torch.from_numpy(np.ascontiguousarray(synth.make_triplets(n, start=0).transpose(0, 3, 1, 2)))
+    meta = torch.from_numpy(synth.make_metadata(n, start=0))
+    lab = torch.from_numpy(synth.make_labels(n, start=0)).float().unsqueeze(1)
+    cfg = dict(cfg, meta_dropout=0.0, comb_dropout=0.0)         # the oracle's dropout layers are identity
+
+    def one(lo):
+        opt.zero_grad()
+        lg = O.forward_train(sd, cfg, img[lo:lo + batch], meta[lo:lo + batch])
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(lg, lab[lo:lo + batch])
+        loss.backward()
+        opt.step()
+    one(0)                                                      # warm-up
+    t0 = time.perf_counter()
+    for lo in range(0, n, batch):
+        one(lo)
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def run_c5(args, rank, local_rank, world, dev, cfg, sd_np, wl):
+    """BASELINE config C5: one training step per `step`, data parallel over the ranks."""
+    import torch.distributed as dist
+    import btsbot_b200 as btsbot
+    from btsbot_b200 import synth, _lib
+    from btsbot_b200._autograd import BCEWithLogitsLoss, FusedAdamW
+    from btsbot_b200.parallel import DistributedDataParallel
+    B = args.batch
+    model = getattr(btsbot, wl["model"])(cfg)
+    model.load_state_dict(synth.to_torch(sd_np), strict=True)
+    model = model.to(dev).train()
+    ddp = DistributedDataParallel(model, bucket_mb=8.0)
+    opt = FusedAdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    loss_fn = BCEWithLogitsLoss(pos_weight=torch.tensor([1.0]))
+    pool, nres = 1024, 2
+    trip = synth.make_triplets(pool, start=(rank * B) % (1 << 20))
+    meta_pool = synth.make_metadata(pool, start=(rank * B) % (1 << 20))
+    lab_pool = synth.make_labels(pool, start=(rank * B) % (1 << 20)).astype(np.float32)
+    img_pool = torch.from_numpy(np.ascontiguousarray(trip.astype(np.float32).transpose(0, 3, 1, 2)))
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    host, res = [], []
+    for r in range(nres):
+        idx = torch.randint(0, pool, (B,), generator=g)
+        h = (img_pool[idx].contiguous().pin_memory(), torch.from_numpy(meta_pool)[idx].contiguous().pin_memory(),
+             torch.from_numpy(lab_pool)[idx].unsqueeze(1).contiguous().pin_memory())
+        host.append(h)
+        res.append(tuple(t.to(dev) for t in h))
+    torch.cuda.synchronize()
+
+    def train_step(img, meta, lab):
+        ddp.zero_grad()
+        loss = loss_fn(ddp(image_input=img, metadata_input=meta), lab)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step(i):
+        return train_step(*res[i % nres])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e: the step a train.py user runs -- pinned host batch -> device (inside the timed region), step, loss -> host
+    loss_host = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        h = host[i % nres]
+        loss = train_step(*(t.to(dev, non_blocking=True) for t in h))
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    prof = _lib.KernelProfiler()
+    _lib.profiler = prof
+    for i in range(min(args.steps, 5)):
+        step(i)
+    _lib.profiler = None
+    kern = prof.summary()
+    nprof = min(args.steps, 5)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    total = world * B * args.steps
+    tot_ms = sum(v["ms"] for v in kern.values())
+    kernels = {}
+    for name, a in sorted(kern.items(), key=lambda kv: -kv[1]["ms"]):
+        per = a["ms"] / a["launches"]
+        kernels[name] = {"launches_per_step": a["launches"] / nprof, "ms_per_launch": per,
+                         "gbs": a["bytes"] / a["launches"] / (per * 1e-3) / 1e9,
+                         "tflops": a["flops"] / a["launches"] / (per * 1e-3) / 1e12, "share": a["ms"] / tot_ms}
+    # the roofline entry is the tensor-core GEMM family with the largest share (the three GEMMs of every Linear are
+    # 92 % of the step's FLOPs); the element-wise fp32 kernels around them are listed in `kernels`
+    tc_names = [k for k in kernels if k in ("t_gemm_tc", "t_wgrad_tc")]
+    top = tc_names[0] if tc_names else next(iter(kernels))
+    tk = kernels[top]
+    if tc_names:
+        roof = {"kernel": top, "bound": "tensor", "achieved": tk["tflops"], "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                "frac": tk["tflops"] / pk["tf_sust"], "traffic": None,
+                "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "share_of_step": tk["share"],
+                "note": "average over every launch of this family in a step (all layer shapes)"}
+    else:
+        roof = {"kernel": top, "bound": "hbm", "achieved": tk["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                "frac": tk["gbs"] / pk["hbm"], "traffic": None, "peak_source": pk["source"]}
+    roof["kernel_time_sum_ms_per_step"] = tot_ms / nprof
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, dt = cpu_train_port(args.cpu_sample, dict(cfg), sd_np, threads)
+        cpu = {"value": rate, "unit": "alerts/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_sample} synthetic alerts in training steps of 64 ({dt:.1f} s): CPU oracle fp32 + torch "
+                         f"autograd + torch.optim.AdamW, torch {torch.__version__}, {threads} threads"}
+    in_bytes = B * (ALERT_IN_BYTES + 4)
+    line = {
+        "metric": "alerts/sec", "value": total / (ms * 1e-3), "unit": "alerts/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": wl["label"], "model_kind": wl["kind"], "alerts_per_gpu_per_step": B,
+                   "global_batch": world * B, "optimizer": "AdamW (fused kernel)",
+                   "parallelism": f"dp{world}: NCCL all-reduce (avg) of 8 MB gradient buckets on a side stream",
+                   "l2_policy": f"a step touches > 3 GB of activations (L2 126 MB); {nres} resident batches rotated"},
+        "clocks": clocks,
+        "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "alerts/s", "h2d_bytes_per_step": world * in_bytes,
+                "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -227,6 +410,8 @@ def main():
     wl = WORKLOADS[args.workload]
     cfg = dict(synth.canonical_config(wl["model"], wl["kind"]), precision=args.precision)
     sd_np = synth.make_state_dict(cfg, seed=2)
+    if args.workload == "c5":
+        return run_c5(args, rank, local_rank, world, dev, cfg, sd_np, wl)
     model = getattr(btsbot, wl["model"])(cfg)
     model.load_state_dict(synth.to_torch(sd_np), strict=True)
     model = model.to(dev).eval()

@@ -1,4 +1,7 @@
-"""Training-mode forward + hand-written backward of the reference models on the fp32 CUDA kernels (K7).
+"""Training-mode forward + hand-written backward of the reference models on the CUDA kernels (K7): all-fp32
+(``precision="fp32"``, the reference-numerics path) or mixed precision (``precision="bf16"``: the fc1 / fc2 /
+downsample GEMMs -- forward, dgrad and split-K wgrad -- on tcgen05 tensor cores with bf16 operands and fp32
+accumulation, everything else in fp32; the arithmetic torch autocast(bf16) would give train.py).
 
 Replaces, for one step of `btsbot/train.py:496-547`, everything PyTorch autograd + cuDNN/ATen would do between
 ``logits = model(...)`` and ``loss.backward()``: the forward saves the intermediates each backward kernel needs and
@@ -64,6 +67,52 @@ def gemm_tn(a, b):
     L.launch("t_gemm_tn", L.lib().btsb_gemm_f32_strided, _p(a), 1, N, _p(b), K, 1, _p(out), N, K, M, 0, _st(),
              flops=2.0 * M * N * K)
     return out
+
+
+# ---- bf16 tensor-core GEMMs (mixed-precision mode: fp32 residual stream / LayerNorm / element-wise, bf16 operands) ---
+def _ld(M):
+    return (M + 7) // 8 * 8
+
+
+def cast_dual(x, rm=True, t=True, op=0, x2=None, colvec=None, want_colsum=False):
+    """One pass over fp32 ``x`` [M,N]: bf16 row-major copy, bf16 transposed copy [N, ld], optional fused GELU (op 1) /
+    GELU backward (op 2, x = pre-activation, x2 = upstream gradient), column scale and column sums."""
+    M, N = x.shape
+    ld = _ld(M)
+    o_rm = torch.empty((M, N), device=x.device, dtype=torch.bfloat16) if rm else None
+    o_t = torch.empty((N, ld), device=x.device, dtype=torch.bfloat16) if t else None
+    cs = torch.zeros((N,), device=x.device, dtype=torch.float32) if want_colsum else None
+    L.launch("t_cast_dual", L.lib().btsb_cast_dual_bf16, _p(x), _p(x2), _p(colvec), _p(o_rm), _p(o_t), _p(cs), M, N, ld,
+             op, _st(), nbytes=float(x.numel()) * (4 + (4 if x2 is not None else 0) + (2 if rm else 0) + (2 if t else 0)))
+    return o_rm, o_t, cs
+
+
+def tc_gemm(a16, w16, bias=None):
+    """fp32 [M,N] = a16 [M,K] @ w16 [N,K]^T (+ bias) on tcgen05."""
+    M, K = a16.shape
+    N = w16.shape[0]
+    out = torch.empty((M, N), device=a16.device, dtype=torch.float32)
+    L.launch("t_gemm_tc", L.lib().btsb_gemm_bf16_f32out, _p(a16), _p(w16), _p(bias), _p(out), M, N, K, _st(),
+             flops=2.0 * M * N * K, nbytes=2.0 * (M * K + N * K) + 4.0 * M * N)
+    return out
+
+
+def tc_wgrad(at16, bt16, K):
+    """fp32 [Mo,No] = at16 [Mo, ld] (first K columns) @ bt16 [No, ld]^T: contraction over the activation rows."""
+    Mo, ld = at16.shape
+    No = bt16.shape[0]
+    out = torch.zeros((Mo, No), device=at16.device, dtype=torch.float32)
+    L.launch("t_wgrad_tc", L.lib().btsb_gemm_bf16_wgrad, _p(at16), _p(bt16), ld, _p(out), Mo, No, K, _st(),
+             flops=2.0 * Mo * No * K, nbytes=2.0 * K * (Mo + No) + 4.0 * Mo * No)
+    return out
+
+
+def _w16(w2d):
+    """bf16 copies of a weight matrix [N,K]: (row-major [N,K] for the forward, transposed [K,N] for dgrad)."""
+    N, K = w2d.shape
+    assert N % 8 == 0
+    rm, t, _ = cast_dual(w2d.contiguous())
+    return rm, t            # t is [K, ld = N]
 
 
 def colsum(x, y=None):
@@ -254,6 +303,102 @@ def _trunk_bwd(tr, tape, dcur, G):
     G.put(stem_c.bias, colsum(du0))
 
 
+def _trunk_fwd_tc(tr, x):
+    """Mixed-precision twin of :func:`_trunk_fwd`: the fc1 / fc2 / downsample GEMMs run on the tensor cores (bf16
+    operands, fp32 accumulate and fp32 results); the hidden activation gelu(fc1) only ever exists in bf16.  The stem
+    GEMM (K = 48, 0.7 % of the FLOPs) stays on the fp32 kernel."""
+    B, _, H, W = x.shape
+    arch = tr.arch
+    dims = arch["dims"]
+    h, w = (H - 4) // 4 + 1, (W - 4) // 4 + 1
+    c0 = dims[0]
+    patches = _new((B * h * w, 48), x)
+    L.launch("t_im2col", L.lib().btsb_stem_im2col_f32, _p(x), _p(patches), B, H, W, _st())
+    stem_c, stem_n = tr.stem[0], tr.stem[1]
+    u0 = gemm_nt(patches, stem_c.weight.detach().reshape(c0, 48), stem_c.bias.detach())
+    cur = ln_fwd(u0, stem_n.weight.detach(), stem_n.bias.detach())
+    tape = {"B": B, "stem": (patches, u0), "stages": [], "tc": True}
+    for i, stage in enumerate(tr.stages):
+        c = dims[i]
+        st = {"blocks": []}
+        if i > 0:
+            cin = dims[i - 1]
+            ln_m, conv_m = stage.downsample[0], stage.downsample[1]
+            yln = ln_fwd(cur, ln_m.weight.detach(), ln_m.bias.detach())
+            pt = patch2x2(yln, B, h, w, cin, reverse=False)
+            wds = conv_m.weight.detach().permute(0, 2, 3, 1).reshape(c, 4 * cin).contiguous()
+            wds16, wds16t = _w16(wds)
+            pt16, pt16t, _ = cast_dual(pt)
+            st["down"] = (cur, pt16t, wds16t, h, w)
+            h, w = (h - 2) // 2 + 1, (w - 2) // 2 + 1
+            cur = tc_gemm(pt16, wds16, conv_m.bias.detach())
+        for blk in stage.blocks:
+            w49 = blk.conv_dw.weight.detach().reshape(c, 49).t().contiguous()
+            u = dwconv(cur, w49, blk.conv_dw.bias.detach(), B, h, w)
+            y = ln_fwd(u, blk.norm.weight.detach(), blk.norm.bias.detach())
+            w1_16, w1_16t = _w16(blk.mlp.fc1.weight.detach().reshape(4 * c, c))
+            w2_16, w2_16t = _w16(blk.mlp.fc2.weight.detach().reshape(c, 4 * c))
+            y16, y16t, _ = cast_dual(y)
+            hp = tc_gemm(y16, w1_16, blk.mlp.fc1.bias.detach())
+            hh16, hh16t, _ = cast_dual(hp, op=1)                         # gelu fused into the cast
+            v = tc_gemm(hh16, w2_16, blk.mlp.fc2.bias.detach())
+            out = colscale(v, blk.gamma.detach(), res=cur)
+            st["blocks"].append((cur, u, y16t, hp, hh16t, v, w49, w1_16t, w2_16t, h, w))
+            cur = out
+        tape["stages"].append(st)
+    return cur, h, w, tape
+
+
+def _trunk_bwd_tc(tr, tape, dcur, G):
+    B = tape["B"]
+    dims = tr.arch["dims"]
+    for i in reversed(range(len(tr.stages))):
+        stage, st, c = tr.stages[i], tape["stages"][i], dims[i]
+        ones = torch.ones((c,), device=dcur.device, dtype=torch.float32)
+        for blk, saved in zip(reversed(list(stage.blocks)), reversed(st["blocks"])):
+            xin, u, y16t, hp, hh16t, v, w49, w1_16t, w2_16t, h, w = saved
+            M = dcur.shape[0]
+            G.put(blk.gamma, colsum(dcur, v))
+            # dv = gamma * dcur: bf16 copies + its column sums (= d fc2.bias) in one pass, never stored in fp32
+            dv16, dv16t, db2 = cast_dual(dcur, colvec=blk.gamma.detach(), want_colsum=True)
+            G.put(blk.mlp.fc2.weight, tc_wgrad(hh16t, dv16t, M).t().contiguous())      # [4c, c]^T -> [c, 4c]
+            G.put(blk.mlp.fc2.bias, db2)
+            dhh = tc_gemm(dv16, w2_16t)                                                  # [M, 4c]
+            dhp16, dhp16t, db1 = cast_dual(hp, op=2, x2=dhh, want_colsum=True)           # dhh * gelu'(hp)
+            G.put(blk.mlp.fc1.weight, tc_wgrad(dhp16t, y16t, M))                         # [4c, c]
+            G.put(blk.mlp.fc1.bias, db1)
+            dy = tc_gemm(dhp16, w1_16t)                                                  # [M, c]
+            du, dlw, dlb = ln_bwd(u, blk.norm.weight.detach(), dy)
+            G.put(blk.norm.weight, dlw)
+            G.put(blk.norm.bias, dlb)
+            dw49, dbias = dwconv_wgrad(xin, du, B, h, w)
+            G.put(blk.conv_dw.weight, dw49.t().contiguous())
+            G.put(blk.conv_dw.bias, dbias)
+            dconv = dwconv(du, w49, None, B, h, w, flip=1)
+            dcur = colscale(dconv, ones, res=dcur)
+        if i > 0:
+            xin, pt16t, wds16t, h, w = st["down"]
+            cin = dims[i - 1]
+            ln_m, conv_m = stage.downsample[0], stage.downsample[1]
+            Mo = dcur.shape[0]
+            d16, d16t, dbd = cast_dual(dcur, want_colsum=True)
+            dwds = tc_wgrad(pt16t, d16t, Mo).t().contiguous()       # [4cin, c]^T -> [c, (dy,dx,cin)]
+            G.put(conv_m.weight, dwds.view(c, 2, 2, cin).permute(0, 3, 1, 2).contiguous())
+            G.put(conv_m.bias, dbd)
+            dpt = tc_gemm(d16, wds16t)                               # [Mo, 4cin]
+            dyln = patch2x2(dpt, B, h, w, cin, reverse=True)
+            dcur, dlw, dlb = ln_bwd(xin, ln_m.weight.detach(), dyln)
+            G.put(ln_m.weight, dlw)
+            G.put(ln_m.bias, dlb)
+    patches, u0 = tape["stem"]
+    stem_c, stem_n = tr.stem[0], tr.stem[1]
+    du0, dlw, dlb = ln_bwd(u0, stem_n.weight.detach(), dcur)
+    G.put(stem_n.weight, dlw)
+    G.put(stem_n.bias, dlb)
+    G.put(stem_c.weight, gemm_tn(du0, patches))
+    G.put(stem_c.bias, colsum(du0))
+
+
 # ---- dense stacks (metadata branch, heads) -------------------------------------------------------------------------
 class _Dense:
     """Sequential of Linear / act / Dropout / BatchNorm1d modules executed with the training kernels."""
@@ -357,7 +502,8 @@ class _ModelFn(torch.autograd.Function):
             B = image.shape[0]
             train_trunk = _needs(*tr.parameters())
             if train_trunk:
-                rows, h, w, tape = _trunk_fwd(tr, image)
+                tc = getattr(model, "_precision", "fp32") == "bf16"
+                rows, h, w, tape = (_trunk_fwd_tc if tc else _trunk_fwd)(tr, image)
                 ctx.trunk_tape = (tape, h, w)
                 if pool_ln is not None:
                     pooled = pool(rows, B, h * w, rows.shape[1], reverse=False)
@@ -416,14 +562,15 @@ class _ModelFn(torch.autograd.Function):
                 G.put(pool_ln.weight, dlw)
                 G.put(pool_ln.bias, dlb)
                 dfeat = pool(dpooled, tape["B"], h * w, dpooled.shape[1], reverse=True)
-            _trunk_bwd(tr, tape, dfeat, G)
+            (_trunk_bwd_tc if tape.get("tc") else _trunk_bwd)(tr, tape, dfeat, G)
         if G.sink is not None:
             G.sink.flush()
         return None, None, None, None
 
 
 def training_forward(model, image_input=None, metadata_input=None):
-    """Called by the model classes when ``model.training`` and grad mode is on (fp32 kernels)."""
+    """Called by the model classes when ``model.training`` and grad mode is on (fp32 kernels; tensor-core GEMMs when
+    the model's precision is ``"bf16"``)."""
     anchor = next((p for p in model.parameters() if p.requires_grad), None)
     if anchor is None:
         return model.scorer()(image_input=image_input, metadata_input=metadata_input)

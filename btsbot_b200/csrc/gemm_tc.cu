@@ -41,13 +41,17 @@ struct OutMaps {          // out [M, N] bf16: boxes of 32 rows x 64 | 32 | 16 co
 };
 
 constexpr int EPI_LN = 100;   // internal: out = LayerNorm(acc + bias) * gamma(ln_w) + aux(ln_b), whole rows per thread
+// training GEMMs (train_tc.cu): bf16 operands, fp32 results written / accumulated straight from the TMEM registers
+constexpr int EPI_F32OUT = 101;   // out32[M,N] = acc (+ bias)                      -- forward Linear / dgrad
+constexpr int EPI_WGRAD = 102;    // out32[M,N] += acc over a K split (red.global)  -- wgrad, K = the huge row dimension
 
 template <int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ OutMaps tmO,
                const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ aux,
-               const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out, int M, int N, int K, int BN, int dbg) {
+               const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out, int M, int N, int K, int BN, int dbg,
+               float* __restrict__ out32 = nullptr, int splits = 1) {
   using namespace tc;
   // LN mode: rows must stay in one thread, so 4 warps (one per TMEM lane quarter) own a whole tile; the 16 epilogue
   // warps form 4 such groups working on 4 accumulator stages of 128 columns (BN = N <= 128).
@@ -74,12 +78,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + BK - 1) / BK;
+  // split-K (wgrad only, splits == 1 otherwise): work item w = (tile, split) covers k-blocks [kb0, kb1) of its tile
+  const int kb_per = (k_blocks + splits - 1) / splits;
+  const int num_work = num_tiles * splits;
 
   // per-column vectors -> shared memory (the epilogue re-reads them for every tile; a global load per 16-column chunk
   // was the top stall of the GELU epilogue: profiles/r01c)
   float* bias_s = reinterpret_cast<float*>(smem_al + kOffVec);
   float* gamma_s = bias_s + kMaxNBias;
-  for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = __ldg(bias + i);
+  for (int i = threadIdx.x; i < N; i += kThreads) bias_s[i] = bias ? __ldg(bias + i) : 0.f;
   const bool gamma_staged = N <= kMaxNGamma;
   if (EPI == BTSB_EPI_SCALE_RES && gamma_staged)
     for (int i = threadIdx.x; i < N; i += kThreads) gamma_s[i] = __ldg(gamma + i);
@@ -106,9 +113,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     const uint32_t tx_bytes = (uint32_t)(BM + BN) * BK * 2;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int wk = blockIdx.x; wk < num_work; wk += gridDim.x) {
+      const int tile = wk / splits, kb0 = (wk - tile * splits) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait_spin(empty_bar(stage), phase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(full_bar(stage), tx_bytes);
@@ -125,29 +133,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
     const uint32_t idesc = idesc_bf16_f32(BM, BN);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int wk = blockIdx.x; wk < num_work; wk += gridDim.x) {
+      const int kb0 = (wk % splits) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait_spin(tempty_bar(as), aphase ^ 1u);     // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * kAccCols);
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait_spin(full_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * kStageBytes;
           const uint64_t adesc = smem_desc_sw128(sa);
           const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
-          const int kmax = min(BK, K - kb * BK) / 16;    // K tail: TMA zero-fills, but skip the useless MMAs
+          const int kmax = (min(BK, K - kb * BK) + 15) / 16;   // K tail: TMA zero-fills, but skip the useless MMAs
           if (kmax == 4) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
           } else {
             for (int kk = 0; kk < kmax; ++kk)
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (kb | kk) != 0 ? 1u : 0u);
+              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));                  // frees this smem stage when the MMAs retire
-          if (kb == k_blocks - 1) umma_commit(tfull_bar(as));   // accumulator complete -> epilogue
+          if (kb == kb1 - 1) umma_commit(tfull_bar(as));        // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -240,7 +249,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c_lo = (chunks * part) / kParts;
     const int c_hi = (chunks * (part + 1)) / kParts;
     int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    for (int wk = blockIdx.x; wk < num_work; wk += gridDim.x, ++lt) {
+      const int tile = wk / splits;
       const int as = lt & 1;
       const uint32_t aphase = (uint32_t)(lt >> 1) & 1u;
       const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
@@ -248,6 +258,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccCols);
+      if (EPI == EPI_F32OUT || EPI == EPI_WGRAD) {
+        // fp32 results leave straight from the TMEM registers: 64 contiguous bytes per thread and chunk (F32OUT), or
+        // 16 reductions into the small [N_out, K_in] weight-gradient matrix (WGRAD; ~1e6 red ops per GEMM in total)
+        for (int ch = c_lo; ch < c_hi; ++ch) {
+          uint32_t r[16];
+          tmem_ld16(taddr + (uint32_t)(ch * 16), r);
+          tmem_ld_wait();
+          const int n = n0 + ch * 16;
+          if (row < M) {
+            float* op = out32 + (size_t)row * N + n;
+            if (EPI == EPI_WGRAD) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) atomicAdd(op + i, __uint_as_float(r[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + i);
+                *reinterpret_cast<float4*>(op + i) =
+                    make_float4(__uint_as_float(r[i]) + b4.x, __uint_as_float(r[i + 1]) + b4.y,
+                                __uint_as_float(r[i + 2]) + b4.z, __uint_as_float(r[i + 3]) + b4.w);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        continue;
+      }
       if (dbg & 1) {                                    // timing experiment: main loop only, accumulator released unread
         tc_fence_before();
         __syncwarp();
@@ -397,16 +436,17 @@ static EncodeTiledFn get_encoder() {
 
 // 2-D bf16 row-major [rows, cols] tensor map with a [box_rows x box_cols] box whose rows are exactly one swizzle span
 // (box_cols * 2 == swizzle_bytes in {128, 64, 32})
-int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                         uint32_t box_cols, int swizzle_bytes) {
+int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                            uint32_t box_cols, int swizzle_bytes, uint64_t pitch_elems) {
   EncodeTiledFn enc = get_encoder();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return BTSB_ECUDA; }
-  BTSB_REQUIRE(((uintptr_t)base % 16) == 0 && (cols * 2) % 16 == 0, "tensor map: base/pitch must be 16-byte aligned");
+  BTSB_REQUIRE(((uintptr_t)base % 16) == 0 && (pitch_elems * 2) % 16 == 0 && pitch_elems >= cols,
+               "tensor map: base/pitch must be 16-byte aligned");
   BTSB_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u not in [1,256]", box_rows);
   BTSB_REQUIRE((int)box_cols * 2 == swizzle_bytes && (swizzle_bytes == 128 || swizzle_bytes == 64 || swizzle_bytes == 32),
                "tensor map: box of %u columns does not match a %d-byte swizzle", box_cols, swizzle_bytes);
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * 2};
+  const cuuint64_t strides[1] = {pitch_elems * 2};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -416,6 +456,11 @@ int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return BTSB_ECUDA; }
   return BTSB_OK;
+}
+
+int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         uint32_t box_cols, int swizzle_bytes) {
+  return make_tmap_bf16_2d_pitch(out, base, rows, cols, box_rows, box_cols, swizzle_bytes, cols);
 }
 
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
@@ -478,6 +523,65 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
   else
     gemm_tc_kernel<BTSB_EPI_SCALE_RES><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, gamma, nullptr, r, o, (int)M, N, K, BN, dbg);
   return launch_done("gemm_bf16");
+}
+
+
+// ---- training GEMMs (bf16 operands on the tensor cores, fp32 results) ---------------------------------------------
+static int train_attrs() {
+  static bool done = false;
+  if (!done) {
+    BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+    BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+    done = true;
+  }
+  return BTSB_OK;
+}
+
+// out32[M,N] = A[M,K] . Wt[N,K]^T (+ bias)
+int gemm_bf16_f32out(const void* A, const void* Wt, const float* bias, float* out, int64_t M, int N, int K, cudaStream_t st) {
+  BTSB_REQUIRE(N % 16 == 0 && K % 8 == 0, "gemm bf16->f32: N=%d must be a multiple of 16 and K=%d of 8", N, K);
+  BTSB_REQUIRE(M < (1ll << 31) && N <= kMaxNBias, "gemm bf16->f32: M too large or N=%d > %d", N, kMaxNBias);
+  BTSB_REQUIRE(((uintptr_t)out % 16) == 0 && (!bias || ((uintptr_t)bias % 16) == 0), "gemm bf16->f32: out/bias must be 16-byte aligned");
+  if (int e = train_attrs()) return e;
+  const int BN = pick_bn(N);
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM)) return e;
+  if (int e = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint32_t)BN)) return e;
+  OutMaps tmO;
+  memset(&tmO, 0, sizeof(tmO));
+  const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = N / BN;
+  const int grid = min(m_tiles * n_tiles, num_sms());
+  gemm_tc_kernel<EPI_F32OUT><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, nullptr, nullptr, nullptr, nullptr,
+                                                                 (int)M, N, K, BN, 0, out, 1);
+  return launch_done("gemm_bf16_f32out");
+}
+
+// out32[M,N] += At[M,K] . Bt[N,K]^T with K (the row count of the activations, huge) split over the SMs; At / Bt are the
+// transposed bf16 copies written by cast_dual (row pitch `ld` elements, ld % 8 == 0, columns >= K are never read:
+// the tensor maps stop at K and TMA zero-fills the tail of the last k-block)
+int gemm_bf16_wgrad(const void* At, const void* Bt, int64_t ld, float* out, int M, int N, int64_t K, cudaStream_t st) {
+  BTSB_REQUIRE(N % 16 == 0 && ld % 8 == 0 && ld >= K, "wgrad: N=%d must be a multiple of 16, ld=%lld of 8 and >= K", N, (long long)ld);
+  BTSB_REQUIRE(K < (1ll << 31) && K >= 1 && M >= 1, "wgrad: bad shape");
+  BTSB_REQUIRE(((uintptr_t)out % 16) == 0, "wgrad: out must be 16-byte aligned");
+  if (int e = train_attrs()) return e;
+  const int BN = pick_bn(N);
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap_bf16_2d_pitch(&tmA, At, (uint64_t)M, (uint64_t)K, BM, BK, 128, (uint64_t)ld)) return e;
+  if (int e = make_tmap_bf16_2d_pitch(&tmB, Bt, (uint64_t)N, (uint64_t)K, (uint32_t)BN, BK, 128, (uint64_t)ld)) return e;
+  OutMaps tmO;
+  memset(&tmO, 0, sizeof(tmO));
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int k_blocks = (int)((K + BK - 1) / BK);
+  int splits = (num_sms() + tiles - 1) / tiles;
+  if (splits > k_blocks) splits = k_blocks;
+  if (splits < 1) splits = 1;
+  const int kb_per = (k_blocks + splits - 1) / splits;
+  splits = (k_blocks + kb_per - 1) / kb_per;               // no empty split: every work item commits its accumulator
+  const int grid = min(tiles * splits, num_sms());
+  gemm_tc_kernel<EPI_WGRAD><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                M, N, (int)K, BN, 0, out, splits);
+  return launch_done("gemm_bf16_wgrad");
 }
 
 int gemm_f32(const float* A, const float* Wt, const float* bias, const float* gamma, const float* res, float* out,
@@ -552,6 +656,24 @@ extern "C" int btsb_stem_im2col_bf16(const float* x, void* patches, int64_t B, i
   if (grid > 148 * 32) grid = 148 * 32;
   stem_im2col_bf16_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)patches, B, H, W, ho, wo);
   return launch_done("im2col_bf16");
+}
+
+
+extern "C" int btsb_gemm_bf16_f32out(const void* A, const void* Wt, const float* bias, float* out, int64_t M, int N, int K,
+                                     void* stream) {
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(M >= 0 && N >= 1 && K >= 1, "gemm bf16->f32: bad shape");
+  if (M == 0) return BTSB_OK;
+  BTSB_REQUIRE(A && Wt && out, "gemm bf16->f32: null pointer");
+  return gemm_bf16_f32out(A, Wt, bias, out, M, N, K, (cudaStream_t)stream);
+}
+
+extern "C" int btsb_gemm_bf16_wgrad(const void* At, const void* Bt, int64_t ld, float* out, int M, int N, int64_t K,
+                                    void* stream) {
+  if (int e = check_device()) return e;
+  if (K == 0) return BTSB_OK;
+  BTSB_REQUIRE(At && Bt && out, "wgrad: null pointer");
+  return gemm_bf16_wgrad(At, Bt, ld, out, M, N, K, (cudaStream_t)stream);
 }
 
 extern "C" int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res,

@@ -1,0 +1,114 @@
+// K7 (bf16 mode): operand preparation for the tensor-core training GEMMs of gemm_tc.cu.
+//
+// The mixed-precision training step (what torch autocast(bf16) does to btsbot/train.py:496-547) keeps the residual
+// stream, LayerNorm and the element-wise backward in fp32 and runs the three GEMMs of every Linear / 1x1 conv
+// (forward, dgrad, wgrad -- 92 % of the FLOPs) on tcgen05 with bf16 operands and fp32 accumulation.  The wgrad GEMM
+// contracts over the ROW dimension of the activations (B*H*W, up to ~2 M), so it wants both operands "transposed":
+// one pass over the fp32 tensor therefore emits
+//     rm [M, N]  bf16   (A operand of the forward / dgrad GEMM)
+//     t  [N, ld] bf16   (operand of the wgrad GEMM, ld = M rounded up to 8 so that the TMA row pitch is 16-byte aligned)
+// with the element-wise op that would otherwise be its own kernel folded into the load:
+//     OP 0: v = in                         OP 1: v = gelu(in)                (hidden activation, never stored in fp32)
+//     OP 2: v = in2 * gelu'(in)            (in = saved pre-activation, in2 = upstream gradient)
+// then v *= colvec[n] (layer-scale backward) and colsum[n] += sum_m v (bias gradients) when those pointers are given.
+#include "common.cuh"
+
+namespace btsb {
+namespace {
+
+__device__ __forceinline__ float gelu_grad_erf(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+constexpr int TM = 64, TN = 64;
+
+template <int OP>
+__global__ void __launch_bounds__(256)
+cast_dual_kernel(const float* __restrict__ in, const float* __restrict__ in2, const float* __restrict__ colvec,
+                 __nv_bfloat16* __restrict__ rm, __nv_bfloat16* __restrict__ t, float* __restrict__ colsum, int64_t M, int N,
+                 int64_t ld) {
+  __shared__ float tile[TN][TM + 1];        // [n][m]
+  __shared__ float red[8][TN];
+  const int64_t m0 = (int64_t)blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = n0 + 2 * tx;
+  const bool ncol = n < N;                  // N is even: n + 1 < N as well
+  float g0 = 1.f, g1 = 1.f;
+  if (colvec && ncol) { g0 = __ldg(colvec + n); g1 = __ldg(colvec + n + 1); }
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < TM / 8; ++i) {
+    const int m = ty + 8 * i;
+    const int64_t gm = m0 + m;
+    float2 v = make_float2(0.f, 0.f);
+    if (gm < M && ncol) {
+      v = *reinterpret_cast<const float2*>(in + gm * N + n);
+      if (OP == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); }
+      if (OP == 2) {
+        const float2 d = *reinterpret_cast<const float2*>(in2 + gm * N + n);
+        v.x = d.x * gelu_grad_erf(v.x); v.y = d.y * gelu_grad_erf(v.y);
+      }
+      v.x *= g0; v.y *= g1;
+      if (rm) *reinterpret_cast<uint32_t*>(rm + gm * N + n) = pack2(v.x, v.y);
+    }
+    s0 += v.x; s1 += v.y;
+    tile[2 * tx][m] = v.x;
+    tile[2 * tx + 1][m] = v.y;
+  }
+  if (colsum) { red[ty][2 * tx] = s0; red[ty][2 * tx + 1] = s1; }
+  __syncthreads();
+  if (colsum && threadIdx.x < TN && n0 + (int)threadIdx.x < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    atomicAdd(colsum + n0 + threadIdx.x, s);
+  }
+  if (t) {
+    const int64_t gm = m0 + 2 * tx;         // ld is even and >= M rounded up to 8: the pair never leaves its row
+#pragma unroll
+    for (int i = 0; i < TN / 8; ++i) {
+      const int nn = ty + 8 * i;
+      const int gn = n0 + nn;
+      if (gn < N && gm < M) {
+        const float a = tile[nn][2 * tx];
+        const float b = gm + 1 < M ? tile[nn][2 * tx + 1] : 0.f;
+        *reinterpret_cast<uint32_t*>(t + (int64_t)gn * ld + gm) = pack2(a, b);
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace btsb
+
+using namespace btsb;
+
+extern "C" int btsb_cast_dual_bf16(const float* in, const float* in2, const float* colvec, void* out_rm, void* out_t,
+                                   float* colsum, int64_t M, int N, int64_t ld, int op, void* stream) {
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(M >= 0 && N >= 2 && N % 2 == 0, "cast_dual: N=%d must be even", N);
+  if (M == 0) return BTSB_OK;
+  BTSB_REQUIRE(in && (out_rm || out_t || colsum), "cast_dual: null pointer");
+  BTSB_REQUIRE(op >= 0 && op <= 2 && (op != 2 || in2), "cast_dual: bad op %d", op);
+  BTSB_REQUIRE(!out_t || (ld % 8 == 0 && ld >= M), "cast_dual: ld=%lld must be a multiple of 8 and >= M", (long long)ld);
+  BTSB_REQUIRE(((uintptr_t)in % 8) == 0 && (!in2 || ((uintptr_t)in2 % 8) == 0) && ((uintptr_t)out_rm % 4) == 0 &&
+                   ((uintptr_t)out_t % 4) == 0, "cast_dual: misaligned pointer");
+  const int64_t gx = (M + TM - 1) / TM;
+  BTSB_REQUIRE(gx < (1ll << 31) && (N + TN - 1) / TN <= 65535, "cast_dual: shape too large");
+  dim3 grid((unsigned)gx, (unsigned)((N + TN - 1) / TN));
+  __nv_bfloat16* rm = (__nv_bfloat16*)out_rm;
+  __nv_bfloat16* t = (__nv_bfloat16*)out_t;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op == 0) cast_dual_kernel<0><<<grid, 256, 0, st>>>(in, in2, colvec, rm, t, colsum, M, N, ld);
+  else if (op == 1) cast_dual_kernel<1><<<grid, 256, 0, st>>>(in, in2, colvec, rm, t, colsum, M, N, ld);
+  else cast_dual_kernel<2><<<grid, 256, 0, st>>>(in, in2, colvec, rm, t, colsum, M, N, ld);
+  return launch_done("cast_dual_bf16");
+}

@@ -213,6 +213,24 @@ int btsb_bce_logits_f32(const float* logits, const float* labels, float pos_weig
 int btsb_adamw_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float wd, int64_t step, float grad_scale, void* stream);
 
+/* ---- K7 on tensor cores (bf16 mode of the training step; what autocast(bf16) + cuBLAS do under train.py:496-547).
+ * The three GEMMs of every Linear / 1x1 conv run on tcgen05 with bf16 operands and fp32 accumulation; results are
+ * fp32 so that the residual stream, LayerNorm and the element-wise backward stay in fp32.
+ * cast_dual_bf16: one pass over a fp32 [M,N] tensor writes the row-major bf16 copy out_rm [M,N] (forward / dgrad
+ *   operand) and/or the transposed copy out_t [N,ld] (wgrad operand; ld % 8 == 0, ld >= M), folding in
+ *   op 0: v = in;  op 1: v = gelu(in);  op 2: v = in2 * gelu'(in);  then v *= colvec[n] (if colvec) and
+ *   colsum[n] += sum_m v (if colsum; bias / layer-scale gradients).  N even.
+ * gemm_bf16_f32out: out[M,N] fp32 = A[M,K] . Wt[N,K]^T (+ bias[N] if not NULL); N % 16 == 0, K % 8 == 0.
+ * gemm_bf16_wgrad:  out[M,N] fp32 += At[M,K] . Bt[N,K]^T where K is the (huge) activation row count and At / Bt are
+ *   transposed copies with row pitch ld; K is split over the SMs and partial tiles are reduced with red.global.add
+ *   (the caller zeroes `out`; summation order, hence the last fp32 bits, varies run to run).  N % 16 == 0. */
+int btsb_cast_dual_bf16(const float* in, const float* in2, const float* colvec, void* out_rm, void* out_t,
+                        float* colsum, int64_t M, int N, int64_t ld, int op, void* stream);
+int btsb_gemm_bf16_f32out(const void* A, const void* Wt, const float* bias, float* out, int64_t M, int N, int K,
+                          void* stream);
+int btsb_gemm_bf16_wgrad(const void* At, const void* Bt, int64_t ld, float* out, int M, int N, int64_t K,
+                         void* stream);
+
 /* ---- MaxViT (timm maxvit_tiny_rw_224 behind btsbot/architectures.py:25-101) -------------
  * The 1x1 convolutions / Linear layers of the MBConv, attention and MLP blocks are btsb_gemm_fwd calls (tcgen05 in
  * bf16) with BatchNorm folded into the weights; the kernels below are everything between those GEMMs.  Activations

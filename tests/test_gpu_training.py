@@ -163,3 +163,123 @@ def test_dropout_statistics_and_eval_mode(cuda_dev):
     model.eval()
     b = model(image_input=img.to(cuda_dev), metadata_input=meta.to(cuda_dev))
     assert torch.equal(a, b) and not a.requires_grad
+
+
+# ---- mixed-precision (bf16 tensor-core GEMM) training step -----------------------------------------------------------
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("M,N", [(1350, 80), (6, 512), (257, 320), (64, 64)])
+def test_cast_dual_ops(cuda_dev, M, N):
+    from btsbot_b200 import _autograd as A
+    g = torch.Generator().manual_seed(M * 7 + N)
+    x = (torch.randn(M, N, generator=g) * 1.5).to(cuda_dev)
+    d = torch.randn(M, N, generator=g).to(cuda_dev)
+    vec = torch.randn(N, generator=g).to(cuda_dev)
+    gelu = torch.nn.functional.gelu
+    xr = x.clone().requires_grad_(True)
+    gelu(xr).backward(d)
+    cases = [(0, None, None, x), (0, None, vec, x * vec), (1, None, None, gelu(x)), (2, d, None, xr.grad)]
+    for op, x2, cv, want in cases:
+        rm, t, cs = A.cast_dual(x, op=op, x2=x2, colvec=cv, want_colsum=True)
+        torch.cuda.synchronize()
+        ld = t.shape[1]
+        assert ld % 8 == 0 and ld >= M and rm.shape == (M, N) and t.shape[0] == N
+        # values: bf16 rounding of the fp32 result (erf / exp differ from torch's in the last fp32 bits -> 1 bf16 ulp)
+        assert (rm.float() - want).abs().max() <= 2 ** -7 * want.abs().max() + 1e-6, op
+        assert torch.equal(t[:, :M].t().contiguous(), rm), op       # the transposed copy holds the same bits
+        assert (cs - want.sum(0)).abs().max() <= 1e-4 * max(1.0, want.abs().sum(0).max().item()), op
+
+
+@pytest.mark.parametrize("M,N,K", [(1350, 320, 80), (300, 80, 320), (6, 2048, 512), (128, 640, 1280), (5000, 160, 640)])
+def test_tc_training_gemms_match_fp32_on_bf16_operands(cuda_dev, M, N, K):
+    """forward/dgrad GEMM (bf16 operands -> fp32) and the split-K wgrad GEMM against torch fp32 matmul on the same
+    bf16-rounded operands: only the fp32 summation order differs."""
+    from btsbot_b200 import _autograd as A
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda_dev)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).to(cuda_dev)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    dy = torch.randn(M, N, generator=g).to(cuda_dev)
+    a16, a16t, _ = A.cast_dual(a)
+    w16, w16t = A._w16(w)
+    out = A.tc_gemm(a16, w16, bias)
+    ref = _bf(a) @ _bf(w).t() + bias
+    assert (out - ref).abs().max() <= 2e-4 * ref.abs().max(), "forward"
+    out_nb = A.tc_gemm(a16, w16)
+    assert (out_nb - (ref - bias)).abs().max() <= 2e-4 * ref.abs().max(), "forward without bias"
+    dy16, dy16t, _ = A.cast_dual(dy)
+    dx = A.tc_gemm(dy16, w16t)                       # [M,N] @ [N,K]
+    ref_dx = _bf(dy) @ _bf(w)
+    assert (dx - ref_dx).abs().max() <= 2e-4 * ref_dx.abs().max(), "dgrad"
+    dw = A.tc_wgrad(dy16t, a16t, M)                  # [N,K] = dy^T a
+    ref_dw = _bf(dy).t() @ _bf(a)
+    assert (dw - ref_dw).abs().max() <= 2e-4 * ref_dw.abs().max() + 1e-5, "wgrad"
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("case", ["mm_pico", "mm_nano_LS", "img_pico"])
+def test_bf16_training_step_close_to_fp32_autograd(cuda_dev, case):
+    """precision="bf16": GEMMs on tcgen05 with bf16 operands.  Logits within the north-star bf16 bar (2e-2) of the fp32
+    oracle; every gradient tensor within 6 % of its max-norm and > 0.995 cosine of torch autograd in fp32."""
+    cfg = _nodrop(case_config(case))
+    sd_np = synth.make_state_dict(cfg, seed=11)
+    B, pw = 6, 1.7
+    img, meta, lab = _batch(B)
+    ref_sd, ref_logits, ref_loss = _oracle_step(cfg, sd_np, img, meta, lab, pw)
+    model = getattr(btsbot, cfg["model_name"])(dict(cfg, precision="bf16"))
+    model.load_state_dict(synth.to_torch(sd_np), strict=True)
+    model = model.to(cuda_dev).train()
+    loss_fn = BCEWithLogitsLoss(pos_weight=torch.tensor([pw])).to(cuda_dev)
+    model.zero_grad()
+    from btsbot_b200 import _lib
+    prof = _lib.KernelProfiler()
+    _lib.profiler = prof
+    try:
+        logits = _call(model, cfg, img.to(cuda_dev), meta.to(cuda_dev))
+        loss = loss_fn(logits, lab.to(cuda_dev))
+        loss.backward()
+    finally:
+        _lib.profiler = None
+    names = {r[0] for r in prof.records}
+    assert {"t_gemm_tc", "t_wgrad_tc", "t_cast_dual"} <= names, names      # the tensor-core path really ran
+    torch.cuda.synchronize()
+    assert (logits.detach().cpu() - ref_logits).abs().max() < 2e-2
+    worst, worst_cos = ("", 0.0), ("", 1.0)
+    for name, p in model.named_parameters():
+        ref = ref_sd[name].grad
+        assert p.grad is not None and ref is not None, name
+        g = p.grad.cpu()
+        assert torch.isfinite(g).all(), name
+        scale = max(ref.abs().max().item(), 1e-6)
+        err = (g - ref).abs().max().item() / scale
+        if err > worst[1]:
+            worst = (name, err)
+        if ref.numel() >= 64 and ref.norm() > 1e-6:
+            cos = float((g.flatten() @ ref.flatten()) / (g.norm() * ref.norm() + 1e-30))
+            if cos < worst_cos[1]:
+                worst_cos = (name, cos)
+    print(f"[parity] {case} bf16 training step: loss {loss.item():.5f} (fp32 oracle {ref_loss.item():.5f}); worst "
+          f"gradient error {worst[1]:.2e} of max-norm at {worst[0]}; worst cosine {worst_cos[1]:.5f} at {worst_cos[0]}")
+    assert worst[1] < 6e-2, worst
+    assert worst_cos[1] > 0.995, worst_cos
+
+
+def test_bf16_training_loss_decreases(cuda_dev):
+    cfg = _nodrop(case_config("mm_pico"))
+    sd_np = synth.make_state_dict(cfg, seed=12)
+    img, meta, lab = _batch(32, start=900)
+    model = btsbot.mm_ConvNeXt(dict(cfg, precision="bf16"))
+    model.load_state_dict(synth.to_torch(sd_np), strict=True)
+    model = model.to(cuda_dev).train()
+    opt = FusedAdamW(model.parameters(), lr=1e-3, betas=(0.9, 0.99))
+    loss_fn = BCEWithLogitsLoss(pos_weight=torch.tensor([1.0]))
+    losses = []
+    for _ in range(6):
+        model.zero_grad()
+        loss = loss_fn(model(image_input=img.to(cuda_dev), metadata_input=meta.to(cuda_dev)), lab.to(cuda_dev))
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
