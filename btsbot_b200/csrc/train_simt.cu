@@ -264,6 +264,109 @@ dwconv7_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ du, 
   }
 }
 
+// ---- square-map fast paths (S x S maps, S in {15, 7, 3, 1}: every ConvNeXt stage of a 63 x 63 cutout) ----------------
+// thread = (channel, output row): the S outputs of the row live in registers, each of the <= 7 input rows is read once
+// (coalesced over channels, re-reads by the neighbouring row threads hit L1) and its 7 taps are applied to the whole
+// row with compile-time bounds -- 7*S FMAs per S + 7 loads instead of one global load per FMA.
+template <int S>
+__global__ void __launch_bounds__(32 * S)
+dwconv7_rows_kernel(const float* __restrict__ x, const float* __restrict__ w49, const float* __restrict__ bias,
+                    float* __restrict__ out, int64_t B, int C, int flip) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int oy = threadIdx.y;
+  if (c >= C) return;
+  const float bv = bias ? bias[c] : 0.f;
+  for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+    const float* xb = x + b * S * S * (int64_t)C + c;
+    float acc[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) acc[i] = bv;
+#pragma unroll 1
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = oy + ky - 3;
+      if (iy < 0 || iy >= S) continue;
+      float xr[S], wv[7];
+#pragma unroll
+      for (int ix = 0; ix < S; ++ix) xr[ix] = xb[(iy * S + ix) * (int64_t)C];
+      const float* wr = w49 + (flip ? (6 - ky) * 7 : ky * 7) * C + c;
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) wv[kx] = __ldg(wr + (flip ? 6 - kx : kx) * C);
+#pragma unroll
+      for (int ox = 0; ox < S; ++ox)
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const int ix = ox + kx - 3;
+          if (ix >= 0 && ix < S) acc[ox] = fmaf(wv[kx], xr[ix], acc[ox]);
+        }
+    }
+    float* ob = out + (b * S * S + oy * S) * (int64_t)C + c;
+#pragma unroll
+    for (int ox = 0; ox < S; ++ox) ob[ox * (int64_t)C] = acc[ox];
+  }
+}
+
+// thread = (channel, tap row ky): its 7 tap accumulators stay in registers over `ipb` images and every output row
+// (du row oy against x row oy + ky - 3: 7*S FMAs per 2*S loads); every (tap, channel) is owned by exactly one thread
+// of the block, so the only reduction is one atomicAdd per block at the end
+template <int S>
+__global__ void __launch_bounds__(32 * 7)
+dwconv7_wgrad_rows_kernel(const float* __restrict__ x, const float* __restrict__ du, float* __restrict__ dw,
+                          float* __restrict__ db, int64_t B, int C, int ipb) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int ky = threadIdx.y;
+  if (c >= C) return;
+  float acc[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) acc[k] = 0.f;
+  float accb = 0.f;
+  const int64_t b0 = (int64_t)blockIdx.y * ipb, b1 = min(B, b0 + (int64_t)ipb);
+  for (int64_t b = b0; b < b1; ++b) {
+    const float* xb = x + b * S * S * (int64_t)C + c;
+    const float* gb = du + b * S * S * (int64_t)C + c;
+#pragma unroll 1
+    for (int oy = 0; oy < S; ++oy) {
+      const int iy = oy + ky - 3;
+      if (iy < 0 || iy >= S) continue;
+      float xr[S], dr[S];
+#pragma unroll
+      for (int i = 0; i < S; ++i) { xr[i] = xb[(iy * S + i) * (int64_t)C]; dr[i] = gb[(oy * S + i) * (int64_t)C]; }
+      if (ky == 3) {
+#pragma unroll
+        for (int i = 0; i < S; ++i) accb += dr[i];               // iy == oy: every du row is summed exactly once
+      }
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+        for (int ox = 0; ox < S; ++ox) {
+          const int ix = ox + kx - 3;
+          if (ix >= 0 && ix < S) acc[kx] = fmaf(dr[ox], xr[ix], acc[kx]);
+        }
+    }
+  }
+#pragma unroll
+  for (int kx = 0; kx < 7; ++kx) atomicAdd(dw + (ky * 7 + kx) * C + c, acc[kx]);
+  if (ky == 3) atomicAdd(db + c, accb);
+}
+
+template <int S>
+static void launch_dwconv_rows(const float* x, const float* w49, const float* bias, float* out, int64_t B, int C, int flip,
+                               cudaStream_t st) {
+  const int cblocks = (C + 31) / 32;
+  int64_t gy = B;
+  const int64_t cap = (int64_t)148 * 16 / cblocks + 1;            // a few waves; blocks loop over images beyond that
+  if (gy > cap) gy = cap;
+  dwconv7_rows_kernel<S><<<dim3((unsigned)cblocks, (unsigned)gy), dim3(32, S), 0, st>>>(x, w49, bias, out, B, C, flip);
+}
+
+template <int S>
+static void launch_dwconv_wgrad_rows(const float* x, const float* du, float* dw, float* db, int64_t B, int C, cudaStream_t st) {
+  const int cblocks = (C + 31) / 32;
+  int64_t ipb = (B * cblocks + 148 * 4 - 1) / (148 * 4);          // ~4 blocks per SM in total
+  if (ipb < 1) ipb = 1;
+  dwconv7_wgrad_rows_kernel<S><<<dim3((unsigned)cblocks, (unsigned)((B + ipb - 1) / ipb)), dim3(32, 7), 0, st>>>(
+      x, du, dw, db, B, C, (int)ipb);
+}
+
 // stem im2col: x [B,3,H,W] -> patches [B*ho*wo, 48], k = (ci*4+ky)*4+kx
 __global__ void stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ p, int64_t B, int H, int W, int ho, int wo) {
   const int64_t total = B * ho * wo * 48;
@@ -520,7 +623,12 @@ extern "C" int btsb_dwconv7_f32(const float* x, const float* w49, const float* b
   if (int e = check_device()) return e;
   if (B <= 0) return BTSB_OK;
   BTSB_REQUIRE(x && w49 && out && H >= 1 && W >= 1 && C >= 1, "dwconv7: bad arguments");
-  dwconv7_kernel<<<ew_grid(B * H * W * C), 256, 0, (cudaStream_t)stream>>>(x, w49, bias, out, B, H, W, C, flip);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H == W && H == 15) launch_dwconv_rows<15>(x, w49, bias, out, B, C, flip, st);
+  else if (H == W && H == 7) launch_dwconv_rows<7>(x, w49, bias, out, B, C, flip, st);
+  else if (H == W && H == 3) launch_dwconv_rows<3>(x, w49, bias, out, B, C, flip, st);
+  else if (H == W && H == 1) launch_dwconv_rows<1>(x, w49, bias, out, B, C, flip, st);
+  else dwconv7_kernel<<<ew_grid(B * H * W * C), 256, 0, st>>>(x, w49, bias, out, B, H, W, C, flip);
   return launch_done("dwconv7");
 }
 
@@ -529,11 +637,19 @@ extern "C" int btsb_dwconv7_wgrad_f32(const float* x, const float* du, float* dw
   if (int e = check_device()) return e;
   if (B <= 0) return BTSB_OK;
   BTSB_REQUIRE(x && du && dw49 && dbias, "dwconv7 wgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (H == W && (H == 15 || H == 7 || H == 3 || H == 1)) {
+    if (H == 15) launch_dwconv_wgrad_rows<15>(x, du, dw49, dbias, B, C, st);
+    else if (H == 7) launch_dwconv_wgrad_rows<7>(x, du, dw49, dbias, B, C, st);
+    else if (H == 3) launch_dwconv_wgrad_rows<3>(x, du, dw49, dbias, B, C, st);
+    else launch_dwconv_wgrad_rows<1>(x, du, dw49, dbias, B, C, st);
+    return launch_done("dwconv7_wgrad");
+  }
   const int cblocks = (C + 31) / 32;
   int64_t ipb = (B * cblocks + 148 * 4 - 1) / (148 * 4);        // ~4 blocks per SM in total
   if (ipb < 1) ipb = 1;
   dim3 grid((unsigned)cblocks, (unsigned)((B + ipb - 1) / ipb));
-  dwconv7_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, du, dw49, dbias, B, H, W, C, (int)ipb);
+  dwconv7_wgrad_kernel<<<grid, 256, 0, st>>>(x, du, dw49, dbias, B, H, W, C, (int)ipb);
   return launch_done("dwconv7_wgrad");
 }
 
