@@ -624,6 +624,7 @@ class FusedAdamW(torch.optim.Optimizer):
         lib = L.lib()
         for group in self.param_groups:
             b1, b2 = group["betas"]
+            by_step = {}
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -634,8 +635,19 @@ class FusedAdamW(torch.optim.Optimizer):
                     st["m"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["v"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 st["step"] += 1
-                g = p.grad.contiguous()
-                L.launch("t_adamw", lib.btsb_adamw_f32, _p(p), _p(g), _p(st["m"]), _p(st["v"]), p.numel(),
-                         float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                         int(st["step"]), 1.0, _st())
+                if not p.is_contiguous():
+                    raise RuntimeError("FusedAdamW: parameters must be contiguous")
+                by_step.setdefault(st["step"], []).append((p, p.grad.contiguous(), st))
+            # parameters that share a step count (all of them, unless some had no gradient in earlier steps) go through
+            # the multi-tensor kernel, BTSB_ADAMW_BATCH tensors per launch
+            for step, items in by_step.items():
+                for lo in range(0, len(items), L.ADAMW_BATCH):
+                    part = items[lo:lo + L.ADAMW_BATCH]
+                    batch = L.AdamwBatch()
+                    for i, (p, g, st) in enumerate(part):
+                        batch.p[i], batch.g[i], batch.m[i], batch.v[i] = p.data_ptr(), g.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr()
+                        batch.n[i] = p.numel()
+                    batch.count = len(part)
+                    L.launch("t_adamw", lib.btsb_adamw_multi_f32, C.byref(batch), float(group["lr"]), float(b1), float(b2),
+                             float(group["eps"]), float(group["weight_decay"]), int(step), 1.0, _st())
         return loss

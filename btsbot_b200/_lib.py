@@ -38,6 +38,15 @@ class HeadParams(C.Structure):
     ]
 
 
+ADAMW_BATCH = 48
+
+
+class AdamwBatch(C.Structure):
+    """``btsb_adamw_batch`` (include/btsbot_b200.h)."""
+    _fields_ = [("p", vp * ADAMW_BATCH), ("g", vp * ADAMW_BATCH), ("m", vp * ADAMW_BATCH), ("v", vp * ADAMW_BATCH),
+                ("n", i64 * ADAMW_BATCH), ("first_block", i32 * (ADAMW_BATCH + 1)), ("count", i32)]
+
+
 #: every symbol include/btsbot_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "btsb_version": (i32, []),
@@ -75,6 +84,8 @@ SIGNATURES = {
     "btsb_bce_logits_f32": (i32, [vp, vp, C.c_float, vp, vp, i64, C.c_float, vp]),
     "btsb_adamw_f32": (i32, [vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64,
                              C.c_float, vp]),
+    "btsb_adamw_multi_f32": (i32, [C.POINTER(AdamwBatch), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64,
+                                   C.c_float, vp]),
     "btsb_maxvit_stem1_fwd": (i32, [vp, i64, i32, i32, i32, vp, vp, i32, vp, i32, vp]),
     "btsb_maxvit_im2col3_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
     "btsb_maxvit_avgpool2_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
@@ -84,6 +95,7 @@ SIGNATURES = {
     "btsb_layernorm_rows_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     "btsb_maxvit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp, i32, vp]),
     "btsb_maxvit_lnpool_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "btsb_debug_mlp_trace": (i32, [vp]),
     "btsb_cast_dual_bf16": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, vp]),
     "btsb_gemm_bf16_f32out": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     "btsb_gemm_bf16_wgrad": (i32, [vp, vp, i64, vp, i32, i32, i64, vp]),

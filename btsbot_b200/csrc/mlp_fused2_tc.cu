@@ -144,8 +144,15 @@ template <int C, bool TE, bool HT>
 __global__ void __launch_bounds__(kThreads2, 1)   // 18 warps -> 5 on two SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
-                  __nv_bfloat16* __restrict__ out, int M) {
+                  __nv_bfloat16* __restrict__ out, int M, long long* __restrict__ trace) {
   using namespace tc;
+  // timeline debugging (btsb_debug_mlp_trace): block 0 records clock64() at the hand-off points of its first
+  // kTraceChunks hidden chunks; trace == nullptr in production (one uniform branch per event)
+  constexpr int kTraceChunks = 64, kTraceEv = 8;
+  const bool tracing = trace != nullptr && blockIdx.x == 0;
+  auto tr = [&](int role, uint32_t g, int ev) {
+    if (tracing && g < (uint32_t)kTraceChunks) trace[((size_t)role * kTraceChunks + g) * kTraceEv + ev] = clock64();
+  };
   constexpr Plan2 P = plan2_for(C, TE, HT);
   static_assert(P.ok, "no shared-memory plan for this C");
   constexpr int kHCol = kD2Col + 2 * C;                          // TMEM columns of H[0], H[1] (32 each) in HT mode
@@ -341,8 +348,8 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
     long long t0 = 0;
     while (n2 < total) {
       bool progressed = false;
-      if (n1 < total && g1_ready()) { do_g1(); ++n1; progressed = true; }
-      if (n2 < n1 && g2_ready()) { do_g2(); ++n2; progressed = true; }
+      if (n1 < total && g1_ready()) { do_g1(); if (lane == 0) tr(0, n1, 0); ++n1; progressed = true; }
+      if (n2 < n1 && g2_ready()) { do_g2(); if (lane == 0) tr(0, n2, 1); ++n2; progressed = true; }
       if (progressed) { idle = 0; t0 = 0; continue; }
       __nanosleep(32);
       if ((++idle & 4095u) == 0) {                                   // bounded: a protocol bug traps instead of hanging
@@ -521,14 +528,16 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         }
         prev_tl = tl;
       }
+      if (lane == 0) tr(1 + ew, g, 0);
       mbar_wait_spin(d1_full(grp), use & 1u);
       tc_fence_after();
+      if (lane == 0) tr(1 + ew, g, 1);
       uint32_t r[32];
       tmem_ld32(lane_addr + (uint32_t)(grp * NH + half * 32), r);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(d1_empty(grp));         // D1[grp] may be overwritten by G1 of chunk g+2
+      if (lane == 0) { mbar_arrive(d1_empty(grp)); tr(1 + ew, g, 2); }   // D1[grp] may be overwritten by G1 of chunk g+2
       const int hcol = j * NH + half * 32;
       uint32_t o[16];
 #pragma unroll
@@ -541,7 +550,9 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         o[i / 2] = pack_bf16x2(v0, v1);
         o[i / 2 + 1] = pack_bf16x2(v2, v3);
       }
+      if (lane == 0) tr(1 + ew, g, 3);
       mbar_wait_spin(h_empty(grp), (use & 1u) ^ 1u);         // G2 of chunk g-2 has finished reading H[grp]
+      if (lane == 0) tr(1 + ew, g, 4);
       if (HT) {
         // H never touches shared memory: packed bf16 pairs go straight into the TMEM columns G2 reads its A operand
         // from (thread = row / TMEM lane, 16 columns = this warp's 32 hidden values)
@@ -557,11 +568,12 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         fence_proxy_async();                               // generic-proxy writes -> visible to the tensor core
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(h_full(grp));
+      if (lane == 0) { mbar_arrive(h_full(grp)); tr(1 + ew, g, 5); }
       if (pend_tl >= 0) {
         if (TE) d2_epilogue_te(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl);
         else d2_epilogue(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl);
         pend_tl = -1;
+        if (lane == 0) tr(1 + ew, g, 6);
       }
     }
     if (nt > 0) {
@@ -582,6 +594,8 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+static long long* g_mlp_trace = nullptr;    // debugging only (btsb_debug_mlp_trace); caller-owned device buffer
+
 int num_sms();
 int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                          uint32_t box_cols, int swizzle_bytes);
@@ -598,7 +612,7 @@ static int launch2(const Maps2& tm, const float* b1, const float* b2, const floa
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
-  kern<<<grid, kThreads2, P.total, st>>>(tm, b1, b2, gamma, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (int)M);
+  kern<<<grid, kThreads2, P.total, st>>>(tm, b1, b2, gamma, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (int)M, g_mlp_trace);
   return launch_done("mlp_fused2");
 }
 
@@ -652,3 +666,11 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
 }
 
 }  // namespace btsb
+
+// Debugging aid (scripts/mlp_trace.py): when `buf` is non-NULL, block 0 of every following fused-MLP launch records
+// clock64() timestamps into buf[(role * 64 + chunk) * 8 + event] (17 roles: MMA warp + 16 epilogue warps; >= 69632 B).
+// Pass NULL to switch tracing off.  Not part of the reference-facing surface.
+extern "C" int btsb_debug_mlp_trace(void* buf) {
+  btsb::g_mlp_trace = (long long*)buf;
+  return BTSB_OK;
+}

@@ -75,8 +75,25 @@ colsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, float* _
   const int sub = threadIdx.x >> 5;                      // 8 row lanes
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   float s = 0.f;
-  if (n < N)
-    for (int64_t m = r0 + sub; m < r1; m += 8) s += Y ? X[m * N + n] * Y[m * N + n] : X[m * N + n];
+  if (n < N) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // four loads in flight per thread
+    int64_t m = r0 + sub;
+    if (Y) {
+      for (; m + 24 < r1; m += 32) {
+        s0 = fmaf(X[m * N + n], Y[m * N + n], s0);
+        s1 = fmaf(X[(m + 8) * N + n], Y[(m + 8) * N + n], s1);
+        s2 = fmaf(X[(m + 16) * N + n], Y[(m + 16) * N + n], s2);
+        s3 = fmaf(X[(m + 24) * N + n], Y[(m + 24) * N + n], s3);
+      }
+      for (; m < r1; m += 8) s0 = fmaf(X[m * N + n], Y[m * N + n], s0);
+    } else {
+      for (; m + 24 < r1; m += 32) {
+        s0 += X[m * N + n]; s1 += X[(m + 8) * N + n]; s2 += X[(m + 16) * N + n]; s3 += X[(m + 24) * N + n];
+      }
+      for (; m < r1; m += 8) s0 += X[m * N + n];
+    }
+    s = (s0 + s1) + (s2 + s3);
+  }
   __shared__ float red[8][33];
   red[sub][threadIdx.x & 31] = s;
   __syncthreads();
@@ -124,8 +141,10 @@ __global__ void bias_add_kernel(float* __restrict__ X, const float* __restrict__
 }
 
 // ---- LayerNorm over the last dim of rows [M,C]; one warp per row, two-pass -----------------------------------
-constexpr int LN_MAXJ = 20;   // C <= 640
+constexpr int kLnMaxJ = 20;   // C <= 640; the kernels are instantiated for 3 / 5 / 10 / 20 elements per lane so that
+                              // C = 80 rows do not execute 17 predicated-off iterations of every loop
 
+template <int LN_MAXJ>
 __global__ void __launch_bounds__(256)
 ln_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ b,
               float* __restrict__ y, int64_t M, int C, float eps) {
@@ -147,6 +166,7 @@ ln_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, const fl
   }
 }
 
+template <int LN_MAXJ>
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ dy,
               float* __restrict__ du, float* __restrict__ dw, float* __restrict__ db, int64_t M, int C, float eps) {
@@ -518,6 +538,32 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// multi-tensor AdamW: up to BTSB_ADAMW_BATCH parameter tensors per launch, described BY VALUE in the kernel parameters
+// (no device-side table to keep alive); block b works on 2048 consecutive elements of the tensor whose block range holds b
+constexpr int kAdamwChunk = 2048;
+__global__ void __launch_bounds__(256)
+adamw_multi_kernel(const __grid_constant__ btsb_adamw_batch t, float lr, float beta1, float beta2, float eps, float wd,
+                   float bc1, float bc2_sqrt, float grad_scale) {
+  int ti = 0;
+  while (ti + 1 < t.count && (int)blockIdx.x >= t.first_block[ti + 1]) ++ti;
+  const int64_t base = (int64_t)((int)blockIdx.x - t.first_block[ti]) * kAdamwChunk;
+  float* __restrict__ p = t.p[ti];
+  const float* __restrict__ g = t.g[ti];
+  float* __restrict__ m = t.m[ti];
+  float* __restrict__ v = t.v[ti];
+  const int64_t end = min(t.n[ti], base + kAdamwChunk);
+  for (int64_t i = base + threadIdx.x; i < end; i += 256) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+  }
+}
+
 static int ew_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   if (g > 148 * 32) g = 148 * 32;
@@ -566,7 +612,7 @@ extern "C" int btsb_colsum_f32(const float* X, const float* Y, float* out, int64
   cudaStream_t st = (cudaStream_t)stream;
   if (!accumulate) BTSB_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st), "colsum memset");
   if (M == 0) return BTSB_OK;
-  int64_t rpb = 2048;
+  int64_t rpb = 512;
   dim3 grid((unsigned)((N + 31) / 32), (unsigned)((M + rpb - 1) / rpb));
   colsum_kernel<<<grid, 256, 0, st>>>(X, Y, out, M, N, rpb);
   return launch_done("colsum");
@@ -599,22 +645,31 @@ extern "C" int btsb_bias_add_f32(float* X, const float* b, int64_t M, int N, voi
 extern "C" int btsb_layernorm_fwd_f32(const float* u, const float* w, const float* b, float* y, int64_t M, int C, float eps,
                                       void* stream) {
   if (int e = check_device()) return e;
-  BTSB_REQUIRE(C >= 1 && C <= 32 * LN_MAXJ, "layernorm: C=%d not in [1,640]", C);
+  BTSB_REQUIRE(C >= 1 && C <= 32 * kLnMaxJ, "layernorm: C=%d not in [1,640]", C);
   if (M <= 0) return BTSB_OK;
   BTSB_REQUIRE(u && w && b && y, "layernorm: null pointer");
-  ln_fwd_kernel<<<ew_grid(M * 32), 256, 0, (cudaStream_t)stream>>>(u, w, b, y, M, C, eps);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid(M * 32);
+  if (C <= 96) ln_fwd_kernel<3><<<grid, 256, 0, st>>>(u, w, b, y, M, C, eps);
+  else if (C <= 160) ln_fwd_kernel<5><<<grid, 256, 0, st>>>(u, w, b, y, M, C, eps);
+  else if (C <= 320) ln_fwd_kernel<10><<<grid, 256, 0, st>>>(u, w, b, y, M, C, eps);
+  else ln_fwd_kernel<20><<<grid, 256, 0, st>>>(u, w, b, y, M, C, eps);
   return launch_done("ln_fwd");
 }
 
 extern "C" int btsb_layernorm_bwd_f32(const float* u, const float* w, const float* dy, float* du, float* dw, float* db,
                                       int64_t M, int C, float eps, void* stream) {
   if (int e = check_device()) return e;
-  BTSB_REQUIRE(C >= 1 && C <= 32 * LN_MAXJ, "layernorm bwd: C=%d not in [1,640]", C);
+  BTSB_REQUIRE(C >= 1 && C <= 32 * kLnMaxJ, "layernorm bwd: C=%d not in [1,640]", C);
   if (M <= 0) return BTSB_OK;
   BTSB_REQUIRE(u && w && dy && dw && db, "layernorm bwd: null pointer");
   int grid = ew_grid(M * 32);
   if (grid > 148 * 4) grid = 148 * 4;          // bounds the number of atomic flushes
-  ln_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(u, w, dy, du, dw, db, M, C, eps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 96) ln_bwd_kernel<3><<<grid, 256, 0, st>>>(u, w, dy, du, dw, db, M, C, eps);
+  else if (C <= 160) ln_bwd_kernel<5><<<grid, 256, 0, st>>>(u, w, dy, du, dw, db, M, C, eps);
+  else if (C <= 320) ln_bwd_kernel<10><<<grid, 256, 0, st>>>(u, w, dy, du, dw, db, M, C, eps);
+  else ln_bwd_kernel<20><<<grid, 256, 0, st>>>(u, w, dy, du, dw, db, M, C, eps);
   return launch_done("ln_bwd");
 }
 
@@ -727,4 +782,22 @@ extern "C" int btsb_adamw_f32(float* p, const float* g, float* m, float* v, int6
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
   adamw_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
   return launch_done("adamw");
+}
+
+extern "C" int btsb_adamw_multi_f32(btsb_adamw_batch* batch, float lr, float beta1, float beta2, float eps, float wd,
+                                    int64_t step, float grad_scale, void* stream) {
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(batch && batch->count >= 0 && batch->count <= BTSB_ADAMW_BATCH && step >= 1, "adamw_multi: bad arguments");
+  if (batch->count == 0) return BTSB_OK;
+  int blocks = 0;
+  for (int i = 0; i < batch->count; ++i) {
+    BTSB_REQUIRE(batch->p[i] && batch->g[i] && batch->m[i] && batch->v[i] && batch->n[i] >= 1, "adamw_multi: bad tensor %d", i);
+    batch->first_block[i] = blocks;
+    blocks += (int)((batch->n[i] + kAdamwChunk - 1) / kAdamwChunk);
+  }
+  batch->first_block[batch->count] = blocks;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  adamw_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*batch, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  return launch_done("adamw_multi");
 }

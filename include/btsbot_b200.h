@@ -213,6 +213,21 @@ int btsb_bce_logits_f32(const float* logits, const float* labels, float pos_weig
 int btsb_adamw_f32(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float wd, int64_t step, float grad_scale, void* stream);
 
+/* the same update for up to BTSB_ADAMW_BATCH parameter tensors in ONE launch (torch's "foreach"/fused AdamW role):
+ * the caller fills p/g/m/v/n[0..count); first_block is scratch written by the call.  All tensors share `step`. */
+#define BTSB_ADAMW_BATCH 48
+typedef struct {
+  float* p[BTSB_ADAMW_BATCH];
+  const float* g[BTSB_ADAMW_BATCH];
+  float* m[BTSB_ADAMW_BATCH];
+  float* v[BTSB_ADAMW_BATCH];
+  int64_t n[BTSB_ADAMW_BATCH];
+  int32_t first_block[BTSB_ADAMW_BATCH + 1];
+  int32_t count;
+} btsb_adamw_batch;
+int btsb_adamw_multi_f32(btsb_adamw_batch* batch, float lr, float beta1, float beta2, float eps, float wd,
+                         int64_t step, float grad_scale, void* stream);
+
 /* ---- K7 on tensor cores (bf16 mode of the training step; what autocast(bf16) + cuBLAS do under train.py:496-547).
  * The three GEMMs of every Linear / 1x1 conv run on tcgen05 with bf16 operands and fp32 accumulation; results are
  * fp32 so that the residual stream, LayerNorm and the element-wise backward stay in fp32.
@@ -268,6 +283,10 @@ int btsb_maxvit_attn_fwd(const void* qkv, void* out, int64_t B, int H, int W, in
                          int dtype, void* stream);
 int btsb_maxvit_lnpool_fwd(const void* x, const float* ln_w, const float* ln_b, float* out, int64_t B, int HW, int C,
                            int dtype, void* stream);
+
+/* debugging aid: device buffer (>= 17*64*8 int64) that block 0 of the fused-MLP kernel fills with clock64() stamps of its
+ * pipeline hand-offs (scripts/mlp_trace.py); NULL switches it off (default). */
+int btsb_debug_mlp_trace(void* buf);
 
 /* dtype helpers used by the weight packer: float32 -> bf16 (round-to-nearest-even) and back. */
 int btsb_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream);
