@@ -16,7 +16,8 @@
 //
 // Per CTA (persistent over 128-row tiles), hidden processed in chunks of 64 columns, global chunk index g:
 //   warp 0      TMA producer : y tiles, W1 chunk [64 x C], W2 chunk [C x 64]
-//   warp 1      MMA issuer   : G1_g: D1[g&1] = y . W1_g^T (M128 x N64, K = C);  G2_g: D2[tile&1] += H[g&1] . W2_g^T
+//   warp 1      MMA issuer 1 : G1_g: D1[g&1] = y . W1_g^T (M128 x N64, K = C)
+//   warp 18     MMA issuer 2 : G2_g: D2[tile&1] += H[g&1] . W2_g^T     (one warp per stream: see the issuer comment)
 //   warps 2..17 epilogue     : group g&1: tcgen05.ld D1 -> +b1 -> GELU -> bf16 -> H[g&1] (SW128 K-major, what UMMA
 //                              reads); all 16 warps: D2 -> +b2 -> *gamma + res -> bf16 rows (deferred by one chunk)
 #include <stdlib.h>
@@ -29,7 +30,8 @@ namespace {
 constexpr int FM = 128;            // rows per tile
 constexpr int NH = 64;             // hidden chunk
 constexpr int kEpiWarps2 = 16;
-constexpr int kThreads2 = 64 + kEpiWarps2 * 32;
+constexpr int kG2Warp = 2 + kEpiWarps2;                 // second MMA-issuing warp (G2 stream)
+constexpr int kThreads2 = 64 + kEpiWarps2 * 32 + 32;
 constexpr int kHBytes = FM * 128;  // [128 x 64] bf16
 constexpr int kD2Col = 2 * NH;     // TMEM column of D2 (D1 buffers occupy [0,128))
 constexpr int kMaxSlots = 16;
@@ -141,7 +143,7 @@ struct Maps2 {
 }  // namespace
 
 template <int C, bool TE, bool HT>
-__global__ void __launch_bounds__(kThreads2, 1)   // 18 warps -> 5 on two SMSPs: 96 registers is the hardware ceiling
+__global__ void __launch_bounds__(kThreads2, 1)   // 19 warps -> 5 on three SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
                   __nv_bfloat16* __restrict__ out, int M, long long* __restrict__ trace) {
@@ -264,23 +266,14 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       if (g + 2 < total) load_g1_inputs();
       load_w2();
     }
-  } else if (warp == 1) {
-    // ============================== MMA issuer (whole warp walks the schedule, one elected lane issues) ================
+  } else if (warp == 1 || warp == kG2Warp) {
+    // ============================== MMA issuers (whole warp walks its schedule, one elected lane issues) ===============
     constexpr uint32_t idesc1 = idesc_bf16_f32(FM, NH);
     constexpr uint32_t idesc2 = idesc_bf16_f32(FM, C);
     // G1 stream state
     int j1 = 0, s1 = 0, yb = 0, b1i = 0; uint32_t ph1 = 0, yph = 0, dph1 = 0, t1 = 0;
     // G2 stream state
     int j2 = 0, s2 = 0, b2i = 0, tb = 0; uint32_t ph2 = 0, hph = 0, d2ph = 0, t2 = 0;
-    // Both streams are polled (non-blocking mbarrier.test_wait), G1 first: a G1 whose inputs are ready is never held
-    // back behind a G2 that still waits for the GELU warps, so D1 of chunk g+2 is complete long before its epilogue
-    // group asks for it, whatever the relative phase of the two groups (profiles/r01f: with in-order blocking waits
-    // 16 % of all samples sat on the D1 barrier).
-    auto g1_ready = [&]() -> bool {
-      if (j1 == 0 && !mbar_test(y_full(yb), yph)) return false;
-      if ((!P.resident || t1 == 0) && !mbar_test(w1_full(s1), ph1)) return false;
-      return mbar_test(d1_empty(b1i), dph1 ^ 1u);              // the epilogue has pulled chunk g-2 out of D1[b]
-    };
     auto do_g1 = [&]() {
       tc_fence_after();
       if (elect_one()) {
@@ -309,11 +302,6 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         if (P.resident) s1 = 0;
         if (P.ny == 2) { yb ^= 1; if (yb == 0) yph ^= 1u; } else { yph ^= 1u; }
       }
-    };
-    auto g2_ready = [&]() -> bool {
-      if ((!P.resident || t2 == 0) && !mbar_test(w2_full(s2), ph2)) return false;
-      if (j2 == 0 && !mbar_test(d2_empty(tb), d2ph ^ 1u)) return false;
-      return mbar_test(h_full(b2i), hph);
     };
     auto do_g2 = [&]() {
       tc_fence_after();
@@ -344,24 +332,32 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         tb ^= 1; if (tb == 0) d2ph ^= 1u;
       }
     };
-    uint32_t n1 = 0, n2 = 0, idle = 0;
-    long long t0 = 0;
-    while (n2 < total) {
-      bool progressed = false;
-      if (n1 < total && g1_ready()) { do_g1(); if (lane == 0) tr(0, n1, 0); ++n1; progressed = true; }
-      if (n2 < n1 && g2_ready()) { do_g2(); if (lane == 0) tr(0, n2, 1); ++n2; progressed = true; }
-      if (progressed) { idle = 0; t0 = 0; continue; }
-      __nanosleep(32);
-      if ((++idle & 4095u) == 0) {                                   // bounded: a protocol bug traps instead of hanging
-        if (t0 == 0) t0 = clock64();
-        else if (clock64() - t0 > 4000000000LL) {
-          if (lane == 0) printf("btsbot_b200: mlp_fused2 MMA schedule stalled (block %d, G1 %u G2 %u of %u)\n", blockIdx.x, n1, n2, total);
-          __trap();
-        }
+    // Two issuing warps, one per GEMM stream, each with plain blocking waits.  A single warp alternating between the two
+    // streams was the pacing element of the whole kernel (scripts/mlp_trace.py, profiles/r01i): issuing one chunk's
+    // G1 or G2 holds the warp for 350-400 clk and the next mbarrier poll answers only 200-550 clk later, so one warp
+    // delivered a chunk every ~1500 clk while the tensor pipe sat at 21-33 % and the epilogue warps spent half their
+    // time waiting for D1.  With the streams on separate warps the two hand-off latencies overlap.
+    if (warp == 1) {
+      for (uint32_t n1 = 0; n1 < total; ++n1) {
+        if (j1 == 0) mbar_wait_spin(y_full(yb), yph);
+        if (!P.resident || t1 == 0) mbar_wait_spin(w1_full(s1), ph1);
+        mbar_wait_spin(d1_empty(b1i), dph1 ^ 1u);            // the epilogue has pulled chunk g-2 out of D1[b]
+        if (lane == 0) tr(0, n1, 2);
+        do_g1();
+        if (lane == 0) tr(0, n1, 0);
+      }
+    } else {
+      for (uint32_t n2 = 0; n2 < total; ++n2) {
+        if (!P.resident || t2 == 0) mbar_wait_spin(w2_full(s2), ph2);
+        if (j2 == 0) mbar_wait_spin(d2_empty(tb), d2ph ^ 1u);
+        mbar_wait_spin(h_full(b2i), hph);
+        if (lane == 0) tr(0, n2, 3);
+        do_g2();
+        if (lane == 0) tr(0, n2, 1);
       }
     }
-  } else if (warp >= 2) {
-    // ============================== epilogue warps ==============================
+  } else {
+    // ============================== epilogue warps (2 .. 17) ==============================
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
     const int k4 = (warp - 2) >> 2;         // 0..3
     const int grp = k4 & 1;                 // owns hidden chunks g with (g & 1) == grp
