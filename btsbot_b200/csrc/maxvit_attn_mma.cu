@@ -29,6 +29,13 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// 16-byte asynchronous copy global -> shared (L2 only): the whole (window, head) gather is in flight at once instead of
+// one load round trip per 32 pieces (the kernel ran at 1.2 TB/s with 12 resident warps waiting on ~19 dependent trips)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -65,20 +72,20 @@ mv_attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
     return (b * H + y) * (int64_t)W + x;
   };
   constexpr float kLog2e = 1.4426950408889634f;
-  for (int i = lane; i < 169; i += 32) tb[i] = table[i * heads + h] * kLog2e;
-  // gather: 49 tokens x 12 pieces of 16 B (q: 4, k: 4, v: 4)
+  // gather: 49 tokens x 12 pieces of 16 B (q: 4, k: 4, v: 4), all issued before anything is waited for
   for (int i = lane; i < kTok * 12; i += 32) {
     const int t = i / 12, piece = i - t * 12;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(qkv + token_row(t) * 3 * C + h * 3 * kDh) + piece);
     __nv_bfloat16* dst = (piece < 4 ? qs : piece < 8 ? ks : vs) + t * kRow + (piece & 3) * 8;
-    *reinterpret_cast<uint4*>(dst) = v;
+    cp_async16(dst, reinterpret_cast<const uint4*>(qkv + token_row(t) * 3 * C + h * 3 * kDh) + piece);
   }
+  for (int i = lane; i < 169; i += 32) tb[i] = table[i * heads + h] * kLog2e;
   // zero the padding rows (q 49..63, k 49..55, v 49..63): P is exactly 0 there, but 0 * NaN garbage would poison O
   for (int i = lane; i < (15 + 7 + 15) * 4; i += 32) {
     const int r = i >> 2, piece = i & 3;
     __nv_bfloat16* dst = r < 15 ? qs + (kTok + r) * kRow : r < 22 ? ks + (kTok + r - 15) * kRow : vs + (kTok + r - 22) * kRow;
     *reinterpret_cast<uint4*>(dst + piece * 8) = make_uint4(0, 0, 0, 0);
   }
+  cp_async_wait_all();
   __syncwarp();
 
   const int g = lane >> 2, t4 = lane & 3;

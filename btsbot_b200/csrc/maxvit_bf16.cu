@@ -1,8 +1,8 @@
 // bf16 fast paths of the MaxViT CUDA-core kernels (the generic float / bf16 versions live in maxvit.cu): every thread
 // moves 16 bytes (8 channels) per access so a warp reads / writes whole 512-byte pixel rows.
-//   dw3   : depthwise 3x3 + folded BatchNorm + SiLU + SE squeeze.  CTA = (image, 256-channel slab), 16 warps; a warp
-//           walks one output row with the 3x3x8-channel window in registers (one new column = 3 loads per output),
-//           taps in shared memory; the per-channel mean is reduced in a fixed order (deterministic).
+//   dw3   : depthwise 3x3 + folded BatchNorm + SiLU + SE squeeze.  CTA = (image, 128-channel slab), 16 warps; a warp
+//           walks one output row with the 3x3x4-channel window AND the 36 taps in registers (one new column = 3 loads
+//           per output, fetched two outputs ahead); the per-channel mean is reduced in a fixed order (deterministic).
 //   ln    : row LayerNorm with C/8 lanes per row (4 / 2 / 1 rows per warp for C = 64 / 128 / 256, 2 chunks for 512).
 //   scale : SE gate multiply, avgpool2: 2x2 mean -- plain streaming kernels.
 #include "common.cuh"
@@ -26,79 +26,128 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 __device__ __forceinline__ uint4 pack8(const F8& f) {
   return make_uint4(pack2(f.v[0], f.v[1]), pack2(f.v[2], f.v[3]), pack2(f.v[4], f.v[5]), pack2(f.v[6], f.v[7]));
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) == 0.5 x (1 + tanh(x / 2)): one MUFU op (tanh.approx, rel. error 2^-11, below the bf16 rounding of the
+// stored result) instead of ex2 + rcp -- the bf16 dw3 kernel is instruction-issue-bound
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // ---- depthwise 3x3 ----------------------------------------------------------------------------------------
-constexpr int kDwThreads = 512, kDwWarps = 16, kDwSlab = 256;
+// CTA = (image, 128-channel slab), 16 warps, lane = 4 channels.  The 36 taps of a lane's channels live in REGISTERS:
+// with 8 channels per lane they had to stay in shared memory and every output re-read 9 KB of taps per warp (18
+// LDS.128), which made the kernel shared-memory-bandwidth-bound at ~72 clk per warp-output (1.2-1.4 TB/s, r01h/r01j).
+constexpr int kDwThreads = 512, kDwWarps = 16, kDwSlab = 128;
+
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 unpack4(const uint2& u) {
+  F4 r;
+  r.v[0] = __uint_as_float(u.x << 16); r.v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  r.v[2] = __uint_as_float(u.y << 16); r.v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  return r;
+}
 
 template <int STRIDE>
 __global__ void __launch_bounds__(kDwThreads, 1)
 mv_dw3_bf16_kernel(const __nv_bfloat16* __restrict__ x, int H, int W, int C, int Ho, int Wo, const float* __restrict__ w,
                    const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, float* __restrict__ pooled) {
-  __shared__ __align__(16) float ws[9][kDwSlab];
   __shared__ float red[kDwWarps][kDwSlab];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c0 = blockIdx.x * kDwSlab;
   const int64_t b = blockIdx.y;
-  for (int i = threadIdx.x; i < 9 * kDwSlab; i += kDwThreads) ws[i / kDwSlab][i % kDwSlab] = w[(i / kDwSlab) * C + c0 + i % kDwSlab];
-  __syncthreads();
-  const int cl = lane * 8;                                  // this lane's 8 channels inside the slab
-  float sh[8], pool[8];
+  const int cl = lane * 4;                                  // this lane's 4 channels inside the slab
+  float wt[9][4], sh[4], pool[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sh[i] = shift[c0 + cl + i]; pool[i] = 0.f; }
+  for (int k = 0; k < 9; ++k) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(w + (size_t)k * C + c0 + cl));
+    wt[k][0] = t.x; wt[k][1] = t.y; wt[k][2] = t.z; wt[k][3] = t.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { sh[i] = shift[c0 + cl + i]; pool[i] = 0.f; }
   const __nv_bfloat16* xb = x + b * (int64_t)H * W * C + c0 + cl;
   __nv_bfloat16* ob = out + b * (int64_t)Ho * Wo * C + c0 + cl;
-  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const uint2 zero = make_uint2(0, 0);
   for (int oy = wid; oy < Ho; oy += kDwWarps) {
     const int iy0 = oy * STRIDE - 1;
     const bool rv[3] = {iy0 >= 0, true, iy0 + 2 < H};
     const __nv_bfloat16* rp[3] = {xb + (int64_t)(iy0 < 0 ? 0 : iy0) * W * C, xb + (int64_t)(iy0 + 1) * W * C,
                                   xb + (int64_t)(iy0 + 2 < H ? iy0 + 2 : H - 1) * W * C};
-    auto ldcol = [&](int ix, F8 (&col)[3]) {
+    // raw (still packed) input columns are fetched two outputs ahead of their use: a warp walks its row serially
+    auto ldraw = [&](int ix, uint2 (&raw)[3]) {
       const bool cv = ix >= 0 && ix < W;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
-        col[r] = unpack8((cv && rv[r]) ? __ldg(reinterpret_cast<const uint4*>(rp[r] + (int64_t)ix * C)) : zero);
+        raw[r] = (cv && rv[r]) ? __ldg(reinterpret_cast<const uint2*>(rp[r] + (int64_t)ix * C)) : zero;
     };
-    F8 win[3][3];                                           // [column][row]
-    ldcol(-1, win[0]);                                      // zero pad column
-    if (STRIDE == 1) ldcol(0, win[1]);
-    for (int ox = 0; ox < Wo; ++ox) {
-      if (STRIDE == 1) {
-        ldcol(ox + 1, win[2]);
-      } else {
-        ldcol(2 * ox, win[1]);
-        ldcol(2 * ox + 1, win[2]);
-      }
-      F8 acc;
+    auto unpack_col = [&](const uint2 (&raw)[3], F4 (&col)[3]) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc.v[i] = sh[i];
+      for (int r = 0; r < 3; ++r) col[r] = unpack4(raw[r]);
+    };
+    F4 win[3][3];                                           // [column][row]
+    auto emit = [&](int ox) {
+      float acc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = sh[i];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const float4 w0 = *reinterpret_cast<const float4*>(&ws[ky * 3 + kx][cl]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&ws[ky * 3 + kx][cl + 4]);
-          const F8& v = win[kx][ky];
-          acc.v[0] = fmaf(v.v[0], w0.x, acc.v[0]); acc.v[1] = fmaf(v.v[1], w0.y, acc.v[1]);
-          acc.v[2] = fmaf(v.v[2], w0.z, acc.v[2]); acc.v[3] = fmaf(v.v[3], w0.w, acc.v[3]);
-          acc.v[4] = fmaf(v.v[4], w1.x, acc.v[4]); acc.v[5] = fmaf(v.v[5], w1.y, acc.v[5]);
-          acc.v[6] = fmaf(v.v[6], w1.z, acc.v[6]); acc.v[7] = fmaf(v.v[7], w1.w, acc.v[7]);
+          const F4& v = win[kx][ky];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(v.v[i], wt[ky * 3 + kx][i], acc[i]);
         }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { acc.v[i] = silu_f(acc.v[i]); pool[i] += acc.v[i]; }
-      *reinterpret_cast<uint4*>(ob + ((int64_t)oy * Wo + ox) * C) = pack8(acc);
-      if (STRIDE == 1) {
+      for (int i = 0; i < 4; ++i) { acc[i] = silu_f(acc[i]); pool[i] += acc[i]; }
+      *reinterpret_cast<uint2*>(ob + ((int64_t)oy * Wo + ox) * C) = make_uint2(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]));
+    };
+    {
+      uint2 z3[3] = {zero, zero, zero};
+      unpack_col(z3, win[0]);                               // zero pad column (ix = -1)
+    }
+    if (STRIDE == 1) {
+      uint2 ra[3], rb[3];
+      ldraw(0, ra);
+      unpack_col(ra, win[1]);
+      ldraw(1, ra);                                         // column of output 0
+      ldraw(2, rb);                                         // column of output 1
+      for (int ox = 0; ox < Wo; ox += 2) {
+        unpack_col(ra, win[2]);
+        ldraw(ox + 3, ra);                                  // for output ox + 2
+        emit(ox);
 #pragma unroll
         for (int r = 0; r < 3; ++r) { win[0][r] = win[1][r]; win[1][r] = win[2][r]; }
-      } else {
+        if (ox + 1 < Wo) {
+          unpack_col(rb, win[2]);
+          ldraw(ox + 4, rb);                                // for output ox + 3
+          emit(ox + 1);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) { win[0][r] = win[1][r]; win[1][r] = win[2][r]; }
+        }
+      }
+    } else {
+      uint2 a0[3], a1[3], b0[3], b1[3];                     // columns (2ox, 2ox+1) of the next two outputs
+      ldraw(0, a0); ldraw(1, a1);
+      ldraw(2, b0); ldraw(3, b1);
+      for (int ox = 0; ox < Wo; ox += 2) {
+        unpack_col(a0, win[1]); unpack_col(a1, win[2]);
+        ldraw(2 * ox + 4, a0); ldraw(2 * ox + 5, a1);       // for output ox + 2
+        emit(ox);
 #pragma unroll
         for (int r = 0; r < 3; ++r) win[0][r] = win[2][r];
+        if (ox + 1 < Wo) {
+          unpack_col(b0, win[1]); unpack_col(b1, win[2]);
+          ldraw(2 * ox + 6, b0); ldraw(2 * ox + 7, b1);     // for output ox + 3
+          emit(ox + 1);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) win[0][r] = win[2][r];
+        }
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) red[wid][cl + i] = pool[i];
+  for (int i = 0; i < 4; ++i) red[wid][cl + i] = pool[i];
   __syncthreads();
   if (threadIdx.x < kDwSlab) {
     float s = 0.f;
