@@ -113,6 +113,21 @@ __device__ __forceinline__ f32x2_t bf16x2_to_f32x2(uint32_t v) {
 __device__ __forceinline__ void fma_f32x2(f32x2_t& acc, f32x2_t a, f32x2_t b) {
   asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
+__device__ __forceinline__ f32x2_t fma3_f32x2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2_t mul_f32x2(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2_t add_f32x2(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 
 constexpr float kLnEps = 1e-6f;  // timm LayerNorm2d eps for ConvNeXt
 

@@ -344,15 +344,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const int n = n0 + ch * 16;
         float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + i);
-          v[i] = __uint_as_float(cur[i]) + b4.x; v[i + 1] = __uint_as_float(cur[i + 1]) + b4.y;
-          v[i + 2] = __uint_as_float(cur[i + 2]) + b4.z; v[i + 3] = __uint_as_float(cur[i + 3]) + b4.w;
-        }
         if (EPI == BTSB_EPI_BIAS_GELU) {
+          // bias add and GELU on packed fp32 pairs: 6 instead of ~10 issue slots per element
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + i);
+            const float2 g0 = unpack_f32x2(gelu_fast2(add_f32x2(pack_f32x2(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])),
+                                                                 pack_f32x2(b4.x, b4.y))));
+            const float2 g1 = unpack_f32x2(gelu_fast2(add_f32x2(pack_f32x2(__uint_as_float(cur[i + 2]), __uint_as_float(cur[i + 3])),
+                                                                 pack_f32x2(b4.z, b4.w))));
+            v[i] = g0.x; v[i + 1] = g0.y; v[i + 2] = g1.x; v[i + 3] = g1.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + i);
+            v[i] = __uint_as_float(cur[i]) + b4.x; v[i + 1] = __uint_as_float(cur[i + 1]) + b4.y;
+            v[i + 2] = __uint_as_float(cur[i + 2]) + b4.z; v[i + 3] = __uint_as_float(cur[i + 3]) + b4.w;
+          }
         }
         if (EPI == BTSB_EPI_BIAS_SILU) {
 #pragma unroll

@@ -539,12 +539,12 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
-        const float v0 = gelu_fast(__uint_as_float(r[i]) + b4.x);
-        const float v1 = gelu_fast(__uint_as_float(r[i + 1]) + b4.y);
-        const float v2 = gelu_fast(__uint_as_float(r[i + 2]) + b4.z);
-        const float v3 = gelu_fast(__uint_as_float(r[i + 3]) + b4.w);
-        o[i / 2] = pack_bf16x2(v0, v1);
-        o[i / 2 + 1] = pack_bf16x2(v2, v3);
+        const float2 g0 = unpack_f32x2(gelu_fast2(add_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                                             pack_f32x2(b4.x, b4.y))));
+        const float2 g1 = unpack_f32x2(gelu_fast2(add_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
+                                                             pack_f32x2(b4.z, b4.w))));
+        o[i / 2] = pack_bf16x2(g0.x, g0.y);
+        o[i / 2 + 1] = pack_bf16x2(g1.x, g1.y);
       }
       if (lane == 0) tr(1 + ew, g, 3);
       mbar_wait_spin(h_empty(grp), (use & 1u) ^ 1u);         // G2 of chunk g-2 has finished reading H[grp]

@@ -177,6 +177,36 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(h, t, h);
 }
 
+// Two GELUs per call on packed fp32 pairs (sm_100 FMUL2 / FFMA2): the scalar form issues 9-10 instructions per
+// element and is issue-bound at 10.1 clk per warp-element and SMSP, just above the MUFU floor of 8.1
+// (profiles/r01d_micro_gelu.txt); packed, the FMA-pipe part is 3 instructions per element.
+// BTSB_GELU_F16X2 additionally evaluates the two tanh with ONE MUFU op (tanh.approx.f16x2; argument rounded to fp16:
+// |error| of the result <= ~1e-3 at |x| = 3, still below the bf16 rounding of the stored hidden activation).
+#ifndef BTSB_GELU_F16X2
+#define BTSB_GELU_F16X2 0
+#endif
+__device__ __forceinline__ f32x2_t gelu_fast2(f32x2_t x) {
+  const f32x2_t k5 = pack_f32x2(-3.5151679e-4f, -3.5151679e-4f), k3 = pack_f32x2(0.037005646f, 0.037005646f);
+  const f32x2_t k1 = pack_f32x2(0.7975078843f, 0.7975078843f), kh = pack_f32x2(0.5f, 0.5f);
+  const float2 sq = unpack_f32x2(mul_f32x2(x, x));
+  const f32x2_t x2 = pack_f32x2(fminf(sq.x, 64.0f), fminf(sq.y, 64.0f));
+  f32x2_t p = fma3_f32x2(x2, k5, k3);
+  p = fma3_f32x2(x2, p, k1);
+  const float2 a = unpack_f32x2(mul_f32x2(p, x));
+  float t0, t1;
+#if BTSB_GELU_F16X2
+  uint32_t hv, tv;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hv) : "f"(a.y), "f"(a.x));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tv) : "r"(hv));
+  asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(t0), "=f"(t1) : "r"(tv));
+#else
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a.y));
+#endif
+  const f32x2_t h = mul_f32x2(x, kh);
+  return fma3_f32x2(h, pack_f32x2(t0, t1), h);
+}
+
 // SiLU x * sigmoid(x) == 0.5 x (1 + tanh(x / 2)) for bf16 outputs: one MUFU op
 __device__ __forceinline__ float silu_fast(float x) {
   const float h = 0.5f * x;
