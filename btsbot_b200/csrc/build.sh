@@ -5,7 +5,7 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="$HERE/../libbtsbot_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
-       --expt-relaxed-constexpr -Xptxas -v)
+       --expt-relaxed-constexpr -Xptxas -v ${BTSB_NVCC_EXTRA:-})
 mkdir -p "$HERE/build"
 OBJS=()
 pids=()

@@ -180,11 +180,8 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // Two GELUs per call on packed fp32 pairs (sm_100 FMUL2 / FFMA2): the scalar form issues 9-10 instructions per
 // element and is issue-bound at 10.1 clk per warp-element and SMSP, just above the MUFU floor of 8.1
 // (profiles/r01d_micro_gelu.txt); packed, the FMA-pipe part is 3 instructions per element.
-// BTSB_GELU_F16X2 additionally evaluates the two tanh with ONE MUFU op (tanh.approx.f16x2; argument rounded to fp16:
-// |error| of the result <= ~1e-3 at |x| = 3, still below the bf16 rounding of the stored hidden activation).
-#ifndef BTSB_GELU_F16X2
-#define BTSB_GELU_F16X2 0
-#endif
+// (Evaluating both tanh with one tanh.approx.f16x2 was tried: the two cvt it needs made the fused MLP 9 % SLOWER --
+// 346 vs 317 us at C = 80 -- and the fp16 argument rounding broke the 2e-2 logit bar of one model; not kept.)
 __device__ __forceinline__ f32x2_t gelu_fast2(f32x2_t x) {
   const f32x2_t k5 = pack_f32x2(-3.5151679e-4f, -3.5151679e-4f), k3 = pack_f32x2(0.037005646f, 0.037005646f);
   const f32x2_t k1 = pack_f32x2(0.7975078843f, 0.7975078843f), kh = pack_f32x2(0.5f, 0.5f);
@@ -194,15 +191,8 @@ __device__ __forceinline__ f32x2_t gelu_fast2(f32x2_t x) {
   p = fma3_f32x2(x2, p, k1);
   const float2 a = unpack_f32x2(mul_f32x2(p, x));
   float t0, t1;
-#if BTSB_GELU_F16X2
-  uint32_t hv, tv;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hv) : "f"(a.y), "f"(a.x));
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(tv) : "r"(hv));
-  asm("{\n\t.reg .f16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(t0), "=f"(t1) : "r"(tv));
-#else
   asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a.x));
   asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a.y));
-#endif
   const f32x2_t h = mul_f32x2(x, kh);
   return fma3_f32x2(h, pack_f32x2(t0, t1), h);
 }
