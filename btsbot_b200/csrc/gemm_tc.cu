@@ -45,7 +45,10 @@ constexpr int EPI_LN = 100;   // internal: out = LayerNorm(acc + bias) * gamma(l
 constexpr int EPI_F32OUT = 101;   // out32[M,N] = acc (+ bias)                      -- forward Linear / dgrad
 constexpr int EPI_WGRAD = 102;    // out32[M,N] += acc over a K split (red.global)  -- wgrad, K = the huge row dimension
 
-template <int EPI>
+// CTA2: the kernel is launched in clusters of two CTAs that issue one M = 256 UMMA (cta_group::2) per K step; a work
+// unit is then a 256 x BN tile, CTA rank r owns rows [128 r, 128 r + 128) of it and stages rows [r BN/2, (r+1) BN/2) of
+// the B tile.  Everything per-CTA (epilogue, TMEM columns, smem ring) is unchanged.
+template <int EPI, bool CTA2 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ OutMaps tmO,
@@ -61,7 +64,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
   // ring geometry: a stage is the A box [128 x 64] plus the B box [BN x 64]; narrower B tiles buy deeper pipelines
-  const int kStageBytes = kABytes + ((BN * BK * 2 + 1023) & ~1023);
+  const int kStageBytes = kABytes + (((CTA2 ? BN / 2 : BN) * BK * 2 + 1023) & ~1023);
   const int kStages = min(kMaxStages, kRingBytes / kStageBytes);
   const uint32_t bar_base = smem_base + kRingBytes;
   // barrier map (8 B each): full[kMaxStages], empty[kMaxStages], tfull[kAcc], tempty[kAcc], then tmem address slot
@@ -75,7 +78,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // warp index made provably warp-uniform: the TMA / MMA roles below run converged and elect one issuing lane
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const int unit0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work unit of this CTA (pair)
+  const int unit_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int BMU = CTA2 ? 2 * BM : BM;                                 // rows per work unit
+  const int m_tiles = (M + BMU - 1) / BMU, n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + BK - 1) / BK;
   // split-K (wgrad only, splits == 1 otherwise): work item w = (tile, split) covers k-blocks [kb0, kb1) of its tile
@@ -97,43 +104,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < kAcc; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI == EPI_LN ? 4 : kEpiWarps); }
+    for (int s = 0; s < kAcc; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), EPI == EPI_LN ? 4 : (CTA2 ? 2 * kEpiWarps : kEpiWarps));   // pair: both CTAs' epilogue warps
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32((const void*)tmem_slot), kTmemCols);
-    tmem_relinquish();
+    if (CTA2) { tmem_alloc_pair(smem_u32((const void*)tmem_slot), kTmemCols); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32((const void*)tmem_slot), kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / pair TMA
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
-    const uint32_t tx_bytes = (uint32_t)(BM + BN) * BK * 2;
-    for (int wk = blockIdx.x; wk < num_work; wk += gridDim.x) {
+    const uint32_t tx_bytes = CTA2 ? (uint32_t)(2 * BM + BN) * BK * 2 : (uint32_t)(BM + BN) * BK * 2;
+    for (int wk = unit0; wk < num_work; wk += unit_step) {
       const int tile = wk / splits, kb0 = (wk - tile * splits) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * BMU + (int)cta_rank * BM;
+      const int n0 = (tile % n_tiles) * BN + (CTA2 ? (int)cta_rank * (BN / 2) : 0);
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait_spin(empty_bar(stage), phase ^ 1u);
+        mbar_wait_spin(empty_bar(stage), phase ^ 1u);      // this CTA's stage is free (pair: commit is multicast)
         if (elect_one()) {
-          mbar_expect_tx(full_bar(stage), tx_bytes);
           const uint32_t sa = smem_base + stage * kStageBytes;
-          tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sa + kABytes, &tmB, full_bar(stage), kb * BK, n0);
+          if (CTA2) {
+            // both CTAs' bytes are counted on the LEADER's full barrier, which its MMA warp waits on
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
+            const uint32_t lead = mapa_shared(full_bar(stage), 0);
+            tma_load_2d_pair(sa, &tmA, lead, kb * BK, m0);
+            tma_load_2d_pair(sa + kABytes, &tmB, lead, kb * BK, n0);
+          } else {
+            mbar_expect_tx(full_bar(stage), tx_bytes);
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sa + kABytes, &tmB, full_bar(stage), kb * BK, n0);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+  } else if (warp == 1 && cta_rank == 0) {
+    // ===================== MMA issuer (converged warp, one elected lane issues; pair: the leader CTA only) ==========
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
-    const uint32_t idesc = idesc_bf16_f32(BM, BN);
-    for (int wk = blockIdx.x; wk < num_work; wk += gridDim.x) {
+    const uint32_t idesc = idesc_bf16_f32(BMU, BN);
+    for (int wk = unit0; wk < num_work; wk += unit_step) {
       const int kb0 = (wk % splits) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait_spin(tempty_bar(as), aphase ^ 1u);     // epilogue has drained this accumulator
       tc_fence_after();
@@ -146,17 +166,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t adesc = smem_desc_sw128(sa);
           const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
           const int kmax = (min(BK, K - kb * BK) + 15) / 16;   // K tail: TMA zero-fills, but skip the useless MMAs
-          if (kmax == 4) {
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
-          } else {
+          if (CTA2) {
             for (int kk = 0; kk < kmax; ++kk)
-              umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
+              umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
+            umma_commit_pair(empty_bar(stage));             // frees this stage in BOTH CTAs when the MMAs retire
+            if (kb == kb1 - 1) umma_commit_pair(tfull_bar(as));
+          } else {
+            if (kmax == 4) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                // advance 16 elements (32 B) along K inside the 128B swizzle row: +2 in the (addr >> 4) field
+                umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
+            } else {
+              for (int kk = 0; kk < kmax; ++kk)
+                umma_bf16(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(empty_bar(stage));                  // frees this smem stage when the MMAs retire
+            if (kb == kb1 - 1) umma_commit(tfull_bar(as));        // accumulator complete -> epilogue
           }
-          umma_commit(empty_bar(stage));                  // frees this smem stage when the MMAs retire
-          if (kb == kb1 - 1) umma_commit(tfull_bar(as));        // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -248,12 +275,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int chunks = BN / 16;
     const int c_lo = (chunks * part) / kParts;
     const int c_hi = (chunks * (part + 1)) / kParts;
+    // releasing an accumulator stage: one arrival per epilogue warp on the (leader's) accumulator-empty barrier
+    auto release_acc = [&](int as_) {
+      if (CTA2) mbar_arrive_cluster(mapa_shared(tempty_bar(as_), 0));
+      else mbar_arrive(tempty_bar(as_));
+    };
     int lt = 0;
-    for (int wk = blockIdx.x; wk < num_work; wk += gridDim.x, ++lt) {
+    for (int wk = unit0; wk < num_work; wk += unit_step, ++lt) {
       const int tile = wk / splits;
       const int as = lt & 1;
       const uint32_t aphase = (uint32_t)(lt >> 1) & 1u;
-      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+      const int m0 = (tile / n_tiles) * BMU + (int)cta_rank * BM, n0 = (tile % n_tiles) * BN;
       mbar_wait_spin(tfull_bar(as), aphase);
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
@@ -284,13 +316,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) release_acc(as);
         continue;
       }
       if (dbg & 1) {                                    // timing experiment: main loop only, accumulator released unread
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) release_acc(as);
         continue;
       }
       if (dbg & 12) {                                   // timing experiments: TMEM reads only (4) / + math, no stores (8)
@@ -304,14 +336,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) release_acc(as);
         if (acc == 123.456f) out[0] = __float2bfloat16(acc);
         continue;
       }
       if (c_lo >= c_hi) {                               // narrow tile: this warp has no columns, release at once
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (lane == 0) release_acc(as);
         continue;
       }
       // The warp's columns are cut into slabs of 4 / 2 / 1 chunks (64 / 32 / 16 columns).  Each thread packs its row of
@@ -340,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {                                          // last TMEM read of this warp for this tile
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
+          if (lane == 0) release_acc(as);
         }
         const int n = n0 + ch * 16;
         float v[16];
@@ -417,10 +449,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) tma_store_wait_all();                  // smem must outlive the last bulk store's reads
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();      // the peer may still be read by the leader's MMAs / signalled by its TMA until here
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CTA2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -502,15 +536,59 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
     BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)gamma % 16) == 0, "gemm bf16: res/gamma must be 16-byte aligned");
   BTSB_REQUIRE(N <= kMaxNBias, "gemm bf16: N=%d exceeds the staged bias capacity (%d)", N, kMaxNBias);
   static const int dbg = getenv("BTSB_GEMM_DBG") ? atoi(getenv("BTSB_GEMM_DBG")) : 0;   // timing experiments only
+  // CTA pairs (cta_group::2, M = 256 UMMA over two SMs): opt-in with BTSB_GEMM_2CTA=1.  Measured on B200 (profiles/r01j):
+  // parity-green on every tested shape but performance-neutral for this network (fc1_320 75.2 -> 74.3 us, fc2_320
+  // 73.0 -> 70.7 us, C3 1.78 M -> 1.76 M alerts/s, C4 23.7 k -> 22.3 k): these GEMMs carry the 4C-wide hidden tensor
+  // through HBM (189 MB per launch) and are bound by that and by the epilogue, not by shared-memory operand bandwidth.
+  static const int pair_mode = getenv("BTSB_GEMM_2CTA") ? atoi(getenv("BTSB_GEMM_2CTA")) : 0;
   int BN = pick_bn(N);
   if ((dbg & 2) && BN > 128 && N % 128 == 0) BN = 128;
+  const bool pair_ok = BN % 32 == 0 && dbg == 0;           // each CTA stages BN/2 rows of B: whole 8-row swizzle atoms
+  const int64_t units2 = ((M + 2 * BM - 1) / (2 * BM)) * (int64_t)(N / BN);
+  const bool pair = pair_ok && pair_mode == 1;
   CUtensorMap tmA, tmB;
   if (int e = make_tmap_bf16_2d(&tmA, A, (uint64_t)M, (uint64_t)K, BM)) return e;
-  if (int e = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint32_t)BN)) return e;
+  if (int e = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint32_t)(pair ? BN / 2 : BN))) return e;
   OutMaps tmO;
   if (int e = make_tmap_bf16_2d_sw(&tmO.o128, out, (uint64_t)M, (uint64_t)N, 32, 64, 128)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tmO.o64, out, (uint64_t)M, (uint64_t)N, 32, 32, 64)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tmO.o32, out, (uint64_t)M, (uint64_t)N, 32, 16, 32)) return e;
+  const __nv_bfloat16* r = (const __nv_bfloat16*)res;
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  if (pair) {
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+      BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_GELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+      BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_SCALE_RES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+      BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_SILU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+      attr2_done = true;
+    }
+    const int64_t pairs = units2 < num_sms() / 2 ? units2 : num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const float* nf = nullptr;
+    float* no32 = nullptr;
+    const int Mi = (int)M, one = 1;
+    cudaError_t le;
+    if (epilogue == BTSB_EPI_BIAS)
+      le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BTSB_EPI_BIAS, true>, tmA, tmB, tmO, bias, gamma, nf, r, o, Mi, N, K, BN, dbg, no32, one);
+    else if (epilogue == BTSB_EPI_BIAS_GELU)
+      le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BTSB_EPI_BIAS_GELU, true>, tmA, tmB, tmO, bias, gamma, nf, r, o, Mi, N, K, BN, dbg, no32, one);
+    else if (epilogue == BTSB_EPI_BIAS_SILU)
+      le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BTSB_EPI_BIAS_SILU, true>, tmA, tmB, tmO, bias, gamma, nf, r, o, Mi, N, K, BN, dbg, no32, one);
+    else
+      le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BTSB_EPI_SCALE_RES, true>, tmA, tmB, tmO, bias, gamma, nf, r, o, Mi, N, K, BN, dbg, no32, one);
+    if (le != cudaSuccess) { set_error("gemm_bf16 (pair): launch failed: %s", cudaGetErrorString(le)); return BTSB_ECUDA; }
+    return launch_done("gemm_bf16_pair");
+  }
   const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
   const int grid = min(m_tiles * n_tiles, num_sms());
   static bool attr_done = false;
@@ -521,8 +599,6 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     attr_done = true;
   }
-  const __nv_bfloat16* r = (const __nv_bfloat16*)res;
-  __nv_bfloat16* o = (__nv_bfloat16*)out;
   if (epilogue == BTSB_EPI_BIAS)
     gemm_tc_kernel<BTSB_EPI_BIAS><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, gamma, nullptr, r, o, (int)M, N, K, BN, dbg);
   else if (epilogue == BTSB_EPI_BIAS_GELU)

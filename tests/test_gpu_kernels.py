@@ -144,6 +144,32 @@ def test_gemm_bf16_tcgen05(cuda_dev, M, N, K, epi):
     assert err < 3.2e-2 and (got - ref).abs().mean().item() < 4e-3
 
 
+def test_gemm_bf16_cta_pair_mode_in_subprocess(cuda_dev):
+    """The opt-in cta_group::2 path (BTSB_GEMM_2CTA=1: clusters of two CTAs, one M=256 UMMA, B halves staged per CTA)
+    must give the same results as the default path; the switch is read once per process, hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import torch, sys; sys.path.insert(0, %r)\n"
+        "from btsbot_b200 import ops\n"
+        "g = torch.Generator().manual_seed(6); worst = 0.0\n"
+        "for M, N, K, epi in [(1000, 320, 80, 0), (513, 2560, 640, 1), (5000, 256, 1024, 2), (257, 512, 2048, 2), (1, 640, 2560, 0), (73, 1280, 320, 1)]:\n"
+        "    a = torch.randn(M, K, generator=g).bfloat16(); w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()\n"
+        "    bias, gamma = torch.randn(N, generator=g) * 0.1, torch.rand(N, generator=g) + 0.5\n"
+        "    res = torch.randn(M, N, generator=g).bfloat16()\n"
+        "    acc = a.float() @ w.float().t() + bias\n"
+        "    ref = acc if epi == 0 else (torch.nn.functional.gelu(acc) if epi == 1 else res.float() + gamma * acc)\n"
+        "    got = ops.gemm(a.cuda(), w.cuda(), bias.cuda(), epi, gamma.cuda() if epi == 2 else None, res.cuda() if epi == 2 else None)\n"
+        "    torch.cuda.synchronize(); worst = max(worst, (got.float().cpu() - ref).abs().max().item())\n"
+        "print('PAIR_WORST', worst)\n" % root)
+    env = dict(os.environ, BTSB_GEMM_2CTA="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    worst = float(out.stdout.strip().split("PAIR_WORST")[-1])
+    print(f"[parity] gemm bf16 cta_group::2 path: worst |err| over 6 shapes = {worst:.3e}")
+    assert worst < 3.2e-2
+
+
 @pytest.mark.parametrize("C,M", [(80, 1000), (160, 777), (64, 4096), (128, 129), (80, 128 * 300 + 5), (96, 50)])
 def test_mlp_fused_tcgen05(cuda_dev, C, M):
     """fused fc1->GELU->fc2->*gamma->+res vs fp32 math on the same bf16 operands (hidden rounded to bf16 as the
