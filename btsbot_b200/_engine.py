@@ -9,6 +9,8 @@ kernels activations are NHWC pixel rows ``[B*H*W, C]`` in the compute dtype (flo
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import torch
@@ -18,7 +20,10 @@ from .synth import convnext_arch
 
 BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by the reference (architectures.py:147)
 
-#: use the fused fc1->GELU->fc2 kernel where it applies (bf16, C <= 160); tests flip this to cover both paths
+#: the wide variants of the fused kernel (C = 256 / 320: single D2 accumulator, G2 split in two UMMAs); BTSB_FUSE_WIDE=0
+#: falls back to the two separate GEMMs for A/B timing
+FUSE_MLP_WIDE = os.environ.get("BTSB_FUSE_WIDE", "1") != "0"
+#: use the fused fc1->GELU->fc2 kernel where it applies (bf16, C <= 160, 256, 320); tests flip this to cover both paths
 FUSE_MLP = True
 #: bf16 stem as im2col + tcgen05 GEMM with the LayerNorm in the epilogue (else the CUDA-core stem kernel)
 TC_STEM = True
@@ -136,7 +141,7 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
                 capture[f"down{i}"] = (cur, h, wd)
         M = B * h * wd
         y = torch.empty((M, c), device=dev, dtype=adt)
-        fused = FUSE_MLP and code == L.BF16 and c % 16 == 0 and 64 <= c <= 160
+        fused = FUSE_MLP and code == L.BF16 and c % 16 == 0 and (64 <= c <= 160 or (FUSE_MLP_WIDE and c in (256, 320)))
         hid = None if fused else torch.empty((M, 4 * c), device=dev, dtype=adt)
         for j, blk in enumerate(stg["blocks"]):
             L.launch(f"dwln_{wd}x{c}", lib.btsb_convnext_dwln_fwd, _p(cur), code, B, h, wd, c, _p(blk["dw_w"]),

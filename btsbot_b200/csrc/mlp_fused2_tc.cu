@@ -73,7 +73,8 @@ __host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht)
   if (plan2_try(P, 2, 3, 4, 0)) return true;
   if (plan2_try(P, 1, 3, 4, 0)) return true;
   if (plan2_try(P, 1, 2, 3, 0)) return true;
-  return plan2_try(P, 1, 2, 2, 0);
+  if (plan2_try(P, 1, 2, 2, 0)) return true;
+  return plan2_try(P, 1, 2, 1, 0);                      // C = 320: 80 KB y tile, 40 KB weight chunks
 }
 
 __host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht) {
@@ -157,8 +158,14 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   };
   constexpr Plan2 P = plan2_for(C, TE, HT);
   static_assert(P.ok, "no shared-memory plan for this C");
-  constexpr int kHCol = kD2Col + 2 * C;                          // TMEM columns of H[0], H[1] (32 each) in HT mode
-  static_assert(!HT || kHCol + 64 <= 512, "TMEM column budget");
+  // wide C (256, 320): one D2 accumulator instead of two (the D2 epilogue of a tile then holds back the first G2 of the
+  // next one), and for C > 256 every G2 step is two UMMAs of N = C/2 columns
+  constexpr int D2B = (kD2Col + 2 * C + (HT ? 64 : 0) <= 512) ? 2 : 1;
+  constexpr int NSPLIT = C > 256 ? 2 : 1;
+  constexpr int NC = C / NSPLIT;
+  constexpr int kHCol = kD2Col + D2B * C;                        // TMEM columns of H[0], H[1] (32 each) in HT mode
+  static_assert(kD2Col + D2B * C + (HT ? 64 : 0) <= 512, "TMEM column budget");
+  static_assert(NC % 16 == 0 && NC <= 256, "G2 UMMA width");
   constexpr int NJ = P.NJ;
   constexpr int nkb = P.nfull + P.t32 + P.t16;
   extern __shared__ unsigned char smem_dyn[];
@@ -252,7 +259,9 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         mbar_wait_spin(w2_empty(s2), ph2 ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(w2_full(s2), (uint32_t)(C * 128));
-          tma_load_2d(sbase + P.off_w2 + s2 * P.w2_bytes, &tm.w2, w2_full(s2), j2 * NH, 0);
+#pragma unroll
+          for (int h = 0; h < NSPLIT; ++h)
+            tma_load_2d(sbase + P.off_w2 + s2 * P.w2_bytes + h * NC * 128, &tm.w2, w2_full(s2), j2 * NH, h * NC);
         }
         __syncwarp();
       }
@@ -269,7 +278,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   } else if (warp == 1 || warp == kG2Warp) {
     // ============================== MMA issuers (whole warp walks its schedule, one elected lane issues) ===============
     constexpr uint32_t idesc1 = idesc_bf16_f32(FM, NH);
-    constexpr uint32_t idesc2 = idesc_bf16_f32(FM, C);
+    constexpr uint32_t idesc2 = idesc_bf16_f32(FM, NC);
     // G1 stream state
     int j1 = 0, s1 = 0, yb = 0, b1i = 0; uint32_t ph1 = 0, yph = 0, dph1 = 0, t1 = 0;
     // G2 stream state
@@ -312,12 +321,18 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           const uint32_t acol = tmem_base + (uint32_t)(kHCol + b2i * 32);
 #pragma unroll
           for (int kk = 0; kk < NH / 16; ++kk)
-            umma_bf16_ts(dcol, acol + (uint32_t)(8 * kk), bd + (uint64_t)(2 * kk), idesc2, (j2 | kk) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < NSPLIT; ++h)      // rows [h NC, (h+1) NC) of the W2 chunk -> D2 columns [h NC, (h+1) NC)
+              umma_bf16_ts(dcol + (uint32_t)(h * NC), acol + (uint32_t)(8 * kk), bd + (uint64_t)(h * NC * 8 + 2 * kk), idesc2,
+                           (j2 | kk) != 0 ? 1u : 0u);
         } else {
           const uint64_t ad = smem_desc_sw128(sbase + P.off_h + b2i * kHBytes);
 #pragma unroll
           for (int kk = 0; kk < NH / 16; ++kk)
-            umma_bf16(dcol, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc2, (j2 | kk) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < NSPLIT; ++h)
+              umma_bf16(dcol + (uint32_t)(h * NC), ad + (uint64_t)(2 * kk), bd + (uint64_t)(h * NC * 8 + 2 * kk), idesc2,
+                        (j2 | kk) != 0 ? 1u : 0u);
         }
         umma_commit(h_empty(b2i));
         if (!P.resident) umma_commit(w2_empty(s2));
@@ -329,7 +344,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       if (++j2 == NJ) {
         j2 = 0; ++t2;
         if (P.resident) s2 = 0;
-        tb ^= 1; if (tb == 0) d2ph ^= 1u;
+        if (++tb == D2B) { tb = 0; d2ph ^= 1u; }
       }
     };
     // Two issuing warps, one per GEMM stream, each with plain blocking waits.  A single warp alternating between the two
@@ -366,25 +381,27 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int groups2 = C / 16;
     constexpr int NU = (groups2 + 3) / 4;   // 16-column groups of D2 per warp
-    uint4 rpre[NU][2];                       // residual rows of the tile whose D2 epilogue is pending
+    constexpr bool PRE = NU <= 3;           // wide C: 5 groups per warp would cost 40 registers -> load at use instead
+    uint4 rpre[PRE ? NU : 1][2];             // residual rows of the tile whose D2 epilogue is pending
 
     auto prefetch_res = [&](int tile) {
+      if (!PRE) return;
       const int row = tile * FM + r_in_tile;
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
         const int gi = k4 + 4 * u;
         if (gi < groups2 && row < M) {
           const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + gi * 16);
-          rpre[u][0] = __ldg(rp); rpre[u][1] = __ldg(rp + 1);
+          rpre[PRE ? u : 0][0] = __ldg(rp); rpre[PRE ? u : 0][1] = __ldg(rp + 1);
         } else {
-          rpre[u][0] = make_uint4(0, 0, 0, 0); rpre[u][1] = make_uint4(0, 0, 0, 0);
+          rpre[PRE ? u : 0][0] = make_uint4(0, 0, 0, 0); rpre[PRE ? u : 0][1] = make_uint4(0, 0, 0, 0);
         }
       }
     };
     // D2 -> +b2 -> *gamma + res -> bf16 rows of tile `tile` (local index tl); column groups k4, k4+4, k4+8
     auto d2_epilogue = [&](int tile, uint32_t tl) {
-      const int tb = (int)(tl & 1u);
-      mbar_wait_spin(d2_full(tb), (tl >> 1) & 1u);
+      const int tb = (int)(tl % (uint32_t)D2B);
+      mbar_wait_spin(d2_full(tb), (tl / (uint32_t)D2B) & 1u);
       tc_fence_after();
       const int row = tile * FM + r_in_tile;
 #pragma unroll
@@ -393,6 +410,12 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         if (gi >= groups2) break;
         uint32_t r[16];
         tmem_ld16(lane_addr + (uint32_t)(kD2Col + tb * C + gi * 16), r);
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        if (PRE) { r0 = rpre[PRE ? u : 0][0]; r1 = rpre[PRE ? u : 0][1]; }
+        else if (row < M) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + gi * 16);
+          r0 = __ldg(rp); r1 = __ldg(rp + 1);
+        }
         tmem_ld_wait();
         if (gi + 4 >= groups2) {                         // last D2 read of this warp for this tile
           tc_fence_before();
@@ -401,7 +424,6 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         }
         if (row < M) {
           const int n = gi * 16;
-          const uint4 r0 = rpre[u][0], r1 = rpre[u][1];
           const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
           float v[16];
 #pragma unroll
@@ -449,8 +471,8 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       __syncwarp();
     };
     auto d2_epilogue_te = [&](int tile, uint32_t tl) {
-      const int tb = (int)(tl & 1u);
-      mbar_wait_spin(d2_full(tb), (tl >> 1) & 1u);
+      const int tb = (int)(tl % (uint32_t)D2B);
+      mbar_wait_spin(d2_full(tb), (tl / (uint32_t)D2B) & 1u);
       tc_fence_after();
       if (c_lo >= c_hi) {                                  // (cannot happen for C >= 64: every warp owns >= 1 chunk)
         tc_fence_before(); __syncwarp();
@@ -597,7 +619,7 @@ int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint
                          uint32_t box_cols, int swizzle_bytes);
 
 int mlp_fused2_supported(int C) {
-  return C % 16 == 0 && C >= 64 && C <= 160;
+  return C % 16 == 0 && ((C >= 64 && C <= 160) || C == 256 || C == 320);
 }
 
 template <int C, bool TE, bool HT>
@@ -628,7 +650,8 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
     if (int e = make_tmap_bf16_2d_sw(&tm.y32, y, (uint64_t)M, (uint64_t)C, FM, 16, 32)) return e;
     if (int e = make_tmap_bf16_2d_sw(&tm.a32, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 16, 32)) return e;
   }
-  if (int e = make_tmap_bf16_2d_sw(&tm.w2, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)C, 64, 128)) return e;
+  const int NC = C > 256 ? C / 2 : C;                      // W2 chunk rows per bulk copy / per G2 UMMA
+  if (int e = make_tmap_bf16_2d_sw(&tm.w2, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)NC, 64, 128)) return e;
   // BTSB_MLP_HSMEM=1 keeps the hidden chunk in shared memory (first version of this kernel) for A/B timing
   static const int hsmem = getenv("BTSB_MLP_HSMEM") ? atoi(getenv("BTSB_MLP_HSMEM")) : 0;
   if (int e = make_tmap_bf16_2d_sw(&tm.r128, res, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
@@ -637,6 +660,9 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
   if (int e = make_tmap_bf16_2d_sw(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
+  // wide C: no room for the staging tile next to the 80 KB y tile -> residual / output rows go straight to global
+  if (C == 256) return launch2<256, false, true>(tm, b1, b2, gamma, res, out, M, st);
+  if (C == 320) return launch2<320, false, true>(tm, b1, b2, gamma, res, out, M, st);
   if (hsmem) {
     switch (C) {
       case 64: return launch2<64, true, false>(tm, b1, b2, gamma, res, out, M, st);

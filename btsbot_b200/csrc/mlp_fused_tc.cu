@@ -306,7 +306,7 @@ extern "C" int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const
                                            int C, void* stream) {
   if (int e = check_device()) return e;
   BTSB_REQUIRE(M >= 0 && M < (1ll << 31), "mlp_fused: bad M");
-  BTSB_REQUIRE(C % 16 == 0 && C >= 64 && C <= 160, "mlp_fused: C=%d unsupported (multiple of 16 in [64,160])", C);
+  BTSB_REQUIRE(mlp_fused2_supported(C), "mlp_fused: C=%d unsupported (multiple of 16 in [64,160], 256 or 320)", C);
   if (M == 0) return BTSB_OK;
   BTSB_REQUIRE(y && res && W1 && b1 && W2 && b2 && gamma && out, "mlp_fused: null pointer");
   BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)b1 % 16) == 0 &&

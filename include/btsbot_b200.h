@@ -131,8 +131,8 @@ int btsb_gemm_ln_fwd(const void* A, const void* Wt, const float* bias, const flo
                      void* out, int64_t M, int N, int K, void* stream);
 
 /* ---- K4 fused: ONE kernel for fc1 -> GELU -> fc2 -> *gamma -> +shortcut; the 4C hidden activation stays in
- * TMEM / shared memory (timm blocks.j.mlp + gamma + residual).  BF16 only; C a multiple of 16 in [64,160]
- * (ConvNeXt nano/pico stages 0-1, where the hidden tensor would be 4x the activation traffic).
+ * TMEM / shared memory (timm blocks.j.mlp + gamma + residual).  BF16 only; C a multiple of 16 in [64,160], 256 or 320
+ * (ConvNeXt nano/pico stages 0-2, where the hidden tensor would be 4x the activation traffic).
  * y: dw+LN output [M,C]; res: block input [M,C]; W1 [4C,C], W2 [C,4C] bf16 row-major; b1 [4C], b2/gamma [C] f32.
  */
 int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const void* W1, const float* b1,

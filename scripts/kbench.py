@@ -87,7 +87,7 @@ def head():
 
 
 print(f"kbench: batch {B}, reps {args.reps}, BTSB_MLP_V1={os.environ.get('BTSB_MLP_V1', '')}")
-mlp(80, 225); mlp(160, 49); mlp(64, 225); mlp(128, 49)
+mlp(80, 225); mlp(160, 49); mlp(64, 225); mlp(128, 49); mlp(320, 9); mlp(256, 9)
 fc(320, 9); fc(640, 1)
 dw(80, 15); dw(160, 7); dw(320, 3)
 lnp(80, 15); lnp(160, 7)

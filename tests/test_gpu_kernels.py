@@ -170,7 +170,8 @@ def test_gemm_bf16_cta_pair_mode_in_subprocess(cuda_dev):
     assert worst < 3.2e-2
 
 
-@pytest.mark.parametrize("C,M", [(80, 1000), (160, 777), (64, 4096), (128, 129), (80, 128 * 300 + 5), (96, 50)])
+@pytest.mark.parametrize("C,M", [(80, 1000), (160, 777), (64, 4096), (128, 129), (80, 128 * 300 + 5), (96, 50),
+                                 (320, 1000), (256, 777), (320, 128 * 150 + 5), (256, 128 * 149)])
 def test_mlp_fused_tcgen05(cuda_dev, C, M):
     """fused fc1->GELU->fc2->*gamma->+res vs fp32 math on the same bf16 operands (hidden rounded to bf16 as the
     kernel does before the second GEMM)."""
