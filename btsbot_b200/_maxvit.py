@@ -25,7 +25,7 @@ BN2D_EPS = 1e-5     # timm conv_cfg.norm_eps for the 'rw' MaxViT variants (SURVE
 
 #: images per pass through the trunk (bounds the largest activation: chunk x 112 x 112 x 256 elements)
 CHUNK = {"fp32": 128, "bf16": 1024}
-#: use the fused fc1->GELU->fc2 kernel in the attention MLPs where it applies (bf16, C <= 160)
+#: use the fused fc1->GELU->fc2 kernel in the attention MLPs where it applies (bf16, C <= 160 and C = 256)
 FUSE_MLP = True
 
 _DT = {"fp32": (L.F32, torch.float32), "bf16": (L.BF16, torch.bfloat16)}
@@ -138,7 +138,7 @@ def _attention_block(w: MaxVitWeights, a: dict, cur, B, H, W, c, grid_mode, tag,
              flops=4.0 * 49 * 32 * M * heads, nbytes=es * (qkv.numel() + o.numel()))
     cur = _gemm(f"mv_proj_{c}", o, a["proj_w"], a["proj_b"], w.ones(c), cur, code, L.EPI_SCALE_RES, st)
     y = _ln(f"mv_ln_{c}", cur, a["n2_w"], a["n2_b"], code, st)
-    if FUSE_MLP and code == L.BF16 and c % 16 == 0 and 64 <= c <= 160:
+    if FUSE_MLP and code == L.BF16 and c % 16 == 0 and (64 <= c <= 160 or c == 256):
         nxt = torch.empty_like(cur)
         L.launch(f"mv_mlp_fused_{c}", lib.btsb_convnext_mlp_fused_fwd, _p(y), _p(cur), _p(a["fc1_w"]), _p(a["fc1_b"]),
                  _p(a["fc2_w"]), _p(a["fc2_b"]), _p(w.ones(c)), _p(nxt), M, c, st,
