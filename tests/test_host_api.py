@@ -122,3 +122,27 @@ def test_flexible_dataset_and_rotation():
     import torchvision.transforms.v2.functional as TF
     for a in angles:
         assert torch.equal(rot(img[0]), TF.rotate(img[0], a))               # exact permutation, same RNG stream
+
+
+def test_adamw_batch_struct_matches_header():
+    """ctypes mirror of btsb_adamw_batch (multi-tensor AdamW descriptors passed by value to the kernel)."""
+    import ctypes
+    import re
+    from btsbot_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "btsbot_b200.h")).read()
+    n = int(re.search(r"#define\s+BTSB_ADAMW_BATCH\s+(\d+)", hdr).group(1))
+    assert _lib.ADAMW_BATCH == n
+    assert ctypes.sizeof(_lib.AdamwBatch) == 5 * 8 * n + 4 * (n + 1) + 4
+    assert ctypes.sizeof(_lib.AdamwBatch) < 4096          # must fit the kernel parameter space next to the scalars
+
+
+def test_training_precision_switch_is_host_logic_only():
+    """precision="bf16" selects the tensor-core training GEMMs by model attribute; building the model needs no GPU."""
+    import btsbot_b200 as btsbot
+    from btsbot_b200 import synth, _autograd
+    cfg = dict(synth.canonical_config("mm_ConvNeXt", "convnext_pico.d1_in1k"), precision="bf16")
+    model = btsbot.mm_ConvNeXt(cfg)
+    assert model._precision == "bf16" and model.set_precision("fp32")._precision == "fp32"
+    assert _autograd._ld(1350) == 1352 and _autograd._ld(8) == 8       # transposed-operand pitch: multiple of 8 (16 B)
+    with pytest.raises(ValueError):
+        model.set_precision("fp8")
