@@ -11,14 +11,18 @@
 
 namespace btsb {
 
-template <int S>
-__global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C, const float* __restrict__ wt,
+// CT > 0: channel count known at compile time (nano 320/640, pico 256/512): the 9 loads, 9 stores and 25 tap reads become
+// immediate offsets -- the kernel was instruction-issue-bound with ~240 of its ~800 instructions per image being 64-bit
+// address arithmetic (3 CTAs of 120 registers per SM leave no latency slack either).  CT == 0: generic runtime C.
+template <int S, int CT>
+__global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C_rt, const float* __restrict__ wt,
                                   const float* __restrict__ bias, const float* __restrict__ ln_w,
                                   const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
   constexpr int R = S - 1;
   constexpr int NT = 2 * R + 1;
   constexpr int HW = S * S;
   static_assert(HW <= 16, "statistics layout: sums in [0,16), sums of squares in [16,32)");
+  const int C = CT > 0 ? CT : C_rt;
   extern __shared__ __align__(16) unsigned char sm[];
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = T >> 5;
   float* wsm = reinterpret_cast<float*>(sm);                 // [NT*NT][C] reachable taps
@@ -117,7 +121,7 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
 
 int num_sms();
 
-template <int S>
+template <int S, int CT>
 static int launch_small(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
   constexpr int NT = 2 * (S - 1) + 1;
@@ -126,7 +130,7 @@ static int launch_small(const void* x, int64_t B, int C, const float* w, const f
   const int nw = threads / 32;
   const size_t smem = (size_t)NT * NT * C * 4 + 2 * nw * 32 * 4 + 2 * 16 * 8;
   if (smem > 200 * 1024) return 1;
-  auto kern = dwln_small_kernel<S>;
+  auto kern = dwln_small_kernel<S, CT>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dwln_small attr");
   int per_sm = 1;
   BTSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem), "dwln_small occupancy");
@@ -144,8 +148,16 @@ int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* 
   if (((uintptr_t)x % 4) != 0 || ((uintptr_t)out % 4) != 0 || ((uintptr_t)bias % 8) != 0 || ((uintptr_t)ln_w % 8) != 0 ||
       ((uintptr_t)ln_b % 8) != 0)
     return 1;
-  if (H == 3) return launch_small<3>(x, B, C, w, bias, ln_w, ln_b, out, st);
-  if (H == 1) return launch_small<1>(x, B, C, w, bias, ln_w, ln_b, out, st);
+  if (H == 3) {
+    if (C == 320) return launch_small<3, 320>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    if (C == 256) return launch_small<3, 256>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    return launch_small<3, 0>(x, B, C, w, bias, ln_w, ln_b, out, st);
+  }
+  if (H == 1) {
+    if (C == 640) return launch_small<1, 640>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    if (C == 512) return launch_small<1, 512>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    return launch_small<1, 0>(x, B, C, w, bias, ln_w, ln_b, out, st);
+  }
   return 1;
 }
 
