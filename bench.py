@@ -408,6 +408,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    # NUMA: allocate the pinned host batches next to this rank's GPU (restored before the CPU baseline leg)
+    from btsbot_b200.parallel import bind_to_device_numa
+    prev_affinity = bind_to_device_numa(local_rank) if args.workload != "c5" else None
 
     wl = WORKLOADS[args.workload]
     cfg = dict(synth.canonical_config(wl["model"], wl["kind"]), precision=args.precision)
@@ -540,6 +543,8 @@ def main():
     roof["kernel_time_sum_ms_per_step"] = sum(v["ms"] for v in kern.values()) / args.steps
 
     cpu = None
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)              # the CPU baseline uses every host core
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         rate, dt = cpu_port(args.cpu_sample, dict(cfg), sd_np, threads)
@@ -558,7 +563,9 @@ def main():
                                 f"{nres} resident batches rotated"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "alerts/s", "h2d_bytes_per_step": world * B * ALERT_IN_BYTES,
-                "d2h_bytes_per_step": world * B * 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": world * B * 4, "ms_per_step": ms_e2e / args.steps,
+                "h2d_gbs_per_gpu": B * ALERT_IN_BYTES / (ms_e2e / args.steps * 1e-3) / 1e9,
+                "numa_bound": prev_affinity is not None},
         "gpu_launches": int(launches),
         "roofline": roof,
         "kernels": kernels,

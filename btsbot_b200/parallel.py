@@ -17,6 +17,40 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_device_numa(device_index: int):
+    """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA node), so that pinned
+    host buffers allocated afterwards are first-touched next to the GPU's PCIe root: the H2D copy of a bulk-scoring
+    step (391 MB per 8192 alerts) otherwise crosses the socket interconnect on multi-socket hosts and the end-to-end
+    rate halves.  Returns the previous affinity set (restore it with ``os.sched_setaffinity(0, prev)``) or ``None``
+    when NVML / affinity control is unavailable."""
+    import os
+    if os.environ.get("BTSB_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_getaffinity"):
+        return None
+    try:
+        import pynvml
+        prev = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        try:
+            bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if int(pynvml.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                    handle = h
+        except Exception:
+            pass
+        n_words = (max(prev) // 64) + 1 if prev else 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, max(n_words, (os.cpu_count() or 64 + 63) // 64 + 1))
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= prev
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return prev
+    except Exception:
+        return None
+
+
 def shard_range(n: int, rank: int, world: int):
     """Contiguous, balanced index range of ``rank``: sizes differ by at most one, concatenation order = rank order."""
     base, rem = divmod(n, world)
