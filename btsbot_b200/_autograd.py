@@ -79,11 +79,15 @@ def cast_dual(x, rm=True, t=True, op=0, x2=None, colvec=None, want_colsum=False)
     GELU backward (op 2, x = pre-activation, x2 = upstream gradient), column scale and column sums."""
     M, N = x.shape
     ld = _ld(M)
+    in16 = x.dtype == torch.bfloat16
+    assert x2 is None or x2.dtype == x.dtype
     o_rm = torch.empty((M, N), device=x.device, dtype=torch.bfloat16) if rm else None
     o_t = torch.empty((N, ld), device=x.device, dtype=torch.bfloat16) if t else None
     cs = torch.zeros((N,), device=x.device, dtype=torch.float32) if want_colsum else None
+    eb = 2 if in16 else 4
     L.launch("t_cast_dual", L.lib().btsb_cast_dual_bf16, _p(x), _p(x2), _p(colvec), _p(o_rm), _p(o_t), _p(cs), M, N, ld,
-             op, _st(), nbytes=float(x.numel()) * (4 + (4 if x2 is not None else 0) + (2 if rm else 0) + (2 if t else 0)))
+             op, L.BF16 if in16 else L.F32, _st(),
+             nbytes=float(x.numel()) * (eb + (eb if x2 is not None else 0) + (2 if rm else 0) + (2 if t else 0)))
     return o_rm, o_t, cs
 
 
@@ -94,6 +98,17 @@ def tc_gemm(a16, w16, bias=None):
     out = torch.empty((M, N), device=a16.device, dtype=torch.float32)
     L.launch("t_gemm_tc", L.lib().btsb_gemm_bf16_f32out, _p(a16), _p(w16), _p(bias), _p(out), M, N, K, _st(),
              flops=2.0 * M * N * K, nbytes=2.0 * (M * K + N * K) + 4.0 * M * N)
+    return out
+
+
+def tc_gemm16(a16, w16, bias):
+    """bf16 [M,N] = a16 [M,K] @ w16 [N,K]^T + bias through the inference GEMM (bulk-tensor-store epilogue): used for the
+    4C-wide tensors (fc1 pre-activation, fc2 dgrad), which autocast would keep in bf16 as well."""
+    M, K = a16.shape
+    N = w16.shape[0]
+    out = torch.empty((M, N), device=a16.device, dtype=torch.bfloat16)
+    L.launch("t_gemm_tc16", L.lib().btsb_gemm_fwd, _p(a16), _p(w16), _p(bias), None, None, _p(out), M, N, K, L.BF16,
+             L.EPI_BIAS, _st(), flops=2.0 * M * N * K, nbytes=2.0 * (M * K + N * K + M * N))
     return out
 
 
@@ -179,12 +194,18 @@ def pool(src, B, HW, c, reverse):
     return dst
 
 
-def dropout(x, p, mask=None, seed=0):
+def dropout(x, p, mask=None, seed=0, counter=None):
+    """``counter``: optional device int64 tensor mixed into the seed inside the kernel (CUDA-graph replays keep the
+    host-side ``seed`` of the captured launch; the counter, bumped once per forward, still changes the mask)."""
     y = torch.empty_like(x)
     reuse = mask is not None
     if mask is None:
         mask = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
-    L.launch("t_dropout", L.lib().btsb_dropout_f32, _p(x), _p(y), _p(mask), x.numel(), float(p), int(seed), int(reuse), _st())
+    if counter is not None and not reuse:
+        L.launch("t_dropout", L.lib().btsb_dropout_ctr_f32, _p(x), _p(y), _p(mask), x.numel(), float(p), int(seed),
+                 _p(counter), 0, _st())
+    else:
+        L.launch("t_dropout", L.lib().btsb_dropout_f32, _p(x), _p(y), _p(mask), x.numel(), float(p), int(seed), int(reuse), _st())
     return y, mask
 
 
@@ -339,7 +360,7 @@ def _trunk_fwd_tc(tr, x):
             w1_16, w1_16t = _w16(blk.mlp.fc1.weight.detach().reshape(4 * c, c))
             w2_16, w2_16t = _w16(blk.mlp.fc2.weight.detach().reshape(c, 4 * c))
             y16, y16t, _ = cast_dual(y)
-            hp = tc_gemm(y16, w1_16, blk.mlp.fc1.bias.detach())
+            hp = tc_gemm16(y16, w1_16, blk.mlp.fc1.bias.detach())         # bf16 [M, 4c]
             hh16, hh16t, _ = cast_dual(hp, op=1)                         # gelu fused into the cast
             v = tc_gemm(hh16, w2_16, blk.mlp.fc2.bias.detach())
             out = colscale(v, blk.gamma.detach(), res=cur)
@@ -363,7 +384,7 @@ def _trunk_bwd_tc(tr, tape, dcur, G):
             dv16, dv16t, db2 = cast_dual(dcur, colvec=blk.gamma.detach(), want_colsum=True)
             G.put(blk.mlp.fc2.weight, tc_wgrad(hh16t, dv16t, M).t().contiguous())      # [4c, c]^T -> [c, 4c]
             G.put(blk.mlp.fc2.bias, db2)
-            dhh = tc_gemm(dv16, w2_16t)                                                  # [M, 4c]
+            dhh = tc_gemm16(dv16, w2_16t, torch.zeros((4 * c,), device=dcur.device, dtype=torch.float32))   # bf16 [M, 4c]
             dhp16, dhp16t, db1 = cast_dual(hp, op=2, x2=dhh, want_colsum=True)           # dhh * gelu'(hp)
             G.put(blk.mlp.fc1.weight, tc_wgrad(dhp16t, y16t, M))                         # [4c, c]
             G.put(blk.mlp.fc1.bias, db1)
@@ -403,9 +424,10 @@ def _trunk_bwd_tc(tr, tape, dcur, G):
 class _Dense:
     """Sequential of Linear / act / Dropout / BatchNorm1d modules executed with the training kernels."""
 
-    def __init__(self, modules, training=True):
+    def __init__(self, modules, training=True, counter=None):
         self.mods = list(modules)
         self.training = training
+        self.counter = counter
         self.saved = []
 
     def forward(self, x):
@@ -420,7 +442,7 @@ class _Dense:
                 x = act(x, L.ACT_GELU if isinstance(m, nn.GELU) else L.ACT_RELU)
             elif isinstance(m, nn.Dropout):
                 if self.training and m.p > 0:
-                    x, mask = dropout(x, m.p, seed=_seed())
+                    x, mask = dropout(x, m.p, seed=_seed(), counter=self.counter)
                     self.saved.append(mask)
                 else:
                     self.saved.append(None)
@@ -496,6 +518,9 @@ class _ModelFn(torch.autograd.Function):
         ctx.model = model
         feat = None
         ctx.trunk_tape = None
+        counter = getattr(model, "_graph_counter", None)        # set by GraphedTrainStep: device-side step counter
+        if counter is not None:
+            L.launch("t_counter", L.lib().btsb_counter_add_i64, _p(counter), 1, _st())
         if tr is not None:
             L.require_cuda(image, "image input")
             image = image.to(torch.float32).contiguous()
@@ -522,12 +547,12 @@ class _ModelFn(torch.autograd.Function):
         ctx.meta_stack = ctx.head_stack = None
         if meta_mods is not None:
             L.require_cuda(meta, "metadata input")
-            ctx.meta_stack = _Dense(meta_mods)
+            ctx.meta_stack = _Dense(meta_mods, counter=counter)
             emb = ctx.meta_stack.forward(meta.to(torch.float32).contiguous())
         if head_mods is not None:
             cat = feat if emb is None else torch.cat((feat, emb), dim=1)
             ctx.split = feat.shape[1] if feat is not None else 0
-            ctx.head_stack = _Dense(head_mods)
+            ctx.head_stack = _Dense(head_mods, counter=counter)
             logits = ctx.head_stack.forward(cat.contiguous())
         else:
             logits = emb                                            # um_nn: the stack ends in Linear(m2, 1)
@@ -615,8 +640,12 @@ class FusedAdamW(torch.optim.Optimizer):
     fused kernel per parameter tensor, or one per flat bucket when the parameters were flattened by
     ``btsbot_b200.parallel.flatten_parameters``."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, capturable=False):
+        """``capturable=True`` (torch.optim's name for it) keeps the step count in a device tensor that the kernels read,
+        so that ``step()`` can be captured in a CUDA graph and replayed (see :class:`GraphedTrainStep`)."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.capturable = bool(capturable)
+        self._step_dev = None
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -640,6 +669,11 @@ class FusedAdamW(torch.optim.Optimizer):
                 by_step.setdefault(st["step"], []).append((p, p.grad.contiguous(), st))
             # parameters that share a step count (all of them, unless some had no gradient in earlier steps) go through
             # the multi-tensor kernel, BTSB_ADAMW_BATCH tensors per launch
+            if self.capturable and by_step:
+                dev = next(iter(by_step.values()))[0][0].device
+                if self._step_dev is None:
+                    self._step_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+                L.launch("t_counter", lib.btsb_counter_add_i64, _p(self._step_dev), 1, _st())
             for step, items in by_step.items():
                 for lo in range(0, len(items), L.ADAMW_BATCH):
                     part = items[lo:lo + L.ADAMW_BATCH]
@@ -648,6 +682,71 @@ class FusedAdamW(torch.optim.Optimizer):
                         batch.p[i], batch.g[i], batch.m[i], batch.v[i] = p.data_ptr(), g.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr()
                         batch.n[i] = p.numel()
                     batch.count = len(part)
-                    L.launch("t_adamw", lib.btsb_adamw_multi_f32, C.byref(batch), float(group["lr"]), float(b1), float(b2),
-                             float(group["eps"]), float(group["weight_decay"]), int(step), 1.0, _st())
+                    if self.capturable:
+                        L.launch("t_adamw", lib.btsb_adamw_multi_ctr_f32, C.byref(batch), float(group["lr"]), float(b1),
+                                 float(b2), float(group["eps"]), float(group["weight_decay"]), _p(self._step_dev), 1.0, _st())
+                    else:
+                        L.launch("t_adamw", lib.btsb_adamw_multi_f32, C.byref(batch), float(group["lr"]), float(b1), float(b2),
+                                 float(group["eps"]), float(group["weight_decay"]), int(step), 1.0, _st())
         return loss
+
+
+class GraphedTrainStep:
+    """One training step of ``train.py:496-547`` (zero_grad -> forward -> loss -> backward -> optimizer.step) captured once
+    in a CUDA graph and replayed: the eager step issues ~360 kernels from Python (a third of them a few microseconds
+    long), which makes the host the pacing side at batch 1024; a replay costs one launch.
+
+    ``model`` is a btsbot_b200 model (or its DistributedDataParallel wrapper) in train mode, ``optimizer`` a
+    :class:`FusedAdamW` built with ``capturable=True``, ``loss_fn`` a :class:`BCEWithLogitsLoss`.  Inputs of every call
+    must have the shapes / dtypes of ``example``; they are copied into static buffers.  Dropout masks and the AdamW bias
+    correction follow a device-side counter, so replays are not frozen at the captured step.  ``warmup`` eager steps run
+    first (they DO update the parameters, like any other step).  Single-process use (gradient all-reduce is not
+    captured); with ``torch.distributed`` initialised and world size > 1 the step runs eagerly."""
+
+    def __init__(self, model, optimizer, loss_fn, example, warmup: int = 2):
+        self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
+        if not getattr(optimizer, "capturable", False):
+            raise ValueError("GraphedTrainStep needs FusedAdamW(..., capturable=True)")
+        inner = getattr(model, "module", model)
+        dev = next(inner.parameters()).device
+        self.static = [t.to(dev).clone() if t is not None else None for t in example]
+        inner._graph_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
+        import torch.distributed as dist
+        self.eager = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.graph, self.loss, self.kernels_per_step = None, None, 0
+        if self.eager:
+            return
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._step()
+        #: kernels of libbtsbot_b200.so inside one replay (the library's launch counter does not see replays)
+        self.kernels_per_step = L.launch_count() - n0
+
+    def _step(self):
+        img, meta, lab = self.static
+        self.model.zero_grad()
+        if img is not None and meta is not None:
+            logits = self.model(image_input=img, metadata_input=meta)
+        else:
+            logits = self.model(input_data=img if img is not None else meta)
+        loss = self.loss_fn(logits, lab)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def __call__(self, img, meta, lab):
+        for dst, src in zip(self.static, (img, meta, lab)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        if self.graph is None:
+            return self._step()
+        self.graph.replay()
+        return self.loss

@@ -86,6 +86,10 @@ SIGNATURES = {
                              C.c_float, vp]),
     "btsb_adamw_multi_f32": (i32, [C.POINTER(AdamwBatch), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, i64,
                                    C.c_float, vp]),
+    "btsb_adamw_multi_ctr_f32": (i32, [C.POINTER(AdamwBatch), C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp,
+                                       C.c_float, vp]),
+    "btsb_dropout_ctr_f32": (i32, [vp, vp, vp, i64, C.c_float, C.c_uint64, vp, i32, vp]),
+    "btsb_counter_add_i64": (i32, [vp, i64, vp]),
     "btsb_maxvit_stem1_fwd": (i32, [vp, i64, i32, i32, i32, vp, vp, i32, vp, i32, vp]),
     "btsb_maxvit_im2col3_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
     "btsb_maxvit_avgpool2_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
@@ -96,7 +100,7 @@ SIGNATURES = {
     "btsb_maxvit_attn_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp, i32, vp]),
     "btsb_maxvit_lnpool_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "btsb_debug_mlp_trace": (i32, [vp]),
-    "btsb_cast_dual_bf16": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, vp]),
+    "btsb_cast_dual_bf16": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, i32, vp]),
     "btsb_gemm_bf16_f32out": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     "btsb_gemm_bf16_wgrad": (i32, [vp, vp, i64, vp, i32, i32, i64, vp]),
     "btsb_cast_f32_to_bf16": (i32, [vp, vp, i64, vp]),

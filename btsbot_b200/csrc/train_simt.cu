@@ -489,8 +489,11 @@ __device__ __forceinline__ uint32_t hash_u64(uint64_t z) {   // splitmix64 final
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 // reuse_mask=0: draw mask (keep prob 1-p), y = x*mask/(1-p); reuse_mask=1: y = x*mask/(1-p) with the stored mask (backward)
+// `counter` (may be NULL) is a device-side step counter mixed into the seed: a CUDA graph replays the launch with the same
+// host-side `seed`, the counter (bumped once per forward by btsb_counter_add_i64) still gives every step a fresh mask
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
-                               float p, uint64_t seed, int reuse_mask) {
+                               float p, uint64_t seed, const int64_t* __restrict__ counter, int reuse_mask) {
+  if (counter) seed += (uint64_t)(*counter) * 0x9E3779B97F4A7C15ull;
   const float scale = 1.0f / (1.0f - p);
   const uint32_t thr = (uint32_t)((double)p * 4294967296.0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -543,7 +546,12 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 constexpr int kAdamwChunk = 2048;
 __global__ void __launch_bounds__(256)
 adamw_multi_kernel(const __grid_constant__ btsb_adamw_batch t, float lr, float beta1, float beta2, float eps, float wd,
-                   float bc1, float bc2_sqrt, float grad_scale) {
+                   float bc1, float bc2_sqrt, float grad_scale, const int64_t* __restrict__ step_dev) {
+  if (step_dev) {                       // capturable mode: the step count lives on the device (CUDA-graph replays)
+    const float st = (float)(*step_dev);
+    bc1 = 1.0f - powf(beta1, st);
+    bc2_sqrt = sqrtf(1.0f - powf(beta2, st));
+  }
   int ti = 0;
   while (ti + 1 < t.count && (int)blockIdx.x >= t.first_block[ti + 1]) ++ti;
   const int64_t base = (int64_t)((int)blockIdx.x - t.first_block[ti]) * kAdamwChunk;
@@ -757,8 +765,26 @@ extern "C" int btsb_dropout_f32(const float* x, float* y, uint8_t* mask, int64_t
   if (int e = check_device()) return e;
   if (n <= 0) return BTSB_OK;
   BTSB_REQUIRE(x && y && mask && p >= 0.f && p < 1.f, "dropout: bad arguments (0 <= p < 1)");
-  dropout_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, mask, n, p, seed, reuse_mask);
+  dropout_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, mask, n, p, seed, nullptr, reuse_mask);
   return launch_done("dropout");
+}
+
+extern "C" int btsb_dropout_ctr_f32(const float* x, float* y, uint8_t* mask, int64_t n, float p, uint64_t seed,
+                                    const int64_t* counter, int reuse_mask, void* stream) {
+  if (int e = check_device()) return e;
+  if (n <= 0) return BTSB_OK;
+  BTSB_REQUIRE(x && y && mask && p >= 0.f && p < 1.f, "dropout: bad arguments (0 <= p < 1)");
+  dropout_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, y, mask, n, p, seed, counter, reuse_mask);
+  return launch_done("dropout");
+}
+
+__global__ void counter_add_kernel(int64_t* c, int64_t v) { *c += v; }
+
+extern "C" int btsb_counter_add_i64(int64_t* counter, int64_t v, void* stream) {
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(counter, "counter_add: null pointer");
+  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, v);
+  return launch_done("counter_add");
 }
 
 extern "C" int btsb_bce_logits_f32(const float* logits, const float* labels, float pos_weight, float* loss, float* dlogits,
@@ -798,6 +824,22 @@ extern "C" int btsb_adamw_multi_f32(btsb_adamw_batch* batch, float lr, float bet
   batch->first_block[batch->count] = blocks;
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
-  adamw_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*batch, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  adamw_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*batch, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale, nullptr);
+  return launch_done("adamw_multi");
+}
+
+extern "C" int btsb_adamw_multi_ctr_f32(btsb_adamw_batch* batch, float lr, float beta1, float beta2, float eps, float wd,
+                                        const int64_t* step_dev, float grad_scale, void* stream) {
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(batch && batch->count >= 0 && batch->count <= BTSB_ADAMW_BATCH && step_dev, "adamw_multi_ctr: bad arguments");
+  if (batch->count == 0) return BTSB_OK;
+  int blocks = 0;
+  for (int i = 0; i < batch->count; ++i) {
+    BTSB_REQUIRE(batch->p[i] && batch->g[i] && batch->m[i] && batch->v[i] && batch->n[i] >= 1, "adamw_multi: bad tensor %d", i);
+    batch->first_block[i] = blocks;
+    blocks += (int)((batch->n[i] + kAdamwChunk - 1) / kAdamwChunk);
+  }
+  batch->first_block[batch->count] = blocks;
+  adamw_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*batch, lr, beta1, beta2, eps, wd, 1.f, 1.f, grad_scale, step_dev);
   return launch_done("adamw_multi");
 }

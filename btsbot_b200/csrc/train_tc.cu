@@ -10,16 +10,37 @@
 // with the element-wise op that would otherwise be its own kernel folded into the load:
 //     OP 0: v = in                         OP 1: v = gelu(in)                (hidden activation, never stored in fp32)
 //     OP 2: v = in2 * gelu'(in)            (in = saved pre-activation, in2 = upstream gradient)
+// `in` / `in2` are fp32 or bf16 (the bf16-output GEMM epilogue writes the 4C-wide tensors in bf16, as autocast keeps them)
 // then v *= colvec[n] (layer-scale backward) and colsum[n] += sum_m v (bias gradients) when those pointers are given.
 #include "common.cuh"
 
 namespace btsb {
 namespace {
 
-__device__ __forceinline__ float gelu_grad_erf(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-  return cdf + x * pdf;
+// GELU and its derivative in the same one-MUFU form the bf16 inference epilogues use (tc_common.cuh gelu_fast):
+// gelu(x) = 0.5 x (1 + tanh(a(x))), a(x) = x (k1 + k3 x^2 + k5 x^4) with x^2 clamped at 64 (formula error 2.5e-5, tanh.approx
+// 2^-11) -- the erff / expf versions made this kernel ALU-bound (~40 instructions per element at 2.3 TB/s); forward and
+// backward use the SAME function, so the gradient is exact for the function that was evaluated.
+//   gelu'(x) = 0.5 (1 + t) + 0.5 x (1 - t^2) a'(x),   a'(x) = k1 + 3 k3 x^2 + 5 k5 x^4   (= the frozen slope beyond |x| = 8)
+constexpr float kG1 = 0.7975078843f, kG3 = 0.037005646f, kG5 = -3.5151679e-4f;
+__device__ __forceinline__ float tanh_fast(float a) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(a));
+  return t;
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float x2 = fminf(x * x, 64.0f);
+  const float p = fmaf(x2, fmaf(x2, kG5, kG3), kG1);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_fast(p * x), h);
+}
+__device__ __forceinline__ float gelu_grad_tanh(float x) {
+  const float xx = x * x;
+  const float x2 = fminf(xx, 64.0f);
+  const float p = fmaf(x2, fmaf(x2, kG5, kG3), kG1);
+  const float t = tanh_fast(p * x);
+  const float da = xx > 64.0f ? p : fmaf(x2, fmaf(x2, 5.0f * kG5, 3.0f * kG3), kG1);
+  return fmaf(0.5f * x * da, fmaf(-t, t, 1.0f), 0.5f + 0.5f * t);
 }
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
@@ -29,9 +50,17 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 
 constexpr int TM = 64, TN = 64;
 
-template <int OP>
+// IN16: `in` (and, for OP 2, `in2`) are bf16 -- the wide tensors of the step (fc1 pre-activation, its upstream gradient)
+// are written by the bf16-output GEMM epilogue (bulk tensor stores, half the bytes) exactly as autocast would keep them
+__device__ __forceinline__ float2 ld2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld2(const __nv_bfloat16* p) {
+  const uint32_t v = *reinterpret_cast<const uint32_t*>(p);
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+
+template <int OP, typename TI>
 __global__ void __launch_bounds__(256)
-cast_dual_kernel(const float* __restrict__ in, const float* __restrict__ in2, const float* __restrict__ colvec,
+cast_dual_kernel(const TI* __restrict__ in, const TI* __restrict__ in2, const float* __restrict__ colvec,
                  __nv_bfloat16* __restrict__ rm, __nv_bfloat16* __restrict__ t, float* __restrict__ colsum, int64_t M, int N,
                  int64_t ld) {
   __shared__ float tile[TN][TM + 1];        // [n][m]
@@ -50,11 +79,11 @@ cast_dual_kernel(const float* __restrict__ in, const float* __restrict__ in2, co
     const int64_t gm = m0 + m;
     float2 v = make_float2(0.f, 0.f);
     if (gm < M && ncol) {
-      v = *reinterpret_cast<const float2*>(in + gm * N + n);
-      if (OP == 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); }
+      v = ld2(in + gm * N + n);
+      if (OP == 1) { v.x = gelu_tanh(v.x); v.y = gelu_tanh(v.y); }
       if (OP == 2) {
-        const float2 d = *reinterpret_cast<const float2*>(in2 + gm * N + n);
-        v.x = d.x * gelu_grad_erf(v.x); v.y = d.y * gelu_grad_erf(v.y);
+        const float2 d = ld2(in2 + gm * N + n);
+        v.x = d.x * gelu_grad_tanh(v.x); v.y = d.y * gelu_grad_tanh(v.y);
       }
       v.x *= g0; v.y *= g1;
       if (rm) *reinterpret_cast<uint32_t*>(rm + gm * N + n) = pack2(v.x, v.y);
@@ -91,13 +120,14 @@ cast_dual_kernel(const float* __restrict__ in, const float* __restrict__ in2, co
 
 using namespace btsb;
 
-extern "C" int btsb_cast_dual_bf16(const float* in, const float* in2, const float* colvec, void* out_rm, void* out_t,
-                                   float* colsum, int64_t M, int N, int64_t ld, int op, void* stream) {
+extern "C" int btsb_cast_dual_bf16(const void* in, const void* in2, const float* colvec, void* out_rm, void* out_t,
+                                   float* colsum, int64_t M, int N, int64_t ld, int op, int in_dtype, void* stream) {
   if (int e = check_device()) return e;
   BTSB_REQUIRE(M >= 0 && N >= 2 && N % 2 == 0, "cast_dual: N=%d must be even", N);
   if (M == 0) return BTSB_OK;
   BTSB_REQUIRE(in && (out_rm || out_t || colsum), "cast_dual: null pointer");
   BTSB_REQUIRE(op >= 0 && op <= 2 && (op != 2 || in2), "cast_dual: bad op %d", op);
+  BTSB_REQUIRE(in_dtype == BTSB_F32 || in_dtype == BTSB_BF16, "cast_dual: in_dtype must be F32 or BF16");
   BTSB_REQUIRE(!out_t || (ld % 8 == 0 && ld >= M), "cast_dual: ld=%lld must be a multiple of 8 and >= M", (long long)ld);
   BTSB_REQUIRE(((uintptr_t)in % 8) == 0 && (!in2 || ((uintptr_t)in2 % 8) == 0) && ((uintptr_t)out_rm % 4) == 0 &&
                    ((uintptr_t)out_t % 4) == 0, "cast_dual: misaligned pointer");
@@ -107,8 +137,16 @@ extern "C" int btsb_cast_dual_bf16(const float* in, const float* in2, const floa
   __nv_bfloat16* rm = (__nv_bfloat16*)out_rm;
   __nv_bfloat16* t = (__nv_bfloat16*)out_t;
   cudaStream_t st = (cudaStream_t)stream;
-  if (op == 0) cast_dual_kernel<0><<<grid, 256, 0, st>>>(in, in2, colvec, rm, t, colsum, M, N, ld);
-  else if (op == 1) cast_dual_kernel<1><<<grid, 256, 0, st>>>(in, in2, colvec, rm, t, colsum, M, N, ld);
-  else cast_dual_kernel<2><<<grid, 256, 0, st>>>(in, in2, colvec, rm, t, colsum, M, N, ld);
+  if (in_dtype == BTSB_F32) {
+    const float* a = (const float*)in; const float* b = (const float*)in2;
+    if (op == 0) cast_dual_kernel<0, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
+    else if (op == 1) cast_dual_kernel<1, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
+    else cast_dual_kernel<2, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
+  } else {
+    const __nv_bfloat16* a = (const __nv_bfloat16*)in; const __nv_bfloat16* b = (const __nv_bfloat16*)in2;
+    if (op == 0) cast_dual_kernel<0, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
+    else if (op == 1) cast_dual_kernel<1, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
+    else cast_dual_kernel<2, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
+  }
   return launch_done("cast_dual_bf16");
 }

@@ -214,7 +214,7 @@ class GradSink:
         self.in_flush = True
         for i in range(len(self.bounds)):
             self._launch(i)
-        if self.cuda:
+        if self.cuda and _world()[1] > 1:                 # nothing ran on the side stream in a single-process job
             torch.cuda.current_stream().wait_stream(self.stream)
         for h, chunk, world in self.handles:
             h.wait()

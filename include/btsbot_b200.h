@@ -227,11 +227,19 @@ typedef struct {
 } btsb_adamw_batch;
 int btsb_adamw_multi_f32(btsb_adamw_batch* batch, float lr, float beta1, float beta2, float eps, float wd,
                          int64_t step, float grad_scale, void* stream);
+/* CUDA-graph-capturable variants (a captured training step is replayed with the host-side scalars frozen): the AdamW step
+ * count and the dropout seed offset are read from a device counter that btsb_counter_add_i64 bumps inside the graph
+ * (torch.optim's `capturable=True` idea). */
+int btsb_adamw_multi_ctr_f32(btsb_adamw_batch* batch, float lr, float beta1, float beta2, float eps, float wd,
+                             const int64_t* step_dev, float grad_scale, void* stream);
+int btsb_dropout_ctr_f32(const float* x, float* y, uint8_t* mask, int64_t n, float p, uint64_t seed,
+                         const int64_t* counter, int reuse_mask, void* stream);
+int btsb_counter_add_i64(int64_t* counter, int64_t v, void* stream);
 
 /* ---- K7 on tensor cores (bf16 mode of the training step; what autocast(bf16) + cuBLAS do under train.py:496-547).
  * The three GEMMs of every Linear / 1x1 conv run on tcgen05 with bf16 operands and fp32 accumulation; results are
  * fp32 so that the residual stream, LayerNorm and the element-wise backward stay in fp32.
- * cast_dual_bf16: one pass over a fp32 [M,N] tensor writes the row-major bf16 copy out_rm [M,N] (forward / dgrad
+ * cast_dual_bf16: one pass over a [M,N] tensor (in / in2 both of in_dtype F32 | BF16) writes the row-major bf16 copy out_rm [M,N] (forward / dgrad
  *   operand) and/or the transposed copy out_t [N,ld] (wgrad operand; ld % 8 == 0, ld >= M), folding in
  *   op 0: v = in;  op 1: v = gelu(in);  op 2: v = in2 * gelu'(in);  then v *= colvec[n] (if colvec) and
  *   colsum[n] += sum_m v (if colsum; bias / layer-scale gradients).  N even.
@@ -239,8 +247,8 @@ int btsb_adamw_multi_f32(btsb_adamw_batch* batch, float lr, float beta1, float b
  * gemm_bf16_wgrad:  out[M,N] fp32 += At[M,K] . Bt[N,K]^T where K is the (huge) activation row count and At / Bt are
  *   transposed copies with row pitch ld; K is split over the SMs and partial tiles are reduced with red.global.add
  *   (the caller zeroes `out`; summation order, hence the last fp32 bits, varies run to run).  N % 16 == 0. */
-int btsb_cast_dual_bf16(const float* in, const float* in2, const float* colvec, void* out_rm, void* out_t,
-                        float* colsum, int64_t M, int N, int64_t ld, int op, void* stream);
+int btsb_cast_dual_bf16(const void* in, const void* in2, const float* colvec, void* out_rm, void* out_t,
+                        float* colsum, int64_t M, int N, int64_t ld, int op, int in_dtype, void* stream);
 int btsb_gemm_bf16_f32out(const void* A, const void* Wt, const float* bias, float* out, int64_t M, int N, int K,
                           void* stream);
 int btsb_gemm_bf16_wgrad(const void* At, const void* Bt, int64_t ld, float* out, int M, int N, int64_t K,

@@ -190,6 +190,16 @@ def test_cast_dual_ops(cuda_dev, M, N):
         assert (rm.float() - want).abs().max() <= 2 ** -7 * want.abs().max() + 1e-6, op
         assert torch.equal(t[:, :M].t().contiguous(), rm), op       # the transposed copy holds the same bits
         assert (cs - want.sum(0)).abs().max() <= 1e-4 * max(1.0, want.abs().sum(0).max().item()), op
+    # bf16 inputs (the 4C-wide tensors are written by the bf16-output GEMM epilogue)
+    xb, db = x.bfloat16(), d.bfloat16()
+    xr = xb.float().clone().requires_grad_(True)
+    gelu(xr).backward(db.float())
+    for op, x2, want in [(0, None, xb.float()), (1, None, gelu(xb.float())), (2, db, xr.grad)]:
+        rm, t, cs = A.cast_dual(xb, op=op, x2=x2, want_colsum=True)
+        torch.cuda.synchronize()
+        assert (rm.float() - want).abs().max() <= 2 ** -7 * want.abs().max() + 1e-6, ("bf16 in", op)
+        assert torch.equal(t[:, :M].t().contiguous(), rm), ("bf16 in", op)
+        assert (cs - want.sum(0)).abs().max() <= 1e-4 * max(1.0, want.abs().sum(0).max().item()), ("bf16 in", op)
 
 
 @pytest.mark.parametrize("M,N,K", [(1350, 320, 80), (300, 80, 320), (6, 2048, 512), (128, 640, 1280), (5000, 160, 640)])
@@ -243,7 +253,7 @@ def test_bf16_training_step_close_to_fp32_autograd(cuda_dev, case):
     finally:
         _lib.profiler = None
     names = {r[0] for r in prof.records}
-    assert {"t_gemm_tc", "t_wgrad_tc", "t_cast_dual"} <= names, names      # the tensor-core path really ran
+    assert {"t_gemm_tc", "t_gemm_tc16", "t_wgrad_tc", "t_cast_dual"} <= names, names      # the tensor-core path really ran
     torch.cuda.synchronize()
     assert (logits.detach().cpu() - ref_logits).abs().max() < 2e-2
     worst, worst_cos = ("", 0.0), ("", 1.0)
@@ -283,3 +293,44 @@ def test_bf16_training_loss_decreases(cuda_dev):
         opt.step()
         losses.append(loss.item())
     assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+
+def test_graphed_train_step_matches_eager(cuda_dev):
+    """CUDA-graph replay of the whole step == the same number of eager steps (dropout 0; split-K wgrad reductions are
+    unordered, hence a tolerance), and the device-side counters move: AdamW bias correction is not frozen at capture."""
+    from btsbot_b200._autograd import GraphedTrainStep
+    cfg = dict(_nodrop(case_config("mm_pico")), precision="bf16")
+    sd_np = synth.make_state_dict(cfg, seed=13)
+    img, meta, lab = (t.to(cuda_dev) for t in _batch(16, start=500))
+    img2, meta2, lab2 = (t.to(cuda_dev) for t in _batch(16, start=700))
+    loss_fn = BCEWithLogitsLoss(pos_weight=torch.tensor([1.0]))
+
+    def make(capturable):
+        m = btsbot.mm_ConvNeXt(cfg)
+        m.load_state_dict(synth.to_torch(sd_np), strict=True)
+        m = m.to(cuda_dev).train()
+        return m, FusedAdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.99), capturable=capturable)
+
+    ref, ropt = make(False)
+    batches = [(img, meta, lab), (img, meta, lab), (img2, meta2, lab2), (img, meta, lab), (img2, meta2, lab2)]
+    ref_losses = []
+    for b in batches:
+        ref.zero_grad()
+        l = loss_fn(ref(image_input=b[0], metadata_input=b[1]), b[2])
+        l.backward()
+        ropt.step()
+        ref_losses.append(l.item())
+    g, gopt = make(True)
+    stepper = GraphedTrainStep(g, gopt, loss_fn, example=batches[0], warmup=2)     # the 2 warm-up steps use batches[0]
+    assert stepper.graph is not None and stepper.kernels_per_step > 100
+    got_losses = [stepper(*b).item() for b in batches[2:]]
+    torch.cuda.synchronize()
+    # the capture pass itself is not executed: warm-up (2) + 3 replays = 5 forwards and 5 optimizer steps, like the reference
+    assert int(gopt._step_dev.item()) == 5 and int(g._graph_counter.item()) == 5
+    worst = 0.0
+    for (n, a), (_, b) in zip(ref.named_parameters(), g.named_parameters()):
+        upd = (a.detach() - synth.to_torch(sd_np)[n].to(cuda_dev)).norm().item()
+        worst = max(worst, (a.detach() - b.detach()).norm().item() / max(upd, 1e-12))
+    print(f"[parity] graphed vs eager training: losses {got_losses} vs {ref_losses[2:]}, worst |dp|_F / |update|_F = {worst:.2e}")
+    assert worst < 5e-2
+    assert all(abs(x - y) < 5e-3 for x, y in zip(got_losses, ref_losses[2:]))
