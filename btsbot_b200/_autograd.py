@@ -596,9 +596,14 @@ class _ModelFn(torch.autograd.Function):
 def training_forward(model, image_input=None, metadata_input=None):
     """Called by the model classes when ``model.training`` and grad mode is on (fp32 kernels; tensor-core GEMMs when
     the model's precision is ``"bf16"``)."""
-    anchor = next((p for p in model.parameters() if p.requires_grad), None)
-    if anchor is None:
+    first = next((p for p in model.parameters() if p.requires_grad), None)
+    if first is None:
         return model.scorer()(image_input=image_input, metadata_input=metadata_input)
+    # The Function needs one input that requires grad so that its output does.  A fresh scalar leaf, made on the CURRENT
+    # stream, instead of a parameter: a parameter's AccumulateGrad node is created once and remembers the stream of its
+    # first use, and an eager step on the default stream followed by a CUDA-graph capture of the same model then makes the
+    # autograd engine wait on that (uncaptured) stream -- cudaErrorStreamCaptureIsolation.
+    anchor = torch.zeros((), device=first.device, dtype=torch.float32, requires_grad=True)
     return _ModelFn.apply(anchor, model, image_input, metadata_input)
 
 
@@ -716,11 +721,17 @@ class GraphedTrainStep:
         self.graph, self.loss, self.kernels_per_step = None, None, 0
         if self.eager:
             return
+        # warm-up steps on the capture side stream (lazy one-time initialisation -- kernel attributes, optimizer state,
+        # autograd's per-stream bookkeeping -- must not happen during capture: capturing without one fails with
+        # cudaErrorStreamCaptureIsolation).  They are real training steps on `example`; their loss / logits are kept in
+        # `warmup_loss` / `warmup_logits` for callers that account for every batch (train_epoch).
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
+        self.warmup_loss = self.warmup_logits = None
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):
-                self._step()
+                self.warmup_loss = self._step()
+                self.warmup_logits = self.last_logits.clone()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
@@ -740,6 +751,7 @@ class GraphedTrainStep:
         loss = self.loss_fn(logits, lab)
         loss.backward()
         self.opt.step()
+        self.last_logits = logits.detach()          # static tensor inside the graph: overwritten by every replay
         return loss.detach()
 
     def __call__(self, img, meta, lab):

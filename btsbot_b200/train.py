@@ -58,7 +58,24 @@ def train_epoch(dataloader, epoch, epochs, optimizer, loss_fn, model, need_tripl
     t0 = time.time()
     num_batches = len(dataloader)
     all_logits, all_labels = [], []
+    # opt-in (config "cuda_graph": true -> FusedAdamW(capturable=True), single process): batch 0 of the epoch runs eagerly,
+    # then the step is captured once (the epoch's learning rate is baked into the graph) and replayed for the rest
+    graphed = getattr(optimizer, "capturable", False) and not dist.is_initialized() and need_triplets and need_metadata
+    stepper = None
     for i, items in enumerate(dataloader):
+        if graphed and i >= 1:
+            from ._autograd import GraphedTrainStep
+            images, meta, labels = items
+            labels = labels.unsqueeze(1).to(device, non_blocking=True).float()
+            batch = (images.to(device, non_blocking=True), meta.to(device, non_blocking=True), labels)
+            if stepper is None:                       # this batch is trained by the (eager) warm-up step of the capture
+                stepper = GraphedTrainStep(model, optimizer, loss_fn, example=batch, warmup=1)
+                all_logits.append(stepper.warmup_logits)
+            else:
+                stepper(*batch)
+                all_logits.append(stepper.last_logits.clone())
+            all_labels.append(labels)
+            continue
         model.zero_grad()
         if need_triplets and need_metadata:
             images, meta, labels = items
@@ -130,10 +147,13 @@ def run_training(config, run_name: str = "", sweeping: bool = False):
             p.requires_grad = False
         for p in model.meta_branch.parameters():
             p.requires_grad = False
-    if world > 1:
+    if world > 1 or config.get("cuda_graph", False):
+        # the wrapper owns one flat gradient buffer (static addresses: what a replayed CUDA graph needs); with a single
+        # process its all-reduce is a no-op
         model = DistributedDataParallel(model)
 
-    optimizer = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=learning_rate, betas=(beta1, beta2))
+    optimizer = FusedAdamW([p for p in model.parameters() if p.requires_grad], lr=learning_rate, betas=(beta1, beta2),
+                           capturable=bool(config.get("cuda_graph", False)) and world == 1)
     scheduler = torch.optim.lr_scheduler.SequentialLR(
         optimizer,
         schedulers=[torch.optim.lr_scheduler.LinearLR(optimizer, start_factor=0.01, total_iters=warmup_epochs),

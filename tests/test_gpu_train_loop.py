@@ -78,6 +78,10 @@ def test_run_training_and_run_val_on_synthetic_fixture(cuda_dev, tmp_path, monke
         assert os.path.isfile(os.path.join(mdir, f)), f
     rep = json.load(open(os.path.join(mdir, "report.json")))
     assert rep["train_config"]["model_name"] == "mm_ConvNeXt" and "Training history" in rep
+    # the same run with the step replayed from a CUDA graph (mixed precision): finite, learning
+    hist_g = train.run_training(dict(cfg, cuda_graph=True, precision="bf16", epochs=2))
+    assert len(hist_g["loss"]) == 2 and all(np.isfinite(hist_g["loss"])) and all(np.isfinite(hist_g["val_loss"]))
+    assert hist_g["loss"][-1] < hist_g["loss"][0] + 0.02
     loss, acc, raw_preds, labels = val.run_val(cfg, mdir, "best_model.pth", torch.tensor([1.0]), True, True)
     assert raw_preds.shape == (200,) and labels.shape == (200,) and np.array_equal(labels, lab_val.astype(np.float32))
     assert 0.0 <= acc <= 1.0 and np.isfinite(loss) and raw_preds.min() >= 0 and raw_preds.max() <= 1
