@@ -74,7 +74,7 @@ def _ld(M):
     return (M + 7) // 8 * 8
 
 
-def cast_dual(x, rm=True, t=True, op=0, x2=None, colvec=None, want_colsum=False):
+def cast_dual(x, rm=True, t=True, op=0, x2=None, colvec=None, want_colsum=False, aux=None):
     """One pass over fp32 ``x`` [M,N]: bf16 row-major copy, bf16 transposed copy [N, ld], optional fused GELU (op 1) /
     GELU backward (op 2, x = pre-activation, x2 = upstream gradient), column scale and column sums."""
     M, N = x.shape
@@ -85,9 +85,13 @@ def cast_dual(x, rm=True, t=True, op=0, x2=None, colvec=None, want_colsum=False)
     o_t = torch.empty((N, ld), device=x.device, dtype=torch.bfloat16) if t else None
     cs = torch.zeros((N,), device=x.device, dtype=torch.float32) if want_colsum else None
     eb = 2 if in16 else 4
+    asum = torch.zeros((N,), device=x.device, dtype=torch.float32) if aux is not None else None
     L.launch("t_cast_dual", L.lib().btsb_cast_dual_bf16, _p(x), _p(x2), _p(colvec), _p(o_rm), _p(o_t), _p(cs), M, N, ld,
-             op, L.BF16 if in16 else L.F32, _st(),
-             nbytes=float(x.numel()) * (eb + (eb if x2 is not None else 0) + (2 if rm else 0) + (2 if t else 0)))
+             op, L.BF16 if in16 else L.F32, _p(aux), _p(asum), _st(),
+             nbytes=float(x.numel()) * (eb + (eb if x2 is not None else 0) + (2 if rm else 0) + (2 if t else 0) +
+                                        (4 if aux is not None else 0)))
+    if aux is not None:
+        return o_rm, o_t, cs, asum
     return o_rm, o_t, cs
 
 
@@ -379,9 +383,9 @@ def _trunk_bwd_tc(tr, tape, dcur, G):
         for blk, saved in zip(reversed(list(stage.blocks)), reversed(st["blocks"])):
             xin, u, y16t, hp, hh16t, v, w49, w1_16t, w2_16t, h, w = saved
             M = dcur.shape[0]
-            G.put(blk.gamma, colsum(dcur, v))
-            # dv = gamma * dcur: bf16 copies + its column sums (= d fc2.bias) in one pass, never stored in fp32
-            dv16, dv16t, db2 = cast_dual(dcur, colvec=blk.gamma.detach(), want_colsum=True)
+            # dv = gamma * dcur: bf16 copies + its column sums (= d fc2.bias) + d gamma = sum(dcur * v) in ONE pass over dcur
+            dv16, dv16t, db2, dgamma = cast_dual(dcur, colvec=blk.gamma.detach(), want_colsum=True, aux=v)
+            G.put(blk.gamma, dgamma)
             G.put(blk.mlp.fc2.weight, tc_wgrad(hh16t, dv16t, M).t().contiguous())      # [4c, c]^T -> [c, 4c]
             G.put(blk.mlp.fc2.bias, db2)
             dhh = tc_gemm16(dv16, w2_16t, torch.zeros((4 * c,), device=dcur.device, dtype=torch.float32))   # bf16 [M, 4c]
@@ -416,8 +420,15 @@ def _trunk_bwd_tc(tr, tape, dcur, G):
     du0, dlw, dlb = ln_bwd(u0, stem_n.weight.detach(), dcur)
     G.put(stem_n.weight, dlw)
     G.put(stem_n.bias, dlb)
-    G.put(stem_c.weight, gemm_tn(du0, patches))
-    G.put(stem_c.bias, colsum(du0))
+    if tape.get("tc"):
+        # stem wgrad [c0, 48] = du0^T patches on the tensor cores as well (the fp32 split-K kernel took 0.4 ms of the step)
+        _, du16t, db0 = cast_dual(du0, rm=False, want_colsum=True)
+        _, p16t, _ = cast_dual(patches, rm=False)
+        G.put(stem_c.weight, tc_wgrad(du16t, p16t, du0.shape[0]))
+        G.put(stem_c.bias, db0)
+    else:
+        G.put(stem_c.weight, gemm_tn(du0, patches))
+        G.put(stem_c.bias, colsum(du0))
 
 
 # ---- dense stacks (metadata branch, heads) -------------------------------------------------------------------------

@@ -62,9 +62,10 @@ template <int OP, typename TI>
 __global__ void __launch_bounds__(256)
 cast_dual_kernel(const TI* __restrict__ in, const TI* __restrict__ in2, const float* __restrict__ colvec,
                  __nv_bfloat16* __restrict__ rm, __nv_bfloat16* __restrict__ t, float* __restrict__ colsum, int64_t M, int N,
-                 int64_t ld) {
+                 int64_t ld, const float* __restrict__ aux, float* __restrict__ auxsum) {
   __shared__ float tile[TN][TM + 1];        // [n][m]
   __shared__ float red[8][TN];
+  __shared__ float red2[8][TN];
   const int64_t m0 = (int64_t)blockIdx.x * TM;
   const int n0 = blockIdx.y * TN;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -72,7 +73,7 @@ cast_dual_kernel(const TI* __restrict__ in, const TI* __restrict__ in2, const fl
   const bool ncol = n < N;                  // N is even: n + 1 < N as well
   float g0 = 1.f, g1 = 1.f;
   if (colvec && ncol) { g0 = __ldg(colvec + n); g1 = __ldg(colvec + n + 1); }
-  float s0 = 0.f, s1 = 0.f;
+  float s0 = 0.f, s1 = 0.f, a0 = 0.f, a1 = 0.f;
 #pragma unroll
   for (int i = 0; i < TM / 8; ++i) {
     const int m = ty + 8 * i;
@@ -80,6 +81,10 @@ cast_dual_kernel(const TI* __restrict__ in, const TI* __restrict__ in2, const fl
     float2 v = make_float2(0.f, 0.f);
     if (gm < M && ncol) {
       v = ld2(in + gm * N + n);
+      if (auxsum) {                           // auxsum[n] += sum_m in[m,n] * aux[m,n]  (layer-scale gradient: dcur . v)
+        const float2 x = *reinterpret_cast<const float2*>(aux + gm * N + n);
+        a0 = fmaf(v.x, x.x, a0); a1 = fmaf(v.y, x.y, a1);
+      }
       if (OP == 1) { v.x = gelu_tanh(v.x); v.y = gelu_tanh(v.y); }
       if (OP == 2) {
         const float2 d = ld2(in2 + gm * N + n);
@@ -93,12 +98,19 @@ cast_dual_kernel(const TI* __restrict__ in, const TI* __restrict__ in2, const fl
     tile[2 * tx + 1][m] = v.y;
   }
   if (colsum) { red[ty][2 * tx] = s0; red[ty][2 * tx + 1] = s1; }
+  if (auxsum) { red2[ty][2 * tx] = a0; red2[ty][2 * tx + 1] = a1; }
   __syncthreads();
   if (colsum && threadIdx.x < TN && n0 + (int)threadIdx.x < N) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
     atomicAdd(colsum + n0 + threadIdx.x, s);
+  }
+  if (auxsum && threadIdx.x >= 64 && threadIdx.x < 64 + TN && n0 + (int)threadIdx.x - 64 < N) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red2[w][threadIdx.x - 64];
+    atomicAdd(auxsum + n0 + threadIdx.x - 64, s);
   }
   if (t) {
     const int64_t gm = m0 + 2 * tx;         // ld is even and >= M rounded up to 8: the pair never leaves its row
@@ -121,11 +133,13 @@ cast_dual_kernel(const TI* __restrict__ in, const TI* __restrict__ in2, const fl
 using namespace btsb;
 
 extern "C" int btsb_cast_dual_bf16(const void* in, const void* in2, const float* colvec, void* out_rm, void* out_t,
-                                   float* colsum, int64_t M, int N, int64_t ld, int op, int in_dtype, void* stream) {
+                                   float* colsum, int64_t M, int N, int64_t ld, int op, int in_dtype, const float* aux,
+                                   float* auxsum, void* stream) {
   if (int e = check_device()) return e;
   BTSB_REQUIRE(M >= 0 && N >= 2 && N % 2 == 0, "cast_dual: N=%d must be even", N);
   if (M == 0) return BTSB_OK;
   BTSB_REQUIRE(in && (out_rm || out_t || colsum), "cast_dual: null pointer");
+  BTSB_REQUIRE((aux == nullptr) == (auxsum == nullptr) && (!aux || ((uintptr_t)aux % 8) == 0), "cast_dual: aux / auxsum go together");
   BTSB_REQUIRE(op >= 0 && op <= 2 && (op != 2 || in2), "cast_dual: bad op %d", op);
   BTSB_REQUIRE(in_dtype == BTSB_F32 || in_dtype == BTSB_BF16, "cast_dual: in_dtype must be F32 or BF16");
   BTSB_REQUIRE(!out_t || (ld % 8 == 0 && ld >= M), "cast_dual: ld=%lld must be a multiple of 8 and >= M", (long long)ld);
@@ -139,14 +153,14 @@ extern "C" int btsb_cast_dual_bf16(const void* in, const void* in2, const float*
   cudaStream_t st = (cudaStream_t)stream;
   if (in_dtype == BTSB_F32) {
     const float* a = (const float*)in; const float* b = (const float*)in2;
-    if (op == 0) cast_dual_kernel<0, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
-    else if (op == 1) cast_dual_kernel<1, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
-    else cast_dual_kernel<2, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
+    if (op == 0) cast_dual_kernel<0, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld, aux, auxsum);
+    else if (op == 1) cast_dual_kernel<1, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld, aux, auxsum);
+    else cast_dual_kernel<2, float><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld, aux, auxsum);
   } else {
     const __nv_bfloat16* a = (const __nv_bfloat16*)in; const __nv_bfloat16* b = (const __nv_bfloat16*)in2;
-    if (op == 0) cast_dual_kernel<0, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
-    else if (op == 1) cast_dual_kernel<1, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
-    else cast_dual_kernel<2, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld);
+    if (op == 0) cast_dual_kernel<0, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld, aux, auxsum);
+    else if (op == 1) cast_dual_kernel<1, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld, aux, auxsum);
+    else cast_dual_kernel<2, __nv_bfloat16><<<grid, 256, 0, st>>>(a, b, colvec, rm, t, colsum, M, N, ld, aux, auxsum);
   }
   return launch_done("cast_dual_bf16");
 }

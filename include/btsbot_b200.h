@@ -242,13 +242,15 @@ int btsb_counter_add_i64(int64_t* counter, int64_t v, void* stream);
  * cast_dual_bf16: one pass over a [M,N] tensor (in / in2 both of in_dtype F32 | BF16) writes the row-major bf16 copy out_rm [M,N] (forward / dgrad
  *   operand) and/or the transposed copy out_t [N,ld] (wgrad operand; ld % 8 == 0, ld >= M), folding in
  *   op 0: v = in;  op 1: v = gelu(in);  op 2: v = in2 * gelu'(in);  then v *= colvec[n] (if colvec) and
- *   colsum[n] += sum_m v (if colsum; bias / layer-scale gradients).  N even.
+ *   colsum[n] += sum_m v (if colsum; bias gradients); auxsum[n] += sum_m in[m,n] * aux[m,n] (if aux, fp32 [M,N]: the
+ *   layer-scale gradient sum(dout * v) rides on the pass that scales dout by gamma).  N even.
  * gemm_bf16_f32out: out[M,N] fp32 = A[M,K] . Wt[N,K]^T (+ bias[N] if not NULL); N % 16 == 0, K % 8 == 0.
  * gemm_bf16_wgrad:  out[M,N] fp32 += At[M,K] . Bt[N,K]^T where K is the (huge) activation row count and At / Bt are
  *   transposed copies with row pitch ld; K is split over the SMs and partial tiles are reduced with red.global.add
  *   (the caller zeroes `out`; summation order, hence the last fp32 bits, varies run to run).  N % 16 == 0. */
 int btsb_cast_dual_bf16(const void* in, const void* in2, const float* colvec, void* out_rm, void* out_t,
-                        float* colsum, int64_t M, int N, int64_t ld, int op, int in_dtype, void* stream);
+                        float* colsum, int64_t M, int N, int64_t ld, int op, int in_dtype, const float* aux,
+                        float* auxsum, void* stream);
 int btsb_gemm_bf16_f32out(const void* A, const void* Wt, const float* bias, float* out, int64_t M, int N, int K,
                           void* stream);
 int btsb_gemm_bf16_wgrad(const void* At, const void* Bt, int64_t ld, float* out, int M, int N, int64_t K,
