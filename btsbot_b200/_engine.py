@@ -20,6 +20,8 @@ from .synth import convnext_arch
 
 BN_EPS = 1e-5  # torch.nn.BatchNorm1d default, used by the reference (architectures.py:147)
 
+#: one-kernel stem (im2col rows built in shared memory by producer warps); BTSB_STEM_FUSED=0 -> im2col + GEMM-with-LN
+STEM_FUSED = os.environ.get("BTSB_STEM_FUSED", "1") != "0"
 #: the wide variants of the fused kernel (C = 256 / 320: single D2 accumulator, G2 split in two UMMAs); BTSB_FUSE_WIDE=0
 #: falls back to the two separate GEMMs for A/B timing
 FUSE_MLP_WIDE = os.environ.get("BTSB_FUSE_WIDE", "1") != "0"
@@ -110,7 +112,10 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
     c = w.dims[0]
     cur = torch.empty((B * h * wd, c), device=dev, dtype=adt)
     es = cur.element_size()
-    if TC_STEM and w.stem_w_tc is not None:
+    if TC_STEM and STEM_FUSED and w.stem_w_tc is not None and c in (64, 80, 96):
+        L.launch("stem_fused", lib.btsb_stem_fused_fwd, _p(x), B, H, W, _p(w.stem_w_tc), _p(w.stem_b), _p(w.stem_ln_w),
+                 _p(w.stem_ln_b), _p(cur), c, st, flops=2.0 * 48 * c * B * h * wd, nbytes=4.0 * x.numel() + es * cur.numel())
+    elif TC_STEM and w.stem_w_tc is not None:
         patches = torch.empty((B * h * wd, 64), device=dev, dtype=torch.bfloat16)
         L.launch("stem_im2col", lib.btsb_stem_im2col_bf16, _p(x), _p(patches), B, H, W, st,
                  nbytes=4.0 * x.numel() + 2.0 * patches.numel())

@@ -62,6 +62,7 @@ SIGNATURES = {
     "btsb_convnext_poolln_fwd": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, vp]),
     "btsb_gemm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "btsb_stem_im2col_bf16": (i32, [vp, vp, i64, i32, i32, vp]),
+    "btsb_stem_fused_fwd": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
     "btsb_gemm_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "btsb_convnext_mlp_fused_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]),
     "btsb_meta_head_fwd": (i32, [C.POINTER(HeadParams), i64, vp, vp]),

@@ -100,6 +100,18 @@ def stem_tc(x, w_pad, bias, ln_w, ln_b):
     return out, patches
 
 
+def stem_fused(x, w_pad, bias, ln_w, ln_b):
+    """one-kernel bf16 stem (producer warps build the im2col rows in shared memory): rows [B*h*w, C0] bf16."""
+    _chk(x, w_pad, bias, ln_w, ln_b)
+    B, _, H, W = x.shape
+    h, w = (H - 4) // 4 + 1, (W - 4) // 4 + 1
+    c0 = w_pad.shape[0]
+    out = torch.empty((B * h * w, c0), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().btsb_stem_fused_fwd(_p(x), B, H, W, _p(w_pad), _p(bias), _p(ln_w), _p(ln_b), _p(out), c0,
+                                        L.stream_ptr()), "stem_fused")
+    return out
+
+
 def score(logits):
     """sigmoid + 0.5 threshold on device -> (scores f32, labels uint8)."""
     _chk(logits)

@@ -127,6 +127,10 @@ int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float*
  * im2col: x [B,3,H,W] fp32 -> patches [B*h*w, 64] bf16 (k = (ci*4+ky)*4+kx, columns 48..63 zero).
  * gemm_ln: out[M,N] = LayerNorm_rows(A[M,K] . Wt[N,K]^T + bias) * ln_w + ln_b, bf16 operands/output, N <= 128. */
 int btsb_stem_im2col_bf16(const float* x, void* patches, int64_t B, int H, int W, void* stream);
+/* the same stem as ONE kernel: the im2col rows are built in shared memory by producer warps straight from the NCHW fp32
+ * image (the [M,64] patch matrix never exists in HBM).  w_pad: [C0,64] bf16 (columns 48..63 zero); out [B*h*w, C0] bf16. */
+int btsb_stem_fused_fwd(const float* x, int64_t B, int H, int W, const void* w_pad, const float* bias,
+                        const float* ln_w, const float* ln_b, void* out, int C0, void* stream);
 int btsb_gemm_ln_fwd(const void* A, const void* Wt, const float* bias, const float* ln_w, const float* ln_b,
                      void* out, int64_t M, int N, int K, void* stream);
 

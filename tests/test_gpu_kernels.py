@@ -193,7 +193,8 @@ def test_mlp_fused_tcgen05(cuda_dev, C, M):
     assert err < 4e-2 and (got - ref).abs().mean().item() < 5e-3
 
 
-@pytest.mark.parametrize("C0,H,W,B", [(80, 63, 63, 37), (64, 63, 63, 5), (128, 20, 36, 3), (16, 8, 8, 700)])
+@pytest.mark.parametrize("C0,H,W,B", [(80, 63, 63, 37), (64, 63, 63, 5), (128, 20, 36, 3), (16, 8, 8, 700), (96, 31, 47, 9),
+                                      (80, 63, 63, 1200)])
 def test_stem_tcgen05(cuda_dev, C0, H, W, B):
     """tensor-core stem (im2col + GEMM with bias+LayerNorm epilogue) vs fp32 conv+LN on the bf16-rounded operands."""
     from btsbot_b200 import ops
@@ -212,6 +213,14 @@ def test_stem_tcgen05(cuda_dev, C0, H, W, B):
     assert torch.equal(patches[:, :48].float().cpu(), unf) and patches[:, 48:].abs().max().item() == 0
     err = _report(f"stem tcgen05 C0={C0} {H}x{W}", _rows_to_nchw(got.cpu(), B, h, wd), ref)
     assert err < 3e-2
+    # the one-kernel stem (producer warps build the same im2col rows in shared memory) must give the same rows: the MMA
+    # sees identical operands, only the zero K-step 48..63 is skipped
+    if C0 in (64, 80, 96):
+        fused = ops.stem_fused(x.to(cuda_dev), wp.bfloat16().to(cuda_dev), b.to(cuda_dev), lw.to(cuda_dev), lb.to(cuda_dev))
+        torch.cuda.synchronize()
+        # same MMA operands; the LayerNorm statistics are summed in a different order (one pass over the row)
+        assert (fused.float().cpu() - got.float().cpu()).abs().max() <= 2 ** -6, (fused.float().cpu() - got.float().cpu()).abs().max()
+        assert _report(f"stem fused C0={C0} {H}x{W}", _rows_to_nchw(fused.cpu(), B, h, wd), ref) < 3e-2
 
 
 def test_gemm_rejects_bad_arguments(cuda_dev):
