@@ -93,6 +93,7 @@ SIGNATURES = {
     "btsb_counter_add_i64": (i32, [vp, i64, vp]),
     "btsb_maxvit_stem1_fwd": (i32, [vp, i64, i32, i32, i32, vp, vp, i32, vp, i32, vp]),
     "btsb_maxvit_im2col3_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
+    "btsb_conv3x3_c32_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "btsb_maxvit_avgpool2_fwd": (i32, [vp, vp, i64, i32, i32, i32, i32, vp]),
     "btsb_maxvit_dw3_fwd": (i32, [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp]),
     "btsb_maxvit_se_fwd": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp]),

@@ -14,6 +14,8 @@ CUDA library.  Structure follows SURVEY.md Appendix A.2:
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import torch
@@ -27,6 +29,8 @@ BN2D_EPS = 1e-5     # timm conv_cfg.norm_eps for the 'rw' MaxViT variants (SURVE
 CHUNK = {"fp32": 128, "bf16": 1024}
 #: use the fused fc1->GELU->fc2 kernel in the attention MLPs where it applies (bf16, C <= 160 and C = 256)
 FUSE_MLP = True
+#: stem.conv2 as an implicit GEMM with 4-D bulk-tensor operand loads; BTSB_CONV3_TC=0 -> im2col3 + GEMM
+CONV3_TC = os.environ.get("BTSB_CONV3_TC", "1") != "0"
 
 _DT = {"fp32": (L.F32, torch.float32), "bf16": (L.BF16, torch.bfloat16)}
 
@@ -166,11 +170,18 @@ def _trunk_chunk(w: MaxVitWeights, x: torch.Tensor, capture: dict | None, feat: 
              _p(a), code, st, flops=2.0 * 27 * sw[0] * B * H * W, nbytes=4.0 * x.numel() + es * a.numel())
     if capture is not None:
         capture["stem1"] = (a, H, W)
-    col = torch.empty((B * H * W, 9 * sw[0]), device=dev, dtype=adt)
-    L.launch("mv_im2col3", lib.btsb_maxvit_im2col3_fwd, _p(a), _p(col), B, H, W, sw[0], code, st,
-             nbytes=es * (a.numel() + col.numel()))
-    cur = _gemm("mv_stem2", col, w.stem2_w, w.zeros(sw[1]), None, None, code, L.EPI_BIAS, st)
-    del col, a
+    if CONV3_TC and code == L.BF16 and sw[0] == 32 and sw[1] == 64 and H % 8 == 0 and W % 16 == 0:
+        # implicit GEMM: every tap's A operand is one 4-D bulk tensor copy of the shifted input box (no patch matrix)
+        cur = torch.empty((B * H * W, sw[1]), device=dev, dtype=adt)
+        L.launch("mv_stem2_conv", lib.btsb_conv3x3_c32_fwd, _p(a), _p(w.stem2_w), None, _p(cur), B, H, W, sw[1], st,
+                 flops=2.0 * 9 * sw[0] * sw[1] * B * H * W, nbytes=es * (a.numel() + cur.numel()))
+        del a
+    else:
+        col = torch.empty((B * H * W, 9 * sw[0]), device=dev, dtype=adt)
+        L.launch("mv_im2col3", lib.btsb_maxvit_im2col3_fwd, _p(a), _p(col), B, H, W, sw[0], code, st,
+                 nbytes=es * (a.numel() + col.numel()))
+        cur = _gemm("mv_stem2", col, w.stem2_w, w.zeros(sw[1]), None, None, code, L.EPI_BIAS, st)
+        del col, a
     if capture is not None:
         capture["stem"] = (cur, H, W)
     for blk in w.blocks:

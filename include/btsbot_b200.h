@@ -286,6 +286,12 @@ int btsb_maxvit_stem1_fwd(const float* x, int64_t B, int Hin, int Win, int S, co
                           int C1, void* out, int dtype, void* stream);
 int btsb_maxvit_im2col3_fwd(const void* x, void* out, int64_t B, int H, int W, int C, int dtype, void* stream);
 int btsb_maxvit_avgpool2_fwd(const void* x, void* out, int64_t B, int H, int W, int C, int dtype, void* stream);
+/* stem.conv2 as an implicit GEMM on tcgen05 (bf16): 3x3 / stride 1 / pad 1, 32 input channels, N = 64 output channels.
+ * The A operand of every tap is one 4-D bulk tensor copy of the shifted 8 x 16 x 32 input box (TMA zero-fills the
+ * padding); no patch matrix.  x [B,H,W,32] bf16 NHWC, w [N, 288] bf16 (k = (ky*3+kx)*32 + c), bias [N] fp32 or NULL,
+ * out [B*H*W, N] bf16.  H % 8 == 0, W % 16 == 0; BTSB_EINVAL otherwise (use im2col3 + gemm). */
+int btsb_conv3x3_c32_fwd(const void* x, const void* w, const float* bias, void* out, int64_t B, int H, int W, int N,
+                         void* stream);
 int btsb_maxvit_dw3_fwd(const void* x, int64_t B, int H, int W, int C, int stride, const float* w, const float* shift,
                         void* out, float* pooled, int dtype, void* stream);
 int btsb_maxvit_se_fwd(const float* pooled, int64_t B, int C, int R, const float* w1, const float* b1, const float* w2t,
