@@ -420,15 +420,11 @@ def _trunk_bwd_tc(tr, tape, dcur, G):
     du0, dlw, dlb = ln_bwd(u0, stem_n.weight.detach(), dcur)
     G.put(stem_n.weight, dlw)
     G.put(stem_n.bias, dlb)
-    if tape.get("tc"):
-        # stem wgrad [c0, 48] = du0^T patches on the tensor cores as well (the fp32 split-K kernel took 0.4 ms of the step)
-        _, du16t, db0 = cast_dual(du0, rm=False, want_colsum=True)
-        _, p16t, _ = cast_dual(patches, rm=False)
-        G.put(stem_c.weight, tc_wgrad(du16t, p16t, du0.shape[0]))
-        G.put(stem_c.bias, db0)
-    else:
-        G.put(stem_c.weight, gemm_tn(du0, patches))
-        G.put(stem_c.bias, colsum(du0))
+    # stem wgrad [c0, 48] = du0^T patches on the tensor cores as well (the fp32 split-K kernel took 0.4 ms of the step)
+    _, du16t, db0 = cast_dual(du0, rm=False, want_colsum=True)
+    _, p16t, _ = cast_dual(patches, rm=False)
+    G.put(stem_c.weight, tc_wgrad(du16t, p16t, du0.shape[0]))
+    G.put(stem_c.bias, db0)
 
 
 # ---- dense stacks (metadata branch, heads) -------------------------------------------------------------------------
