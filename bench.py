@@ -21,8 +21,9 @@ A "step" is one forward pass of every rank over one micro-batch of B alerts ([B,
 
 `--workload c4` runs BASELINE.json configs[3] instead (multimodal MaxViT-tiny-rw-224, batch 4096 per GPU per step, bf16);
 `--workload c5` runs configs[4]: one TRAINING step (train.py:496-547: zero_grad, forward, BCE-with-logits, backward,
-AdamW) of the multimodal ConvNeXt-nano on 1024 alerts per GPU in mixed precision (tcgen05 bf16 GEMMs), gradients
-all-reduced over NCCL, overlapped with the backward, when N > 1.  The default (and what the driver measures) is C3.
+AdamW) of the multimodal ConvNeXt-nano on 1024 alerts per GPU in mixed precision (tcgen05 bf16 GEMMs); with one process
+the whole step is ONE CUDA-graph replay (--no-graph issues it eagerly), with N > 1 it is issued eagerly and the gradients
+are all-reduced over NCCL on a side stream, overlapped with the backward.  The default (what the driver measures) is C3.
 
 `--impl reference` times that CPU port alone with all host threads (the reference itself cannot run offline:
 timm is not installable).
