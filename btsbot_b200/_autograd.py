@@ -1,7 +1,8 @@
 """Training-mode forward + hand-written backward of the reference models on the CUDA kernels (K7): all-fp32
 (``precision="fp32"``, the reference-numerics path) or mixed precision (``precision="bf16"``: the fc1 / fc2 /
-downsample GEMMs -- forward, dgrad and split-K wgrad -- on tcgen05 tensor cores with bf16 operands and fp32
-accumulation, everything else in fp32; the arithmetic torch autocast(bf16) would give train.py).
+downsample GEMMs -- forward, dgrad and split-K wgrad (MN-major operands: no transposed activation copies) -- on tcgen05
+tensor cores with bf16 operands and fp32 accumulation, everything else in fp32; the arithmetic torch autocast(bf16)
+would give train.py).
 
 Replaces, for one step of `btsbot/train.py:496-547`, everything PyTorch autograd + cuDNN/ATen would do between
 ``logits = model(...)`` and ``loss.backward()``: the forward saves the intermediates each backward kernel needs and
@@ -122,6 +123,17 @@ def tc_wgrad(at16, bt16, K):
     No = bt16.shape[0]
     out = torch.zeros((Mo, No), device=at16.device, dtype=torch.float32)
     L.launch("t_wgrad_tc", L.lib().btsb_gemm_bf16_wgrad, _p(at16), _p(bt16), ld, _p(out), Mo, No, K, _st(),
+             flops=2.0 * Mo * No * K, nbytes=2.0 * K * (Mo + No) + 4.0 * Mo * No)
+    return out
+
+
+def tc_wgrad_mn(a16, b16):
+    """fp32 [Mo,No] = a16 [K, Mo]^T @ b16 [K, No] with both operands ROW-MAJOR bf16 (MN-major UMMA operands): the wgrad
+    GEMM reads dY and X as the forward / dgrad GEMMs do, no transposed copies."""
+    K, Mo = a16.shape
+    No = b16.shape[1]
+    out = torch.zeros((Mo, No), device=a16.device, dtype=torch.float32)
+    L.launch("t_wgrad_tc", L.lib().btsb_gemm_bf16_wgrad_mn, _p(a16), _p(b16), _p(out), Mo, No, K, _st(),
              flops=2.0 * Mo * No * K, nbytes=2.0 * K * (Mo + No) + 4.0 * Mo * No)
     return out
 
@@ -353,8 +365,8 @@ def _trunk_fwd_tc(tr, x):
             pt = patch2x2(yln, B, h, w, cin, reverse=False)
             wds = conv_m.weight.detach().permute(0, 2, 3, 1).reshape(c, 4 * cin).contiguous()
             wds16, wds16t = _w16(wds)
-            pt16, pt16t, _ = cast_dual(pt)
-            st["down"] = (cur, pt16t, wds16t, h, w)
+            pt16, _, _ = cast_dual(pt, t=False)
+            st["down"] = (cur, pt16, wds16t, h, w)
             h, w = (h - 2) // 2 + 1, (w - 2) // 2 + 1
             cur = tc_gemm(pt16, wds16, conv_m.bias.detach())
         for blk in stage.blocks:
@@ -363,12 +375,12 @@ def _trunk_fwd_tc(tr, x):
             y = ln_fwd(u, blk.norm.weight.detach(), blk.norm.bias.detach())
             w1_16, w1_16t = _w16(blk.mlp.fc1.weight.detach().reshape(4 * c, c))
             w2_16, w2_16t = _w16(blk.mlp.fc2.weight.detach().reshape(c, 4 * c))
-            y16, y16t, _ = cast_dual(y)
+            y16, _, _ = cast_dual(y, t=False)
             hp = tc_gemm16(y16, w1_16, blk.mlp.fc1.bias.detach())         # bf16 [M, 4c]
-            hh16, hh16t, _ = cast_dual(hp, op=1)                         # gelu fused into the cast
+            hh16, _, _ = cast_dual(hp, t=False, op=1)                    # gelu fused into the cast
             v = tc_gemm(hh16, w2_16, blk.mlp.fc2.bias.detach())
             out = colscale(v, blk.gamma.detach(), res=cur)
-            st["blocks"].append((cur, u, y16t, hp, hh16t, v, w49, w1_16t, w2_16t, h, w))
+            st["blocks"].append((cur, u, y16, hp, hh16, v, w49, w1_16t, w2_16t, h, w))
             cur = out
         tape["stages"].append(st)
     return cur, h, w, tape
@@ -381,16 +393,16 @@ def _trunk_bwd_tc(tr, tape, dcur, G):
         stage, st, c = tr.stages[i], tape["stages"][i], dims[i]
         ones = torch.ones((c,), device=dcur.device, dtype=torch.float32)
         for blk, saved in zip(reversed(list(stage.blocks)), reversed(st["blocks"])):
-            xin, u, y16t, hp, hh16t, v, w49, w1_16t, w2_16t, h, w = saved
-            M = dcur.shape[0]
+            xin, u, y16, hp, hh16, v, w49, w1_16t, w2_16t, h, w = saved
             # dv = gamma * dcur: bf16 copies + its column sums (= d fc2.bias) + d gamma = sum(dcur * v) in ONE pass over dcur
-            dv16, dv16t, db2, dgamma = cast_dual(dcur, colvec=blk.gamma.detach(), want_colsum=True, aux=v)
+            # the wgrad GEMMs read the same row-major bf16 copies as the forward / dgrad GEMMs (MN-major UMMA operands)
+            dv16, _, db2, dgamma = cast_dual(dcur, t=False, colvec=blk.gamma.detach(), want_colsum=True, aux=v)
             G.put(blk.gamma, dgamma)
-            G.put(blk.mlp.fc2.weight, tc_wgrad(hh16t, dv16t, M).t().contiguous())      # [4c, c]^T -> [c, 4c]
+            G.put(blk.mlp.fc2.weight, tc_wgrad_mn(hh16, dv16).t().contiguous())         # [4c, c]^T -> [c, 4c]
             G.put(blk.mlp.fc2.bias, db2)
             dhh = tc_gemm16(dv16, w2_16t, torch.zeros((4 * c,), device=dcur.device, dtype=torch.float32))   # bf16 [M, 4c]
-            dhp16, dhp16t, db1 = cast_dual(hp, op=2, x2=dhh, want_colsum=True)           # dhh * gelu'(hp)
-            G.put(blk.mlp.fc1.weight, tc_wgrad(dhp16t, y16t, M))                         # [4c, c]
+            dhp16, _, db1 = cast_dual(hp, t=False, op=2, x2=dhh, want_colsum=True)       # dhh * gelu'(hp)
+            G.put(blk.mlp.fc1.weight, tc_wgrad_mn(dhp16, y16))                           # [4c, c]
             G.put(blk.mlp.fc1.bias, db1)
             dy = tc_gemm(dhp16, w1_16t)                                                  # [M, c]
             du, dlw, dlb = ln_bwd(u, blk.norm.weight.detach(), dy)
@@ -402,12 +414,11 @@ def _trunk_bwd_tc(tr, tape, dcur, G):
             dconv = dwconv(du, w49, None, B, h, w, flip=1)
             dcur = colscale(dconv, ones, res=dcur)
         if i > 0:
-            xin, pt16t, wds16t, h, w = st["down"]
+            xin, pt16, wds16t, h, w = st["down"]
             cin = dims[i - 1]
             ln_m, conv_m = stage.downsample[0], stage.downsample[1]
-            Mo = dcur.shape[0]
-            d16, d16t, dbd = cast_dual(dcur, want_colsum=True)
-            dwds = tc_wgrad(pt16t, d16t, Mo).t().contiguous()       # [4cin, c]^T -> [c, (dy,dx,cin)]
+            d16, _, dbd = cast_dual(dcur, t=False, want_colsum=True)
+            dwds = tc_wgrad_mn(pt16, d16).t().contiguous()          # [4cin, c]^T -> [c, (dy,dx,cin)]
             G.put(conv_m.weight, dwds.view(c, 2, 2, cin).permute(0, 3, 1, 2).contiguous())
             G.put(conv_m.bias, dbd)
             dpt = tc_gemm(d16, wds16t)                               # [Mo, 4cin]
@@ -421,9 +432,9 @@ def _trunk_bwd_tc(tr, tape, dcur, G):
     G.put(stem_n.weight, dlw)
     G.put(stem_n.bias, dlb)
     # stem wgrad [c0, 48] = du0^T patches on the tensor cores as well (the fp32 split-K kernel took 0.4 ms of the step)
-    _, du16t, db0 = cast_dual(du0, rm=False, want_colsum=True)
-    _, p16t, _ = cast_dual(patches, rm=False)
-    G.put(stem_c.weight, tc_wgrad(du16t, p16t, du0.shape[0]))
+    du16, _, db0 = cast_dual(du0, t=False, want_colsum=True)
+    p16, _, _ = cast_dual(patches, t=False)
+    G.put(stem_c.weight, tc_wgrad_mn(du16, p16))
     G.put(stem_c.bias, db0)
 
 

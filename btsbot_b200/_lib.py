@@ -105,6 +105,7 @@ SIGNATURES = {
     "btsb_cast_dual_bf16": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, i32, vp, vp, vp]),
     "btsb_gemm_bf16_f32out": (i32, [vp, vp, vp, vp, i64, i32, i32, vp]),
     "btsb_gemm_bf16_wgrad": (i32, [vp, vp, i64, vp, i32, i32, i64, vp]),
+    "btsb_gemm_bf16_wgrad_mn": (i32, [vp, vp, vp, i32, i32, i64, vp]),
     "btsb_cast_f32_to_bf16": (i32, [vp, vp, i64, vp]),
     "btsb_cast_bf16_to_f32": (i32, [vp, vp, i64, vp]),
 }

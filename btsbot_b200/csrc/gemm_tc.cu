@@ -44,6 +44,11 @@ constexpr int EPI_LN = 100;   // internal: out = LayerNorm(acc + bias) * gamma(l
 // training GEMMs (train_tc.cu): bf16 operands, fp32 results written / accumulated straight from the TMEM registers
 constexpr int EPI_F32OUT = 101;   // out32[M,N] = acc (+ bias)                      -- forward Linear / dgrad
 constexpr int EPI_WGRAD = 102;    // out32[M,N] += acc over a K split (red.global)  -- wgrad, K = the huge row dimension
+// wgrad straight from the ROW-MAJOR activations: out32[M,N] += sum_k A[k,m] B[k,n], A = [K, M] and B = [K, N] row-major
+// (dY and X as the forward / dgrad GEMMs use them).  Both operands are MN-major for UMMA: a TMA box of 64 columns x 64 rows
+// with the 128-byte swizzle IS the canonical MN-major SW128 atom (64 contiguous M/N elements per 128-byte row, one row per
+// K index), so no transposed copies of the activations are needed.  BN is N rounded up to 64-column slabs (TMA zero-fills).
+constexpr int EPI_WGRAD_MN = 103;
 
 // CTA2: the kernel is launched in clusters of two CTAs that issue one M = 256 UMMA (cta_group::2) per K step; a work
 // unit is then a 256 x BN tile, CTA rank r owns rows [128 r, 128 r + 128) of it and stages rows [r BN/2, (r+1) BN/2) of
@@ -64,7 +69,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* smem_al = smem_dyn + (smem_base - smem_u32(smem_dyn));
   // ring geometry: a stage is the A box [128 x 64] plus the B box [BN x 64]; narrower B tiles buy deeper pipelines
-  const int kStageBytes = kABytes + (((CTA2 ? BN / 2 : BN) * BK * 2 + 1023) & ~1023);
+  const int kStageBytes = EPI == EPI_WGRAD_MN ? (2 + BN / 64) * 8192
+                                              : kABytes + (((CTA2 ? BN / 2 : BN) * BK * 2 + 1023) & ~1023);
   const int kStages = min(kMaxStages, kRingBytes / kStageBytes);
   const uint32_t bar_base = smem_base + kRingBytes;
   // barrier map (8 B each): full[kMaxStages], empty[kMaxStages], tfull[kAcc], tempty[kAcc], then tmem address slot
@@ -123,7 +129,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer (converged warp, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
-    const uint32_t tx_bytes = CTA2 ? (uint32_t)(2 * BM + BN) * BK * 2 : (uint32_t)(BM + BN) * BK * 2;
+    const uint32_t tx_bytes = EPI == EPI_WGRAD_MN ? (uint32_t)((2 + BN / 64) * 8192)
+                              : (CTA2 ? (uint32_t)(2 * BM + BN) * BK * 2 : (uint32_t)(BM + BN) * BK * 2);
     for (int wk = unit0; wk < num_work; wk += unit_step) {
       const int tile = wk / splits, kb0 = (wk - tile * splits) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       const int m0 = (tile / n_tiles) * BMU + (int)cta_rank * BM;
@@ -132,7 +139,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait_spin(empty_bar(stage), phase ^ 1u);      // this CTA's stage is free (pair: commit is multicast)
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * kStageBytes;
-          if (CTA2) {
+          if (EPI == EPI_WGRAD_MN) {
+            // 64 K-rows x 64-column slabs: two slabs of A (128 output rows), BN / 64 slabs of B; rows / columns past the
+            // tensors are zero-filled
+            mbar_expect_tx(full_bar(stage), tx_bytes);
+            tma_load_2d(sa, &tmA, full_bar(stage), m0, kb * BK);
+            tma_load_2d(sa + 8192, &tmA, full_bar(stage), m0 + 64, kb * BK);
+            for (int sl = 0; sl < BN / 64; ++sl)
+              tma_load_2d(sa + 16384 + sl * 8192, &tmB, full_bar(stage), n0 + 64 * sl, kb * BK);
+          } else if (CTA2) {
             // both CTAs' bytes are counted on the LEADER's full barrier, which its MMA warp waits on
             if (cta_rank == 0) mbar_expect_tx(full_bar(stage), tx_bytes);
             const uint32_t lead = mapa_shared(full_bar(stage), 0);
@@ -152,7 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer (converged warp, one elected lane issues; pair: the leader CTA only) ==========
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
-    const uint32_t idesc = idesc_bf16_f32(BMU, BN);
+    const uint32_t idesc = idesc_bf16_f32(BMU, BN) | (EPI == EPI_WGRAD_MN ? ((1u << 15) | (1u << 16)) : 0u);   // A, B MN-major
     for (int wk = unit0; wk < num_work; wk += unit_step) {
       const int kb0 = (wk % splits) * kb_per, kb1 = min(k_blocks, kb0 + kb_per);
       mbar_wait_spin(tempty_bar(as), aphase ^ 1u);     // epilogue has drained this accumulator
@@ -166,7 +181,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t adesc = smem_desc_sw128(sa);
           const uint64_t bdesc = smem_desc_sw128(sa + kABytes);
           const int kmax = (min(BK, K - kb * BK) + 15) / 16;   // K tail: TMA zero-fills, but skip the useless MMAs
-          if (CTA2) {
+          if (EPI == EPI_WGRAD_MN) {
+            // MN-major SW128 descriptors: 64-element slabs 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO);
+            // one K = 16 step = 16 rows of 128 B
+            auto desc_mn = [](uint32_t addr) {
+              uint64_t d = 0;
+              d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+              d |= (uint64_t)(8192 >> 4) << 16;
+              d |= (uint64_t)(1024 >> 4) << 32;
+              d |= (uint64_t)1 << 46;
+              d |= (uint64_t)2 << 61;
+              return d;
+            };
+            const uint64_t am = desc_mn(sa), bm = desc_mn(sa + 16384);
+            for (int kk = 0; kk < kmax; ++kk)
+              umma_bf16(tmem_d, am + (uint64_t)(128 * kk), bm + (uint64_t)(128 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
+            umma_commit(empty_bar(stage));
+            if (kb == kb1 - 1) umma_commit(tfull_bar(as));
+          } else if (CTA2) {
             for (int kk = 0; kk < kmax; ++kk)
               umma_bf16_pair(tmem_d, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, ((kb - kb0) | kk) != 0 ? 1u : 0u);
             umma_commit_pair(empty_bar(stage));             // frees this stage in BOTH CTAs when the MMAs retire
@@ -290,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * kAccCols);
-      if (EPI == EPI_F32OUT || EPI == EPI_WGRAD) {
+      if (EPI == EPI_F32OUT || EPI == EPI_WGRAD || EPI == EPI_WGRAD_MN) {
         // fp32 results leave straight from the TMEM registers: 64 contiguous bytes per thread and chunk (F32OUT), or
         // 16 reductions into the small [N_out, K_in] weight-gradient matrix (WGRAD; ~1e6 red ops per GEMM in total)
         for (int ch = c_lo; ch < c_hi; ++ch) {
@@ -298,9 +330,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld16(taddr + (uint32_t)(ch * 16), r);
           tmem_ld_wait();
           const int n = n0 + ch * 16;
-          if (row < M) {
+          if (row < M && n < N) {
             float* op = out32 + (size_t)row * N + n;
-            if (EPI == EPI_WGRAD) {
+            if (EPI == EPI_WGRAD || EPI == EPI_WGRAD_MN) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) atomicAdd(op + i, __uint_as_float(r[i]));
             } else {
@@ -617,6 +649,7 @@ static int train_attrs() {
   if (!done) {
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
+    BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_WGRAD_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     done = true;
   }
   return BTSB_OK;
@@ -667,6 +700,33 @@ int gemm_bf16_wgrad(const void* At, const void* Bt, int64_t ld, float* out, int 
   gemm_tc_kernel<EPI_WGRAD><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                                 M, N, (int)K, BN, 0, out, splits);
   return launch_done("gemm_bf16_wgrad");
+}
+
+
+// out32[M,N] += A[K,M]^T . B[K,N] with A, B row-major bf16 (leading dimensions M and N): wgrad without transposed copies
+int gemm_bf16_wgrad_mn(const void* A, const void* Bm, float* out, int M, int N, int64_t K, cudaStream_t st) {
+  BTSB_REQUIRE(M % 8 == 0 && N % 16 == 0 && M >= 8 && N >= 16, "wgrad_mn: M=%d must be a multiple of 8 and N=%d of 16", M, N);
+  BTSB_REQUIRE(K < (1ll << 31) && K >= 1, "wgrad_mn: bad K");
+  BTSB_REQUIRE(((uintptr_t)out % 16) == 0, "wgrad_mn: out must be 16-byte aligned");
+  if (int e = train_attrs()) return e;
+  const int BN = N >= 256 ? 256 : ((N + 63) / 64) * 64;
+  CUtensorMap tmA, tmB;
+  if (int e = make_tmap_bf16_2d_pitch(&tmA, A, (uint64_t)K, (uint64_t)M, 64, 64, 128, (uint64_t)M)) return e;
+  if (int e = make_tmap_bf16_2d_pitch(&tmB, Bm, (uint64_t)K, (uint64_t)N, 64, 64, 128, (uint64_t)N)) return e;
+  OutMaps tmO;
+  memset(&tmO, 0, sizeof(tmO));
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int k_blocks = (int)((K + BK - 1) / BK);
+  int splits = (num_sms() + tiles - 1) / tiles;
+  if (splits > k_blocks) splits = k_blocks;
+  if (splits < 1) splits = 1;
+  const int kb_per = (k_blocks + splits - 1) / splits;
+  splits = (k_blocks + kb_per - 1) / kb_per;
+  const int grid = min(tiles * splits, num_sms());
+  gemm_tc_kernel<EPI_WGRAD_MN><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                   M, N, (int)K, BN, 0, out, splits);
+  return launch_done("gemm_bf16_wgrad_mn");
 }
 
 int gemm_f32(const float* A, const float* Wt, const float* bias, const float* gamma, const float* res, float* out,
@@ -759,6 +819,14 @@ extern "C" int btsb_gemm_bf16_wgrad(const void* At, const void* Bt, int64_t ld, 
   if (K == 0) return BTSB_OK;
   BTSB_REQUIRE(At && Bt && out, "wgrad: null pointer");
   return gemm_bf16_wgrad(At, Bt, ld, out, M, N, K, (cudaStream_t)stream);
+}
+
+
+extern "C" int btsb_gemm_bf16_wgrad_mn(const void* A, const void* Bm, float* out, int M, int N, int64_t K, void* stream) {
+  if (int e = check_device()) return e;
+  if (K == 0) return BTSB_OK;
+  BTSB_REQUIRE(A && Bm && out, "wgrad_mn: null pointer");
+  return gemm_bf16_wgrad_mn(A, Bm, out, M, N, K, (cudaStream_t)stream);
 }
 
 extern "C" int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res,

@@ -259,6 +259,10 @@ int btsb_gemm_bf16_f32out(const void* A, const void* Wt, const float* bias, floa
                           void* stream);
 int btsb_gemm_bf16_wgrad(const void* At, const void* Bt, int64_t ld, float* out, int M, int N, int64_t K,
                          void* stream);
+/* the same reduction straight from the ROW-MAJOR activations (no transposed copies): out[M,N] fp32 += A[K,M]^T . B[K,N],
+ * A and B row-major bf16 with leading dimensions M and N -- both operands are fed to UMMA as MN-major (a 64-column x
+ * 64-row TMA box with the 128-byte swizzle is the canonical MN-major atom).  M % 8 == 0, N % 16 == 0. */
+int btsb_gemm_bf16_wgrad_mn(const void* A, const void* B, float* out, int M, int N, int64_t K, void* stream);
 
 /* ---- MaxViT (timm maxvit_tiny_rw_224 behind btsbot/architectures.py:25-101) -------------
  * The 1x1 convolutions / Linear layers of the MBConv, attention and MLP blocks are btsb_gemm_fwd calls (tcgen05 in

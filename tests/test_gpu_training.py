@@ -202,7 +202,8 @@ def test_cast_dual_ops(cuda_dev, M, N):
         assert (cs - want.sum(0)).abs().max() <= 1e-4 * max(1.0, want.abs().sum(0).max().item()), ("bf16 in", op)
 
 
-@pytest.mark.parametrize("M,N,K", [(1350, 320, 80), (300, 80, 320), (6, 2048, 512), (128, 640, 1280), (5000, 160, 640)])
+@pytest.mark.parametrize("M,N,K", [(1350, 320, 80), (300, 80, 320), (6, 2048, 512), (128, 640, 1280), (5000, 160, 640),
+                                   (1000, 80, 48), (4097, 1280, 320)])
 def test_tc_training_gemms_match_fp32_on_bf16_operands(cuda_dev, M, N, K):
     """forward/dgrad GEMM (bf16 operands -> fp32) and the split-K wgrad GEMM against torch fp32 matmul on the same
     bf16-rounded operands: only the fp32 summation order differs."""
@@ -226,6 +227,8 @@ def test_tc_training_gemms_match_fp32_on_bf16_operands(cuda_dev, M, N, K):
     dw = A.tc_wgrad(dy16t, a16t, M)                  # [N,K] = dy^T a
     ref_dw = _bf(dy).t() @ _bf(a)
     assert (dw - ref_dw).abs().max() <= 2e-4 * ref_dw.abs().max() + 1e-5, "wgrad"
+    dw2 = A.tc_wgrad_mn(dy16, a16)                   # the same from the row-major copies (MN-major UMMA operands)
+    assert (dw2 - ref_dw).abs().max() <= 2e-4 * ref_dw.abs().max() + 1e-5, "wgrad (MN-major)"
     torch.cuda.synchronize()
 
 
