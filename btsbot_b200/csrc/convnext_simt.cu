@@ -488,6 +488,8 @@ int dwln_bf16_v3(const void* x, int64_t B, int H, int W, int C, const float* w, 
                  const float* ln_b, void* out, cudaStream_t st);
 int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
                     const float* ln_b, void* out, cudaStream_t st);
+int dwln_bf16_v5(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
+                 const float* ln_b, void* out, cudaStream_t st);
 }
 extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* w,
                                       const float* bias, const float* ln_w, const float* ln_b, void* out,
@@ -503,6 +505,10 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
   static const int force = getenv("BTSB_DWLN") ? atoi(getenv("BTSB_DWLN")) : 0;
   if (force == 0) {
     const int rc = dwln_bf16_small(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);   // 3x3 and 1x1 maps
+    if (rc != 1) return rc;
+  }
+  if (force == 0) {
+    const int rc = dwln_bf16_v5(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);      // conv and LayerNorm on different warps
     if (rc != 1) return rc;
   }
   if (force == 0 || force == 3) {
