@@ -2,7 +2,7 @@
 # ncu evidence for one C3 bench step (gpurun -- 'bash scripts/gpu_profile.sh <tag>'):
 #   (1) launch list with per-launch device time (cold-cache, serialised: compare SHARES with bench.py's `kernels`),
 #   (2) --set full + source on the top kernels.  Per step the fused-MLP launches are 2 x <80>, 2 x <160>, 8 x <320> and
-#       the dw7x7+LN launches 2 x <15,80>, 2 x <7,160>; -s skips two warm-up steps.
+#       the dw7x7+LN (dwln5) launches 2 x <15,80>, 2 x <7,160>; -s skips two warm-up steps.
 TAG=${1:-r01}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
@@ -10,5 +10,5 @@ BENCH="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_c3.csv $BENCH > $OUT/ncu_launches.log 2>&1; echo "launch list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlp_fused2_kernel -s 24 -c 1 -o $OUT/mlp2_80 -f $BENCH > $OUT/ncu_mlp80.log 2>&1; echo "ncu mlp80 rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:mlp_fused2_kernel -s 28 -c 1 -o $OUT/mlp2_320 -f $BENCH > $OUT/ncu_mlp320.log 2>&1; echo "ncu mlp320 rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:dwln3_kernel -s 8 -c 1 -o $OUT/dwln15 -f $BENCH > $OUT/ncu_dw.log 2>&1; echo "ncu dwln rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:dwln5_kernel -s 8 -c 1 -o $OUT/dwln15 -f $BENCH > $OUT/ncu_dw.log 2>&1; echo "ncu dwln rc=$?"
 ls -la $OUT
