@@ -1,7 +1,7 @@
 // K3 v5 (bf16 activations, 15x15 and 7x7 maps, compile-time C): depthwise 7x7 + bias + LayerNorm2d with the two halves
 // of the work on DIFFERENT warps so that they overlap in time.
 //
-// ncu on v3 (dwln3.cu, profiles/r01l/dwln15.*): during the convolution the FP32 pipe is the limiter (top stall "math
+// ncu on v3 (dwln3.cu, profiles/r01m/dwln15.*): during the convolution the FP32 pipe is the limiter (top stall "math
 // pipe throttle" on the FFMA2s), but over the whole kernel it is busy only 55 % of the time -- the LayerNorm statistics
 // (shuffle tree), the normalisation and two CTA barriers per image run on the SAME threads after the convolution, with the
 // FMA pipe idle.  Here
