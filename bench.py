@@ -350,6 +350,8 @@ def run_c5(args, rank, local_rank, world, dev, cfg, sd_np, wl):
         t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+    if stepper is not None:
+        stepper.release()                       # a graph that captured NCCL work must go before its communicator
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

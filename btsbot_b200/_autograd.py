@@ -779,6 +779,14 @@ class GraphedTrainStep:
         self.last_logits = logits.detach()          # static tensor inside the graph: overwritten by every replay
         return loss.detach()
 
+    def release(self):
+        """Destroy the captured graph (call before ``torch.distributed.destroy_process_group()`` when the NCCL all-reduce
+        was captured: a communicator must outlive the graphs that use it)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
     def __call__(self, img, meta, lab):
         for dst, src in zip(self.static, (img, meta, lab)):
             if dst is not None:

@@ -2,9 +2,10 @@
 //
 // stem_im2col_bf16 + gemm_ln (gemm_tc.cu) moved the im2col matrix through HBM: 390 MB of fp32 pixels in, 236 MB of bf16
 // patches out and in again, 295 MB of rows out per 8192 alerts (127 + 137 us).  Here the A operand of the GEMM is built
-// in shared memory by four producer warps straight from the NCHW fp32 image:
-//   warps 10-17  producers : two tile slots of four warps, thread = output pixel of a 128-row tile; 48 scalar loads (3 ch x 4 x 4 patch, neighbouring
-//                            lanes read neighbouring patches so every 32-byte sector is used by the 4 kx loads), packed
+// in shared memory by eight producer warps straight from the NCHW fp32 image:
+//   warps 10-17  producers : two tile slots of four warps, thread = output pixel of a 128-row tile; 48 scalar loads
+//                            (3 ch x 4 x 4 patch, neighbouring lanes read neighbouring patches so every 32-byte sector is
+//                            used by the 4 kx loads; two tiles' loads are in flight per SM), packed
 //                            to bf16 and stored as the six 16-byte chunks of its row in the 128B-swizzled K-major layout
 //                            UMMA reads (chunks 6, 7 = K 48..63 are never touched: only K = 48 is multiplied);
 //                            fence.proxy.async + one mbarrier arrival per warp
