@@ -22,8 +22,8 @@ A "step" is one forward pass of every rank over one micro-batch of B alerts ([B,
 `--workload c4` runs BASELINE.json configs[3] instead (multimodal MaxViT-tiny-rw-224, batch 4096 per GPU per step, bf16);
 `--workload c5` runs configs[4]: one TRAINING step (train.py:496-547: zero_grad, forward, BCE-with-logits, backward,
 AdamW) of the multimodal ConvNeXt-nano on 1024 alerts per GPU in mixed precision (tcgen05 bf16 GEMMs); with one process
-the whole step is ONE CUDA-graph replay (--no-graph issues it eagerly), with N > 1 it is issued eagerly and the gradients
-are all-reduced over NCCL on a side stream, overlapped with the backward.  The default (what the driver measures) is C3.
+the whole step is ONE CUDA-graph replay (--no-graph issues it eagerly); with N > 1 the gradients are all-reduced over NCCL
+on a side stream, overlapped with the backward, and those collectives are part of the captured graph.  The default (what the driver measures) is C3.
 
 `--impl reference` times that CPU port alone with all host threads (the reference itself cannot run offline:
 timm is not installable).
@@ -259,7 +259,7 @@ def run_c5(args, rank, local_rank, world, dev, cfg, sd_np, wl):
     model.load_state_dict(synth.to_torch(sd_np), strict=True)
     model = model.to(dev).train()
     ddp = DistributedDataParallel(model, bucket_mb=8.0)
-    use_graph = not args.no_graph and (world == 1 or os.environ.get("BTSB_GRAPH_DDP", "0") == "1")
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("BTSB_GRAPH_DDP", "1") != "0")
     opt = FusedAdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), capturable=use_graph)
     loss_fn = BCEWithLogitsLoss(pos_weight=torch.tensor([1.0]))
     pool, nres = 1024, 2
@@ -284,9 +284,8 @@ def run_c5(args, rank, local_rank, world, dev, cfg, sd_np, wl):
         opt.step()
         return loss
 
-    # single process: the whole step (~360 kernels, a third of them a few microseconds long) is captured once in a CUDA
-    # graph and replayed; with N > 1 the NCCL all-reduce runs on a side stream and the step is issued eagerly
-    # (BTSB_GRAPH_DDP=1 captures the all-reduces too: 212 k vs 158 k alerts/s at N = 2, but the NCCL teardown hung)
+    # the whole step (~360 kernels, a third of them a few microseconds long; with N > 1 also the NCCL bucket all-reduces
+    # on the side stream: 212 k vs 158 k alerts/s at N = 2) is captured once in a CUDA graph and replayed
     stepper = GraphedTrainStep(ddp, opt, loss_fn, example=res[0], warmup=2) if use_graph else None
     train_step = stepper if use_graph else eager_step
 

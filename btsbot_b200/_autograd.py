@@ -724,8 +724,8 @@ class GraphedTrainStep:
     must have the shapes / dtypes of ``example``; they are copied into static buffers.  Dropout masks and the AdamW bias
     correction follow a device-side counter, so replays are not frozen at the captured step.  ``warmup`` eager steps run
     first (they DO update the parameters, like any other step).  With ``torch.distributed`` initialised and world size > 1
-    the step runs eagerly unless ``BTSB_GRAPH_DDP=1`` (NCCL all-reduce captured in the graph: works and is 1.34x faster at
-    N = 2, but the process hung in NCCL teardown afterwards -- opt-in until fixed)."""
+    the NCCL bucket all-reduces of the DistributedDataParallel wrapper are captured too (every rank captures and replays
+    in lockstep; 1.34x faster than eager issue at N = 2); call :meth:`release` before destroying the process group."""
 
     def __init__(self, model, optimizer, loss_fn, example, warmup: int = 2):
         self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
@@ -737,12 +737,12 @@ class GraphedTrainStep:
         inner._graph_counter = torch.zeros((1,), dtype=torch.int64, device=dev)
         import os
         import torch.distributed as dist
-        # N > 1: with BTSB_GRAPH_DDP=1 the gradient all-reduce (NCCL, on the sink's side stream, forked from and joined back
-        # into the capture stream) is captured with the rest of the step.  Measured at N = 2: 212 k alerts/s against 158 k
-        # eager -- but the process then hung in its NCCL teardown (profiles/r01m/bench_c5_n2_graph.txt), so the default for
-        # N > 1 stays eager issue until that is understood.
+        # N > 1: the gradient all-reduces (NCCL, on the sink's side stream, forked from and joined back into the capture
+        # stream) are captured with the rest of the step: 212 k alerts/s against 158 k eager at N = 2.  The graph must be
+        # destroyed BEFORE the communicator (release()): tearing the process group down first hangs in NCCL.
+        # BTSB_GRAPH_DDP=0 falls back to eager issue.
         multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        self.eager = multi and os.environ.get("BTSB_GRAPH_DDP", "0") != "1"
+        self.eager = multi and os.environ.get("BTSB_GRAPH_DDP", "1") == "0"
         self.graph, self.loss, self.kernels_per_step = None, None, 0
         if self.eager:
             return
