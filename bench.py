@@ -45,11 +45,11 @@ sys.path.insert(0, ROOT)
 MODEL_KIND = "convnext_nano.d1h_in1k"
 ALERT_IN_BYTES = 63 * 63 * 3 * 4 + 25 * 4
 #: DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` captures at
-#: 8192 alerts per launch (profiles/r01k/*.summary.txt; gemm_* from profiles/r01f)
+#: 8192 alerts per launch (profiles/r01m/*.summary.txt; gemm_* from profiles/r01f)
 NCU_TRAFFIC_8192 = {
-    "mlp_fused_320": 96.07e6 + 12.99e6,
-    "mlp_fused_80": 590.0e6 + 267.3e6,
-    "dwln_15x80": 295.0e6 + 253.8e6,
+    "mlp_fused_320": 96.09e6 + 13.36e6,
+    "mlp_fused_80": 590.0e6 + 267.1e6,
+    "dwln_15x80": 295.1e6 + 242.3e6,
     "gemm_fc1_320": 48.0e6 + 132.8e6,
     "gemm_fc2_320": 236.8e6 + 33.1e6,
 }
