@@ -66,6 +66,26 @@ WORKLOADS = {
 }
 
 
+#: kernel families that are dense contractions on the tcgen05 tensor cores (K4/K5 GEMMs incl. the fused
+#: fc1-GELU-fc2 kernel, the tensor-core stem, MaxViT 1x1 / Linear) -> tensor roofline; everything else -> HBM roofline
+TENSOR_FAMILIES = ("gemm", "mlp_fused", "mv_expand", "mv_project", "mv_qkv", "mv_proj", "mv_fc", "mv_stem2",
+                   "mv_shortcut", "t_wgrad_tc")
+
+
+def kernel_bound(name: str, precision: str) -> str:
+    if name == "t_gemm_tn":        # fp32 CUDA-core split-K GEMM of the training path (tiny head / metadata Linears)
+        return "hbm"
+    return "tensor" if precision == "bf16" and any(t in name for t in TENSOR_FAMILIES) else "hbm"
+
+
+def add_roofline_fractions(kernels: dict, pk: dict, precision: str) -> None:
+    """Per kernel family: which roofline SURVEY.md 8d files it under and the fraction of the measured peak it reaches
+    (algorithmic bytes or flops per launch / CUDA-event time per launch)."""
+    for name, k in kernels.items():
+        k["bound"] = kernel_bound(name, precision)
+        k["frac"] = k["tflops"] / pk["tf_sust"] if k["bound"] == "tensor" else k["gbs"] / pk["hbm"]
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,6 +386,7 @@ def run_c5(args, rank, local_rank, world, dev, cfg, sd_np, wl):
                          "tflops": a["flops"] / a["launches"] / (per * 1e-3) / 1e12, "share": a["ms"] / tot_ms}
     # the roofline entry is the tensor-core GEMM family with the largest share (the three GEMMs of every Linear are
     # 92 % of the step's FLOPs); the element-wise fp32 kernels around them are listed in `kernels`
+    add_roofline_fractions(kernels, pk, args.precision)
     tc_names = [k for k in kernels if k in ("t_gemm_tc", "t_wgrad_tc")]
     top = tc_names[0] if tc_names else next(iter(kernels))
     tk = kernels[top]
@@ -540,8 +561,8 @@ def main():
     tk = kernels[top]
     # dense contractions (K4/K5 GEMMs incl. the fused fc1-GELU-fc2 kernel, MaxViT 1x1 / Linear) are
     # reported against the tensor roofline, everything else (dw conv + LN, LN, preprocessing ...) against HBM
-    tensor_bound = args.precision == "bf16" and any(t in top for t in ("gemm", "mlp_fused", "mv_expand", "mv_project", "mv_qkv",
-                                                                       "mv_proj", "mv_fc", "mv_stem2", "mv_shortcut"))
+    tensor_bound = kernel_bound(top, args.precision) == "tensor"
+    add_roofline_fractions(kernels, pk, args.precision)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures at 8192 alerts
     # per launch (profiles/r01f/*.summary.txt, profiles/r01g/*.summary.txt), scaled to this run's batch
     traffic = NCU_TRAFFIC_8192.get(top)
