@@ -27,6 +27,9 @@ STEM_FUSED = os.environ.get("BTSB_STEM_FUSED", "1") != "0"
 FUSE_MLP_WIDE = os.environ.get("BTSB_FUSE_WIDE", "1") != "0"
 #: use the fused fc1->GELU->fc2 kernel where it applies (bf16, C <= 160, 256, 320); tests flip this to cover both paths
 FUSE_MLP = True
+#: head layer 0: contract the F image features on the tensor cores (bf16 features x bf16 weights, fp32 accumulate and
+#: output, bias included) and let the head kernel add the metadata-embedding rows; BTSB_HEAD_TC=1 opts in
+HEAD_TC = os.environ.get("BTSB_HEAD_TC", "0") == "1"
 #: bf16 stem as im2col + tcgen05 GEMM with the LayerNorm in the epilogue (else the CUDA-core stem kernel)
 TC_STEM = True
 
@@ -204,10 +207,24 @@ class HeadWeights:
             self.h0t, self.h0b = t(f"{head_prefix}{a}.weight"), _f32c(sd[f"{head_prefix}{a}.bias"])
             self.h1t, self.h1b = t(f"{head_prefix}{b}.weight"), _f32c(sd[f"{head_prefix}{b}.bias"])
             self.c1, self.c2 = self.h0t.shape[1], self.h1t.shape[1]
+            self._h0w = sd[f"{head_prefix}{a}.weight"]          # [c1, F + m2]; bf16 feature slice made on first use
+            self._h0w16 = {}
             final_prefix = f"{head_prefix}{c}."
         self.h2 = _f32c(sd[final_prefix + "weight"].reshape(-1))
         self.h2b = _f32c(sd[final_prefix + "bias"].reshape(-1))
         self.in_features = self.h0t.shape[0] if self.h0t is not None else self.m2
+
+
+def _head_feature_gemm(hw: HeadWeights, feat: torch.Tensor) -> torch.Tensor:
+    """``h0b + feat @ h0w[:, :F]^T`` as fp32 ``[B, c1]`` on tcgen05 (the 82 k of the head's 120 k MACs per alert)."""
+    B, F = feat.shape
+    w16 = hw._h0w16.get(F)
+    if w16 is None:
+        w16 = hw._h0w16[F] = hw._h0w.detach()[:, :F].to(torch.bfloat16).contiguous()
+    out = torch.empty((B, hw.c1), device=feat.device, dtype=torch.float32)
+    L.launch("head_gemm", L.lib().btsb_gemm_bf16_f32out, _p(feat), _p(w16), _p(hw.h0b), _p(out), B, hw.c1, F,
+             L.stream_ptr(), flops=2.0 * B * hw.c1 * F, nbytes=2.0 * (B * F + hw.c1 * F) + 4.0 * B * hw.c1)
+    return out
 
 
 def head_forward(hw: HeadWeights, feat: torch.Tensor | None, meta: torch.Tensor | None, B: int) -> torch.Tensor:
@@ -215,11 +232,16 @@ def head_forward(hw: HeadWeights, feat: torch.Tensor | None, meta: torch.Tensor 
     p = L.HeadParams()
     dev = (feat if feat is not None else meta).device
     F = 0
+    h0_init = None
     if feat is not None:
         feat = feat.contiguous()
         F = feat.shape[1]
         p.feat, p.F = feat.data_ptr(), F
         p.feat_dtype = L.BF16 if feat.dtype == torch.bfloat16 else L.F32
+        if (HEAD_TC and feat.dtype == torch.bfloat16 and hw.c1 > 0 and hw.c1 % 16 == 0 and F % 8 == 0
+                and F + (hw.m2 if meta is not None else 0) == hw.in_features):
+            h0_init = _head_feature_gemm(hw, feat)
+            p.h0_init = h0_init.data_ptr()
     if meta is not None:
         L.require_cuda(meta, "metadata input")
         meta = meta.to(torch.float32).contiguous()
@@ -240,8 +262,12 @@ def head_forward(hw: HeadWeights, feat: torch.Tensor | None, meta: torch.Tensor 
     p.h2, p.h2b = hw.h2.data_ptr(), hw.h2b.data_ptr()
     logits = torch.empty((B, 1), device=dev, dtype=torch.float32)
     macs = hw.Mm * hw.m1 + hw.m1 * hw.m2 + hw.in_features * hw.c1 + hw.c1 * hw.c2 + max(hw.c2, 1)
+    nbytes = B * (F * (feat.element_size() if feat is not None else 0) + 4.0 * hw.Mm + 4.0)
+    if h0_init is not None:                                 # the feature rows went through head_gemm
+        macs -= F * hw.c1
+        nbytes = B * (4.0 * hw.c1 + 4.0 * hw.Mm + 4.0)
     L.launch("meta_head", lib.btsb_meta_head_fwd, C.byref(p), B, _p(logits), L.stream_ptr(), flops=2.0 * macs * B,
-             nbytes=B * (F * (feat.element_size() if feat is not None else 0) + 4.0 * hw.Mm + 4.0))
+             nbytes=nbytes)
     return logits
 
 

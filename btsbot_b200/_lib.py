@@ -35,6 +35,7 @@ class HeadParams(C.Structure):
         ("h1t", vp), ("h1b", vp), ("c2", i32),
         ("h2", vp), ("h2b", vp),
         ("head_act", i32),
+        ("h0_init", vp),
     ]
 
 

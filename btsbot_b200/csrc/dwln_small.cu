@@ -7,6 +7,8 @@
 // channel pairs with the 31-shuffle recursive-halving tree (common.cuh) + one shared-memory hop across the warps.
 // The previous path (dwln2: fp32 staging in shared memory + a second warp-per-pixel pass) ran at 1.2 TB/s on this
 // shape; the work is 94 MB of traffic and 0.2 GFMA per 8192 alerts, i.e. this kernel should sit on the HBM roofline.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace btsb {
@@ -14,7 +16,10 @@ namespace btsb {
 // CT > 0: channel count known at compile time (nano 320/640, pico 256/512): the 9 loads, 9 stores and 25 tap reads become
 // immediate offsets -- the kernel was instruction-issue-bound with ~240 of its ~800 instructions per image being 64-bit
 // address arithmetic (3 CTAs of 120 registers per SM leave no latency slack either).  CT == 0: generic runtime C.
-template <int S, int CT>
+// PF: prefetch distance in images.  One image per thread is 9 x 4 B; with 5-6 resident CTAs of C/2 threads an SM has
+// ~35 KB of loads in flight at PF = 1, the bare Little's-law minimum for its share of the HBM bandwidth (the kernel ran
+// at 2.5 of ~6.5 TB/s); PF = 2 keeps two images per thread in flight for 9 more registers.
+template <int S, int CT, int PF>
 __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C_rt, const float* __restrict__ wt,
                                   const float* __restrict__ bias, const float* __restrict__ ln_w,
                                   const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
@@ -42,17 +47,19 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
   const float2 gb = *reinterpret_cast<const float2*>(ln_b + 2 * c2);
   __syncthreads();
 
-  uint32_t cur[HW], nxt[HW];
+  uint32_t cur[HW], nxt[HW], nx2[PF == 2 ? HW : 1];
   auto load_img = [&](int64_t img, uint32_t (&v)[HW]) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(x + img * (int64_t)HW * C) + c2;
 #pragma unroll
     for (int p = 0; p < HW; ++p) v[p] = (active && img < B) ? __ldg(src + (size_t)p * C2) : 0u;
   };
   load_img(blockIdx.x, cur);
+  if (PF == 2) load_img((int64_t)blockIdx.x + gridDim.x, nxt);
   const float invC = 1.0f / (float)C;
   int it = 0;
   for (int64_t img = blockIdx.x; img < B; img += gridDim.x, ++it) {
-    load_img(img + gridDim.x, nxt);                          // prefetch: in flight during the math below
+    if constexpr (PF == 2) load_img(img + 2 * (int64_t)gridDim.x, nx2);   // prefetch: in flight during the math below
+    else load_img(img + gridDim.x, nxt);
     float a0[HW], a1[HW];
     {
       f32x2_t acc[HW], xin[HW];
@@ -115,14 +122,26 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
       }
     }
 #pragma unroll
-    for (int p = 0; p < HW; ++p) cur[p] = nxt[p];
+    for (int p = 0; p < HW; ++p) {
+      cur[p] = nxt[p];
+      if constexpr (PF == 2) nxt[p] = nx2[p];
+    }
   }
 }
 
 int num_sms();
 
-template <int S, int CT>
-static int launch_small(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
+// BTSB_DWS_PF=2 selects the two-image prefetch (A/B timing; default 1 until measured faster)
+static int prefetch_distance() {
+  static const int pf = [] {
+    const char* e = getenv("BTSB_DWS_PF");
+    return (e && e[0] == '2') ? 2 : 1;
+  }();
+  return pf;
+}
+
+template <int S, int CT, int PF>
+static int launch_small_pf(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
   constexpr int NT = 2 * (S - 1) + 1;
   const int threads = ((C / 2 + 31) / 32) * 32;
@@ -130,7 +149,7 @@ static int launch_small(const void* x, int64_t B, int C, const float* w, const f
   const int nw = threads / 32;
   const size_t smem = (size_t)NT * NT * C * 4 + 2 * nw * 32 * 4 + 2 * 16 * 8;
   if (smem > 200 * 1024) return 1;
-  auto kern = dwln_small_kernel<S, CT>;
+  auto kern = dwln_small_kernel<S, CT, PF>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dwln_small attr");
   int per_sm = 1;
   BTSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem), "dwln_small occupancy");
@@ -139,6 +158,13 @@ static int launch_small(const void* x, int64_t B, int C, const float* w, const f
   const int grid = (int)(B < cap ? B : cap);
   kern<<<grid, threads, smem, st>>>((const __nv_bfloat16*)x, B, C, w, bias, ln_w, ln_b, (__nv_bfloat16*)out);
   return launch_done("dwln_small");
+}
+
+template <int S, int CT>
+static int launch_small(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
+                        const float* ln_b, void* out, cudaStream_t st) {
+  return prefetch_distance() == 2 ? launch_small_pf<S, CT, 2>(x, B, C, w, bias, ln_w, ln_b, out, st)
+                                  : launch_small_pf<S, CT, 1>(x, B, C, w, bias, ln_w, ln_b, out, st);
 }
 
 // returns 1 if the shape is not handled here

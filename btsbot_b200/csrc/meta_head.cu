@@ -29,9 +29,18 @@ __device__ __forceinline__ void load_wblock(const float* __restrict__ wp, int N,
   }
 }
 
+// Initial accumulator of output n for the CTA's alert a: bias[n], or -- when the caller pre-computed part of the
+// contraction (`init`, row-major [alerts][N], rows >= na do not exist) -- init[a][n].
+__device__ __forceinline__ float acc_init(const float* __restrict__ bias, const float* __restrict__ init, int N, int n,
+                                          int a, int na) {
+  if (init) return a < na ? __ldg(init + (size_t)a * N + n) : 0.f;
+  return bias ? __ldg(bias + n) : 0.f;
+}
+
 template <int NPT>
 __device__ __forceinline__ void dense_layer_t(const float* __restrict__ in, int K, const float* __restrict__ Wt,
-                                              const float* __restrict__ bias, int N, int act, float* __restrict__ out) {
+                                              const float* __restrict__ bias, int N, int act, float* __restrict__ out,
+                                              const float* __restrict__ init, int na) {
   const int groups = kTA / kAT;
   const int NV = N / NPT;
   for (int it = threadIdx.x; it < NV * groups; it += kHeadThreads) {
@@ -39,9 +48,8 @@ __device__ __forceinline__ void dense_layer_t(const float* __restrict__ in, int 
     float acc[NPT][kAT];
 #pragma unroll
     for (int j = 0; j < NPT; ++j) {
-      const float bv = bias ? __ldg(bias + n + j) : 0.f;
 #pragma unroll
-      for (int a = 0; a < kAT; ++a) acc[j][a] = bv;
+      for (int a = 0; a < kAT; ++a) acc[j][a] = acc_init(bias, init, N, n + j, ag * kAT + a, na);
     }
     const float* src = in + ag * kAT;
     const float* wp = Wt + n;
@@ -93,7 +101,7 @@ __device__ __forceinline__ void cp_async16_h(void* smem_dst, const void* gsrc) {
 
 __device__ __forceinline__ void dense_layer_ring(const float* __restrict__ in, int K, const float* __restrict__ Wt,
                                                  const float* __restrict__ bias, int N, int act, float* __restrict__ out,
-                                                 float* __restrict__ ring) {
+                                                 float* __restrict__ ring, const float* __restrict__ init, int na) {
   const int groups = kTA / kAT;
   const int NV = N >> 1;
   const int items = NV * groups;
@@ -113,10 +121,10 @@ __device__ __forceinline__ void dense_layer_ring(const float* __restrict__ in, i
     const bool live = it < items;
     const int n = live ? (it % NV) * 2 : 0, ag = live ? it / NV : 0;
     float acc0[kAT], acc1[kAT];
-    {
-      const float b0 = bias ? __ldg(bias + n) : 0.f, b1 = bias ? __ldg(bias + n + 1) : 0.f;
 #pragma unroll
-      for (int a = 0; a < kAT; ++a) { acc0[a] = b0; acc1[a] = b1; }
+    for (int a = 0; a < kAT; ++a) {
+      acc0[a] = acc_init(bias, init, N, n, ag * kAT + a, na);
+      acc1[a] = acc_init(bias, init, N, n + 1, ag * kAT + a, na);
     }
     const float* src = in + ag * kAT;
     issue(0);
@@ -157,11 +165,20 @@ __device__ __forceinline__ void dense_layer_ring(const float* __restrict__ in, i
 
 __device__ __forceinline__ void dense_layer(const float* __restrict__ in, int K, const float* __restrict__ Wt,
                                             const float* __restrict__ bias, int N, int act, float* __restrict__ out,
-                                            float* __restrict__ ring) {
+                                            float* __restrict__ ring, const float* __restrict__ init = nullptr,
+                                            int na = kTA) {
+  if (K == 0) {                                     // the whole contraction was pre-computed: out = act(init)
+    for (int i = threadIdx.x; i < N * kTA; i += kHeadThreads) {
+      const int n = i / kTA, a = i - n * kTA;
+      out[n * kTAp + a] = apply_act(acc_init(bias, init, N, n, a, na), act);
+    }
+    return;
+  }
   if ((N & 3) == 0 && N <= kWTileMaxN && (reinterpret_cast<uintptr_t>(Wt) & 15) == 0)
-    dense_layer_ring(in, K, Wt, bias, N, act, out, ring);
-  else if ((N & 1) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 7) == 0) dense_layer_t<2>(in, K, Wt, bias, N, act, out);
-  else dense_layer_t<1>(in, K, Wt, bias, N, act, out);
+    dense_layer_ring(in, K, Wt, bias, N, act, out, ring, init, na);
+  else if ((N & 1) == 0 && (reinterpret_cast<uintptr_t>(Wt) & 7) == 0)
+    dense_layer_t<2>(in, K, Wt, bias, N, act, out, init, na);
+  else dense_layer_t<1>(in, K, Wt, bias, N, act, out, init, na);
 }
 
 __global__ void __launch_bounds__(kHeadThreads)
@@ -172,15 +189,19 @@ meta_head_kernel(btsb_head_params p, int64_t B, float* __restrict__ logits) {
   const int na = (int)min((int64_t)kTA, B - b0);
   const int F = p.F, Mm = p.Mm, m1 = p.m1, m2 = p.m2, c1 = p.c1, c2 = p.c2;
   const int emb = (Mm > 0) ? m2 : 0;
-  float* cat = sm;                                   // [F+emb][kTAp]
-  float* bufM = cat + (size_t)(F + emb) * kTAp;      // [Mm][kTAp]
+  // h0_init: the caller already contracted the F image features of the head's first layer (tensor-core GEMM, bias
+  // included); the feature rows are then neither staged nor multiplied here
+  const bool pre = p.h0_init != nullptr;
+  const int Fs = pre ? 0 : F;                        // feature rows staged in `cat`
+  float* cat = sm;                                   // [Fs+emb][kTAp]
+  float* bufM = cat + (size_t)(Fs + emb) * kTAp;     // [Mm][kTAp]
   float* buf1 = bufM + (size_t)Mm * kTAp;            // [m1][kTAp]
   float* bufH0 = buf1 + (size_t)m1 * kTAp;           // [c1][kTAp]
   float* bufH1 = bufH0 + (size_t)c1 * kTAp;          // [c2][kTAp]
   float* ring = bufH1 + (size_t)c2 * kTAp;           // [kWRing][kKT][<=128] weight tiles (16-byte aligned: kTAp % 4 == 0)
 
   // stage inputs (zero-fill alerts beyond the batch tail)
-  if (F > 0) {
+  if (Fs > 0) {
     // a warp reads 32 consecutive features of one alert (coalesced) and scatters them down a column of `cat`
     // (4-way bank conflict on the store: 640 warp-stores per CTA, negligible next to the 768-deep contraction)
     for (int i = tid; i < F * kTA; i += kHeadThreads) {
@@ -206,13 +227,14 @@ meta_head_kernel(btsb_head_params p, int64_t B, float* __restrict__ logits) {
   if (Mm > 0) {
     dense_layer(bufM, Mm, p.m1t, p.m1b, m1, p.meta_act, buf1, ring);
     __syncthreads();
-    dense_layer(buf1, m1, p.m2t, p.m2b, m2, p.meta_out_act, cat + (size_t)F * kTAp, ring);
+    dense_layer(buf1, m1, p.m2t, p.m2b, m2, p.meta_out_act, cat + (size_t)Fs * kTAp, ring);
     __syncthreads();
   }
   const float* last = cat;
-  int lastK = F + emb;
+  int lastK = Fs + emb;
   if (c1 > 0) {
-    dense_layer(cat, F + emb, p.h0t, p.h0b, c1, p.head_act, bufH0, ring);
+    dense_layer(cat, Fs + emb, p.h0t + (size_t)(F - Fs) * c1, p.h0b, c1, p.head_act, bufH0, ring,
+                pre ? p.h0_init + (size_t)b0 * c1 : nullptr, na);
     __syncthreads();
     dense_layer(bufH0, c1, p.h1t, p.h1b, c2, p.head_act, bufH1, ring);
     __syncthreads();
@@ -236,7 +258,8 @@ extern "C" int btsb_meta_head_fwd(const btsb_head_params* pp, int64_t B, float* 
   const btsb_head_params& p = *pp;
   BTSB_REQUIRE(B >= 0, "meta_head: B < 0");
   BTSB_REQUIRE(p.F >= 0 && p.Mm >= 0 && (p.F > 0 || p.Mm > 0), "meta_head: need features and/or metadata");
-  BTSB_REQUIRE(p.F == 0 || (p.feat && (p.feat_dtype == BTSB_F32 || p.feat_dtype == BTSB_BF16)), "meta_head: bad feat");
+  BTSB_REQUIRE(p.F == 0 || p.h0_init || (p.feat && (p.feat_dtype == BTSB_F32 || p.feat_dtype == BTSB_BF16)),
+               "meta_head: bad feat");
   if (p.Mm > 0)
     BTSB_REQUIRE(p.meta && p.bn_scale && p.bn_shift && p.m1t && p.m1b && p.m2t && p.m2b && p.m1 > 0 && p.m2 > 0,
                  "meta_head: metadata branch pointers/sizes missing");
@@ -248,7 +271,9 @@ extern "C" int btsb_meta_head_fwd(const btsb_head_params* pp, int64_t B, float* 
   if (B == 0) return BTSB_OK;
   BTSB_REQUIRE(logits, "meta_head: null logits");
   const int emb = p.Mm > 0 ? p.m2 : 0;
-  const size_t smem = (size_t)(p.F + emb + p.Mm + (p.Mm > 0 ? p.m1 : 0) + p.c1 + p.c2) * kTAp * sizeof(float) +
+  if (p.h0_init) BTSB_REQUIRE(p.c1 > 0 && p.F > 0, "meta_head: h0_init needs a head (c1 > 0) and F > 0 (the h0t row offset)");
+  const int Fs = p.h0_init ? 0 : p.F;
+  const size_t smem = (size_t)(Fs + emb + p.Mm + (p.Mm > 0 ? p.m1 : 0) + p.c1 + p.c2) * kTAp * sizeof(float) +
                       (size_t)kWRing * kKT * kWTileMaxN * sizeof(float);
   BTSB_REQUIRE(smem <= 227 * 1024, "meta_head: layer widths need %zu B of shared memory (> 227 KB)", smem);
   BTSB_CUDA(cudaFuncSetAttribute(meta_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "meta_head attr");

@@ -151,6 +151,9 @@ int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const void* W1, 
  * h0t [F+m2 (or F, or m2), c1], h1t [c1,c2], h2 [c2].  meta_act after m1; meta_out_act after m2
  * (GELU for mm_*, NONE for frozen_fusion, RELU for um_nn); head_act after h0 and h1.
  * When Mm>0 and c1==0 the head is just `h2` applied to the meta embedding (um_nn: Linear(m2,1)).
+ * h0_init (optional, NULL = off): [B,c1] float32 = h0b + feat . h0t[:F], the image-feature part of the head's first
+ * layer pre-computed by the caller on the tensor cores (btsb_gemm_bf16_f32out); `feat` is then not read and the
+ * kernel contracts only the m2 embedding rows h0t[F:].
  * logits: [B] float32.
  */
 typedef struct {
@@ -164,6 +167,7 @@ typedef struct {
   const float *h1t, *h1b; int c2;
   const float *h2, *h2b;
   int head_act;
+  const float* h0_init;
 } btsb_head_params;
 int btsb_meta_head_fwd(const btsb_head_params* p, int64_t B, float* logits, void* stream);
 

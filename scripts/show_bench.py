@@ -15,6 +15,7 @@ for f in sys.argv[1:]:
             d["value"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"], d["n_gpus"], d["clocks"]))
         print("  roofline", d["roofline"])
         for k, v in d["kernels"].items():
-            print("   %-16s n=%4.1f  %8.3f ms/launch  %7.0f GB/s %7.1f TF/s  share %.3f" % (
-                k, v["launches_per_step"], v["ms_per_launch"], v["gbs"], v["tflops"], v["share"]))
+            roof = "  %.2f of %s peak" % (v["frac"], v["bound"]) if "frac" in v else ""
+            print("   %-16s n=%4.1f  %8.3f ms/launch  %7.0f GB/s %7.1f TF/s  share %.3f%s" % (
+                k, v["launches_per_step"], v["ms_per_launch"], v["gbs"], v["tflops"], v["share"], roof))
         print("  cpu", d["cpu_baseline"])

@@ -136,6 +136,37 @@ def test_fused_and_unfused_mlp_agree(cuda_dev, golden_logits, golden_batch):
     assert d < 1e-2
 
 
+@pytest.mark.parametrize("case", ["mm_nano", "mm_pico"])
+def test_head_feature_gemm_agrees(cuda_dev, golden_logits, case):
+    """Head layer 0 with the image-feature rows on the tensor cores (btsb_gemm_bf16_f32out -> h0_init) against the
+    all-fp32-FMA head kernel and the oracle, on a ragged batch (77 = 2 CTAs of 32 alerts + a tail of 13)."""
+    from oracle import convnext_oracle as O
+    from btsbot_b200 import _engine
+    if case not in MODEL_CASES:
+        pytest.skip(f"no case {case}")
+    cfg, sd, model = _build(case, golden_logits, cuda_dev, "bf16", shift_only=True)
+    n = 77
+    img = torch.from_numpy(np.ascontiguousarray(synth.make_triplets(n, start=300).transpose(0, 3, 1, 2)))
+    meta = torch.from_numpy(synth.make_metadata(n, start=300))
+    ti, tm = img.to(cuda_dev), meta.to(cuda_dev)
+    a = _call(model, cfg, ti, tm)
+    n0 = btsbot._lib.launch_count()
+    prev = _engine.HEAD_TC
+    try:
+        _engine.HEAD_TC = True
+        b = _call(model, cfg, ti, tm)
+    finally:
+        _engine.HEAD_TC = prev
+    n1 = btsbot._lib.launch_count()
+    c = _call(model, cfg, ti, tm)
+    assert n1 - n0 == (btsbot._lib.launch_count() - n1) + (0 if prev else 1)     # the extra GEMM really ran
+    orc = O.forward(synth.to_torch(sd), cfg, img, meta)
+    d, e = (a - b).abs().max().item(), (b.cpu() - orc).abs().max().item()
+    print(f"[parity] {case} head feature GEMM: max|dlogit| vs fp32-FMA head {d:.3e}, vs oracle {e:.3e}")
+    assert torch.isfinite(b).all() and d < 5e-3 and e < TOL["bf16"]
+    assert torch.equal(a, c)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_batch_and_shard_invariance(cuda_dev, golden_logits, precision):
     """Per-alert results do not depend on batch composition: scoring [0,N) at once == scoring index-range shards

@@ -136,6 +136,25 @@ def test_adamw_batch_struct_matches_header():
     assert ctypes.sizeof(_lib.AdamwBatch) < 4096          # must fit the kernel parameter space next to the scalars
 
 
+def test_head_params_struct_matches_header(tmp_path):
+    """ctypes mirror of btsb_head_params against the C compiler's view of include/btsbot_b200.h (size and the
+    offset of every field)."""
+    import ctypes
+    import subprocess
+    from btsbot_b200 import _lib
+    names = [f[0] for f in _lib.HeadParams._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "btsbot_b200.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(btsb_head_params));\n'
+                   + "".join(f'  printf("%zu\\n", offsetof(btsb_head_params, {n}));\n' for n in names)
+                   + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(_lib.HeadParams)
+    assert out[1:] == [getattr(_lib.HeadParams, n).offset for n in names]
+
+
 def test_training_precision_switch_is_host_logic_only():
     """precision="bf16" selects the tensor-core training GEMMs by model attribute; building the model needs no GPU."""
     import btsbot_b200 as btsbot
