@@ -10,3 +10,6 @@ timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out
 BTSB_DWS_PF=2 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ab_pf2.log 2>&1; echo "pf2 rc=$?"
 BTSB_DWS_PF=2 BTSB_HEAD_TC=1 timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/ab_pf2_head.log 2>&1; echo "pf2+head rc=$?"
 for w in base pf2 pf2_head; do echo "== $w"; python scripts/show_bench.py gpurun_out/ab_$w.log 2>/dev/null | sed -n 1,16p | cut -c1-150; done
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --batch 16384 > gpurun_out/ab_b16k.log 2>&1; echo "b16k rc=$?"
+python scripts/show_bench.py gpurun_out/ab_b16k.log 2>/dev/null | sed -n 1,1p | cut -c1-150
+timeout 90 python scripts/mlp_trace.py 320 9 > gpurun_out/mlp_trace_320.txt 2>&1; echo "trace rc=$?"
