@@ -147,7 +147,7 @@ template <int C, bool TE, bool HT>
 __global__ void __launch_bounds__(kThreads2, 1)   // 19 warps -> 5 on three SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
-                  __nv_bfloat16* __restrict__ out, int M, long long* __restrict__ trace, int res_early) {
+                  __nv_bfloat16* __restrict__ out, int M, long long* __restrict__ trace) {
   using namespace tc;
   // timeline debugging (btsb_debug_mlp_trace): block 0 records clock64() at the hand-off points of its first
   // kTraceChunks hidden chunks; trace == nullptr in production (one uniform branch per event)
@@ -401,30 +401,9 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
     // D2 -> +b2 -> *gamma + res -> bf16 rows of tile `tile` (local index tl); column groups k4, k4+4, k4+8
     auto d2_epilogue = [&](int tile, uint32_t tl) {
       const int tb = (int)(tl % (uint32_t)D2B);
-      const int row = tile * FM + r_in_tile;
-      // Wide C (no PRE): the residual pieces cannot stay in registers across the next chunk's GELU, but they can be
-      // fetched HERE, BEFORE the wait for G2's last commit, kRW pieces (2 x 16 B each) in flight at a time (all NU at
-      // once cost spills at the 96-register ceiling).  Loading each piece at its use serialised NU global-load
-      // latencies behind the TMEM reads: the pipeline trace of C = 320 (profiles/r01n/mlp_trace_320.txt) shows this
-      // epilogue taking ~16 k clocks per tile, during which the single D2 accumulator keeps G2 of the next tile (and,
-      // two chunks later, G1) stalled -- a third of the tile time.
-      constexpr int kRW = 3;
-      uint4 rl[PRE ? 1 : NU][2];
-      auto res_fetch = [&](int u) {
-        const int gi = k4 + 4 * u;
-        if (gi < groups2 && row < M) {
-          const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + gi * 16);
-          rl[PRE ? 0 : u][0] = __ldg(rp); rl[PRE ? 0 : u][1] = __ldg(rp + 1);
-        } else {
-          rl[PRE ? 0 : u][0] = make_uint4(0, 0, 0, 0); rl[PRE ? 0 : u][1] = make_uint4(0, 0, 0, 0);
-        }
-      };
-      if (!PRE && res_early) {
-#pragma unroll
-        for (int u = 0; u < (NU < kRW ? NU : kRW); ++u) res_fetch(u);
-      }
       mbar_wait_spin(d2_full(tb), (tl / (uint32_t)D2B) & 1u);
       tc_fence_after();
+      const int row = tile * FM + r_in_tile;
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
         const int gi = k4 + 4 * u;
@@ -433,7 +412,6 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         tmem_ld16(lane_addr + (uint32_t)(kD2Col + tb * C + gi * 16), r);
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
         if (PRE) { r0 = rpre[PRE ? u : 0][0]; r1 = rpre[PRE ? u : 0][1]; }
-        else if (res_early) { r0 = rl[PRE ? 0 : u][0]; r1 = rl[PRE ? 0 : u][1]; }
         else if (row < M) {
           const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + gi * 16);
           r0 = __ldg(rp); r1 = __ldg(rp + 1);
@@ -465,7 +443,6 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * C + n);
           op[0] = o0; op[1] = o1;
         }
-        if (!PRE && res_early && u + kRW < NU) res_fetch(u + kRW);   // keep kRW pieces in flight
       }
     };
 
@@ -653,10 +630,7 @@ static int launch2(const Maps2& tm, const float* b1, const float* b2, const floa
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
-  // BTSB_MLP_RES_EARLY=0: wide variants load the residual pieces at their use again (A/B timing)
-  static const int res_early = [] { const char* e = getenv("BTSB_MLP_RES_EARLY"); return (e && e[0] == '0') ? 0 : 1; }();
-  kern<<<grid, kThreads2, P.total, st>>>(tm, b1, b2, gamma, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (int)M, g_mlp_trace,
-                                         res_early);
+  kern<<<grid, kThreads2, P.total, st>>>(tm, b1, b2, gamma, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (int)M, g_mlp_trace);
   return launch_done("mlp_fused2");
 }
 
