@@ -143,7 +143,9 @@ struct Maps2 {
 };
 }  // namespace
 
-template <int C, bool TE, bool HT>
+// V8 (wide variants only, opt-in, UNMEASURED): the residual / output pieces of the D2 epilogue move as one 256-bit access
+// per thread instead of two 128-bit ones -- every per-thread access is its own L2 request there (DESIGN.md lesson 9).
+template <int C, bool TE, bool HT, bool V8 = false>
 __global__ void __launch_bounds__(kThreads2, 1)   // 19 warps -> 5 on three SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
@@ -414,7 +416,13 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         if (PRE) { r0 = rpre[PRE ? u : 0][0]; r1 = rpre[PRE ? u : 0][1]; }
         else if (row < M) {
           const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + gi * 16);
-          r0 = __ldg(rp); r1 = __ldg(rp + 1);
+          if constexpr (V8) {
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w), "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w)
+                         : "l"(rp));
+          } else {
+            r0 = __ldg(rp); r1 = __ldg(rp + 1);
+          }
         }
         tmem_ld_wait();
         if (gi + 4 >= groups2) {                         // last D2 read of this warp for this tile
@@ -441,7 +449,13 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
           o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
           uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * C + n);
-          op[0] = o0; op[1] = o1;
+          if constexpr (V8) {
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                         :: "l"(op), "r"(o0.x), "r"(o0.y), "r"(o0.z), "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w)
+                         : "memory");
+          } else {
+            op[0] = o0; op[1] = o1;
+          }
         }
       }
     };
@@ -622,11 +636,11 @@ int mlp_fused2_supported(int C) {
   return C % 16 == 0 && ((C >= 64 && C <= 160) || C == 256 || C == 320);
 }
 
-template <int C, bool TE, bool HT>
+template <int C, bool TE, bool HT, bool V8 = false>
 static int launch2(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res, void* out,
                    int64_t M, cudaStream_t st) {
   constexpr Plan2 P = plan2_for(C, TE, HT);
-  auto kern = mlp_fused2_kernel<C, TE, HT>;
+  auto kern = mlp_fused2_kernel<C, TE, HT, V8>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
@@ -661,6 +675,12 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
   if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
   // wide C: no room for the staging tile next to the 80 KB y tile -> residual / output rows go straight to global
+  // BTSB_MLP_V8=1: 256-bit residual / output accesses in the wide D2 epilogue (needs 32-byte aligned res / out)
+  static const bool v8 = [] { const char* e = getenv("BTSB_MLP_V8"); return e && e[0] == '1'; }();
+  if (v8 && (C == 256 || C == 320) && ((uintptr_t)res % 32) == 0 && ((uintptr_t)out % 32) == 0) {
+    if (C == 256) return launch2<256, false, true, true>(tm, b1, b2, gamma, res, out, M, st);
+    return launch2<320, false, true, true>(tm, b1, b2, gamma, res, out, M, st);
+  }
   if (C == 256) return launch2<256, false, true>(tm, b1, b2, gamma, res, out, M, st);
   if (C == 320) return launch2<320, false, true>(tm, b1, b2, gamma, res, out, M, st);
   if (hsmem) {
