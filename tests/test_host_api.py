@@ -183,3 +183,23 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "alerts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bench_kernel_table_roofline_columns():
+    """bench.py files every kernel family under the tensor or the HBM roofline and reports the fraction of
+    the measured peak it reaches; pure host logic."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.kernel_bound("mlp_fused_320", "bf16") == "tensor"
+    assert bench.kernel_bound("gemm_down", "bf16") == "tensor"
+    assert bench.kernel_bound("head_gemm", "bf16") == "tensor"
+    assert bench.kernel_bound("gemm_down", "fp32") == "hbm"            # CUDA-core fp32 GEMMs: no tensor roofline
+    assert bench.kernel_bound("t_gemm_tn", "bf16") == "hbm"
+    for name in ("dwln_15x80", "lnpatch", "stem_fused", "meta_head", "poolln"):
+        assert bench.kernel_bound(name, "bf16") == "hbm"
+    kernels = {"mlp_fused_320": {"gbs": 1000.0, "tflops": 700.0}, "dwln_15x80": {"gbs": 1600.0, "tflops": 40.0}}
+    bench.add_roofline_fractions(kernels, {"hbm": 6400.0, "tf_sust": 1400.0}, "bf16")
+    assert kernels["mlp_fused_320"]["bound"] == "tensor" and abs(kernels["mlp_fused_320"]["frac"] - 0.5) < 1e-12
+    assert kernels["dwln_15x80"]["bound"] == "hbm" and abs(kernels["dwln_15x80"]["frac"] - 0.25) < 1e-12
