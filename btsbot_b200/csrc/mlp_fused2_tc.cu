@@ -42,12 +42,13 @@ struct Plan2 {
   int nfull = 0, t32 = 0, t16 = 0;   // K blocks: nfull x 64 columns (SW128) [+ 32 columns (SW64)] [+ 16 columns (SW32)]
   int y_bytes = 0, w1_bytes = 0, w2_bytes = 0;
   int ny = 0, n1 = 0, n2 = 0, resident = 0;
-  int off_w1 = 0, off_w2 = 0, off_h = 0, off_stg = 0, off_bar = 0, off_b1 = 0, total = 0;
+  int off_w1 = 0, off_w2 = 0, off_h = 0, off_stg = 0, off_slab = 0, off_bar = 0, off_b1 = 0, total = 0;
+  int slab = 0;              // 1: one 1 KB slab per epilogue warp ([32 rows x 16 columns] bulk tensor copies, wide C)
   int stg = 0;               // 1: residual / output rows move through a [128 x C] bf16 staging tile with bulk tensor copies
   int ht = 0;                // 1: the GELU'd hidden chunk H lives in TMEM (A operand of G2 from TMEM), no shared-memory H tiles
   bool ok = false;
 };
-__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht);
+__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab = false);
 
 __host__ __device__ constexpr int rup1k(int x) { return (x + 1023) & ~1023; }
 
@@ -57,14 +58,15 @@ __host__ __device__ constexpr bool plan2_try(Plan2& P, int ny, int n1, int n2, i
   P.off_w2 = P.off_w1 + n1 * P.w1_bytes;
   P.off_h = P.off_w2 + n2 * P.w2_bytes;
   P.off_stg = P.off_h + (P.ht ? 0 : 2 * kHBytes);
-  P.off_bar = P.off_stg + (P.stg ? P.C * 256 : 0);
+  P.off_slab = P.off_stg + (P.stg ? P.C * 256 : 0);
+  P.off_bar = P.off_slab + (P.slab ? kEpiWarps2 * 1024 : 0);
   P.off_b1 = P.off_bar + 1024;
   P.total = P.off_b1 + 4 * P.C * 4 + 1024 /*alignment slack*/;
   return P.total <= kSmemMax && n1 <= kMaxSlots && n2 <= kMaxSlots;
 }
 
-__host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht) {
-  P.C = C; P.NJ = (4 * C) / NH; P.stg = te ? 1 : 0; P.ht = ht ? 1 : 0;
+__host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht, bool slab) {
+  P.C = C; P.NJ = (4 * C) / NH; P.stg = te ? 1 : 0; P.ht = ht ? 1 : 0; P.slab = slab ? 1 : 0;
   P.nfull = C / 64; P.t32 = (C % 64) >= 32 ? 1 : 0; P.t16 = (C % 32) >= 16 ? 1 : 0;
   P.y_bytes = rup1k(FM * C * 2);
   P.w1_bytes = rup1k(NH * C * 2);
@@ -77,9 +79,9 @@ __host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht)
   return plan2_try(P, 1, 2, 1, 0);                      // C = 320: 80 KB y tile, 40 KB weight chunks
 }
 
-__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht) {
+__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab) {
   Plan2 P;
-  P.ok = make_plan2(P, C, te, ht);
+  P.ok = make_plan2(P, C, te, ht, slab);
   return P;
 }
 
@@ -143,9 +145,12 @@ struct Maps2 {
 };
 }  // namespace
 
-// V8 (wide variants only, opt-in, UNMEASURED): the residual / output pieces of the D2 epilogue move as one 256-bit access
-// per thread instead of two 128-bit ones -- every per-thread access is its own L2 request there (DESIGN.md lesson 9).
-template <int C, bool TE, bool HT, bool V8 = false>
+// EP (wide variants only; 1 and 2 are opt-in and UNMEASURED): how the residual / output pieces of the D2 epilogue move.
+// Every per-thread 16-byte access is its own L2 request there (DESIGN.md lesson 9), so
+//   EP = 1: one 256-bit access per thread and piece instead of two 128-bit ones;
+//   EP = 2: per-warp 1 KB slabs and [32 rows x 16 columns] bulk tensor loads / stores (the narrow variants' staging
+//           scheme at the size that fits next to the 80 KB y tile): no per-thread global access at all.
+template <int C, bool TE, bool HT, int EP = 0>
 __global__ void __launch_bounds__(kThreads2, 1)   // 19 warps -> 5 on three SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
@@ -158,7 +163,9 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   auto tr = [&](int role, uint32_t g, int ev) {
     if (tracing && g < (uint32_t)kTraceChunks) trace[((size_t)role * kTraceChunks + g) * kTraceEv + ev] = clock64();
   };
-  constexpr Plan2 P = plan2_for(C, TE, HT);
+  constexpr bool V8 = EP == 1, TS = EP == 2;
+  static_assert(EP == 0 || !TE, "EP variants belong to the wide (non-staging) kernels");
+  constexpr Plan2 P = plan2_for(C, TE, HT, TS);
   static_assert(P.ok, "no shared-memory plan for this C");
   // wide C (256, 320): one D2 accumulator instead of two (the D2 epilogue of a tile then holds back the first G2 of the
   // next one), and for C > 256 every G2 step is two UMMAs of N = C/2 columns
@@ -546,6 +553,67 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       }
     };
 
+
+    // ---- slab path (TS, wide C): the warp's column groups k4, k4+4, ... go one at a time through its private 1 KB slab:
+    // bulk tensor load of the residual piece [32 rows x 16 columns] -> in-place update (thread = row) -> bulk tensor
+    // store.  The load of the next piece is issued as soon as the store of the current one has read the slab.
+    auto d2_epilogue_ts = [&](int tile, uint32_t tl) {
+      const int tb = (int)(tl % (uint32_t)D2B);
+      const uint32_t slab_addr = sbase + P.off_slab + (uint32_t)(ew * 1024);
+      unsigned char* slab = sal + P.off_slab + ew * 1024;
+      const int row0 = tile * FM + q * 32;
+      auto slab_load = [&](int gi) {
+        if (lane == 0) {
+          tma_store_wait_read();                             // the previous piece's bulk store has drained the slab
+          mbar_expect_tx(res_bar(ew), 1024u);
+          tma_load_2d(slab_addr, &tm.r32, res_bar(ew), gi * 16, row0);
+        }
+        __syncwarp();
+      };
+      slab_load(k4);                                         // in flight while G2's last commit is awaited
+      mbar_wait_spin(d2_full(tb), (tl / (uint32_t)D2B) & 1u);
+      tc_fence_after();
+      const int xr = (lane >> 2) & 1;                        // 32-byte swizzle: 16-byte chunk index ^ address bit 7
+      uint4* p0 = reinterpret_cast<uint4*>(slab + lane * 32 + ((0 ^ xr) << 4));
+      uint4* p1 = reinterpret_cast<uint4*>(slab + lane * 32 + ((1 ^ xr) << 4));
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        const int gi = k4 + 4 * u;
+        if (gi >= groups2) break;
+        uint32_t r[16];
+        tmem_ld16(lane_addr + (uint32_t)(kD2Col + tb * C + gi * 16), r);
+        tmem_ld_wait();
+        if (gi + 4 >= groups2) {                             // last D2 read of this warp for this tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d2_empty(tb));
+        }
+        mbar_wait_spin(res_bar(ew), rph); rph ^= 1u;
+        const uint4 r0 = *p0, r1 = *p1;
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const int n = gi * 16;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
+          v[i] = fmaf(g4.x, __uint_as_float(r[i]) + b4.x, bf16_lo(rr[i / 2]));
+          v[i + 1] = fmaf(g4.y, __uint_as_float(r[i + 1]) + b4.y, bf16_hi(rr[i / 2]));
+          v[i + 2] = fmaf(g4.z, __uint_as_float(r[i + 2]) + b4.z, bf16_lo(rr[i / 2 + 1]));
+          v[i + 3] = fmaf(g4.w, __uint_as_float(r[i + 3]) + b4.w, bf16_hi(rr[i / 2 + 1]));
+        }
+        *p0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        *p1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm.o32, slab_addr, gi * 16, row0);   // rows beyond M are clipped by the tensor map
+          tma_store_commit();
+        }
+        if (gi + 4 < groups2) slab_load(gi + 4);
+      }
+    };
+
     int pend_tl = -1;                       // local tile index whose D2 epilogue this warp still owes
     uint32_t prev_tl = 0xffffffffu;
     for (uint32_t g = (uint32_t)grp; g < total; g += 2) {
@@ -603,6 +671,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       if (lane == 0) { mbar_arrive(h_full(grp)); tr(1 + ew, g, 5); }
       if (pend_tl >= 0) {
         if (TE) d2_epilogue_te(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl);
+        else if (TS) d2_epilogue_ts(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl);
         else d2_epilogue(blockIdx.x + pend_tl * gridDim.x, (uint32_t)pend_tl);
         pend_tl = -1;
         if (lane == 0) tr(1 + ew, g, 6);
@@ -614,6 +683,9 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       if (TE) {
         res_issue(blockIdx.x + last * gridDim.x);
         d2_epilogue_te(blockIdx.x + last * gridDim.x, (uint32_t)last);
+        if (lane == 0) tma_store_wait_all();              // smem must outlive the last bulk store's reads
+      } else if (TS) {
+        d2_epilogue_ts(blockIdx.x + last * gridDim.x, (uint32_t)last);
         if (lane == 0) tma_store_wait_all();              // smem must outlive the last bulk store's reads
       } else {
         prefetch_res(blockIdx.x + last * gridDim.x);
@@ -636,11 +708,11 @@ int mlp_fused2_supported(int C) {
   return C % 16 == 0 && ((C >= 64 && C <= 160) || C == 256 || C == 320);
 }
 
-template <int C, bool TE, bool HT, bool V8 = false>
+template <int C, bool TE, bool HT, int EP = 0>
 static int launch2(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res, void* out,
                    int64_t M, cudaStream_t st) {
-  constexpr Plan2 P = plan2_for(C, TE, HT);
-  auto kern = mlp_fused2_kernel<C, TE, HT, V8>;
+  constexpr Plan2 P = plan2_for(C, TE, HT, EP == 2);
+  auto kern = mlp_fused2_kernel<C, TE, HT, EP>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
@@ -675,11 +747,16 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
   if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
   // wide C: no room for the staging tile next to the 80 KB y tile -> residual / output rows go straight to global
-  // BTSB_MLP_V8=1: 256-bit residual / output accesses in the wide D2 epilogue (needs 32-byte aligned res / out)
-  static const bool v8 = [] { const char* e = getenv("BTSB_MLP_V8"); return e && e[0] == '1'; }();
-  if (v8 && (C == 256 || C == 320) && ((uintptr_t)res % 32) == 0 && ((uintptr_t)out % 32) == 0) {
-    if (C == 256) return launch2<256, false, true, true>(tm, b1, b2, gamma, res, out, M, st);
-    return launch2<320, false, true, true>(tm, b1, b2, gamma, res, out, M, st);
+  // BTSB_MLP_EP=1: 256-bit residual / output accesses in the wide D2 epilogue (needs 32-byte aligned res / out);
+  // BTSB_MLP_EP=2: per-warp slabs + bulk tensor copies.  Both opt-in until measured.
+  static const int ep = [] { const char* e = getenv("BTSB_MLP_EP"); return e ? atoi(e) : 0; }();
+  if (ep == 1 && (C == 256 || C == 320) && ((uintptr_t)res % 32) == 0 && ((uintptr_t)out % 32) == 0) {
+    if (C == 256) return launch2<256, false, true, 1>(tm, b1, b2, gamma, res, out, M, st);
+    return launch2<320, false, true, 1>(tm, b1, b2, gamma, res, out, M, st);
+  }
+  if (ep == 2 && (C == 256 || C == 320)) {
+    if (C == 256) return launch2<256, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
+    return launch2<320, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
   }
   if (C == 256) return launch2<256, false, true>(tm, b1, b2, gamma, res, out, M, st);
   if (C == 320) return launch2<320, false, true>(tm, b1, b2, gamma, res, out, M, st);
