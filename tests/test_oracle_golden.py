@@ -68,3 +68,56 @@ def test_synth_is_sharding_independent():
     assert np.array_equal(m[250:300], synth.make_metadata(50, start=257))
     n = np.sqrt((a.astype(np.float64) ** 2).sum(axis=(1, 2)))
     assert np.allclose(n, 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["convnext_nano.d1h_in1k", "convnext_pico.d1_in1k"])
+def test_trunk_oracle_matches_hf_transformers_convnext(kind):
+    """Third independent implementation of the ConvNeXt trunk arithmetic (after the torchvision one behind the goldens):
+    Hugging Face `transformers.ConvNextModel`, a port of the original FAIR code timm's model also descends from.  Same
+    weights through a key remap -> same [B, C3, 1, 1] feature map as the functional restatement.  (timm itself is not
+    installable offline; this does not pin timm, it pins the block semantics: stem conv4/s4 + LN2d,
+    dw7x7 -> LN -> fc1 -> exact GELU -> fc2 -> layer scale -> + shortcut, LN2d + conv2/s2 downsampling, eps 1e-6.)"""
+    transformers = pytest.importorskip("transformers")
+    cfg = synth.canonical_config("mm_ConvNeXt", kind)
+    sd = synth.to_torch(synth.make_state_dict(cfg, seed=7))
+    arch = O.arch_of(kind)
+    hc = transformers.ConvNextConfig(num_channels=3, patch_size=4, num_stages=4, hidden_sizes=list(arch["dims"]),
+                                     depths=list(arch["depths"]), hidden_act="gelu", layer_scale_init_value=1.0,
+                                     drop_path_rate=0.0, image_size=63)
+    hf = transformers.ConvNextModel(hc).eval()
+    p = "convnext_backbone."
+    remap = {"embeddings.patch_embeddings.": p + "stem.0.", "embeddings.layernorm.": p + "stem.1."}
+    new = {}
+    for k in hf.state_dict():
+        if k.startswith("layernorm."):                     # HF's pooler LayerNorm: not part of forward_features
+            new[k] = hf.state_dict()[k]
+            continue
+        src = None
+        for a, b in remap.items():
+            if k.startswith(a):
+                src = sd[b + k[len(a):]]
+        if src is None:
+            _, _, i, kind_, *rest = k.split(".")            # encoder.stages.{i}.(downsampling_layer|layers).…
+            if kind_ == "downsampling_layer":
+                src = sd[f"{p}stages.{i}.downsample.{rest[0]}.{rest[1]}"]
+            else:
+                j, name = rest[0], ".".join(rest[1:])
+                q = f"{p}stages.{i}.blocks.{j}."
+                src = {"layer_scale_parameter": lambda: sd[q + "gamma"],
+                       "dwconv.weight": lambda: sd[q + "conv_dw.weight"], "dwconv.bias": lambda: sd[q + "conv_dw.bias"],
+                       "layernorm.weight": lambda: sd[q + "norm.weight"], "layernorm.bias": lambda: sd[q + "norm.bias"],
+                       "pwconv1.weight": lambda: sd[q + "mlp.fc1.weight"].flatten(1),      # Conv2d 1x1 -> Linear
+                       "pwconv1.bias": lambda: sd[q + "mlp.fc1.bias"],
+                       "pwconv2.weight": lambda: sd[q + "mlp.fc2.weight"].flatten(1),
+                       "pwconv2.bias": lambda: sd[q + "mlp.fc2.bias"]}[name]()
+        assert tuple(src.shape) == tuple(hf.state_dict()[k].shape), k
+        new[k] = src
+    hf.load_state_dict(new, strict=True)
+    n = 6
+    img = torch.from_numpy(np.ascontiguousarray(synth.make_triplets(n, start=70).transpose(0, 3, 1, 2)))
+    with torch.no_grad():
+        ref = hf(pixel_values=img).last_hidden_state
+        got = O.trunk_features(sd, p, img, arch)
+    assert got.shape == ref.shape == (n, arch["dims"][-1], 1, 1)
+    rel = ((got - ref).abs().max() / ref.abs().max()).item()
+    assert rel < 2e-5, rel
