@@ -19,7 +19,9 @@ namespace btsb {
 // PF: prefetch distance in images.  One image per thread is 9 x 4 B; with 5-6 resident CTAs of C/2 threads an SM has
 // ~35 KB of loads in flight at PF = 1, the bare Little's-law minimum for its share of the HBM bandwidth (the kernel ran
 // at 2.5 of ~6.5 TB/s); PF = 2 keeps two images per thread in flight for 9 more registers.
-template <int S, int CT, int PF>
+// CPA (opt-in, UNMEASURED, CT > 0 only): the reachable taps -- NT contiguous runs of NT*C floats in the [49][C] tap matrix --
+// are staged with one wave of 16-byte cp.async instead of ~NT*NT*C/T dependent batches of scalar loads per thread.
+template <int S, int CT, int PF, bool CPA = false>
 __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C_rt, const float* __restrict__ wt,
                                   const float* __restrict__ bias, const float* __restrict__ ln_w,
                                   const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
@@ -37,10 +39,23 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
   const bool active = tid < C2;
   const int c2 = active ? tid : 0;
 
-  for (int i = tid; i < NT * NT * C; i += T) {
-    const int t = i / C, c = i - t * C;
-    const int ty = t / NT, tx = t - ty * NT;
-    wsm[i] = __ldg(wt + ((ty + 3 - R) * 7 + (tx + 3 - R)) * C + c);
+  if constexpr (CPA && CT > 0) {
+    static_assert(!CPA || CT % 4 == 0, "16-byte granules");
+    constexpr int kRun = NT * (CT > 0 ? CT : 4) / 4;         // 16-byte granules per tap row
+    for (int i = tid; i < NT * kRun; i += T) {
+      const int ty = i / kRun, k = i - ty * kRun;
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(wsm + ty * NT * C + 4 * k);
+      const float* g = wt + ((ty + 3 - R) * 7 + (3 - R)) * C + 4 * k;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    for (int i = tid; i < NT * NT * C; i += T) {
+      const int t = i / C, c = i - t * C;
+      const int ty = t / NT, tx = t - ty * NT;
+      wsm[i] = __ldg(wt + ((ty + 3 - R) * 7 + (tx + 3 - R)) * C + c);
+    }
   }
   const float2 bv = *reinterpret_cast<const float2*>(bias + 2 * c2);
   const float2 gw = *reinterpret_cast<const float2*>(ln_w + 2 * c2);
@@ -140,7 +155,7 @@ static int prefetch_distance() {
   return pf;
 }
 
-template <int S, int CT, int PF>
+template <int S, int CT, int PF, bool CPA = false>
 static int launch_small_pf(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
   constexpr int NT = 2 * (S - 1) + 1;
@@ -149,7 +164,7 @@ static int launch_small_pf(const void* x, int64_t B, int C, const float* w, cons
   const int nw = threads / 32;
   const size_t smem = (size_t)NT * NT * C * 4 + 2 * nw * 32 * 4 + 2 * 16 * 8;
   if (smem > 200 * 1024) return 1;
-  auto kern = dwln_small_kernel<S, CT, PF>;
+  auto kern = dwln_small_kernel<S, CT, PF, CPA>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dwln_small attr");
   int per_sm = 1;
   BTSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem), "dwln_small occupancy");
@@ -160,9 +175,18 @@ static int launch_small_pf(const void* x, int64_t B, int C, const float* w, cons
   return launch_done("dwln_small");
 }
 
+// BTSB_DWS_CPA=1 selects the cp.async tap staging (compile-time C, 16-byte aligned taps)
+static bool cp_async_taps() {
+  static const bool on = [] { const char* e = getenv("BTSB_DWS_CPA"); return e && e[0] == '1'; }();
+  return on;
+}
+
 template <int S, int CT>
 static int launch_small(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
+  if constexpr (CT > 0 && CT % 4 == 0) {
+    if (cp_async_taps() && ((uintptr_t)w % 16) == 0) return launch_small_pf<S, CT, 1, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+  }
   return prefetch_distance() == 2 ? launch_small_pf<S, CT, 2>(x, B, C, w, bias, ln_w, ln_b, out, st)
                                   : launch_small_pf<S, CT, 1>(x, B, C, w, bias, ln_w, ln_b, out, st);
 }
