@@ -239,7 +239,7 @@ def head_forward(hw: HeadWeights, feat: torch.Tensor | None, meta: torch.Tensor 
         F = feat.shape[1]
         p.feat, p.F = feat.data_ptr(), F
         p.feat_dtype = L.BF16 if feat.dtype == torch.bfloat16 else L.F32
-        if (HEAD_TC and feat.dtype == torch.bfloat16 and hw.c1 > 0 and hw.c1 % 16 == 0 and F % 8 == 0
+        if (HEAD_TC and feat.dtype == torch.bfloat16 and 0 < hw.c1 <= 2560 and hw.c1 % 16 == 0 and F % 8 == 0
                 and F + (hw.m2 if meta is not None else 0) == hw.in_features):
             h0_init = _head_feature_gemm(hw, feat)
             p.h0_init = h0_init.data_ptr()
