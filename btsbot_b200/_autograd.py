@@ -522,9 +522,15 @@ def _parts(model):
     if name == "um_nn":
         return None, None, list(model.network), None
     if name == "frozen_fusion":
-        tr = model.image_branch.convnext
-        return tr, tr.head[1], list(model.meta_branch.network), list(model.combined_head)
-    raise ValueError(name)
+        ib = model.image_branch
+        if hasattr(ib, "convnext"):
+            tr, pl = ib.convnext, ib.convnext.head[1]
+        else:                                   # MaxViT image branch (architectures.py:304-308): frozen features only
+            tr, pl = ib.maxvit, None
+        return tr, pl, list(model.meta_branch.network), list(model.combined_head)
+    raise NotImplementedError(
+        f"btsbot_b200: no training (backward) path for model_name {name!r} -- MaxViT / mm_MaxViT run inference only "
+        f"(call model.eval() and use torch.no_grad()); ConvNeXt, mm_ConvNeXt, um_nn and frozen_fusion train")
 
 
 class _ModelFn(torch.autograd.Function):
@@ -544,6 +550,9 @@ class _ModelFn(torch.autograd.Function):
             image = image.to(torch.float32).contiguous()
             B = image.shape[0]
             train_trunk = _needs(*tr.parameters())
+            if train_trunk and type(tr).__name__ == "MaxVitTrunk":
+                raise NotImplementedError("btsbot_b200: the MaxViT trunk has no backward path -- freeze the image branch "
+                                          "(train.py:224-231 does for frozen_fusion) or use a ConvNeXt image branch")
             if train_trunk:
                 tc = getattr(model, "_precision", "fp32") == "bf16"
                 rows, h, w, tape = (_trunk_fwd_tc if tc else _trunk_fwd)(tr, image)
@@ -558,7 +567,7 @@ class _ModelFn(torch.autograd.Function):
                     feat = rows
             else:
                 # frozen image branch (frozen_fusion, train.py:224-231): features from the inference kernels
-                feat = model.scorer().features(image).to(torch.float32)
+                feat = model._frozen_image_scorer().features(image).to(torch.float32)
         else:
             B = meta.shape[0]
         emb = None
@@ -711,6 +720,10 @@ class FusedAdamW(torch.optim.Optimizer):
                     else:
                         L.launch("t_adamw", lib.btsb_adamw_multi_f32, C.byref(batch), float(group["lr"]), float(b1), float(b2),
                                  float(group["eps"]), float(group["weight_decay"]), int(step), 1.0, _st())
+        # the kernels wrote the parameters through raw pointers: autograd's version counters did not move, so packed
+        # inference copies (the models' Scorer cache) are invalidated explicitly
+        from . import _engine
+        _engine.bump_param_generation()
         return loss
 
 
@@ -794,4 +807,6 @@ class GraphedTrainStep:
         if self.graph is None:
             return self._step()
         self.graph.replay()
+        from . import _engine
+        _engine.bump_param_generation()         # the replay re-ran the captured AdamW kernels
         return self.loss

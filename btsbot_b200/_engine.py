@@ -36,6 +36,19 @@ TC_STEM = True
 
 _DT = {"fp32": (L.F32, torch.float32), "bf16": (L.BF16, torch.bfloat16)}
 
+#: bumped by every in-place parameter update that bypasses autograd's version counters (FusedAdamW.step writes through
+#: raw device pointers; a CUDA-graph replay re-runs those kernels) -- part of the models' Scorer cache key
+_PARAM_GENERATION = 0
+
+
+def param_generation() -> int:
+    return _PARAM_GENERATION
+
+
+def bump_param_generation() -> None:
+    global _PARAM_GENERATION
+    _PARAM_GENERATION += 1
+
 
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
@@ -312,12 +325,19 @@ class Scorer:
                                     meta_act=L.ACT_RELU, meta_out_act=L.ACT_RELU)
         elif name == "frozen_fusion":
             icfg = config["image_model_config"]
-            if icfg["model_name"] != "ConvNeXt" or config["meta_model_config"]["model_name"] != "um_nn":
-                raise ValueError("B200 frozen_fusion path: ConvNeXt image branch + um_nn metadata branch only")
-            arch = convnext_arch(icfg.get("model_kind", "convnext_nano.d1h_in1k"))
-            self.trunk = TrunkWeights(sd, "image_branch.convnext.", arch, precision)
-            self.pool_ln = (_f32c(sd["image_branch.convnext.head.1.weight"]),
-                            _f32c(sd["image_branch.convnext.head.1.bias"]))
+            if config["meta_model_config"]["model_name"] != "um_nn":
+                raise ValueError("B200 frozen_fusion path: the metadata branch must be um_nn")
+            if icfg["model_name"] == "ConvNeXt":            # head cut to [pool, LayerNorm2d, flatten] (architectures.py:309-313)
+                arch = convnext_arch(icfg.get("model_kind", "convnext_nano.d1h_in1k"))
+                self.trunk = TrunkWeights(sd, "image_branch.convnext.", arch, precision)
+                self.pool_ln = (_f32c(sd["image_branch.convnext.head.1.weight"]),
+                                _f32c(sd["image_branch.convnext.head.1.bias"]))
+            elif icfg["model_name"] == "MaxViT":            # head cut to [pool] (architectures.py:304-308): what the
+                from . import _maxvit                       # published maxvit-tiny-*-metadata checkpoints are (to_HF.py:143)
+                self.maxvit = _maxvit.MaxVitWeights(sd, "image_branch.maxvit.", _maxvit.arch_for(icfg), precision)
+            else:
+                raise ValueError(f"B200 frozen_fusion path: image branch {icfg['model_name']!r} is not supported "
+                                 f"(ConvNeXt or MaxViT)")
             self.head = HeadWeights(sd, meta_prefix="meta_branch.network.", head_prefix="combined_head.",
                                     meta_act=L.ACT_RELU, meta_out_act=L.ACT_NONE, head_act=L.ACT_RELU)
         else:

@@ -55,8 +55,10 @@ def _crop(triplets, s, normalize, out_hwc):
     shape = (n, s, s, 3) if out_hwc else (n, 3, s, s)
     out = torch.empty(shape, device=dev, dtype=torch.float32)
     code = L.F32 if t.dtype == torch.float32 else L.F64
-    L.check(lib.btsb_preprocess_crop_norm(_p(t), code, n, int(s), int(bool(normalize)), int(bool(out_hwc)), _p(out),
-                                          L.stream_ptr()), "crop_norm")
+    # algorithmic bytes: read 63*63*3*e_in, write 3*s*s*4 per alert
+    L.launch("crop_norm", lib.btsb_preprocess_crop_norm, _p(t), code, n, int(s), int(bool(normalize)), int(bool(out_hwc)),
+             _p(out), L.stream_ptr(), flops=3.0 * n * 63 * 63 * 3,
+             nbytes=float(n) * (63 * 63 * 3 * t.element_size() + 3 * s * s * 4))
     return out
 
 
@@ -129,8 +131,9 @@ def make_triplets(alerts, normalize: bool = True):
     hw_d = torch.from_numpy(hw).to(dev)
     out = torch.empty((n, 63, 63, 3), device=dev, dtype=torch.float64)
     drop = torch.empty((n,), device=dev, dtype=torch.uint8)
-    L.check(lib.btsb_preprocess_pad_norm(_p(s_d), _p(hw_d), n, int(bool(normalize)), _p(out), L.F64, _p(drop),
-                                         L.stream_ptr()), "pad_norm")
+    # algorithmic bytes: the staged float32 stamps in, the float64 63x63x3 triplet + drop flag out
+    L.launch("pad_norm", lib.btsb_preprocess_pad_norm, _p(s_d), _p(hw_d), n, int(bool(normalize)), _p(out), L.F64, _p(drop),
+             L.stream_ptr(), flops=3.0 * n * 63 * 63 * 3, nbytes=float(n) * (3 * 63 * 63 * 4 + 24 + 63 * 63 * 3 * 8 + 1))
     return out.cpu().numpy(), drop.cpu().numpy().astype(bool)
 
 

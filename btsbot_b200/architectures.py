@@ -126,7 +126,11 @@ class ConvNeXtTrunk(nn.Module):
 # shared forward machinery
 # ---------------------------------------------------------------------------------------------------------
 class _B200Model(nn.Module):
-    """Caches a packed :class:`_engine.Scorer` and rebuilds it when parameters change or move."""
+    """Caches a packed :class:`_engine.Scorer` and rebuilds it when parameters change or move.
+
+    Invalidation is explicit where autograd's version counters cannot see the change: ``FusedAdamW.step`` and CUDA-graph
+    replays write parameters through raw device pointers, so they bump ``_engine.param_generation`` (part of the cache
+    key); ``train()`` / ``load_state_dict()`` / ``_apply()`` (``.to()``, ``.cuda()``, ``.half()`` ...) drop the cache."""
 
     def _init_runtime(self, config: dict):
         self._config = dict(config)
@@ -135,11 +139,33 @@ class _B200Model(nn.Module):
         self._scorer_key = None
 
     def _state_key(self):
-        ver, dev = 0, None
-        for t in list(self.parameters()) + list(self.buffers()):
+        ver, n, dev = 0, 0, None
+        for t in self.parameters():
             ver += t._version
+            n += 1
             dev = t.device
-        return (ver, str(dev), self._precision, len(list(self.parameters())))
+        for t in self.buffers():
+            ver += t._version
+        return (ver, str(dev), self._precision, n, _engine.param_generation())
+
+    def _drop_scorer(self):
+        if getattr(self, "_scorer", None) is not None:
+            self._scorer = None
+            self._scorer_key = None
+        if getattr(self, "_frozen_scorer", None) is not None:
+            self._frozen_scorer = None
+
+    def train(self, mode: bool = True):
+        self._drop_scorer()
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._drop_scorer()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._drop_scorer()
+        return super()._apply(fn, *args, **kwargs)
 
     def set_precision(self, precision: str):
         """``"fp32"`` or ``"bf16"``; takes effect on the next forward."""
@@ -154,6 +180,21 @@ class _B200Model(nn.Module):
             self._scorer = _engine.Scorer(self._config, self.state_dict(), self._precision)
             self._scorer_key = key
         return self._scorer
+
+    def _frozen_image_scorer(self) -> _engine.Scorer:
+        """Scorer whose ``features()`` the training path uses while the image trunk is frozen (train.py:224-231).  Keyed
+        on the frozen parameters only -- the trainable ones (and BatchNorm's ``num_batches_tracked``) change every step
+        and would otherwise force a re-pack of the whole trunk per step (and inside a CUDA-graph capture)."""
+        ver, dev = 0, None
+        for t in self.parameters():
+            if not t.requires_grad:
+                ver += t._version
+                dev = t.device
+        key = (ver, str(dev), self._precision)
+        if getattr(self, "_frozen_scorer", None) is None or key != self._frozen_key:
+            self._frozen_scorer = _engine.Scorer(self._config, self.state_dict(), self._precision)
+            self._frozen_key = key
+        return self._frozen_scorer
 
     def _run(self, image_input=None, metadata_input=None):
         if self.training and torch.is_grad_enabled():

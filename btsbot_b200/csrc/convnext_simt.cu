@@ -501,21 +501,20 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
   BTSB_REQUIRE(x && w && bias && ln_w && ln_b && out, "dwln: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == BTSB_F32) return dispatch_dwln<float>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
-  // debugging aids: BTSB_DWLN=1 -> generic kernel, =2 -> v2 (smem-staged LayerNorm); default small/v3 -> v2 -> generic
-  static const int force = getenv("BTSB_DWLN") ? atoi(getenv("BTSB_DWLN")) : 0;
-  if (force == 0) {
+  // each specialised kernel returns 1 when the shape is not its own: small maps -> v5 -> v3 -> v2 -> generic
+  {
     const int rc = dwln_bf16_small(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);   // 3x3 and 1x1 maps
     if (rc != 1) return rc;
   }
-  if (force == 0) {
+  {
     const int rc = dwln_bf16_v5(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);      // conv and LayerNorm on different warps
     if (rc != 1) return rc;
   }
-  if (force == 0 || force == 3) {
+  {
     const int rc = dwln_bf16_v3(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
     if (rc != 1) return rc;
   }
-  if (force != 1) {
+  {
     const int rc = dwln_bf16_v2(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
     if (rc != 1) return rc;
   }
@@ -617,7 +616,7 @@ extern "C" int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, in
   if (dtype == BTSB_F32)
     lnpatch_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, H, W, C, Ho, Wo, ln_w, ln_b, (float*)out);
   else if ((C == 64 || C == 80 || C == 128 || C == 160 || C == 256 || C == 320) && ((uintptr_t)x % 16) == 0 &&
-           ((uintptr_t)out % 16) == 0 && !getenv("BTSB_LNPATCH_V1")) {
+           ((uintptr_t)out % 16) == 0) {
     const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
     __nv_bfloat16* xo = (__nv_bfloat16*)out;
     switch (C) {

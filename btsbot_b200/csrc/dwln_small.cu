@@ -146,15 +146,6 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
 
 int num_sms();
 
-// BTSB_DWS_PF=2 selects the two-image prefetch (A/B timing; default 1 until measured faster)
-static int prefetch_distance() {
-  static const int pf = [] {
-    const char* e = getenv("BTSB_DWS_PF");
-    return (e && e[0] == '2') ? 2 : 1;
-  }();
-  return pf;
-}
-
 template <int S, int CT, int PF, bool CPA = false>
 static int launch_small_pf(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
@@ -175,20 +166,16 @@ static int launch_small_pf(const void* x, int64_t B, int C, const float* w, cons
   return launch_done("dwln_small");
 }
 
-// BTSB_DWS_CPA=1 selects the cp.async tap staging (compile-time C, 16-byte aligned taps)
-static bool cp_async_taps() {
-  static const bool on = [] { const char* e = getenv("BTSB_DWS_CPA"); return e && e[0] == '1'; }();
-  return on;
-}
-
+// cp.async tap staging (compile-time C, 16-byte aligned taps) is the default where it applies: 39 -> 33 us per 8192
+// images at 3x3x320 (profiles/r02a); the two-image prefetch variant (PF = 2) measured slower (37 -> 39 us,
+// profiles/r01n) and is not dispatched.
 template <int S, int CT>
 static int launch_small(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
   if constexpr (CT > 0 && CT % 4 == 0) {
-    if (cp_async_taps() && ((uintptr_t)w % 16) == 0) return launch_small_pf<S, CT, 1, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    if (((uintptr_t)w % 16) == 0) return launch_small_pf<S, CT, 1, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
   }
-  return prefetch_distance() == 2 ? launch_small_pf<S, CT, 2>(x, B, C, w, bias, ln_w, ln_b, out, st)
-                                  : launch_small_pf<S, CT, 1>(x, B, C, w, bias, ln_w, ln_b, out, st);
+  return launch_small_pf<S, CT, 1>(x, B, C, w, bias, ln_w, ln_b, out, st);
 }
 
 // returns 1 if the shape is not handled here

@@ -567,7 +567,7 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
   if (epilogue == BTSB_EPI_SCALE_RES)
     BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)gamma % 16) == 0, "gemm bf16: res/gamma must be 16-byte aligned");
   BTSB_REQUIRE(N <= kMaxNBias, "gemm bf16: N=%d exceeds the staged bias capacity (%d)", N, kMaxNBias);
-  static const int dbg = getenv("BTSB_GEMM_DBG") ? atoi(getenv("BTSB_GEMM_DBG")) : 0;   // timing experiments only
+  constexpr int dbg = 0;   // kernel-side timing experiments (main loop only / TMEM reads only) are compiled in but off
   // CTA pairs (cta_group::2, M = 256 UMMA over two SMs): opt-in with BTSB_GEMM_2CTA=1.  Measured on B200 (profiles/r01j):
   // parity-green on every tested shape but performance-neutral for this network (fc1_320 75.2 -> 74.3 us, fc2_320
   // 73.0 -> 70.7 us, C3 1.78 M -> 1.76 M alerts/s, C4 23.7 k -> 22.3 k): these GEMMs carry the 4C-wide hidden tensor

@@ -2,8 +2,8 @@
 // hidden activation lives only in TMEM / shared memory.  Replaces timm blocks.j.mlp.fc1 -> act -> mlp.fc2 -> *gamma ->
 // +shortcut (and MaxViT's token MLPs) for C <= 160.
 //
-// What changed against mlp_fused_tc.cu (profiles/r01c: 20-28 % of all epilogue-warp samples sat on the D1 barrier
-// because the 3-stage weight ring gave the TMA producer only ~1 chunk of look-ahead against ~1 us of L2 latency):
+// Design points (profiles/r01c: with one 3-stage weight ring 20-28 % of all epilogue-warp samples sat on the D1 barrier
+// because the TMA producer had only ~1 chunk of look-ahead against ~1 us of L2 latency):
 //   * weights RESIDENT in shared memory when they fit (C <= 96: W1 + W2 = 8 C^2 * 2 B <= 147 KB), loaded once per CTA;
 //     otherwise two independent rings (W1 slots are released as soon as G1 retires, W2 slots after G2) so both
 //     streams run 3-4 hidden chunks ahead of the tensor pipe
@@ -32,6 +32,7 @@ constexpr int NH = 64;             // hidden chunk
 constexpr int kEpiWarps2 = 16;
 constexpr int kG2Warp = 2 + kEpiWarps2;                 // second MMA-issuing warp (G2 stream)
 constexpr int kThreads2 = 64 + kEpiWarps2 * 32 + 32;
+
 constexpr int kHBytes = FM * 128;  // [128 x 64] bf16
 constexpr int kD2Col = 2 * NH;     // TMEM column of D2 (D1 buffers occupy [0,128))
 constexpr int kMaxSlots = 16;
@@ -145,11 +146,17 @@ struct Maps2 {
 };
 }  // namespace
 
-// EP (wide variants only; 1 and 2 are opt-in and UNMEASURED): how the residual / output pieces of the D2 epilogue move.
-// Every per-thread 16-byte access is its own L2 request there (DESIGN.md lesson 9), so
-//   EP = 1: one 256-bit access per thread and piece instead of two 128-bit ones;
-//   EP = 2: per-warp 1 KB slabs and [32 rows x 16 columns] bulk tensor loads / stores (the narrow variants' staging
-//           scheme at the size that fits next to the 80 KB y tile): no per-thread global access at all.
+// EP (wide variants only): how the residual / output rows of the D2 epilogue move.  With per-thread 16-byte accesses
+// every access is its own L2 request (2.95 M write requests per launch at C = 320) and the single D2 accumulator is
+// drained for ~18 k of a tile's 54 k clocks while G2 of the next tile waits (DESIGN.md lesson 9).  Measured per launch
+// at M = 73 728, C = 320 (profiles/r02a): per-thread accesses 138 us, 256-bit per-thread accesses 128 us (removed),
+//   EP = 2: per-warp 1 KB slabs and [32 rows x 16 columns] bulk tensor loads / stores: 125 us; the single slab per
+//           warp serialises load -> update -> store per piece, so the drain still takes ~15 k clocks;
+// A third variant (EP = 3: the y tile's own 80 KB as the staging tile, residual rows in by bulk tensor loads, W2 stream on
+// its own producer warp) was parity-green and measured 130 us (profiles/r02b): the drain shrank to ~7 k clocks but the
+// y tile of the next row tile could only be fetched afterwards (~4 k clocks for 80 KB with every SM at its tile boundary
+// at once).  Removed.  In steady state this kernel streams W1 + W2 (1.6 MB per 128-row tile, 80 KB per ~1800-clock hidden
+// chunk = 45 B/clk/SM, 7.1 TB/s chip-wide) -- it sits on the L2 -> SM bandwidth, not on the tensor pipe.
 template <int C, bool TE, bool HT, int EP = 0>
 __global__ void __launch_bounds__(kThreads2, 1)   // 19 warps -> 5 on three SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
@@ -163,7 +170,8 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   auto tr = [&](int role, uint32_t g, int ev) {
     if (tracing && g < (uint32_t)kTraceChunks) trace[((size_t)role * kTraceChunks + g) * kTraceEv + ev] = clock64();
   };
-  constexpr bool V8 = EP == 1, TS = EP == 2;
+  constexpr bool TS = EP == 2;
+  static_assert(EP == 0 || EP == 2, "EP");
   static_assert(EP == 0 || !TE, "EP variants belong to the wide (non-staging) kernels");
   constexpr Plan2 P = plan2_for(C, TE, HT, TS);
   static_assert(P.ok, "no shared-memory plan for this C");
@@ -423,13 +431,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         if (PRE) { r0 = rpre[PRE ? u : 0][0]; r1 = rpre[PRE ? u : 0][1]; }
         else if (row < M) {
           const uint4* rp = reinterpret_cast<const uint4*>(res + (size_t)row * C + gi * 16);
-          if constexpr (V8) {
-            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w), "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w)
-                         : "l"(rp));
-          } else {
-            r0 = __ldg(rp); r1 = __ldg(rp + 1);
-          }
+          r0 = __ldg(rp); r1 = __ldg(rp + 1);
         }
         tmem_ld_wait();
         if (gi + 4 >= groups2) {                         // last D2 read of this warp for this tile
@@ -456,13 +458,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
           o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
           uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * C + n);
-          if constexpr (V8) {
-            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                         :: "l"(op), "r"(o0.x), "r"(o0.y), "r"(o0.z), "r"(o0.w), "r"(o1.x), "r"(o1.y), "r"(o1.z), "r"(o1.w)
-                         : "memory");
-          } else {
-            op[0] = o0; op[1] = o1;
-          }
+          op[0] = o0; op[1] = o1;
         }
       }
     };
@@ -738,39 +734,15 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
   }
   const int NC = C > 256 ? C / 2 : C;                      // W2 chunk rows per bulk copy / per G2 UMMA
   if (int e = make_tmap_bf16_2d_sw(&tm.w2, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)NC, 64, 128)) return e;
-  // BTSB_MLP_HSMEM=1 keeps the hidden chunk in shared memory (first version of this kernel) for A/B timing
-  static const int hsmem = getenv("BTSB_MLP_HSMEM") ? atoi(getenv("BTSB_MLP_HSMEM")) : 0;
   if (int e = make_tmap_bf16_2d_sw(&tm.r128, res, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.r64, res, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.r32, res, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
-  // wide C: no room for the staging tile next to the 80 KB y tile -> residual / output rows go straight to global
-  // BTSB_MLP_EP=1: 256-bit residual / output accesses in the wide D2 epilogue (needs 32-byte aligned res / out);
-  // BTSB_MLP_EP=2: per-warp slabs + bulk tensor copies.  Both opt-in until measured.
-  static const int ep = [] { const char* e = getenv("BTSB_MLP_EP"); return e ? atoi(e) : 0; }();
-  if (ep == 1 && (C == 256 || C == 320) && ((uintptr_t)res % 32) == 0 && ((uintptr_t)out % 32) == 0) {
-    if (C == 256) return launch2<256, false, true, 1>(tm, b1, b2, gamma, res, out, M, st);
-    return launch2<320, false, true, 1>(tm, b1, b2, gamma, res, out, M, st);
-  }
-  if (ep == 2 && (C == 256 || C == 320)) {
-    if (C == 256) return launch2<256, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
-    return launch2<320, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
-  }
-  if (C == 256) return launch2<256, false, true>(tm, b1, b2, gamma, res, out, M, st);
-  if (C == 320) return launch2<320, false, true>(tm, b1, b2, gamma, res, out, M, st);
-  if (hsmem) {
-    switch (C) {
-      case 64: return launch2<64, true, false>(tm, b1, b2, gamma, res, out, M, st);
-      case 80: return launch2<80, true, false>(tm, b1, b2, gamma, res, out, M, st);
-      case 96: return launch2<96, true, false>(tm, b1, b2, gamma, res, out, M, st);
-      case 112: return launch2<112, true, false>(tm, b1, b2, gamma, res, out, M, st);
-      case 128: return launch2<128, true, false>(tm, b1, b2, gamma, res, out, M, st);
-      case 144: return launch2<144, true, false>(tm, b1, b2, gamma, res, out, M, st);
-      case 160: return launch2<160, true, false>(tm, b1, b2, gamma, res, out, M, st);
-    }
-  }
+  // wide C: no room for a separate staging tile next to the 80 KB y tile -> per-warp slabs (EP = 2)
+  if (C == 256) return launch2<256, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
+  if (C == 320) return launch2<320, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
   switch (C) {
     case 64: return launch2<64, true, true>(tm, b1, b2, gamma, res, out, M, st);
     case 80: return launch2<80, true, true>(tm, b1, b2, gamma, res, out, M, st);
@@ -792,4 +764,21 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
 extern "C" int btsb_debug_mlp_trace(void* buf) {
   btsb::g_mlp_trace = (long long*)buf;
   return BTSB_OK;
+}
+
+// K4 fused entry point: replaces timm blocks.j.mlp.fc1 -> GELU -> mlp.fc2 -> *gamma -> +shortcut
+// (called at /root/reference/btsbot/architectures.py:132; oracle/convnext_oracle.py block()).
+extern "C" int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const void* W1, const float* b1,
+                                           const void* W2, const float* b2, const float* gamma, void* out, int64_t M,
+                                           int C, void* stream) {
+  using namespace btsb;
+  if (int e = check_device()) return e;
+  BTSB_REQUIRE(M >= 0 && M < (1ll << 31), "mlp_fused: bad M");
+  BTSB_REQUIRE(mlp_fused2_supported(C), "mlp_fused: C=%d unsupported (multiple of 16 in [64,160], 256 or 320)", C);
+  if (M == 0) return BTSB_OK;
+  BTSB_REQUIRE(y && res && W1 && b1 && W2 && b2 && gamma && out, "mlp_fused: null pointer");
+  BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)b1 % 16) == 0 &&
+                   ((uintptr_t)b2 % 16) == 0 && ((uintptr_t)gamma % 16) == 0,
+               "mlp_fused: pointers must be 16-byte aligned");
+  return mlp_fused2_launch(y, res, W1, b1, W2, b2, gamma, out, M, C, (cudaStream_t)stream);
 }

@@ -161,6 +161,8 @@ class GradSink:
         self.cuda = dev.type == "cuda"
         self.stream = torch.cuda.Stream(device=dev) if self.cuda else None
         self.last_order, self.last_early = [], 0     # bucket launch order / #buckets sent before flush() (last step)
+        #: False skips the collectives (bench.py times a compute-only step to derive the all-reduce overlap fraction)
+        self.comm = True
         self.reset()
 
     def reset(self):
@@ -198,7 +200,7 @@ class GradSink:
         if not self.in_flush:
             self.early += 1
         _, world = _world()
-        if world == 1:
+        if world == 1 or not self.comm:
             return
         lo, hi = self.bounds[i]
         chunk = self.flat[lo:hi]

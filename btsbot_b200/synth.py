@@ -157,10 +157,11 @@ MAXVIT_KINDS = {
 
 
 def maxvit_arch(model_kind: str) -> dict:
-    """Map a timm model name (``maxvit_tiny_rw_224.sw_in1k`` ...) to its MaxViT configuration."""
+    """Map a timm model name (``maxvit_tiny_rw_224.sw_in1k``, ``hf_hub:mwalmsley/baseline-encoder-regression-maxvit_tiny``
+    -- the galaxyzoo-pretrained encoder of to_HF.py:167-168, a maxvit_tiny_rw_224 -- ...) to its MaxViT configuration."""
     k = model_kind.lower()
     for name, arch in MAXVIT_KINDS.items():
-        if name in k:
+        if name in k or (name == "maxvit_tiny_rw" and k.rstrip("/").endswith("maxvit_tiny")):
             return dict(arch, name=name)
     raise ValueError(f"unsupported MaxViT kind for the B200 path: {model_kind!r} (supported: {sorted(MAXVIT_KINDS)})")
 

@@ -127,8 +127,13 @@ def run_training(config, run_name: str = "", sweeping: bool = False):
     num_bts, num_notbts = int((labels == 1).sum()), int((labels == 0).sum())
     if rank == 0:
         print(f"num_notbts: {num_notbts}\nnum_bts: {num_bts}")
+    # One optimizer step still consumes `batch_size` alerts: the reference's DataParallel splits each batch over the GPUs
+    # (train.py:238-240), so every rank takes batch_size // world of it and the averaged gradient is the gradient of the
+    # whole batch -- same effective batch, learning rate and steps per epoch as the single-GPU run.
+    if batch_size % world != 0:
+        raise ValueError(f"batch_size {batch_size} is not divisible by the {world} ranks")
     dataloader = GpuBatchLoader(
-        images, metadata, labels, batch_size=batch_size, shuffle=True, drop_last=True, device=device,
+        images, metadata, labels, batch_size=batch_size // world, shuffle=True, drop_last=True, device=device,
         h_flip=need_triplets and bool(config.get("data_aug_h_flip", True)),
         v_flip=need_triplets and bool(config.get("data_aug_v_flip", True)),
         rot=need_triplets and bool(config.get("data_aug_rot", True)),
@@ -166,7 +171,8 @@ def run_training(config, run_name: str = "", sweeping: bool = False):
                                        f"{device.type}", run_name)
     if rank == 0:
         os.makedirs(model_dir, exist_ok=True)
-    history = {"run_name": run_name, "loss": [], "accuracy": [], "val_loss": [], "val_accuracy": [], "lr": []}
+    # key names of the reference's run_data (train.py:293-299); "lr" is extra
+    history = {"run_name": run_name, "train_loss": [], "train_accuracy": [], "val_loss": [], "val_accuracy": [], "lr": []}
     best_val_loss, epochs_since_improvement = float("inf"), 0
     net = model.module if isinstance(model, DistributedDataParallel) else model
 
@@ -180,10 +186,13 @@ def run_training(config, run_name: str = "", sweeping: bool = False):
             val_loss, val_acc, _, _ = val.run_val(config, model_dir, "latest_model.pth", bts_weight, need_triplets,
                                                   need_metadata)
             print(f"  val_loss {val_loss:.4f} val_acc {val_acc:.4f}")
-            history["loss"].append(loss); history["accuracy"].append(acc)
+            # train.py:334-336: the bar is the minimum over ALL previous epochs' val losses (including improvements of
+            # less than 0.5 % that did not save a model), not the loss of the last saved model
+            prev_best_val_loss = min([float("inf")] + history["val_loss"])
+            history["train_loss"].append(loss); history["train_accuracy"].append(acc)
             history["val_loss"].append(val_loss); history["val_accuracy"].append(val_acc)
             history["lr"].append(optimizer.param_groups[0]["lr"])
-            if 1.005 * val_loss < best_val_loss:                      # train.py:335-336
+            if 1.005 * val_loss < prev_best_val_loss:
                 best_val_loss, epochs_since_improvement = val_loss, 0
                 torch.save(net.state_dict(), os.path.join(model_dir, "best_model.pth"))
             else:

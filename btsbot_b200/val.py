@@ -44,8 +44,17 @@ def load_split(config, split, need_triplets, need_metadata, drop_nan_triplets=Fa
             trip = trip[~bad]
             cand = cand.loc[~bad].reset_index(drop=True)
             print(f"**** Null in triplets ****\nRemoved {int(bad.sum())} alert(s) from triplets and cand/labels.")
-        chunks = [alert_utils.triplets_to_model_input(trip[i:i + 16384]) for i in range(0, len(trip), 16384)]
-        images = torch.cat(chunks) if chunks else torch.empty((0, 3, 63, 63), device=device)
+        if tuple(trip.shape[1:]) == (63, 63, 3):
+            chunks = [alert_utils.triplets_to_model_input(trip[i:i + 16384]) for i in range(0, len(trip), 16384)]
+        else:
+            # "LS" data versions carry larger legacy-survey cutouts (the reason mm_ConvNeXt has its pool+norm head,
+            # architectures.py:136-141); K1 is specialised for the 63x63 ZTF stamp, so any other size takes the
+            # reference's own astype(float32) + transpose(0,3,1,2) (train.py:139-155) as two device copies per chunk
+            if trip.ndim != 4 or trip.shape[3] != 3:
+                raise ValueError(f"expected triplets of shape [N,H,W,3], got {trip.shape}")
+            chunks = [torch.from_numpy(np.ascontiguousarray(trip[i:i + 4096])).to(device).to(torch.float32)
+                      .permute(0, 3, 1, 2).contiguous() for i in range(0, len(trip), 4096)]
+        images = torch.cat(chunks) if chunks else torch.empty((0, 3) + tuple(trip.shape[1:3]), device=device)
     labels = torch.tensor(cand["label"].values, dtype=torch.long)
     metadata = None
     if need_metadata:
