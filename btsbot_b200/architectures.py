@@ -328,12 +328,58 @@ class frozen_fusion(_B200Model):
         return self._run(image_input=image_input, metadata_input=metadata_input)
 
 
-class _NotOnB200(nn.Module):
-    _why = ""
+# ---------------------------------------------------------------------------------------------------------
+# legacy models (architectures.py:174-274): outside the north-star hot path.  SURVEY.md section 8 row a8 keeps them as
+# plain PyTorch pass-through classes so that the package's API surface (btsbot/__init__.py:16-25) and old checkpoints'
+# state-dict keys stay complete; they run on PyTorch's own ops (eager), not on this package's kernels.
+# ---------------------------------------------------------------------------------------------------------
+def _legacy_conv_stack(cfg) -> nn.Sequential:
+    """Two [conv, ReLU, conv, ReLU, max-pool, Dropout2d] groups + Flatten: 5x5 'same' convs 3 -> c1 -> c1 -> pool 2 ->
+    c2 -> c2 -> pool 4 (Sequential indices 0-12 are the checkpoint key contract)."""
+    k, c1, c2 = cfg["conv_kernel"], cfg["conv1_channels"], cfg["conv2_channels"]
+    layers = []
+    for cin, cout, pool, drop in ((3, c1, 2, cfg["conv_dropout1"]), (c1, c2, 4, cfg["conv_dropout2"])):
+        layers += [nn.Conv2d(cin, cout, kernel_size=k, padding="same"), nn.ReLU(),
+                   nn.Conv2d(cout, cout, kernel_size=k, padding="same"), nn.ReLU(),
+                   nn.MaxPool2d(kernel_size=pool, stride=pool), nn.Dropout2d(drop)]
+    return nn.Sequential(*layers, nn.Flatten())
+
+
+def _legacy_feature_dim(cfg) -> int:
+    return cfg["conv2_channels"] * (cfg.get("image_size", 63) // 8) ** 2
+
+
+class mm_cnn(nn.Module):
+    """Legacy multimodal CNN (architectures.py:174-229), PyTorch pass-through."""
 
     def __init__(self, config):
         super().__init__()
-        raise NotImplementedError(f"btsbot_b200: {type(self).__name__} {self._why}")
+        n_meta = len(config.get("metadata_cols", []))
+        self.conv_layers = _legacy_conv_stack(config)
+        self.conv_feature_dim = _legacy_feature_dim(config)
+        self.metadata_branch = nn.Sequential(*_metadata_branch(n_meta, config, nn.ReLU))
+        self.combined_head = _combined_head(self.conv_feature_dim + config["meta_fc2_neurons"], config, nn.ReLU)
+        self._config = dict(config, model_name="mm_cnn")
+
+    def forward(self, image_input: torch.Tensor, metadata_input: torch.Tensor) -> torch.Tensor:
+        both = torch.cat((self.conv_layers(image_input), self.metadata_branch(metadata_input)), dim=1)
+        return self.combined_head(both)
+
+
+class um_cnn(nn.Module):
+    """Legacy image-only CNN (architectures.py:232-274), PyTorch pass-through."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.conv_layers = _legacy_conv_stack(config)
+        self.head = nn.Sequential(
+            nn.Linear(_legacy_feature_dim(config), config["fc1_neurons"]), nn.ReLU(),
+            nn.Linear(config["fc1_neurons"], config["fc2_neurons"]), nn.ReLU(),
+            nn.Dropout(config["dropout"]), nn.Linear(config["fc2_neurons"], 1))
+        self._config = dict(config, model_name="um_cnn")
+
+    def forward(self, input_data: torch.Tensor) -> torch.Tensor:
+        return self.head(self.conv_layers(input_data))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -490,13 +536,3 @@ class mm_MaxViT(_B200Model):
 
     def forward(self, image_input: torch.Tensor, metadata_input: torch.Tensor) -> torch.Tensor:
         return self._run(image_input=image_input, metadata_input=metadata_input)
-
-
-class mm_cnn(_NotOnB200):
-    """architectures.py:174-229 -- legacy 2-block CNN, outside the north-star hot path."""
-    _why = "is a legacy model outside the B200 hot path (SURVEY.md section 8 row a8)"
-
-
-class um_cnn(_NotOnB200):
-    """architectures.py:232-274 -- legacy 2-block CNN, outside the north-star hot path."""
-    _why = "is a legacy model outside the B200 hot path (SURVEY.md section 8 row a8)"

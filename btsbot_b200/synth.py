@@ -342,16 +342,19 @@ def make_state_dict(config: dict, seed: int = 2, perturb: bool = True, gamma_bas
     elif name == "frozen_fusion":
         img = make_state_dict(config["image_model_config"], seed + 101, perturb, gamma_base)
         met = make_state_dict(config["meta_model_config"], seed + 202, perturb, gamma_base)
-        if config["image_model_config"]["model_name"] != "ConvNeXt" or \
-                config["meta_model_config"]["model_name"] != "um_nn":
-            raise ValueError("synthetic frozen_fusion weights: ConvNeXt image branch + um_nn meta branch only")
-        for k, v in img.items():          # head cut to [pool, LN2d, flatten] (architectures.py:309-313)
-            if not k.startswith(("convnext.head.3.", "convnext.head.5.", "convnext.head.8.")):
+        iname = config["image_model_config"]["model_name"]
+        if iname not in ("ConvNeXt", "MaxViT") or config["meta_model_config"]["model_name"] != "um_nn":
+            raise ValueError("synthetic frozen_fusion weights: ConvNeXt or MaxViT image branch + um_nn meta branch only")
+        for k, v in img.items():          # head cut to [pool, LN2d, flatten] (architectures.py:309-313) / [pool] (:304-308)
+            if not k.startswith(("convnext.head.3.", "convnext.head.5.", "convnext.head.8.", "maxvit.head.")):
                 sd["image_branch." + k] = v
         for k, v in met.items():          # network[:-2] (architectures.py:299-303)
             if not k.startswith("network.6."):
                 sd["meta_branch." + k] = v
-        feat = convnext_arch(config["image_model_config"].get("model_kind", "convnext_nano.d1h_in1k"))["dims"][-1]
+        if iname == "ConvNeXt":
+            feat = convnext_arch(config["image_model_config"].get("model_kind", "convnext_nano.d1h_in1k"))["dims"][-1]
+        else:
+            feat = maxvit_arch(config["image_model_config"].get("model_kind", "maxvit_tiny_rw_224.sw_in1k"))["embed_dim"][-1]
         comb_in = feat + config["meta_model_config"]["meta_fc2_neurons"]
         _linear_sd(w, "combined_head.0.", config["comb_fc1_neurons"], comb_in, sd)
         _linear_sd(w, "combined_head.2.", config["comb_fc2_neurons"], config["comb_fc1_neurons"], sd)
@@ -396,9 +399,10 @@ def canonical_config(model_name: str = "mm_ConvNeXt", model_kind: str = "convnex
         batch_size=64, random_seed=2,
     )
     if model_name == "frozen_fusion":
+        # image branch by model kind: ConvNeXt (BTSbot-convnext-*-metadata) or MaxViT (BTSbot-maxvit-tiny-*-metadata)
         base.update(
             image_model_dir="", meta_model_dir="", skip_load_state=True,
-            image_model_config=canonical_config("ConvNeXt", model_kind),
+            image_model_config=canonical_config("MaxViT" if "maxvit" in model_kind.lower() else "ConvNeXt", model_kind),
             meta_model_config=canonical_config("um_nn", model_kind),
         )
     return base

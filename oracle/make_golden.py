@@ -199,6 +199,8 @@ def main():
 MAXVIT_CASES = {
     "mm_maxvit": ("mm_MaxViT", "maxvit_tiny_rw_224.sw_in1k", {}),
     "img_maxvit": ("MaxViT", "maxvit_tiny_rw_224.sw_in1k", {}),
+    # what the published BTSbot-maxvit-tiny-*-metadata checkpoints are (to_HF.py:143-177; architectures.py:304-308)
+    "ff_maxvit": ("frozen_fusion", "maxvit_tiny_rw_224.sw_in1k", {}),
 }
 #: MaxViT is ~40x the FLOPs of ConvNeXt-nano: goldens on 8 shipped example alerts + 8 synthetic ones
 MAXVIT_EXAMPLE, MAXVIT_SYN = 8, 8
@@ -233,7 +235,7 @@ def main_maxvit():
 
         def run(model):
             with torch.no_grad():
-                return model(image_input=img, metadata_input=met) if name == "mm_MaxViT" else model(input_data=img)
+                return model(image_input=img, metadata_input=met) if name != "MaxViT" else model(input_data=img)
         raw = run(model).numpy().astype(np.float64)
         shift, scale = float(np.median(raw)), float(min(10.0, 0.5 / raw.std()))
         sd = synth.apply_calibration(sd, cfg, scale, shift)
@@ -247,8 +249,39 @@ def main_maxvit():
     np.savez_compressed(os.path.join(GOLD, "maxvit_logits.npz"), **out)
 
 
+LEGACY_CFG = dict(conv_kernel=5, conv1_channels=8, conv2_channels=16, conv_dropout1=0.5, conv_dropout2=0.55,
+                  metadata_cols=list(synth.METADATA_COLS), meta_fc1_neurons=16, meta_dropout=0.25, meta_fc2_neurons=8,
+                  comb_fc1_neurons=16, comb_fc2_neurons=4, comb_dropout=0.2, fc1_neurons=16, fc2_neurons=4, dropout=0.2)
+
+
+def main_legacy():
+    """Goldens for the legacy classes (`architectures.py:174-274` mm_cnn / um_cnn) executed verbatim: a small instance
+    (8 / 16 conv channels) whose seeded torch-initialised state dict travels inside the fixture with the logits."""
+    arch = ref_architectures()
+    img = torch.from_numpy(np.ascontiguousarray(synth.make_triplets(6, start=3000).transpose(0, 3, 1, 2))) * 63.0   # O(1) pixels
+    met = torch.from_numpy(synth.make_metadata(6, start=3000))
+    out = {}
+    for name in ("mm_cnn", "um_cnn"):
+        torch.manual_seed(7)
+        model = getattr(arch, name)(dict(LEGACY_CFG)).eval()
+        with torch.no_grad():
+            for k, v in model.state_dict().items():          # non-trivial BatchNorm statistics
+                if k.endswith("running_mean"):
+                    v.copy_(torch.from_numpy(synth.METADATA_MOMENTS[:, 0].astype(np.float32)))
+                if k.endswith("running_var"):
+                    v.copy_(torch.from_numpy((synth.METADATA_MOMENTS[:, 1] ** 2).astype(np.float32)))
+            logits = model(image_input=img, metadata_input=met) if name == "mm_cnn" else model(input_data=img)
+        for k, v in model.state_dict().items():
+            out[f"{name}/{k}"] = v.numpy()
+        out[name] = logits.numpy()
+        print(name, logits.flatten().tolist())
+    np.savez_compressed(os.path.join(GOLD, "legacy_cnn.npz"), **out)
+
+
 if __name__ == "__main__":
-    if "--maxvit" in sys.argv:
+    if "--legacy" in sys.argv:
+        main_legacy()
+    elif "--maxvit" in sys.argv:
         main_maxvit()
     else:
         main()

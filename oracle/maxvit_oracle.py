@@ -152,7 +152,7 @@ def resize(x, arch):
 
 
 def forward(sd: dict, config: dict, image_input=None, metadata_input=None, capture: dict | None = None):
-    """Eval-mode logits ``[B,1]`` for ``config['model_name']`` in {MaxViT, mm_MaxViT}."""
+    """Eval-mode logits ``[B,1]`` for ``config['model_name']`` in {MaxViT, mm_MaxViT, frozen_fusion over MaxViT}."""
     name = config["model_name"]
     arch = arch_of(config.get("model_kind", "maxvit_tiny_rw_224.sw_in1k"))
     with torch.no_grad():
@@ -167,4 +167,14 @@ def forward(sd: dict, config: dict, image_input=None, metadata_input=None, captu
             if capture is not None:
                 capture["features"] = f
             return head3(sd, "maxvit.head.", (1, 3, 6), f, F.gelu)
+        if name == "frozen_fusion":
+            # architectures.py:296-372 with a MaxViT image branch: head cut to [global_pool] (:304-308), metadata branch
+            # um_nn.network[:-2] (pre-activation embedding, :299-303), ReLU fusion head (:357-365)
+            icfg = config["image_model_config"]
+            arch = arch_of(icfg.get("model_kind", "maxvit_tiny_rw_224.sw_in1k"))
+            f = trunk_features(sd, "image_branch.maxvit.", resize(image_input, arch), arch, capture).mean(dim=(2, 3))
+            m = metadata_branch(sd, "meta_branch.network.", metadata_input, F.relu)
+            if capture is not None:
+                capture["features"], capture["meta"] = f, m
+            return head3(sd, "combined_head.", (0, 2, 5), torch.cat((f, m), dim=1), F.relu)
     raise ValueError(name)

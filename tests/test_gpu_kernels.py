@@ -61,6 +61,26 @@ def test_dwln(cuda_dev, C, H, W, B, dt):
     assert err < (3e-5 if dt == torch.float32 else 4e-2)
 
 
+@pytest.mark.parametrize("C,S,B", [(80, 15, 1500), (160, 7, 3000)])
+def test_dwln_warp_specialised_handoff_is_deterministic(cuda_dev, C, S, B):
+    """dwln5 hands the fp32 conv tile from the conv warps to the LayerNorm warps through two mbarriers (compute-sanitizer's
+    racecheck does not model mbarrier phases and flags that hand-off, profiles/r02a_san): a persistent grid with ~10 images
+    per CTA, launched repeatedly, must give bitwise identical rows every time and agree with the fp32 reference."""
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, C, S, S, generator=g).bfloat16()
+    w = torch.randn(C, 1, 7, 7, generator=g) / 7
+    b, lw, lb = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    args = (_nchw_to_rows(x.float()).bfloat16().to(cuda_dev), B, S, S, w.reshape(C, 49).t().contiguous().to(cuda_dev),
+            b.to(cuda_dev), lw.to(cuda_dev), lb.to(cuda_dev))
+    first = ops.dwln(*args)
+    for _ in range(20):
+        assert torch.equal(ops.dwln(*args), first)
+    ref = _ln2d(F.conv2d(x.float()[:64], w, b, padding=3, groups=C), lw, lb)
+    err = _report(f"dwln5 determinism C={C} {S}x{S}", _rows_to_nchw(first[:64 * S * S].cpu(), 64, S, S), ref)
+    assert err < 4e-2
+
+
 @pytest.mark.parametrize("C,H,W,B", [(80, 15, 15, 5), (160, 7, 7, 9), (320, 3, 3, 11), (64, 15, 15, 2), (256, 4, 6, 3)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_lnpatch_then_gemm_is_downsample(cuda_dev, C, H, W, B, dt):

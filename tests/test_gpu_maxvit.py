@@ -184,7 +184,7 @@ def _build(case, golden_mv, dev, precision, gain=None):
 
 def _call(model, cfg, img, meta):
     with torch.no_grad():
-        if cfg["model_name"] == "mm_MaxViT":
+        if cfg["model_name"] in ("mm_MaxViT", "frozen_fusion"):
             return model(image_input=img, metadata_input=meta)
         return model(input_data=img)
 

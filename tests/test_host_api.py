@@ -101,10 +101,30 @@ def test_frozen_fusion_surgery():
     assert m.combined_head[0].in_features == 512 + 128
 
 
+def test_legacy_cnn_pass_through_matches_reference():
+    """mm_cnn / um_cnn (PyTorch pass-through classes outside the hot path): same state-dict keys and
+    the same logits as the reference's architectures.py:174-274 executed verbatim (tests/golden/legacy_cnn.npz, made by
+    `python -m oracle.make_golden --legacy`)."""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "legacy_cnn.npz"))
+    cfg = dict(conv_kernel=5, conv1_channels=8, conv2_channels=16, conv_dropout1=0.5, conv_dropout2=0.55,
+               metadata_cols=list(synth.METADATA_COLS), meta_fc1_neurons=16, meta_dropout=0.25, meta_fc2_neurons=8,
+               comb_fc1_neurons=16, comb_fc2_neurons=4, comb_dropout=0.2, fc1_neurons=16, fc2_neurons=4, dropout=0.2)
+    img = torch.from_numpy(np.ascontiguousarray(synth.make_triplets(6, start=3000).transpose(0, 3, 1, 2))) * 63.0   # O(1) pixels
+    met = torch.from_numpy(synth.make_metadata(6, start=3000))
+    for name in ("mm_cnn", "um_cnn"):
+        model = getattr(btsbot, name)(dict(cfg)).eval()
+        sd = {k[len(name) + 1:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith(name + "/")}
+        assert set(sd) == set(model.state_dict())
+        model.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            out = model(image_input=img, metadata_input=met) if name == "mm_cnn" else model(input_data=img)
+        assert np.abs(out.numpy() - gold[name]).max() < 1e-5
+    # head surgery of frozen_fusion for a um_cnn image branch (architectures.py:314-317)
+    m, dim = btsbot.frozen_fusion.remove_branch_head(btsbot.um_cnn(dict(cfg)), "um_cnn")
+    assert dim == 16 * 7 * 7 and isinstance(m.head, torch.nn.Identity)
+
+
 def test_unsupported_models_fail_loudly():
-    for cls in (btsbot.mm_cnn, btsbot.um_cnn):                              # legacy CNNs: outside the north star
-        with pytest.raises(NotImplementedError):
-            cls({})
     with pytest.raises(ValueError):
         btsbot.ConvNeXt(dict(synth.canonical_config("ConvNeXt"), model_kind="convnext_base"))
 

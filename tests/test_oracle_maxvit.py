@@ -14,7 +14,7 @@ from btsbot_b200 import synth
 from oracle import maxvit_oracle as MO
 from conftest import GOLDEN
 
-CASES = {"mm_maxvit": "mm_MaxViT", "img_maxvit": "MaxViT"}
+CASES = {"mm_maxvit": "mm_MaxViT", "img_maxvit": "MaxViT", "ff_maxvit": "frozen_fusion"}
 KIND = "maxvit_tiny_rw_224.sw_in1k"
 
 
