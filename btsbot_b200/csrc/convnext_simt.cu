@@ -478,7 +478,12 @@ static int dispatch_dwln(const void* x, int64_t B, int H, int W, int C, const fl
   if (W == 7) return launch_dwln<T, 7>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
   if (W == 3) return launch_dwln<T, 3>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
   if (W == 1) return launch_dwln<T, 1>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
-  return launch_dwln<T, 8>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  // any other map width (e.g. the 19 / 9 / 4 / 2 maps of larger "LS" cutouts): 8 outputs per thread while the CTA
+  // (a multiple of C threads) fits that variant's register budget, else the 3-output variant (up to 640 threads)
+  int r = 1;
+  while (C * r < 256) ++r;
+  if (C * r <= DwBounds<8>::kMaxThreads) return launch_dwln<T, 8>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  return launch_dwln<T, 3>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
 }
 
 namespace btsb {

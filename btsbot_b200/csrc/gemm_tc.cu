@@ -533,6 +533,24 @@ int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* base, uint64_t rows, u
   return BTSB_OK;
 }
 
+// 2-D fp32 row-major [rows, cols] tensor map with a [box_rows x 32 columns] box (128-byte rows, 128B swizzle): the
+// operand tiles of the tf32 GEMM (gemm_tf32.cu)
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encoder();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return BTSB_ECUDA; }
+  BTSB_REQUIRE(((uintptr_t)base % 16) == 0 && (cols * 4) % 16 == 0, "tensor map: base/pitch must be 16-byte aligned");
+  BTSB_REQUIRE(box_rows >= 1 && box_rows <= 256, "tensor map: box rows %u not in [1,256]", box_rows);
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 4};
+  const cuuint32_t box[2] = {32, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r); return BTSB_ECUDA; }
+  return BTSB_OK;
+}
+
 int make_tmap_bf16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
                          uint32_t box_cols, int swizzle_bytes) {
   return make_tmap_bf16_2d_pitch(out, base, rows, cols, box_rows, box_cols, swizzle_bytes, cols);
@@ -729,6 +747,8 @@ int gemm_bf16_wgrad_mn(const void* A, const void* Bm, float* out, int M, int N, 
   return launch_done("gemm_bf16_wgrad_mn");
 }
 
+int gemm_tf32x3(const float* A, const float* Wt, const float* bias, const float* gamma, const float* res, float* out,
+                int64_t M, int N, int K, int epilogue, cudaStream_t st);
 int gemm_f32(const float* A, const float* Wt, const float* bias, const float* gamma, const float* res, float* out,
              int64_t M, int N, int K, int epilogue, cudaStream_t st);
 
@@ -839,7 +859,15 @@ extern "C" int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, c
   BTSB_REQUIRE(A && Wt && bias && out, "gemm: null pointer");
   if (epilogue == BTSB_EPI_SCALE_RES) BTSB_REQUIRE(gamma && res, "gemm: SCALE_RES needs gamma and res");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == BTSB_F32)
+  if (dtype == BTSB_F32) {
+    // tensor cores with the 3xTF32 split (fp32-level accuracy); BTSB_F32_SIMT=1 keeps the CUDA-core GEMM for A/B checks
+    static const bool simt = getenv("BTSB_F32_SIMT") && atoi(getenv("BTSB_F32_SIMT")) != 0;
+    if (!simt) {
+      const int rc = gemm_tf32x3((const float*)A, (const float*)Wt, bias, gamma, (const float*)res, (float*)out, M, N, K,
+                                 epilogue, st);
+      if (rc != 1) return rc;
+    }
     return gemm_f32((const float*)A, (const float*)Wt, bias, gamma, (const float*)res, (float*)out, M, N, K, epilogue, st);
+  }
   return gemm_bf16(A, Wt, bias, gamma, res, out, M, N, K, epilogue, st);
 }

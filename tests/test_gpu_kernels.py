@@ -44,7 +44,8 @@ def test_stem(cuda_dev, C0, H, W, B, odt):
 
 @pytest.mark.parametrize("C,H,W,B", [(80, 15, 15, 7), (160, 7, 7, 33), (320, 3, 3, 70), (640, 1, 1, 130),
                                      (64, 15, 15, 3), (128, 7, 7, 5), (256, 3, 3, 5), (512, 1, 1, 5),
-                                     (64, 9, 11, 4), (96, 5, 2, 3), (320, 3, 3, 2500), (640, 1, 1, 3000), (48, 3, 3, 40)])
+                                     (64, 9, 11, 4), (96, 5, 2, 3), (320, 3, 3, 2500), (640, 1, 1, 3000), (48, 3, 3, 40),
+                                     (512, 2, 2, 9), (640, 2, 2, 5), (256, 4, 4, 6), (64, 19, 19, 3)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_dwln(cuda_dev, C, H, W, B, dt):
     from btsbot_b200 import ops

@@ -284,3 +284,33 @@ def test_error_behaviour(cuda_dev, golden_mv):
         model(image_input=torch.zeros(1, 3, 63, 63, device=cuda_dev), metadata_input=torch.zeros(1, 24, device=cuda_dev))
     assert model(image_input=torch.zeros(0, 3, 63, 63, device=cuda_dev),
                  metadata_input=torch.zeros(0, 25, device=cuda_dev)).shape == (0, 1)
+
+
+def test_load_HF_model_maxvit_metadata_checkpoint(cuda_dev, golden_mv, example_inputs, tmp_path, monkeypatch):
+    """`load_HF_model("maxvit", True, ...)`: the published BTSbot-maxvit-tiny-*-metadata models are frozen_fusion over a
+    MaxViT image branch with its head cut to [global_pool] (to_HF.py:143-177, architectures.py:304-308)."""
+    import json
+    cfg, sd = maxvit_case("ff_maxvit", golden_mv)
+    assert cfg["image_model_config"]["model_name"] == "MaxViT"
+    mdir = tmp_path / "models" / "BTSbot-maxvit-tiny-randinit-metadata"
+    mdir.mkdir(parents=True)
+    (mdir / "train_config.json").write_text(json.dumps(cfg))
+    torch.save(synth.to_torch(sd), mdir / "pytorch_model.bin")
+    monkeypatch.chdir(tmp_path)
+    model = btsbot.load_HF_model("maxvit", True, "randinit").eval()
+    img, meta = maxvit_batch(golden_mv, example_inputs)
+    with torch.no_grad():
+        got = model(image_input=torch.from_numpy(img).cuda(), metadata_input=torch.from_numpy(meta).cuda()).cpu().numpy()
+    ref = golden_mv["ff_maxvit"]
+    print(f"[parity] ff_maxvit via load_HF_model fp32: max|logit-ref|={np.abs(got - ref).max():.3e}")
+    assert np.abs(got - ref).max() < 1.5e-4
+    # training it: the frozen MaxViT branch feeds the trainable fusion head; an unfrozen MaxViT trunk has no backward
+    model.train()
+    for p in list(model.image_branch.parameters()) + list(model.meta_branch.parameters()):
+        p.requires_grad = False
+    lg = model(image_input=torch.from_numpy(img).cuda(), metadata_input=torch.from_numpy(meta).cuda())
+    lg.sum().backward()
+    assert model.combined_head[0].weight.grad is not None and torch.isfinite(model.combined_head[0].weight.grad).all()
+    mm = btsbot.mm_MaxViT(dict(synth.canonical_config("mm_MaxViT", KIND))).cuda().train()
+    with pytest.raises(NotImplementedError):
+        mm(image_input=torch.from_numpy(img[:2]).cuda(), metadata_input=torch.from_numpy(meta[:2]).cuda())

@@ -339,3 +339,45 @@ def test_graphed_train_step_matches_eager(cuda_dev):
     # amplified to a few percent of the update norm between ANY two runs, graphed or not (1.7e-2 ... 6.2e-2 observed)
     assert worst < 0.2
     assert all(abs(x - y) < 5e-3 for x, y in zip(got_losses, ref_losses[2:]))
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_eval_after_optimizer_step_sees_the_new_weights(cuda_dev, graphed):
+    """FusedAdamW (and CUDA-graph replays of it) write parameters through raw pointers, which autograd's version counters
+    do not see: the packed inference copy must still be rebuilt.  Image-only ConvNeXt has no BatchNorm buffer whose
+    `num_batches_tracked` bump could mask a stale cache."""
+    from btsbot_b200._autograd import GraphedTrainStep
+    cfg = dict(_nodrop(case_config("img_pico")), precision="bf16")
+    sd_np = synth.make_state_dict(cfg, seed=5)
+    img, meta, lab = (t.to(cuda_dev) for t in _batch(16, start=900))
+    model = btsbot.ConvNeXt(cfg)
+    model.load_state_dict(synth.to_torch(sd_np), strict=True)
+    model = model.to(cuda_dev)
+    loss_fn = BCEWithLogitsLoss(pos_weight=torch.tensor([1.0]))
+    opt = FusedAdamW(model.parameters(), lr=5e-3, betas=(0.9, 0.99), capturable=graphed)
+
+    def score():
+        model.eval()
+        with torch.no_grad():
+            out = model(input_data=img).clone()
+        model.train()
+        return out
+    before = score()
+    if graphed:
+        stepper = GraphedTrainStep(model, opt, loss_fn, example=(img, None, lab), warmup=1)
+        mid = score()
+        stepper(img, None, lab)                                  # a replay: no Python-side optimizer call at all
+        torch.cuda.synchronize()
+        after = score()
+        assert not torch.equal(mid, after)
+    else:
+        model.zero_grad()
+        loss_fn(model(input_data=img), lab).backward()
+        opt.step()
+        after = score()
+    assert not torch.equal(before, after)
+    fresh = btsbot.ConvNeXt(cfg)
+    fresh.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()}, strict=True)
+    fresh = fresh.to(cuda_dev).eval()
+    with torch.no_grad():
+        assert torch.equal(fresh(input_data=img), after)
