@@ -6,7 +6,11 @@
 //                                              the result does not depend on how the hardware rounds its inputs)
 //     a.w ~= a_hi.w_hi + a_hi.w_lo + a_lo.w_hi (the dropped a_lo.w_lo term and the second cut are <= 2^-21 relative)
 //
-// with fp32 accumulation in TMEM.  Replaces the CUDA-core sgemm_kernel (convnext_simt.cu) for the trunk's fc1 / fc2 /
+// The tensor core's fp32 accumulator truncates on every accumulation step: over a long K the error grows linearly (measured
+// 2-7e-5 absolute on O(1) outputs at K = 640 .. 2560 when a whole tile's K was accumulated in TMEM, profiles/r02f).  So TMEM
+// only ever holds the sum over ONE chunk of kChunkKB = 2 K blocks (K = 64: 24 accumulation steps; with 4 blocks the GEMM error was 6e-6, the logits moved by 2e-5); the epilogue warps drain
+// every chunk into fp32 registers (round-to-nearest adds on the CUDA cores) while the next chunk accumulates in the other
+// TMEM buffer.  Replaces the CUDA-core sgemm_kernel (convnext_simt.cu) for the trunk's fc1 / fc2 /
 // downsample GEMMs (timm mlp.fc1, mlp.fc2, downsample.1; MaxViT 1x1 convs / Linears) whenever K % 4 == 0, N % 16 == 0.
 //
 //   warp 0        TMA producer: fp32 tiles A [128 x 32] and W [BN x 32] (128-byte rows, 128B swizzle) into a 3-stage ring
@@ -24,6 +28,7 @@ constexpr int TM = 128;                // rows per tile
 constexpr int TK = 32;                 // fp32 columns per K block (128 bytes)
 constexpr int TBN = 128;               // max tile width
 constexpr int kStagesT = 3;
+constexpr int kChunkKB = 2;            // K blocks accumulated in TMEM before the sum moves to registers
 constexpr int kATile = TM * 128;       // 16 KB
 constexpr int kWTile = TBN * 128;      // 16 KB
 constexpr int kStageT = 2 * kATile + 2 * kWTile;        // A_hi, A_lo, W_hi, W_lo
@@ -121,13 +126,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     int stage = 0; uint32_t phase = 0;
-    int as = 0; uint32_t aphase = 0;
+    uint32_t cidx = 0;                                           // running chunk count: TMEM buffer = cidx & 1
     const uint32_t idesc = idesc_tf32_f32(TM, BN);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait_spin(tempty_bar(as), aphase ^ 1u);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * TBN);
       for (int kb = 0; kb < k_blocks; ++kb) {
+        const int as = (int)(cidx & 1u);
+        const bool first = (kb % kChunkKB) == 0, last = (kb % kChunkKB) == kChunkKB - 1 || kb == k_blocks - 1;
+        if (first) {
+          mbar_wait_spin(tempty_bar(as), ((cidx >> 1) & 1u) ^ 1u);      // the epilogue has drained this buffer
+          tc_fence_after();
+        }
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * TBN);
         mbar_wait_spin(split_bar(stage), phase);
         tc_fence_after();
         if (elect_one()) {
@@ -138,17 +147,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int kk = 0; kk < kmax; ++kk) {
             // 8 fp32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
             const uint64_t o = (uint64_t)(2 * kk);
-            umma_tf32(tmem_d, a_lo + o, w_hi + o, idesc, (kb | kk) != 0 ? 1u : 0u);      // small terms first
+            umma_tf32(tmem_d, a_lo + o, w_hi + o, idesc, (first && kk == 0) ? 0u : 1u);      // small terms first
             umma_tf32(tmem_d, a_hi + o, w_lo + o, idesc, 1u);
             umma_tf32(tmem_d, a_hi + o, w_hi + o, idesc, 1u);
           }
           umma_commit(empty_bar(stage));
-          if (kb == k_blocks - 1) umma_commit(tfull_bar(as));
+          if (last) umma_commit(tfull_bar(as));
         }
         __syncwarp();
+        if (last) ++cidx;
         if (++stage == kStagesT) { stage = 0; phase ^= 1u; }
       }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else if (warp < 2 + kSplitWarps) {
     // ===================== splitters: fp32 tile -> (hi in place, lo twin) =====================
@@ -180,32 +189,46 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int part = ew >> 2;                                    // which half of the tile's 16-column chunks
     const int chunks = BN / 16;
     const int c_lo = (chunks * part) / 2, c_hi = (chunks * (part + 1)) / 2;
-    int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const int as = lt & 1;
-      const uint32_t aphase = (uint32_t)(lt >> 1) & 1u;
+    constexpr int kMaxCh = TBN / 16 / 2;                         // <= 4 column chunks of 16 per warp
+    const int n_kchunks = (k_blocks + kChunkKB - 1) / kChunkKB;
+    uint32_t cidx = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * TM, n0 = (tile % n_tiles) * BN;
-      mbar_wait_spin(tfull_bar(as), aphase);
-      tc_fence_after();
       const int row = m0 + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TBN);
-      for (int ch = c_lo; ch < c_hi; ++ch) {
-        uint32_t r[16];
-        tmem_ld16(taddr + (uint32_t)(ch * 16), r);
-        tmem_ld_wait();
-        if (ch == c_hi - 1) {                                    // accumulator fully read by this warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
+      float acc[kMaxCh][16];
+#pragma unroll
+      for (int c = 0; c < kMaxCh; ++c)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[c][i] = 0.f;
+      for (int kc = 0; kc < n_kchunks; ++kc, ++cidx) {
+        const int as = (int)(cidx & 1u);
+        mbar_wait_spin(tfull_bar(as), (cidx >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TBN);
+#pragma unroll
+        for (int c = 0; c < kMaxCh; ++c) {
+          if (c_lo + c < c_hi) {
+            uint32_t r[16];
+            tmem_ld16(taddr + (uint32_t)((c_lo + c) * 16), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[c][i] += __uint_as_float(r[i]);
+          }
         }
-        const int n = n0 + ch * 16;
-        if (row < M) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));                // this warp is done with the buffer
+      }
+      if (row < M) {
+#pragma unroll
+        for (int c = 0; c < kMaxCh; ++c) {
+          if (c_lo + c >= c_hi) continue;
+          const int n = n0 + (c_lo + c) * 16;
           float* op = out + (size_t)row * N + n;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + n + i);
-            float v[4] = {__uint_as_float(r[i]) + b4.x, __uint_as_float(r[i + 1]) + b4.y,
-                          __uint_as_float(r[i + 2]) + b4.z, __uint_as_float(r[i + 3]) + b4.w};
+            float v[4] = {acc[c][i] + b4.x, acc[c][i + 1] + b4.y, acc[c][i + 2] + b4.z, acc[c][i + 3] + b4.w};
             if (EPI == BTSB_EPI_BIAS_GELU) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
@@ -220,11 +243,6 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             *reinterpret_cast<float4*>(op + i) = make_float4(v[0], v[1], v[2], v[3]);
           }
         }
-      }
-      if (c_lo >= c_hi) {                                        // BN = 16: the second half has no chunk
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
       }
     }
   }

@@ -695,350 +695,12 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
 }
 
 
-// =====================================================================================================================
-// CTA-pair variant of the wide kernel (C = 256 / 320): cta_group::2.
-//
-// Why: in steady state the single-CTA wide kernel streams W1 + W2 once per 128-row tile -- 1.6 MB per tile, 80 KB per
-// ~1800-clock hidden chunk = 45 B/clk/SM, 7.1 TB/s over the chip (profiles/r02a traces, r01m ncu: 913 MB of L2 -> SM
-// traffic per launch) -- it sits on the L2 -> SM path, not on the tensor pipe.  Here two CTAs of a cluster work on one
-// 256-row unit: every tcgen05.mma is issued once, by the leader, with M = 256 (each CTA's tensor core computes its own
-// 128 rows into its own TMEM) and each CTA stages only HALF of every weight chunk (the hardware reads both halves), so
-// the weight stream per SM -- and the L2 read volume -- is halved.  Everything that touches activations stays per CTA:
-// the y tile, the GELU warps, H in TMEM, the D2 drain through per-warp slabs.
-//
-// Protocol (cf. gemm_tc_kernel<.., CTA2>): operand loads of BOTH CTAs complete_tx on the LEADER's full barriers
-// (cp.async.bulk.tensor.cta_group::2); the leader's two MMA warps wait there and on the leader's d1_empty / h_full /
-// d2_empty barriers, which collect arrivals from both CTAs' epilogue warps (remote mbarrier.arrive through mapa);
-// every tcgen05.commit is multicast to the same barrier in both CTAs, where the local producer / epilogue warps wait.
-// Both CTAs walk the same number of units (a missing second tile is all out-of-range rows: TMA zero-fills its loads
-// and clips its stores).
-template <int C>
-struct PairPlan {
-  static constexpr int NJ = (4 * C) / NH;
-  static constexpr int KB = C / 64;                       // 64-column K blocks of the fc1 contraction (C = 256 / 320: no tails)
-  static constexpr int NSPLIT = C > 256 ? 2 : 1;
-  static constexpr int NC = C / NSPLIT;                   // D2 columns per G2 UMMA
-  static constexpr int y_bytes = FM * C * 2;
-  static constexpr int w1_bytes = (NH / 2) * C * 2;       // this CTA's half of a W1 chunk: 32 rows x C
-  static constexpr int w2_bytes = (C / 2) * 128;          // this CTA's half of a W2 chunk: NSPLIT x [NC/2 rows x 64 columns]
-  static constexpr int n1 = 3, n2 = 3;
-  static constexpr int off_w1 = y_bytes;
-  static constexpr int off_w2 = off_w1 + n1 * w1_bytes;
-  static constexpr int off_slab = off_w2 + n2 * w2_bytes;
-  static constexpr int off_bar = off_slab + kEpiWarps2 * 1024;
-  static constexpr int off_b1 = off_bar + 1024;
-  static constexpr int total = off_b1 + 4 * C * 4 + 1024;
-  static_assert(C % 64 == 0 && (NC / 2) % 8 == 0, "whole swizzle atoms per CTA half");
-  static_assert(total <= kSmemMax, "shared-memory plan");
-  static_assert(kD2Col + C + 64 <= 512, "TMEM columns: D1 2 x 64, D2 C, H 2 x 32");
-};
-
-struct MapsPair {
-  CUtensorMap y128;                // [M, C]: box [128 rows x 64 cols], SW128
-  CUtensorMap w1h;                 // W1 [4C, C]: box [32 rows x 64 cols], SW128 (half of a 64-row hidden chunk)
-  CUtensorMap w2h;                 // W2 [C, 4C]: box [NC/2 rows x 64 cols], SW128
-  CUtensorMap r32, o32;            // res / out [M, C]: boxes [32 rows x 16 cols], SW32 (per-warp slabs)
-};
-
-__device__ __forceinline__ void umma_bf16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-template <int C>
-__global__ void __launch_bounds__(kThreads2, 1)
-mlp_pair_kernel(const __grid_constant__ MapsPair tm, const float* __restrict__ b1, const float* __restrict__ b2,
-                const float* __restrict__ gamma, int M) {
-  using namespace tc;
-  using P = PairPlan<C>;
-  constexpr int NJ = P::NJ, KB = P::KB, NSPLIT = P::NSPLIT, NC = P::NC;
-  constexpr int kHCol = kD2Col + C;
-  extern __shared__ unsigned char smem_dyn[];
-  const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  unsigned char* sal = smem_dyn + (sbase - smem_u32(smem_dyn));
-  const uint32_t rank = cluster_ctarank();
-  const int n_clusters = (int)(gridDim.x >> 1), cluster_id = (int)(blockIdx.x >> 1);
-  const int m_tiles = (M + FM - 1) / FM, units = (m_tiles + 1) / 2;
-  const uint32_t nu = cluster_id < units ? (uint32_t)(units - 1 - cluster_id) / (uint32_t)n_clusters + 1u : 0u;
-  const uint32_t total = nu * (uint32_t)NJ;                      // hidden chunks this CTA (pair) processes
-  auto tile_of = [&](uint32_t ul) { return 2 * (cluster_id + (int)ul * n_clusters) + (int)rank; };
-
-  const uint32_t bar0 = sbase + P::off_bar;
-  auto y_full = [&](int i) { return bar0 + 8u * i; };                         // 1   (leader's is used)
-  auto y_empty = [&](int i) { return bar0 + 8u * (2 + i); };                  // 1   local, multicast commit
-  auto d1_full = [&](int i) { return bar0 + 8u * (4 + i); };                  // 2   local, multicast commit
-  auto d1_empty = [&](int i) { return bar0 + 8u * (6 + i); };                 // 2   leader's: 2 x 8 warp arrivals
-  auto h_full = [&](int i) { return bar0 + 8u * (8 + i); };                   // 2   leader's: 2 x 8 warp arrivals
-  auto h_empty = [&](int i) { return bar0 + 8u * (10 + i); };                 // 2   local, multicast commit
-  auto d2_full = [&](int i) { return bar0 + 8u * (12 + i); };                 // 1   local, multicast commit
-  auto d2_empty = [&](int i) { return bar0 + 8u * (14 + i); };                // 1   leader's: 2 x 16 warp arrivals
-  auto w1_full = [&](int i) { return bar0 + 8u * (16 + i); };                 // leader's
-  auto w1_empty = [&](int i) { return bar0 + 8u * (16 + kMaxSlots + i); };    // local, multicast commit
-  auto w2_full = [&](int i) { return bar0 + 8u * (16 + 2 * kMaxSlots + i); };
-  auto w2_empty = [&](int i) { return bar0 + 8u * (16 + 3 * kMaxSlots + i); };
-  auto res_bar = [&](int i) { return bar0 + 8u * (16 + 4 * kMaxSlots + i); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + P::off_bar + 8 * (16 + 4 * kMaxSlots + kEpiWarps2));
-
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tm.y128); tma_prefetch_desc(&tm.w1h); tma_prefetch_desc(&tm.w2h);
-    mbar_init(y_full(0), 1); mbar_init(y_empty(0), 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(d1_full(i), 1); mbar_init(d1_empty(i), kEpiWarps2);           // 8 warps of each CTA
-      mbar_init(h_full(i), kEpiWarps2); mbar_init(h_empty(i), 1);
-    }
-    mbar_init(d2_full(0), 1); mbar_init(d2_empty(0), 2 * kEpiWarps2);
-    for (int i = 0; i < kMaxSlots; ++i) {
-      mbar_init(w1_full(i), 1); mbar_init(w1_empty(i), 1); mbar_init(w2_full(i), 1); mbar_init(w2_empty(i), 1);
-    }
-    for (int i = 0; i < kEpiWarps2; ++i) mbar_init(res_bar(i), 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc_pair(smem_u32((const void*)tmem_slot), 512); tmem_relinquish_pair(); }
-  float* b1s = reinterpret_cast<float*>(sal + P::off_b1);
-  for (int i = threadIdx.x; i < 4 * C; i += kThreads2) b1s[i] = __ldg(b1 + i);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();            // the peer's barriers are initialised before any remote arrive / pair TMA / multicast commit
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ============================== TMA producer: this CTA's y rows and its half of every weight chunk ===============
-    int j1 = 0, s1 = 0; uint32_t ph1 = 0, yph = 0, u1 = 0;
-    int j2 = 0, s2 = 0; uint32_t ph2 = 0;
-    const uint32_t lead_y = mapa_shared(y_full(0), 0);
-    auto load_g1_inputs = [&]() {
-      if (j1 == 0) {
-        const int tile = tile_of(u1);
-        mbar_wait_spin(y_empty(0), yph ^ 1u);
-        if (elect_one()) {
-          if (rank == 0) mbar_expect_tx(y_full(0), (uint32_t)(2 * P::y_bytes));     // both CTAs' rows are counted here
-#pragma unroll
-          for (int kb = 0; kb < KB; ++kb) tma_load_2d_pair(sbase + kb * FM * 128, &tm.y128, lead_y, kb * 64, tile * FM);
-        }
-        __syncwarp();
-        yph ^= 1u;
-      }
-      mbar_wait_spin(w1_empty(s1), ph1 ^ 1u);
-      if (elect_one()) {
-        if (rank == 0) mbar_expect_tx(w1_full(s1), (uint32_t)(2 * P::w1_bytes));
-        const uint32_t lead = mapa_shared(w1_full(s1), 0);
-        const uint32_t dst = sbase + P::off_w1 + s1 * P::w1_bytes;
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d_pair(dst + kb * (NH / 2) * 128, &tm.w1h, lead, kb * 64, j1 * NH + (int)rank * (NH / 2));
-      }
-      __syncwarp();
-      if (++s1 == P::n1) { s1 = 0; ph1 ^= 1u; }
-      if (++j1 == NJ) { j1 = 0; ++u1; }
-    };
-    auto load_w2 = [&]() {
-      mbar_wait_spin(w2_empty(s2), ph2 ^ 1u);
-      if (elect_one()) {
-        if (rank == 0) mbar_expect_tx(w2_full(s2), (uint32_t)(2 * P::w2_bytes));
-        const uint32_t lead = mapa_shared(w2_full(s2), 0);
-#pragma unroll
-        for (int h = 0; h < NSPLIT; ++h)       // rows [h NC + rank NC/2, + NC/2) of W2, hidden columns of chunk j2
-          tma_load_2d_pair(sbase + P::off_w2 + s2 * P::w2_bytes + h * (NC / 2) * 128, &tm.w2h, lead, j2 * NH,
-                           h * NC + (int)rank * (NC / 2));
-      }
-      __syncwarp();
-      if (++s2 == P::n2) { s2 = 0; ph2 ^= 1u; }
-      if (++j2 == NJ) j2 = 0;
-    };
-    if (total > 0) load_g1_inputs();
-    if (total > 1) load_g1_inputs();
-    for (uint32_t g = 0; g < total; ++g) {
-      if (g + 2 < total) load_g1_inputs();
-      load_w2();
-    }
-  } else if ((warp == 1 || warp == kG2Warp) && rank == 0) {
-    // ============================== MMA issuers: the leader CTA only, one warp per GEMM stream ======================
-    constexpr uint32_t idesc1 = idesc_bf16_f32(2 * FM, NH);
-    constexpr uint32_t idesc2 = idesc_bf16_f32(2 * FM, NC);
-    if (warp == 1) {
-      int j1 = 0, s1 = 0, b1i = 0; uint32_t ph1 = 0, yph = 0, dph1 = 0;
-      for (uint32_t n = 0; n < total; ++n) {
-        if (j1 == 0) { mbar_wait_spin(y_full(0), yph); yph ^= 1u; }
-        mbar_wait_spin(w1_full(s1), ph1);
-        mbar_wait_spin(d1_empty(b1i), dph1 ^ 1u);              // both CTAs' epilogue groups have pulled chunk n-2 out of D1[b]
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t wa = sbase + P::off_w1 + s1 * P::w1_bytes;
-          const uint32_t dcol = tmem_base + (uint32_t)(b1i * NH);
-#pragma unroll
-          for (int kb = 0; kb < KB; ++kb) {
-            const uint64_t ad = smem_desc_sw128(sbase + kb * FM * 128), bd = smem_desc_sw128(wa + kb * (NH / 2) * 128);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16_pair(dcol, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc1, (kb | kk) != 0 ? 1u : 0u);
-          }
-          umma_commit_pair(d1_full(b1i));
-          umma_commit_pair(w1_empty(s1));
-          if (j1 == NJ - 1) umma_commit_pair(y_empty(0));
-        }
-        __syncwarp();
-        b1i ^= 1; if (b1i == 0) dph1 ^= 1u;
-        if (++s1 == P::n1) { s1 = 0; ph1 ^= 1u; }
-        if (++j1 == NJ) j1 = 0;
-      }
-    } else {
-      int j2 = 0, s2 = 0, b2i = 0; uint32_t ph2 = 0, hph = 0, d2ph = 0;
-      for (uint32_t n = 0; n < total; ++n) {
-        mbar_wait_spin(w2_full(s2), ph2);
-        if (j2 == 0) mbar_wait_spin(d2_empty(0), d2ph ^ 1u);
-        mbar_wait_spin(h_full(b2i), hph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t bd = smem_desc_sw128(sbase + P::off_w2 + s2 * P::w2_bytes);
-          const uint32_t dcol = tmem_base + (uint32_t)kD2Col;
-          const uint32_t acol = tmem_base + (uint32_t)(kHCol + b2i * 32);
-#pragma unroll
-          for (int kk = 0; kk < NH / 16; ++kk)
-#pragma unroll
-            for (int h = 0; h < NSPLIT; ++h)
-              umma_bf16_ts_pair(dcol + (uint32_t)(h * NC), acol + (uint32_t)(8 * kk),
-                                bd + (uint64_t)(h * (NC / 2) * 8 + 2 * kk), idesc2, (j2 | kk) != 0 ? 1u : 0u);
-          umma_commit_pair(h_empty(b2i));
-          umma_commit_pair(w2_empty(s2));
-          if (j2 == NJ - 1) umma_commit_pair(d2_full(0));
-        }
-        __syncwarp();
-        b2i ^= 1; if (b2i == 0) hph ^= 1u;
-        if (++s2 == P::n2) { s2 = 0; ph2 ^= 1u; }
-        if (++j2 == NJ) { j2 = 0; d2ph ^= 1u; }
-      }
-    }
-  } else if (warp >= 2 && warp < kG2Warp) {
-    // ============================== epilogue warps (2 .. 17), per CTA ==============================
-    const int q = warp & 3;
-    const int k4 = (warp - 2) >> 2;
-    const int grp = k4 & 1;
-    const int half = k4 >> 1;
-    const int r_in_tile = q * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int groups2 = C / 16;
-    constexpr int NU = (groups2 + 3) / 4;
-    const int ew = warp - 2;
-    uint32_t rph = 0;
-    const uint32_t lead_d1e[2] = {mapa_shared(d1_empty(0), 0), mapa_shared(d1_empty(1), 0)};
-    const uint32_t lead_hf[2] = {mapa_shared(h_full(0), 0), mapa_shared(h_full(1), 0)};
-    const uint32_t lead_d2e = mapa_shared(d2_empty(0), 0);
-    (void)r_in_tile;
-
-    // D2 drain through the warp's private 1 KB slab (the single-CTA wide kernel's EP = 2 scheme)
-    auto d2_epilogue = [&](int tile, uint32_t ul) {
-      const uint32_t slab_addr = sbase + P::off_slab + (uint32_t)(ew * 1024);
-      unsigned char* slab = sal + P::off_slab + ew * 1024;
-      const int row0 = tile * FM + q * 32;
-      auto slab_load = [&](int gi) {
-        if (lane == 0) {
-          tma_store_wait_read();
-          mbar_expect_tx(res_bar(ew), 1024u);
-          tma_load_2d(slab_addr, &tm.r32, res_bar(ew), gi * 16, row0);
-        }
-        __syncwarp();
-      };
-      slab_load(k4);
-      mbar_wait_spin(d2_full(0), ul & 1u);
-      tc_fence_after();
-      const int xr = (lane >> 2) & 1;
-      uint4* p0 = reinterpret_cast<uint4*>(slab + lane * 32 + ((0 ^ xr) << 4));
-      uint4* p1 = reinterpret_cast<uint4*>(slab + lane * 32 + ((1 ^ xr) << 4));
-#pragma unroll
-      for (int u = 0; u < NU; ++u) {
-        const int gi = k4 + 4 * u;
-        if (gi >= groups2) break;
-        uint32_t r[16];
-        tmem_ld16(lane_addr + (uint32_t)(kD2Col + gi * 16), r);
-        tmem_ld_wait();
-        if (gi + 4 >= groups2) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(lead_d2e);
-        }
-        mbar_wait_spin(res_bar(ew), rph); rph ^= 1u;
-        const uint4 r0 = *p0, r1 = *p1;
-        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-        const int n = gi * 16;
-        float v[16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
-          v[i] = fmaf(g4.x, __uint_as_float(r[i]) + b4.x, bf16_lo(rr[i / 2]));
-          v[i + 1] = fmaf(g4.y, __uint_as_float(r[i + 1]) + b4.y, bf16_hi(rr[i / 2]));
-          v[i + 2] = fmaf(g4.z, __uint_as_float(r[i + 2]) + b4.z, bf16_lo(rr[i / 2 + 1]));
-          v[i + 3] = fmaf(g4.w, __uint_as_float(r[i + 3]) + b4.w, bf16_hi(rr[i / 2 + 1]));
-        }
-        *p0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        *p1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&tm.o32, slab_addr, gi * 16, row0);
-          tma_store_commit();
-        }
-        if (gi + 4 < groups2) slab_load(gi + 4);
-      }
-    };
-
-    int pend_ul = -1;
-    uint32_t prev_ul = 0xffffffffu;
-    for (uint32_t g = (uint32_t)grp; g < total; g += 2) {
-      const uint32_t ul = g / (uint32_t)NJ; const int j = (int)(g - ul * NJ);
-      const uint32_t use = g >> 1;
-      if (ul != prev_ul) {
-        if (prev_ul != 0xffffffffu) pend_ul = (int)prev_ul;       // previous unit's D2 drain: deferred behind this chunk's GELU
-        prev_ul = ul;
-      }
-      mbar_wait_spin(d1_full(grp), use & 1u);
-      tc_fence_after();
-      uint32_t r[32];
-      tmem_ld32(lane_addr + (uint32_t)(grp * NH + half * 32), r);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_d1e[grp]);
-      const int hcol = j * NH + half * 32;
-      uint32_t o[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
-        const float2 g0 = unpack_f32x2(gelu_fast2(add_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
-                                                             pack_f32x2(b4.x, b4.y))));
-        const float2 g1 = unpack_f32x2(gelu_fast2(add_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
-                                                             pack_f32x2(b4.z, b4.w))));
-        o[i / 2] = pack_bf16x2(g0.x, g0.y);
-        o[i / 2 + 1] = pack_bf16x2(g1.x, g1.y);
-      }
-      mbar_wait_spin(h_empty(grp), (use & 1u) ^ 1u);
-      tmem_st16(lane_addr + (uint32_t)(kHCol + grp * 32 + half * 16), o);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_hf[grp]);
-      if (pend_ul >= 0) {
-        d2_epilogue(tile_of((uint32_t)pend_ul), (uint32_t)pend_ul);
-        pend_ul = -1;
-      }
-    }
-    if (nu > 0) {
-      d2_epilogue(tile_of(nu - 1), nu - 1);
-      if (lane == 0) tma_store_wait_all();
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();            // no CTA leaves (and frees its TMEM / barriers) while its peer may still signal it
-  if (warp == 1) { tc_fence_after(); tmem_dealloc_pair(tmem_base, 512); }
-}
+// A CTA-pair variant of the wide kernel (cta_group::2: one M = 256 UMMA per step issued by the leader, each CTA staging
+// half of every W1 / W2 chunk, remote mbarrier arrivals from both CTAs' GELU warps, multicast commits) was written and
+// is parity-green on every kernel and model test (git history: "CTA-pair (cta_group::2) wide fused MLP"), but measured
+// 128 us against 129 us per launch at C = 320 (profiles/r02e): halving the L2 -> SM weight stream changes nothing, so the
+// steady state is NOT bound by that stream but by shared-memory operand reads (G1 re-reads the 80 KB y tile for every
+// 64-column hidden chunk: 48 clk per N = 64 UMMA instead of 32) plus the tile-boundary drain.  Removed again.
 
 static long long* g_mlp_trace = nullptr;    // debugging only (btsb_debug_mlp_trace); caller-owned device buffer
 
@@ -1063,42 +725,9 @@ static int launch2(const Maps2& tm, const float* b1, const float* b2, const floa
 }
 
 
-template <int C>
-static int launch_pair(const void* y, const void* res, const void* W1, const float* b1, const void* W2, const float* b2,
-                       const float* gamma, void* out, int64_t M, cudaStream_t st) {
-  using P = PairPlan<C>;
-  MapsPair tm;
-  memset(&tm, 0, sizeof(tm));
-  if (int e = make_tmap_bf16_2d_sw(&tm.y128, y, (uint64_t)M, (uint64_t)C, FM, 64, 128)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.w1h, W1, (uint64_t)(4 * C), (uint64_t)C, NH / 2, 64, 128)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.w2h, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)(P::NC / 2), 64, 128)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.r32, res, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
-  auto kern = mlp_pair_kernel<C>;
-  BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_pair attr");
-  const int m_tiles = (int)((M + FM - 1) / FM), units = (m_tiles + 1) / 2;
-  const int clusters = min(units, num_sms() / 2);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(2 * clusters));
-  cfg.blockDim = dim3(kThreads2);
-  cfg.dynamicSmemBytes = P::total;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  BTSB_CUDA(cudaLaunchKernelEx(&cfg, kern, tm, b1, b2, gamma, (int)M), "mlp_pair launch");
-  return launch_done("mlp_pair");
-}
-
 int mlp_fused2_launch(const void* y, const void* res, const void* W1, const float* b1, const void* W2, const float* b2,
                       const float* gamma, void* out, int64_t M, int C, cudaStream_t st) {
   BTSB_REQUIRE(mlp_fused2_supported(C), "mlp_fused: C=%d unsupported", C);
-  // BTSB_MLP_PAIR=1: CTA-pair variant of the wide kernel (opt-in until measured)
-  static const int pair = [] { const char* e = getenv("BTSB_MLP_PAIR"); return e ? atoi(e) : 0; }();
-  if (pair && C == 320) return launch_pair<320>(y, res, W1, b1, W2, b2, gamma, out, M, st);
-  if (pair && C == 256) return launch_pair<256>(y, res, W1, b1, W2, b2, gamma, out, M, st);
   const int t32 = (C % 64) >= 32, t16 = (C % 32) >= 16;
   Maps2 tm;
   memset(&tm, 0, sizeof(tm));
