@@ -27,8 +27,9 @@ A "step" is one forward pass of every rank over one micro-batch of B alerts ([B,
 Sub-records of the default line (same N, a few seconds each; `--no-extras` skips them):
   c5   : BASELINE configs[4], one TRAINING step (zero_grad, forward, BCE, backward, AdamW; train.py:496-547) of
          mm_ConvNeXt-nano on 1024 alerts per GPU in mixed precision, CUDA-graph replay, NCCL bucket all-reduce on a side
-         stream inside the graph: value, ms_per_step, e2e, allreduce_ms (the buckets alone), compute_ms (the same step
-         with the collectives switched off), overlap_frac = 1 - (ms_per_step - compute_ms) / allreduce_ms
+         stream inside the graph: value, ms_per_step, e2e; for N > 1 also allreduce_ms (the buckets alone), compute_ms (the
+         same step of an un-wrapped replica, no collectives), exposed_ms = ms_per_step - compute_ms and
+         overlap_frac = 1 - exposed_ms / allreduce_ms
   c4   : BASELINE configs[3], multimodal MaxViT-tiny-rw-224, batch 4096 per GPU, bf16
   c2   : BASELINE configs[1], image-only ConvNeXt-nano, batch 1024 per GPU
   fp32 : C3 in the package's default precision (the 1e-4 mode)
@@ -667,7 +668,10 @@ def bench_train(ctx, precision: str, B: int, steps: int, warmup: int, use_graph:
         e2e_step(i)
     ms_e2e = timed(e2e_step, steps)
 
-    # ---- the collective alone, and the step without it (N > 1): how much of the all-reduce hides behind the backward
+    # ---- the collective alone, and the step without it (N > 1): how much of the all-reduce hides behind the backward.
+    # The collective-free step is a SECOND model replica without the DistributedDataParallel wrapper (no gradient sink, no
+    # side stream), captured and replayed exactly like the single-GPU step.  (Capturing the wrapped model again with its
+    # collectives switched off made the capturing stream wait on the un-captured side stream and hung the 2-GPU run.)
     comm = None
     if world > 1:
         sink = ddp.sink
@@ -681,23 +685,25 @@ def bench_train(ctx, precision: str, B: int, steps: int, warmup: int, use_graph:
             ar_only(i)
         ms_ar = timed(ar_only, 10) / 10
         sink.flat.copy_(keep)
-        sink.comm = False
-        try:
-            if use_graph:
-                quiet = GraphedTrainStep(ddp, opt, loss_fn, example=res[0], warmup=1)
-                qstep = lambda i: quiet(*res[i % nres])
-            else:
-                qstep = step
+        ms_solo = None
+        if use_graph and os.environ.get("BTSB_BENCH_SOLO", "1") != "0":
+            solo_model = getattr(btsbot, wl["model"])(cfg)
+            solo_model.load_state_dict(synth.to_torch(sd_np), strict=True)
+            solo_model = solo_model.to(dev).train()
+            solo_opt = FusedAdamW(solo_model.parameters(), lr=1e-4, betas=(0.9, 0.999), capturable=True)
+            solo = GraphedTrainStep(solo_model, solo_opt, loss_fn, example=res[0], warmup=2)
             for i in range(2):
-                qstep(i)
-            ms_quiet = timed(qstep, steps) / steps
-            if use_graph:
-                quiet.release()
-        finally:
-            sink.comm = True
-        ms_quiet, ms_ar = ctx.max_over_ranks(ms_quiet, ms_ar)
-        comm = {"allreduce_ms": ms_ar, "compute_ms": ms_quiet, "payload_bytes": int(sink.total * 4),
-                "buckets": len(sink.bounds), "bucket_mb": 8.0, "payload_dtype": "fp32",
+                solo(*res[i % nres])
+            ms_solo = timed(lambda i: solo(*res[i % nres]), steps) / steps
+            solo.release()
+            del solo, solo_opt, solo_model
+            (ms_solo,) = ctx.max_over_ranks(ms_solo)
+        (ms_ar,) = ctx.max_over_ranks(ms_ar)
+        comm = {"allreduce_ms": ms_ar, "compute_ms": ms_solo,
+                "how": "allreduce_ms: the step's 8 MB gradient buckets all-reduced back to back with nothing else running; "
+                       "compute_ms: the same step of an un-wrapped replica (no collectives), CUDA-graph replay, same rank",
+                "payload_bytes": int(sink.total * 4), "buckets": len(sink.bounds), "bucket_mb": 8.0,
+                "payload_dtype": "fp32",
                 "algo": os.environ.get("NCCL_ALGO", "nccl default (NVLS / ring chosen by NCCL; see NCCL_DEBUG=INFO)")}
 
     kern = None
@@ -710,10 +716,12 @@ def bench_train(ctx, precision: str, B: int, steps: int, warmup: int, use_graph:
         _lib.profiler = None
         kern = prof.summary()
     ms, ms_e2e = ctx.max_over_ranks(ms, ms_e2e)
-    if comm is not None:
-        exposed = max(0.0, ms / steps - comm["compute_ms"])
+    if comm is not None and comm["compute_ms"] is not None:
+        exposed = max(0.0, ms / steps - comm["compute_ms"])          # what the collectives add to the replayed step
         comm["exposed_ms"] = exposed
         comm["overlap_frac"] = float(min(1.0, max(0.0, 1.0 - exposed / comm["allreduce_ms"]))) if comm["allreduce_ms"] > 0 else None
+    elif comm is not None:
+        comm["exposed_ms"] = comm["overlap_frac"] = None
     if stepper is not None:
         stepper.release()                       # a graph that captured NCCL work must go before its communicator
     out = {"wl": wl, "cfg": cfg, "sd_np": sd_np, "B": B, "steps": steps, "warmup": warm, "ms": ms, "ms_e2e": ms_e2e,
@@ -926,70 +934,86 @@ def main():
         dist.init_process_group("nccl", device_id=ctx.dev)
     pk = peaks()
     threads = os.cpu_count() or 1
+    # No try/finally around this: after an exception the process group must NOT be torn down (a CUDA graph that captured
+    # NCCL work has to be destroyed before its communicator, and on the failure path nobody does that in order -- the
+    # __main__ guard prints the traceback and leaves at once).
+    run_b200(args, ctx, pk, threads)
+    if ctx.world > 1 and dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def run_b200(args, ctx, pk, threads):
     head = args.workload
     extras_on = not args.no_extras
-    try:
-        if head == "c5":
-            r = bench_train(ctx, args.precision, args.batch, args.steps, args.warmup, use_graph=not args.no_graph)
-            if ctx.rank == 0:
-                cpu = None
-                if not args.no_cpu_baseline:
-                    rate, dt, _ = cpu_train_port(args.cpu_sample, dict(r["cfg"]), r["sd_np"], threads)
-                    cpu = {"value": rate, "unit": "alerts/s", "cores": threads, "kind": "port",
-                           "sample": f"{args.cpu_sample} synthetic alerts in training steps of 64 ({dt:.1f} s): CPU oracle fp32 + "
-                                     f"torch autograd + torch.optim.AdamW, torch {torch.__version__}, {threads} threads"}
-                print(json.dumps(train_line(args, ctx, r, pk, cpu)), flush=True)
-            return
+    if head == "c5":
+        r = bench_train(ctx, args.precision, args.batch, args.steps, args.warmup, use_graph=not args.no_graph)
+        if ctx.rank == 0:
+            cpu = None
+            if not args.no_cpu_baseline:
+                rate, dt, _ = cpu_train_port(args.cpu_sample, dict(r["cfg"]), r["sd_np"], threads)
+                cpu = {"value": rate, "unit": "alerts/s", "cores": threads, "kind": "port",
+                       "sample": f"{args.cpu_sample} synthetic alerts in training steps of 64 ({dt:.1f} s): CPU oracle fp32 + "
+                                 f"torch autograd + torch.optim.AdamW, torch {torch.__version__}, {threads} threads"}
+            print(json.dumps(train_line(args, ctx, r, pk, cpu)), flush=True)
+        return
 
-        # NUMA: allocate the pinned host batches next to this rank's GPU (restored before the CPU baseline leg)
-        from btsbot_b200.parallel import bind_to_device_numa
-        prev_affinity = bind_to_device_numa(ctx.local_rank)
-        r = bench_infer(ctx, head, args.precision, args.batch, args.steps, args.warmup, profile=True,
-                        sustained_alerts=args.alerts if head == "c3" else 0, pcie=True)
-        extras = {"numa_bound": prev_affinity is not None}
-        if extras_on and head == "c3":
-            # every rank runs the same sequence (C5 has collectives); a few seconds each
-            sub_c5 = bench_train(ctx, "bf16", WORKLOADS["c5"]["batch"], 10, 3, profile=False)
-            sub_c4 = bench_infer(ctx, "c4", "bf16", WORKLOADS["c4"]["batch"], 3, 3, profile=False)
-            sub_c2 = bench_infer(ctx, "c2", args.precision, WORKLOADS["c2"]["batch"], 20, 3, profile=False)
-            sub_fp32 = bench_infer(ctx, "c3", "fp32", args.batch, 5, 3, profile=False) if args.precision != "fp32" else None
-            extras["c5"] = train_compact(sub_c5, ctx)
-            extras["c4"] = compact(sub_c4, ctx)
-            extras["c2"] = compact(sub_c2, ctx)
-            if sub_fp32 is not None:
-                extras["fp32"] = compact(sub_fp32, ctx)
-        if ctx.rank != 0:
-            return
-        if prev_affinity is not None:
-            os.sched_setaffinity(0, prev_affinity)              # the CPU legs use every host core
-        line = infer_line(args, ctx, r, pk, extras)
-        if extras_on and ctx.world == 1 and head in ("c3", "c2"):
-            lib = gpu_library_baseline(ctx.dev, head, args.batch)
-            line["gpu_library_baseline"] = lib
-            if head == "c3":
-                tab = library_kernel_table(ctx.dev, args.batch)
-                for name, k in line["kernels"].items():
-                    if name in tab:
-                        k["library_ms"] = tab[name]
-                        k["vs_library"] = tab[name] / k["ms_per_launch"]
-                lib["kernel_table_note"] = ("kernels[*].library_ms = the equivalent eager library ops (cuDNN conv, cuBLASLt "
-                                            "GEMM, ATen LayerNorm/GELU; bf16, channels_last) at the same shapes; vs_library = "
-                                            "library_ms / ms_per_launch (> 1: this repo's kernel is faster)")
-                best = max(lib[k]["value"] for k in ("fp32_tf32_off", "fp32_tf32_on", "bf16_autocast_channels_last"))
-                lib["value_over_best_library"] = line["value"] / best
-        cpu = None
-        if not args.no_cpu_baseline:
-            rate, dt, workers = cpu_port(args.cpu_sample, dict(r["cfg"]), r["sd_np"], threads)
-            cpu = {"value": rate, "unit": "alerts/s", "cores": threads, "kind": "port",
-                   "sample": f"{args.cpu_sample} synthetic alerts in batches of 64, DataLoader num_workers={workers} "
-                             f"({dt:.1f} s), CPU oracle fp32, torch {torch.__version__}, {threads} threads",
-                   "example_alerts_c1": cpu_example_alerts(threads) if head == "c3" else None}
-        line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
-    finally:
-        if ctx.world > 1 and dist.is_initialized():
-            dist.destroy_process_group()
+    # NUMA: allocate the pinned host batches next to this rank's GPU (restored before the CPU baseline leg)
+    from btsbot_b200.parallel import bind_to_device_numa
+    prev_affinity = bind_to_device_numa(ctx.local_rank)
+    r = bench_infer(ctx, head, args.precision, args.batch, args.steps, args.warmup, profile=True,
+                    sustained_alerts=args.alerts if head == "c3" else 0, pcie=True)
+    extras = {"numa_bound": prev_affinity is not None}
+    if extras_on and head == "c3":
+        # every rank runs the same sequence (C5 has collectives); a few seconds each
+        sub_c5 = bench_train(ctx, "bf16", WORKLOADS["c5"]["batch"], 10, 3, profile=False)
+        sub_c4 = bench_infer(ctx, "c4", "bf16", WORKLOADS["c4"]["batch"], 3, 3, profile=False)
+        sub_c2 = bench_infer(ctx, "c2", args.precision, WORKLOADS["c2"]["batch"], 20, 3, profile=False)
+        sub_fp32 = bench_infer(ctx, "c3", "fp32", args.batch, 5, 3, profile=False) if args.precision != "fp32" else None
+        extras["c5"] = train_compact(sub_c5, ctx)
+        extras["c4"] = compact(sub_c4, ctx)
+        extras["c2"] = compact(sub_c2, ctx)
+        if sub_fp32 is not None:
+            extras["fp32"] = compact(sub_fp32, ctx)
+    if ctx.rank != 0:
+        return
+    if prev_affinity is not None:
+        os.sched_setaffinity(0, prev_affinity)              # the CPU legs use every host core
+    line = infer_line(args, ctx, r, pk, extras)
+    if extras_on and ctx.world == 1 and head in ("c3", "c2"):
+        lib = gpu_library_baseline(ctx.dev, head, args.batch)
+        line["gpu_library_baseline"] = lib
+        if head == "c3":
+            tab = library_kernel_table(ctx.dev, args.batch)
+            for name, k in line["kernels"].items():
+                if name in tab:
+                    k["library_ms"] = tab[name]
+                    k["vs_library"] = tab[name] / k["ms_per_launch"]
+            lib["kernel_table_note"] = ("kernels[*].library_ms = the equivalent eager library ops (cuDNN conv, cuBLASLt "
+                                        "GEMM, ATen LayerNorm/GELU; bf16, channels_last) at the same shapes; vs_library = "
+                                        "library_ms / ms_per_launch (> 1: this repo's kernel is faster)")
+            best = max(lib[k]["value"] for k in ("fp32_tf32_off", "fp32_tf32_on", "bf16_autocast_channels_last"))
+            lib["value_over_best_library"] = line["value"] / best
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, dt, workers = cpu_port(args.cpu_sample, dict(r["cfg"]), r["sd_np"], threads)
+        cpu = {"value": rate, "unit": "alerts/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_sample} synthetic alerts in batches of 64, DataLoader num_workers={workers} "
+                         f"({dt:.1f} s), CPU oracle fp32, torch {torch.__version__}, {threads} threads",
+               "example_alerts_c1": cpu_example_alerts(threads) if head == "c3" else None}
+    line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as exc:                 # noqa: BLE001
+        if isinstance(exc, SystemExit) and exc.code in (0, None):
+            raise
+        # a CUDA graph that captured NCCL work must be destroyed before its communicator; after an exception nobody does
+        # that in order, and interpreter teardown then hangs in NCCL -- leave at once instead (torchrun reaps the peers)
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        os._exit(1)

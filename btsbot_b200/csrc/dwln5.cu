@@ -11,8 +11,6 @@
 //   the bf16 rows to global.
 // Hand-off through two mbarriers (tile full: one arrival per conv warp; tile empty: one per LayerNorm warp); the conv
 // warps synchronise among themselves with a named barrier only.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace btsb {
@@ -240,13 +238,11 @@ int dwln_bf16_v5(const void* x, int64_t B, int H, int W, int C, const float* w, 
   if (((uintptr_t)x % 16) != 0 || ((uintptr_t)out % 16) != 0) return 1;
   if (H == 15 && C == 80) return launch_dwln5<15, 80>(x, B, w, bias, ln_w, ln_b, out, st);
   if (H == 7 && C == 160) return launch_dwln5<7, 160>(x, B, w, bias, ln_w, ln_b, out, st);
-  // The pico widths (64 / 128) are instantiated and parity-green per kernel, but stay on v3 unless BTSB_DWLN5_PICO=1: the
-  // synthetic frozen-fusion/pico parity case is the one model whose bf16 logit error sits near the 2e-2 bar (1.34e-2 with
-  // v3's summation order, 2.35e-2 with this kernel's, one- or two-pass variance alike -- rounding noise amplified by that
-  // head, while every other model moved by < 1e-3 in either direction).
-  static const bool pico = getenv("BTSB_DWLN5_PICO") && atoi(getenv("BTSB_DWLN5_PICO")) != 0;
-  if (pico && H == 15 && C == 64) return launch_dwln5<15, 64>(x, B, w, bias, ln_w, ln_b, out, st);
-  if (pico && H == 7 && C == 128) return launch_dwln5<7, 128>(x, B, w, bias, ln_w, ln_b, out, st);
+  // The pico widths (64 / 128) stay on v3 (dwln3.cu).  This kernel is parity-green for them per kernel, and every model
+  // moved by < 1e-3 when it was tried -- except the synthetic frozen-fusion / pico case, whose bf16 logit error went from
+  // 1.34e-2 (v3's summation order of the LayerNorm statistics) to 2.35e-2, across the 2e-2 bar: the two kernels differ
+  // only in fp32 summation order, i.e. by an occasional last bf16 bit per activation, which that model's head amplifies.
+  // Its bf16 error is a noise level of ~1.5-2.5e-2, not a kernel defect; the dispatch keeps the order the goldens pass with.
   return 1;
 }
 

@@ -3,6 +3,8 @@
 // squeeze-excitation pooling, SE gate, gate scaling, row LayerNorm, 7x7 window / grid attention with relative-position
 // bias, final LayerNorm + average pool.  Activations are NHWC pixel rows [B*H*W, C] (float32 or bf16, fp32 math).
 // Contracts and reference citations: include/btsbot_b200.h.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace btsb {
@@ -425,6 +427,8 @@ int maxvit_scale_bf16(void* x, const float* gate, int64_t B, int HW, int C, cuda
 int maxvit_avgpool2_bf16(const void* x, void* out, int64_t B, int H, int W, int C, cudaStream_t st);
 int maxvit_attn_bf16_mma(const void* qkv, void* out, int64_t B, int H, int W, int C, int grid_mode, const float* table,
                          cudaStream_t st);
+int maxvit_attn_bf16_tc(const void* qkv, void* out, int64_t B, int H, int W, int C, int grid_mode, const float* table,
+                        cudaStream_t st);
 }
 using namespace btsb;
 
@@ -559,7 +563,12 @@ extern "C" int btsb_maxvit_attn_fwd(const void* qkv, void* out, int64_t B, int H
   const int64_t nwin = B * (H / kWin) * (W / kWin);
   BTSB_REQUIRE(nwin < (1ll << 31), "maxvit attn: too many windows");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == BTSB_BF16) return maxvit_attn_bf16_mma(qkv, out, B, H, W, C, grid_mode, table, st);   // tensor cores
+  if (dtype == BTSB_BF16) {
+    // tcgen05 / TMEM kernel (maxvit_attn_tc.cu); BTSB_ATTN_MMA=1 keeps the mma.sync kernel for A/B timing
+    static const bool legacy = getenv("BTSB_ATTN_MMA") && atoi(getenv("BTSB_ATTN_MMA")) != 0;
+    return legacy ? maxvit_attn_bf16_mma(qkv, out, B, H, W, C, grid_mode, table, st)
+                  : maxvit_attn_bf16_tc(qkv, out, B, H, W, C, grid_mode, table, st);
+  }
   dim3 grid((unsigned)nwin, C / kDh);
   const float scale = 0.17677669529663687f;   // dim_head ** -0.5
   MV_DISPATCH(dtype,

@@ -51,13 +51,9 @@ crop_norm_kernel(const T* __restrict__ in, int s, int margin, int normalize, int
   const int ss = s * s;
   float* dst = out + a * (int64_t)(3 * ss);
   double nd[3] = {1.0, 1.0, 1.0};
-  float nf[3] = {1.0f, 1.0f, 1.0f};
   if (normalize) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      nd[c] = sqrt(nrm_s[c]);
-      nf[c] = sqrtf((float)nrm_s[c]);   // numpy: float32 dot then float32 sqrt
-    }
+    for (int c = 0; c < 3; ++c) nd[c] = sqrt(nrm_s[c]);
   }
   // i walks the OUTPUT linearly (coalesced stores); NCHW: i = c*ss + p, NHWC: i = p*3 + c
   for (int i = tid; i < 3 * ss; i += kPreThreads) {
@@ -66,12 +62,10 @@ crop_norm_kernel(const T* __restrict__ in, int s, int margin, int normalize, int
     const int y = p / s, x = p - y * s;
     const T v = tile[((y + margin) * kImg + (x + margin)) * 3 + c];
     const double ndc = c == 0 ? nd[0] : (c == 1 ? nd[1] : nd[2]);
-    const float nfc = c == 0 ? nf[0] : (c == 1 ? nf[1] : nf[2]);
-    float o;
-    if (!normalize) o = (float)v;
-    else if (sizeof(T) == 8) o = (float)((double)v / ndc);
-    else o = (float)v / nfc;
-    dst[i] = o;
+    // x / ||x||_2 from the float64 sum of squares, rounded once: within 1 ulp(fp32) of the exact quotient for either
+    // input dtype (the reference's float32 path -- numpy's float32 BLAS dot + sqrt, alert_utils.py:75-76 -- has no
+    // defined summation order and is itself up to ~1.5 ulp away from it)
+    dst[i] = normalize ? (float)((double)v / ndc) : (float)v;
   }
 }
 

@@ -173,6 +173,7 @@ class GradSink:
         self.launched_buckets = []
         self.in_flush = False
         self.early = 0
+        self.side_used = False          # a collective was issued on the side stream in this step
 
     def view(self, p):
         a = self.offset[id(p)]
@@ -205,6 +206,7 @@ class GradSink:
         lo, hi = self.bounds[i]
         chunk = self.flat[lo:hi]
         if self.cuda:
+            self.side_used = True
             self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.pg)
@@ -216,8 +218,8 @@ class GradSink:
         self.in_flush = True
         for i in range(len(self.bounds)):
             self._launch(i)
-        if self.cuda and _world()[1] > 1:                 # nothing ran on the side stream in a single-process job
-            torch.cuda.current_stream().wait_stream(self.stream)
+        if self.cuda and self.side_used:                  # join the side stream only if this step forked work into it (a
+            torch.cuda.current_stream().wait_stream(self.stream)   # capturing stream must not wait on uncaptured work)
         for h, chunk, world in self.handles:
             h.wait()
             chunk.div_(world)

@@ -7,10 +7,10 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=index,name --format=csv,noheader > $OUT/gpus.txt 2>&1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
-timeout 600 $TR tests/ddp_check.py > $OUT/ddp_check.log 2>&1; echo "ddp_check rc=$?"; tail -n 2 $OUT/ddp_check.log
-NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL timeout 900 $TR bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_default.log 2> $OUT/bench_default.err; echo "bench default rc=$?"
+timeout 240 $TR tests/ddp_check.py > $OUT/ddp_check.log 2>&1; echo "ddp_check rc=$?"; tail -n 2 $OUT/ddp_check.log
+NCCL_DEBUG=INFO NCCL_DEBUG_SUBSYS=INIT,COLL timeout 360 $TR bench.py --gpus $N --steps 20 --warmup 5 > $OUT/bench_default.log 2> $OUT/bench_default.err; echo "bench default rc=$?"
 grep -E "NVLS|Ring|Tree|nranks|comm 0x" $OUT/bench_default.log $OUT/bench_default.err | grep -m 12 -E "NVLS|Connected|Channel 00|nranks" | cut -c1-200 > $OUT/nccl_lines.txt
-timeout 600 $TR bench.py --gpus $N --workload c5 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_c5.log 2>$OUT/bench_c5.err; echo "bench c5 rc=$?"
+timeout 240 $TR bench.py --gpus $N --workload c5 --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_c5.log 2>$OUT/bench_c5.err; echo "bench c5 rc=$?"
 python - $OUT <<'PY'
 import json, sys
 out = sys.argv[1]

@@ -223,6 +223,14 @@ def test_bf16_logits_match_reference(cuda_dev, golden_mv, example_inputs, case):
     print(f"[parity] {case} bf16: gain-1 max|err|={err1:.3e} ({int(sure.sum())}/{sure.size} labels compared); "
           f"gain-{gain:.0f} max|err|={err2:.3e} (bar {2e-2 * gain:.2e})")
     assert err2 < 2e-2 * max(1.0, gain)
+    # every alert takes part: labels may only flip where the reference logit is smaller than the measured error, and the
+    # logits must follow the reference's ordering (the image-only model's spread is inside the tolerance band)
+    ref2 = golden_mv[case]
+    flips = (got2 > 0) != (ref2 > 0)
+    corr = float(np.corrcoef(got2[:, 0], ref2[:, 0])[0, 1])
+    print(f"[parity] {case} bf16: {int(flips.sum())}/{flips.size} labels differ over all alerts, corr {corr:.5f}")
+    assert not flips.any() or float(np.abs(ref2[flips]).max()) <= err2
+    assert flips.mean() <= 0.15 and corr > 0.99
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

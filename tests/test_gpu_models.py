@@ -88,6 +88,15 @@ def test_bf16_logits_match_reference(cuda_dev, golden_logits, golden_batch, case
           f"gain-{gain:.1f} max|err|={err2:.3e} (bar {tol2:.2e}, {int(sure2.sum())}/{sure2.size} labels compared)")
     assert err2 < tol2
     assert np.array_equal((got2 > 0)[sure2], (ref > 0)[sure2])
+    # The tolerance band can swallow most of a random-weight model's logit spread (img_pico: 8 of 64 alerts outside it), so
+    # the label check above is backed by two that use EVERY alert: a label may only flip where the reference logit is
+    # closer to 0 than the error actually measured, and the logits must track the reference's ordering.
+    flips = (got2 > 0) != (ref > 0)
+    corr = float(np.corrcoef(got2[:, 0], ref[:, 0])[0, 1])
+    print(f"[parity] {case} bf16: {int(flips.sum())}/{flips.size} labels differ over all alerts, "
+          f"max |ref logit| among them {float(np.abs(ref[flips]).max()) if flips.any() else 0.0:.2e}, corr {corr:.5f}")
+    assert not flips.any() or float(np.abs(ref[flips]).max()) <= err2
+    assert flips.mean() <= 0.1 and corr > 0.98          # img_pico: logit spread only ~6x the bf16 error -> corr 0.985
 
 
 @pytest.mark.parametrize("kind", ["convnext_nano.d1h_in1k", "convnext_pico.d1_in1k"])

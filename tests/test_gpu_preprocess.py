@@ -32,7 +32,16 @@ def test_crop_triplets_matches_reference(cuda_dev, golden_pre, s, dt):
     assert got.shape == ref.shape == (2, s, s, 3) and got.dtype == np.float64
     assert np.array_equal(t, keep)                       # input not mutated
     d = _ulp_diff(got, ref.astype(np.float32))
-    print(f"[parity] crop s={s} {dt}: max ulp diff {d}")
+    # The correctly rounded quotient x / ||x||_2 (norm from a float64 sum of squares) is the bar every value must meet
+    # within 1 ulp.  For float32 input the reference's own norm is numpy's float32 BLAS dot + float32 sqrt
+    # (alert_utils.py:75-76): its summation order is not defined and it sits up to a few ulp away from the exact norm, so
+    # against THAT golden the floor is 2 ulp -- one from the norm, one from the division -- while the indexing stays exact.
+    m = (63 - s) // 2
+    crop = keep[:, m:m + s, m:m + s, :].astype(np.float64)
+    exact = (crop / np.sqrt((crop ** 2).sum(axis=(1, 2), keepdims=True))).astype(np.float32)
+    d_exact = _ulp_diff(got, exact)
+    print(f"[parity] crop s={s} {dt}: max ulp diff {d} vs the reference-made golden, {d_exact} vs the exactly rounded quotient")
+    assert d_exact <= 1
     assert d <= (1 if dt == "f64" else 2)
     # fused model-input form: same values, NCHW float32, left on the device
     x = au.triplets_to_model_input(keep, s, normalize=True)
