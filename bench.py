@@ -62,8 +62,9 @@ ALERT_IN_BYTES = 63 * 63 * 3 * 4 + 25 * 4
 WORKLOADS = {
     "c3": dict(model="mm_ConvNeXt", kind="convnext_nano.d1h_in1k", batch=8192, cpu_sample=8192,
                label="C3 multimodal ConvNeXt-nano bulk scoring, 63x63x3 triplet + 25 metadata per alert"),
-    "c2": dict(model="ConvNeXt", kind="convnext_nano.d1h_in1k", batch=1024, cpu_sample=1024,
-               label="C2 image-only ConvNeXt-nano scoring, 63x63x3 triplet per alert, batch 1024"),
+    "c2": dict(model="ConvNeXt", kind="convnext_nano.d1h_in1k", batch=1024, cpu_sample=1024, graph=True,
+               label="C2 image-only ConvNeXt-nano scoring, 63x63x3 triplet per alert, batch 1024 "
+                     "(forward replayed as one CUDA graph: config infer_cuda_graph)"),
     "c4": dict(model="mm_MaxViT", kind="maxvit_tiny_rw_224.sw_in1k", batch=4096, cpu_sample=64,
                label="C4 multimodal MaxViT-tiny-rw-224 scoring (bilinear 63->224, MBConv, window+grid attention), "
                      "63x63x3 triplet + 25 metadata per alert"),
@@ -411,10 +412,13 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
     wl = WORKLOADS[wl_name]
     multimodal = wl["model"].startswith("mm_")
     cfg = dict(synth.canonical_config(wl["model"], wl["kind"]), precision=precision)
+    if wl.get("graph") and os.environ.get("BTSB_BENCH_GRAPH", "1") != "0":
+        cfg["infer_cuda_graph"] = True                       # small batch: the host paces ~40 launches per forward
     sd_np = synth.make_state_dict(cfg, seed=2)
     model = getattr(btsbot, wl["model"])(cfg)
     model.load_state_dict(synth.to_torch(sd_np), strict=True)
     model = model.to(ctx.dev).eval()
+    from btsbot_b200 import _engine
 
     # ---- synthetic inputs: a pool of unique index-keyed alerts for this rank's shard, tiled on device ----------
     pool = min(2048, max(256, B))
@@ -450,7 +454,7 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
     if ctx.rank == 0:
         sampler.start()
     # ---- timed region: exactly K steps, device-resident inputs -------------------------------------------------
-    n0 = _lib.launch_count()
+    n0 = _lib.launch_count() + _engine.graph_replay_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.barrier()
     e0.record()
@@ -458,7 +462,7 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
         step(i)
     e1.record()
     ctx.barrier()
-    launches = _lib.launch_count() - n0
+    launches = _lib.launch_count() + _engine.graph_replay_launches() - n0      # host-issued + replayed kernels
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if ctx.rank == 0 else None
 
@@ -506,6 +510,7 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
 
     # ---- instrumented replay of the same K steps: per-kernel CUDA-event timing (K1 included) ---------------------
     if profile:
+        model._config["infer_cuda_graph"] = False                # per-kernel events need host-issued launches
         prof = _lib.KernelProfiler()
         _lib.profiler = prof
         hwc_dev = host_trip[0].to(ctx.dev)

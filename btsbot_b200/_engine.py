@@ -50,6 +50,50 @@ def bump_param_generation() -> None:
     _PARAM_GENERATION += 1
 
 
+#: kernels of libbtsbot_b200.so executed through CUDA-graph replays of the inference forward (the library's own launch
+#: counter only sees launches issued from the host, i.e. the capture pass)
+_GRAPH_REPLAY_LAUNCHES = 0
+
+
+def graph_replay_launches() -> int:
+    return _GRAPH_REPLAY_LAUNCHES
+
+
+class _GraphedForward:
+    """One inference forward of a :class:`Scorer` at a fixed input shape, captured in a CUDA graph (config key
+    ``infer_cuda_graph``).  At small batches (BASELINE config C2: 1024 alerts, C1: 39) the ~40-kernel forward is paced by
+    the host: every launch encodes its tensor maps and crosses ctypes, and the GPU idles between kernels.  A replay is one
+    launch; the tensor maps are encoded once, at capture.  Inputs are copied into static buffers, the logits are returned
+    as a fresh tensor."""
+
+    def __init__(self, scorer, image, meta):
+        self.img = image.clone() if image is not None else None
+        self.meta = meta.clone() if meta is not None else None
+        dev = (image if image is not None else meta).device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                       # lazy one-time initialisation must not happen during capture
+            for _ in range(2):
+                scorer(image_input=self.img, metadata_input=self.meta)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = scorer(image_input=self.img, metadata_input=self.meta)
+        self.kernels = L.launch_count() - n0
+
+    def __call__(self, image, meta):
+        global _GRAPH_REPLAY_LAUNCHES
+        if self.img is not None:
+            self.img.copy_(image, non_blocking=True)
+        if self.meta is not None:
+            self.meta.copy_(meta, non_blocking=True)
+        self.graph.replay()
+        _GRAPH_REPLAY_LAUNCHES += self.kernels
+        return self.out.clone()
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -301,6 +345,7 @@ class Scorer:
         self.name = name = config["model_name"]
         self.trunk = self.head = self.maxvit = None
         self.pool_ln = None
+        self._graphs = {}                                   # input shapes -> _GraphedForward (config infer_cuda_graph)
         if name == "mm_ConvNeXt":
             arch = convnext_arch(config.get("model_kind", "convnext_nano.d1h_in1k"))
             self.trunk = TrunkWeights(sd, "convnext_backbone.", arch, precision)
@@ -356,6 +401,29 @@ class Scorer:
             # fail in combined_head (in_features == C), so just build the tensor it would have built
             return rows.view(B, h * w, -1).permute(0, 2, 1).reshape(B, -1).contiguous()
         return rows
+
+    def graphed(self, image_input=None, metadata_input=None) -> torch.Tensor:
+        """``__call__`` through a per-input-shape CUDA graph (at most 8 shapes are kept)."""
+        uses_img = self.trunk is not None or self.maxvit is not None
+        img = meta = None
+        if uses_img:
+            L.require_cuda(image_input, "image input")
+            img = image_input.to(torch.float32).contiguous()
+            if img.shape[0] == 0:
+                return self(image_input=image_input, metadata_input=metadata_input)
+        if self.head.Mm > 0:
+            L.require_cuda(metadata_input, "metadata input")
+            meta = metadata_input.to(torch.float32).contiguous()
+            if meta.shape[0] == 0:
+                return self(image_input=image_input, metadata_input=metadata_input)
+        key = (tuple(img.shape) if img is not None else None, tuple(meta.shape) if meta is not None else None)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            self(image_input=img, metadata_input=meta)      # argument errors surface eagerly, not inside a capture
+            g = self._graphs[key] = _GraphedForward(self, img, meta)
+        return g(img, meta)
 
     def __call__(self, image_input=None, metadata_input=None, capture: dict | None = None) -> torch.Tensor:
         feat = None

@@ -7,8 +7,9 @@ behave exactly like the reference's models.  None of the sub-modules' own ``forw
 ``forward`` hands the whole batch to :class:`btsbot_b200._engine.Scorer`, i.e. to ``libbtsbot_b200.so``.
 There is no CPU / eager fallback -- calling a model on CPU tensors raises.
 
-Extra (opt-in) config key: ``precision`` = ``"fp32"`` (default, reference numerics: logits within 1e-4) or
-``"bf16"`` (tcgen05 tensor cores, logits within 2e-2).
+Extra (opt-in) config keys: ``precision`` = ``"fp32"`` (default, reference numerics: logits within 1e-4; GEMMs on the
+tensor cores through the 3xTF32 split) or ``"bf16"`` (tcgen05 bf16, logits within 2e-2); ``infer_cuda_graph`` = true
+replays the eval-mode forward as one CUDA graph per input shape (small batches are otherwise paced by the host).
 """
 from __future__ import annotations
 
@@ -200,6 +201,9 @@ class _B200Model(nn.Module):
         if self.training and torch.is_grad_enabled():
             from . import _autograd
             return _autograd.training_forward(self, image_input, metadata_input)
+        if self._config.get("infer_cuda_graph", False):
+            # opt-in: replay the whole forward as one CUDA graph per input shape (small-batch scoring is host-paced)
+            return self.scorer().graphed(image_input=image_input, metadata_input=metadata_input)
         return self.scorer()(image_input=image_input, metadata_input=metadata_input)
 
 

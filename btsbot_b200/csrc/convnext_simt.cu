@@ -495,6 +495,8 @@ int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* 
                     const float* ln_b, void* out, cudaStream_t st);
 int dwln_bf16_v5(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
                  const float* ln_b, void* out, cudaStream_t st);
+int dwln_f32_v3(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
+                const float* ln_b, void* out, cudaStream_t st);
 }
 extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* w,
                                       const float* bias, const float* ln_w, const float* ln_b, void* out,
@@ -505,7 +507,11 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
   if (B == 0) return BTSB_OK;
   BTSB_REQUIRE(x && w && bias && ln_w && ln_b && out, "dwln: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == BTSB_F32) return dispatch_dwln<float>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  if (dtype == BTSB_F32) {
+    const int rc = dwln_f32_v3(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);       // 15 x 15 / 7 x 7 at the nano / pico widths
+    if (rc != 1) return rc;
+    return dispatch_dwln<float>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  }
   // each specialised kernel returns 1 when the shape is not its own: small maps -> v5 -> v3 -> v2 -> generic
   {
     const int rc = dwln_bf16_small(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);   // 3x3 and 1x1 maps
@@ -598,6 +604,66 @@ lnpatch_tpp_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int W,
   }
 }
 
+// fp32 rows (the 1e-4 mode): the same scheme with NV float4 per thread (C = 4 * NV * TPP), thread-local two-pass statistics
+template <int NV, int TPP>
+__global__ void __launch_bounds__(256)
+lnpatch_tpp_f32_kernel(const float* __restrict__ x, int64_t B, int H, int W, int Ho, int Wo, const float* __restrict__ ln_w,
+                       const float* __restrict__ ln_b, float* __restrict__ out) {
+  constexpr int CH = 4 * NV, C = CH * TPP;
+  __shared__ __align__(16) float gws[C], gbs[C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { gws[i] = __ldg(ln_w + i); gbs[i] = __ldg(ln_b + i); }
+  __syncthreads();
+  const int Hu = 2 * Ho, Wu = 2 * Wo;
+  const int64_t total = B * (int64_t)Hu * Wu * TPP;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int sub = (int)(i % TPP);
+    const int64_t p = i / TPP;
+    const int ix = (int)(p % Wu);
+    const int64_t t = p / Wu;
+    const int iy = (int)(t % Hu);
+    const int64_t b = t / Hu;
+    const float4* src = reinterpret_cast<const float4*>(x + ((b * H + iy) * (int64_t)W + ix) * C + sub * CH);
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = __ldg(src + j);
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / (float)C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float d0 = v[j].x - mean, d1 = v[j].y - mean, d2 = v[j].z - mean, d3 = v[j].w - mean;
+      q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q))));
+    }
+#pragma unroll
+    for (int o = TPP / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / (float)C) + kLnEps);
+    const int oy = iy >> 1, dy = iy & 1, ox = ix >> 1, dx = ix & 1;
+    float4* dst = reinterpret_cast<float4*>(out + ((b * Ho + oy) * (int64_t)Wo + ox) * (4 * (int64_t)C) + (dy * 2 + dx) * C + sub * CH);
+    const float4* gw4 = reinterpret_cast<const float4*>(gws + sub * CH);
+    const float4* gb4 = reinterpret_cast<const float4*>(gbs + sub * CH);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 w = gw4[j], bb = gb4[j];
+      dst[j] = make_float4((v[j].x - mean) * rstd * w.x + bb.x, (v[j].y - mean) * rstd * w.y + bb.y,
+                           (v[j].z - mean) * rstd * w.z + bb.z, (v[j].w - mean) * rstd * w.w + bb.w);
+    }
+  }
+}
+
+template <int NV, int TPP>
+static void launch_lnpatch_tpp_f32(const float* xi, int64_t B, int H, int W, int Ho, int Wo, const float* ln_w,
+                                   const float* ln_b, float* xo, cudaStream_t st) {
+  const int64_t total = B * 4 * (int64_t)Ho * Wo * TPP;
+  int64_t grid = (total + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  lnpatch_tpp_f32_kernel<NV, TPP><<<(unsigned)grid, 256, 0, st>>>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo);
+}
+
 template <int NV, int TPP>
 static void launch_lnpatch_tpp(const __nv_bfloat16* xi, int64_t B, int H, int W, int Ho, int Wo, const float* ln_w,
                                const float* ln_b, __nv_bfloat16* xo, cudaStream_t st) {
@@ -618,9 +684,18 @@ extern "C" int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, in
   const int64_t total = B * 4 * (int64_t)Ho * Wo;
   const int grid = pick_grid(total, 8 * 4);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == BTSB_F32)
-    lnpatch_kernel<float><<<grid, 256, 0, st>>>((const float*)x, B, H, W, C, Ho, Wo, ln_w, ln_b, (float*)out);
-  else if ((C == 64 || C == 80 || C == 128 || C == 160 || C == 256 || C == 320) && ((uintptr_t)x % 16) == 0 &&
+  if (dtype == BTSB_F32) {
+    const float* xi = (const float*)x;
+    float* xo = (float*)out;
+    const bool al = ((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 16) == 0;
+    if (al && C == 64) launch_lnpatch_tpp_f32<8, 2>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st);
+    else if (al && C == 80) launch_lnpatch_tpp_f32<10, 2>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st);
+    else if (al && C == 128) launch_lnpatch_tpp_f32<8, 4>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st);
+    else if (al && C == 160) launch_lnpatch_tpp_f32<10, 4>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st);
+    else if (al && C == 256) launch_lnpatch_tpp_f32<8, 8>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st);
+    else if (al && C == 320) launch_lnpatch_tpp_f32<10, 8>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st);
+    else lnpatch_kernel<float><<<grid, 256, 0, st>>>(xi, B, H, W, C, Ho, Wo, ln_w, ln_b, xo);
+  } else if ((C == 64 || C == 80 || C == 128 || C == 160 || C == 256 || C == 320) && ((uintptr_t)x % 16) == 0 &&
            ((uintptr_t)out % 16) == 0) {
     const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
     __nv_bfloat16* xo = (__nv_bfloat16*)out;

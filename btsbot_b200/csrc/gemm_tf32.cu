@@ -39,6 +39,7 @@ constexpr int kOffBarT = kStagesT * kStageT;
 constexpr int kOffVecT = kOffBarT + 256;
 constexpr int kSmemT = kOffVecT + 2 * kMaxNT * 4 + 1024;
 static_assert(kSmemT <= 227 * 1024, "shared-memory plan");
+static_assert(kWTile <= kATile, "the splitters handle at most as many W pieces as A pieces");
 
 __host__ __device__ constexpr uint32_t idesc_tf32_f32(int M, int N) {
   // D fp32 (1 << 4), A / B tf32 (format 2 at bits 7 / 10), both K-major
@@ -172,10 +173,36 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         float4* al = reinterpret_cast<float4*>(sa + kATile);
         float4* wh = reinterpret_cast<float4*>(sa + 2 * kATile);
         float4* wl = reinterpret_cast<float4*>(sa + 2 * kATile + kWTile);
+        // all of this thread's 16-byte pieces are loaded before any is processed (the loop was a chain of dependent
+        // LDS -> LOP/FADD -> STS round trips: ncu's top stall of the kernel, with the MMA warp waiting on split_bar)
+        constexpr int kPer = kATile / 16 / (kSplitWarps * 32);     // 4 pieces of A and up to 4 of W per thread
+        float4 va[kPer], vw[kPer];
 #pragma unroll
-        for (int i = 0; i < kATile / 16 / (kSplitWarps * 32); ++i) split4(ah + st + i * kSplitWarps * 32, al + st + i * kSplitWarps * 32);
+        for (int i = 0; i < kPer; ++i) va[i] = ah[st + i * kSplitWarps * 32];
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          const int idx = st + i * kSplitWarps * 32;
+          vw[i] = idx < w_vec ? wh[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          const int idx = st + i * kSplitWarps * 32;
+          const float4 v = va[i];
+          const float4 h = make_float4(cut19(v.x), cut19(v.y), cut19(v.z), cut19(v.w));
+          ah[idx] = h;
+          al[idx] = make_float4(cut19(v.x - h.x), cut19(v.y - h.y), cut19(v.z - h.z), cut19(v.w - h.w));
+        }
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          const int idx = st + i * kSplitWarps * 32;
+          if (idx < w_vec) {
+            const float4 v = vw[i];
+            const float4 h = make_float4(cut19(v.x), cut19(v.y), cut19(v.z), cut19(v.w));
+            wh[idx] = h;
+            wl[idx] = make_float4(cut19(v.x - h.x), cut19(v.y - h.y), cut19(v.z - h.z), cut19(v.w - h.w));
+          }
+        }
         (void)a_vec;
-        for (int i = st; i < w_vec; i += kSplitWarps * 32) split4(wh + i, wl + i);
         fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(split_bar(stage));

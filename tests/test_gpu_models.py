@@ -238,3 +238,27 @@ def test_load_HF_model_from_local_dir(cuda_dev, golden_logits, golden_batch, tmp
     ref = golden_logits["ff_pico"][:39]
     assert np.abs(got.cpu().numpy() - ref).max() < 1.5e-4
     assert np.array_equal(raw_preds[np.abs(ref[:, 0]) > 1e-4], (ref[:, 0] > 0).astype(int)[np.abs(ref[:, 0]) > 1e-4])
+
+
+@pytest.mark.parametrize("case,precision", [("img_nano", "bf16"), ("mm_pico", "fp32")])
+def test_inference_cuda_graph_matches_eager(cuda_dev, golden_logits, golden_batch, case, precision):
+    """config `infer_cuda_graph`: the eval forward replayed as one CUDA graph per input shape gives bitwise the logits of
+    the eagerly issued forward, follows new inputs and new shapes, and sees new weights."""
+    from btsbot_b200 import _engine
+    img, meta = golden_batch
+    ti, tm = torch.from_numpy(img).to(cuda_dev), torch.from_numpy(meta).to(cuda_dev)
+    cfg, sd, eager = _build(case, golden_logits, cuda_dev, precision)
+    graphed = getattr(btsbot, cfg["model_name"])(dict(cfg, infer_cuda_graph=True))
+    graphed.load_state_dict(synth.to_torch(sd), strict=True)
+    graphed = graphed.to(cuda_dev).eval()
+    r0 = _engine.graph_replay_launches()
+    for lo, hi in ((0, 40), (20, 60), (0, 40), (0, 13)):                 # same shape twice with new data, then a new shape
+        a = _call(eager, cfg, ti[lo:hi], tm[lo:hi])
+        b = _call(graphed, cfg, ti[lo:hi], tm[lo:hi])
+        assert torch.equal(a, b), (lo, hi)
+    assert _engine.graph_replay_launches() - r0 > 4 * 20                 # the replays' kernels are accounted for
+    with torch.no_grad():
+        for p in graphed.parameters():
+            p.mul_(1.01)
+    c = _call(graphed, cfg, ti[:40], tm[:40])
+    assert not torch.equal(c, _call(eager, cfg, ti[:40], tm[:40]))       # re-packed weights -> new graph
