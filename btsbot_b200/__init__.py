@@ -6,7 +6,7 @@ reference-style code -- ``btsbot.load_HF_model``, ``btsbot.architectures.mm_Conv
 """
 __version__ = "2.0.6+b200.1"
 
-from . import architectures, utils, alert_utils, from_HF, synth  # noqa: F401
+from . import architectures, utils, alert_utils, from_HF, to_HF, synth  # noqa: F401
 from .utils import FlexibleDataset, RandomRightAngleRotation, make_report  # noqa: F401
 from .architectures import (  # noqa: F401
     MaxViT, ConvNeXt, mm_MaxViT, mm_ConvNeXt, mm_cnn, um_cnn, um_nn, frozen_fusion,
@@ -24,6 +24,6 @@ def install_as_btsbot():
     """Register this package under the name ``btsbot`` so unmodified reference-style scripts import it."""
     import sys
     sys.modules["btsbot"] = sys.modules[__name__]
-    for sub in ("architectures", "utils", "alert_utils", "from_HF"):
+    for sub in ("architectures", "utils", "alert_utils", "from_HF", "to_HF"):
         sys.modules["btsbot." + sub] = sys.modules[__name__ + "." + sub]
     return sys.modules[__name__]

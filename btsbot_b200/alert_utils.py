@@ -1,8 +1,9 @@
 """Array preparation of ZTF alert cutouts on the GPU -- drop-in names from `btsbot/alert_utils.py`.
 
 * :func:`crop_norm_cutout`, :func:`crop_triplets`  (alert_utils.py:54-107) -> kernel ``btsb_preprocess_crop_norm``
-* :func:`make_triplet` / :func:`make_triplets`     (alert_utils.py:110-196) -> host gunzip + FITS parse, then kernel
-  ``btsb_preprocess_pad_norm`` for the numeric tail (nan_to_num, L2 normalise, drop flags, pad with 1e-9)
+* :func:`make_triplet` / :func:`make_triplets`     (alert_utils.py:110-196) -> batched multi-threaded gunzip + FITS parse
+  in the library (``btsb_ingest_fits_gz``, no astropy, no Python per stamp), then kernel ``btsb_preprocess_pad_norm``
+  for the numeric tail (nan_to_num, L2 normalise, drop flags, pad with 1e-9)
 * :func:`triplets_to_model_input`  -- the cast + NHWC->NCHW step every reference caller does next
   (inference_example.py:62-64, train.py:139-155, val.py:92-94), fused with crop/normalise, output left on the GPU.
 * :func:`extract_triplets` (alert_utils.py:199-226) host bookkeeping.
@@ -15,9 +16,6 @@ Plotting / Kowalski query helpers of the reference module are outside the hot pa
 from __future__ import annotations
 
 import ctypes as C
-import gzip
-import io
-
 import numpy as np
 import torch
 
@@ -79,54 +77,32 @@ def crop_norm_cutout(cutout, crop_to_size):
 
 
 # ---- alert ingest: gz-FITS stamps -> triplets -------------------------------------------------------------
-def _parse_fits_image(raw: bytes) -> np.ndarray:
-    """Primary-HDU image of a FITS file as float32 (BITPIX -32/-64/16/32 with BSCALE/BZERO), no astropy."""
-    kv, off, end = {}, 0, False
-    while not end:
-        block = raw[off:off + 2880]
-        if len(block) < 2880:
-            raise ValueError("truncated FITS header")
-        for i in range(0, 2880, 80):
-            card = block[i:i + 80].decode("ascii", "replace")
-            key = card[:8].strip()
-            if key == "END":
-                end = True
-                break
-            if card[8:10] == "= ":
-                kv[key] = card[10:].split("/")[0].strip().strip("'").strip()
-        off += 2880
-    bitpix, naxis = int(kv["BITPIX"]), int(kv["NAXIS"])
-    if naxis != 2:
-        raise ValueError(f"expected a 2-D FITS image, NAXIS={naxis}")
-    w, h = int(kv["NAXIS1"]), int(kv["NAXIS2"])
-    dt = {-32: ">f4", -64: ">f8", 16: ">i2", 32: ">i4", 8: "u1"}[bitpix]
-    data = np.frombuffer(raw, dtype=dt, count=w * h, offset=off).reshape(h, w)
-    if bitpix > 0:
-        data = data * float(kv.get("BSCALE", 1.0)) + float(kv.get("BZERO", 0.0))
-    return np.ascontiguousarray(data, dtype=np.float32)
-
-
-def _stamp(alert, which) -> np.ndarray:
-    blob = alert[f"cutout{which}"]["stampData"]
-    with gzip.open(io.BytesIO(bytes(blob)), "rb") as f:
-        return _parse_fits_image(f.read())
+def decode_stamps(blobs, threads: int = 0):
+    """Batched gunzip + FITS parse of alert stamps on a pool of host threads (``btsb_ingest_fits_gz``; replaces the
+    per-stamp ``gzip.open`` + ``astropy.io.fits.open`` of alert_utils.py:141-147).  ``blobs``: sequence of ``bytes``.
+    Returns ``(stamps float32 [n, 63*63] -- each stamp dense at the start of its slot --, hw int32 [n, 2])``."""
+    n = len(blobs)
+    keep = [bytes(b) for b in blobs]                           # own the buffers for the duration of the call
+    ptrs = (C.c_char_p * n)(*keep)
+    sizes = np.array([len(b) for b in keep], dtype=np.int64)
+    stamps = np.zeros((n, 63 * 63), dtype=np.float32)
+    hw = np.zeros((n, 2), dtype=np.int32)
+    if n:
+        L.check(L.lib().btsb_ingest_fits_gz(C.cast(ptrs, C.c_void_p), C.c_void_p(sizes.ctypes.data), n,
+                                            C.c_void_p(stamps.ctypes.data), C.c_void_p(hw.ctypes.data), int(threads)),
+                "ingest_fits_gz")
+    return stamps, hw
 
 
 def make_triplets(alerts, normalize: bool = True):
-    """Batched :func:`make_triplet`: ``(ndarray[N,63,63,3] float64, ndarray[N] bool)``; one kernel launch."""
+    """Batched :func:`make_triplet`: ``(ndarray[N,63,63,3] float64, ndarray[N] bool)``; one host call that inflates and
+    parses all 3N stamps, one kernel launch for the numeric tail."""
     lib = L.lib()
     dev = _dev()
     n = len(alerts)
-    stamps = np.zeros((n, 3, 63 * 63), dtype=np.float32)
-    hw = np.zeros((n, 3, 2), dtype=np.int32)
-    for i, alert in enumerate(alerts):
-        for c, which in enumerate(("Science", "Template", "Difference")):
-            d = _stamp(alert, which)
-            h, w = d.shape
-            if h < 1 or w < 1 or h > 63 or w > 63:
-                raise ValueError(f"cutout {which} of alert {i} has shape {d.shape}; expected at most 63x63")
-            stamps[i, c, :h * w] = d.reshape(-1)
-            hw[i, c] = (h, w)
+    blobs = [alert[f"cutout{which}"]["stampData"] for alert in alerts for which in ("Science", "Template", "Difference")]
+    stamps, hw = decode_stamps(blobs)
+    stamps, hw = stamps.reshape(n, 3, 63 * 63), hw.reshape(n, 3, 2)
     s_d = torch.from_numpy(stamps).to(dev)
     hw_d = torch.from_numpy(hw).to(dev)
     out = torch.empty((n, 63, 63, 3), device=dev, dtype=torch.float64)

@@ -198,6 +198,15 @@ class _B200Model(nn.Module):
         return self._frozen_scorer
 
     def _run(self, image_input=None, metadata_input=None):
+        # kernels are enqueued on the CURRENT device's current stream: make the inputs' device current for the call
+        # (a process that drives several GPUs may call a model whose tensors live on a non-current device)
+        t = image_input if image_input is not None else metadata_input
+        if t is not None and t.is_cuda and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return self._run_on_device(image_input, metadata_input)
+        return self._run_on_device(image_input, metadata_input)
+
+    def _run_on_device(self, image_input=None, metadata_input=None):
         if self.training and torch.is_grad_enabled():
             from . import _autograd
             return _autograd.training_forward(self, image_input, metadata_input)

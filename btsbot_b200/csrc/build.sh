@@ -19,5 +19,5 @@ for f in "$HERE"/*.cu; do
   fi
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-"$NVCC" -shared -o "$OUT" "${OBJS[@]}" -lcudart
+"$NVCC" -shared -o "$OUT" "${OBJS[@]}" -lcudart -lz
 echo "built $OUT"

@@ -26,6 +26,15 @@ inline int launch_done(const char* what) {
   return BTSB_OK;
 }
 
+// Kernel attributes (opt-in shared memory above 48 KB) and the SM count are per DEVICE: a process that drives several
+// GPUs must set them on each.  `first_use_on_device(mask)` is true once per (call site, device).
+inline bool first_use_on_device(std::atomic<uint64_t>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  return (mask.fetch_or(bit, std::memory_order_relaxed) & bit) == 0;
+}
+
 #define BTSB_REQUIRE(cond, ...)   \
   do {                            \
     if (!(cond)) {                \

@@ -34,9 +34,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encoder() {
   static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::atomic<uint64_t> tried{0};
+  if (first_use_on_device(tried)) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
@@ -224,10 +223,9 @@ extern "C" int btsb_conv3x3_c32_fwd(const void* x, const void* w, const float* b
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv3x3: cuTensorMapEncodeTiled (weights) failed with CUresult %d", (int)r); return BTSB_ECUDA; }
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};
+  if (first_use_on_device(attr_done)) {
     BTSB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemC), "conv3x3 attr");
-    attr_done = true;
   }
   const int64_t tiles = B * (H / TY) * (W / TX);
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());

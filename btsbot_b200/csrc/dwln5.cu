@@ -220,10 +220,9 @@ static int launch_dwln5(const void* x, int64_t B, const float* w, const float* b
                         void* out, cudaStream_t st) {
   using P = Dw5<S, C>;
   auto kern = dwln5_kernel<S, C>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};
+  if (first_use_on_device(attr_done)) {
     BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM), "dwln5 attr");
-    attr_done = true;
   }
   const int64_t cap = num_sms();
   const int grid = (int)(B < cap ? B : cap);

@@ -497,9 +497,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 static EncodeTiledFn get_encoder() {
   static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::atomic<uint64_t> tried{0};
+  if (first_use_on_device(tried)) {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
@@ -567,12 +566,14 @@ static int pick_bn(int N) {
 }
 
 int num_sms() {
-  static int n = 0;
+  static int cache[64] = {0};                     // per device (benign race: every writer stores the same value)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = cache[dev & 63];
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n = v > 0 ? v : 148;
   }
   return n;
 }
@@ -606,13 +607,12 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
   const __nv_bfloat16* r = (const __nv_bfloat16*)res;
   __nv_bfloat16* o = (__nv_bfloat16*)out;
   if (pair) {
-    static bool attr2_done = false;
-    if (!attr2_done) {
+    static std::atomic<uint64_t> attr2_done{0};
+    if (first_use_on_device(attr2_done)) {
       BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
       BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_GELU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
       BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_SCALE_RES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
       BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_SILU, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
-      attr2_done = true;
     }
     const int64_t pairs = units2 < num_sms() / 2 ? units2 : num_sms() / 2;
     cudaLaunchConfig_t cfg = {};
@@ -641,13 +641,12 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
   }
   const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
   const int grid = min(m_tiles * n_tiles, num_sms());
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};
+  if (first_use_on_device(attr_done)) {
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_SCALE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BTSB_EPI_BIAS_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
-    attr_done = true;
   }
   if (epilogue == BTSB_EPI_BIAS)
     gemm_tc_kernel<BTSB_EPI_BIAS><<<grid, kThreads, kSmemBytes, st>>>(tmA, tmB, tmO, bias, gamma, nullptr, r, o, (int)M, N, K, BN, dbg);
@@ -663,12 +662,11 @@ int gemm_bf16(const void* A, const void* Wt, const float* bias, const float* gam
 
 // ---- training GEMMs (bf16 operands on the tensor cores, fp32 results) ---------------------------------------------
 static int train_attrs() {
-  static bool done = false;
-  if (!done) {
+  static std::atomic<uint64_t> done{0};
+  if (first_use_on_device(done)) {
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_F32OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_WGRAD_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm attr");
-    done = true;
   }
   return BTSB_OK;
 }
@@ -764,10 +762,9 @@ int gemm_ln_bf16(const void* A, const void* Wt, const float* bias, const float* 
   if (int e = make_tmap_bf16_2d(&tmB, Wt, (uint64_t)N, (uint64_t)K, (uint32_t)N)) return e;
   const int m_tiles = (int)((M + BM - 1) / BM);
   const int grid = min(m_tiles, num_sms());
-  static bool attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};
+  if (first_use_on_device(attr_done)) {
     BTSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes), "gemm_ln attr");
-    attr_done = true;
   }
   OutMaps tmO;
   memset(&tmO, 0, sizeof(tmO));                           // the LayerNorm epilogue writes rows directly

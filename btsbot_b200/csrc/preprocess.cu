@@ -270,10 +270,9 @@ extern "C" int btsb_preprocess_crop_norm(const void* in, int in_dtype, int64_t n
     crop_norm_kernel<float><<<(unsigned)n, kPreThreads, smem, st>>>((const float*)in, crop_to_size, margin, normalize, out_hwc, out);
   } else {
     const int smem = kTrip * 8;
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<uint64_t> attr{0};
+    if (first_use_on_device(attr)) {
       BTSB_CUDA(cudaFuncSetAttribute(crop_norm_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "crop_norm attr");
-      attr = true;
     }
     crop_norm_kernel<double><<<(unsigned)n, kPreThreads, smem, st>>>((const double*)in, crop_to_size, margin, normalize, out_hwc, out);
   }

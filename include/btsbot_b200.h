@@ -80,6 +80,14 @@ int btsb_preprocess_crop_norm(const void* in, int in_dtype, int64_t n, int crop_
 int btsb_preprocess_pad_norm(const float* stamps, const int32_t* hw, int64_t n, int normalize,
                              void* out, int out_dtype, uint8_t* drop, void* stream);
 
+/* ingest (HOST memory, no device work): batched gunzip + FITS parse of alert stamps -- replaces the per-stamp
+ * gzip.open + astropy.io.fits.open loop of alert_utils.make_triplet (alert_utils.py:137-147).  blobs[i] / sizes[i] are
+ * the gzipped FITS bytes of stamp i (three per alert: science, template, difference); stamps [n,63*63] float32 and
+ * hw [n,2] int32 (rows, cols) are exactly what btsb_preprocess_pad_norm reads.  A pool of `threads` host threads
+ * (<= 0: one per hardware thread, at most 32) inflates and parses; BITPIX -32/-64/16/32/8 with BSCALE/BZERO. */
+int btsb_ingest_fits_gz(const unsigned char* const* blobs, const int64_t* sizes, int64_t n, float* stamps,
+                        int32_t* hw, int threads);
+
 /* training-time batch gather + augmentation (utils.py:44-48, train.py:178-199 RandomHorizontalFlip /
  * RandomVerticalFlip / RandomRightAngleRotation): out[b] = rot90^k(vflip(hflip(images[idx[b]]))), square [3,S,S] fp32
  * images; flags[b] bit0 = hflip, bit1 = vflip, bits2-3 = k counter-clockwise quarter turns (flags NULL = no aug). */

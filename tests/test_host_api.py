@@ -223,3 +223,70 @@ def test_bench_kernel_table_roofline_columns():
     bench.add_roofline_fractions(kernels, {"hbm": 6400.0, "tf_sust": 1400.0}, "bf16")
     assert kernels["mlp_fused_320"]["bound"] == "tensor" and abs(kernels["mlp_fused_320"]["frac"] - 0.5) < 1e-12
     assert kernels["dwln_15x80"]["bound"] == "hbm" and abs(kernels["dwln_15x80"]["frac"] - 0.25) < 1e-12
+
+
+def _fits_gz(arr, bitpix=-32, bscale=None, bzero=None):
+    import gzip
+    cards = [f"SIMPLE  = {'T':>20}", f"BITPIX  = {bitpix:>20}", f"NAXIS   = {2:>20}", f"NAXIS1  = {arr.shape[1]:>20}",
+             f"NAXIS2  = {arr.shape[0]:>20}"]
+    if bscale is not None:
+        cards += [f"BSCALE  = {bscale:>20}", f"BZERO   = {bzero:>20} / offset of the stored integers"]
+    cards.append("END")
+    hdr = "".join(c.ljust(80) for c in cards).ljust(2880).encode("ascii")
+    data = arr.astype({-32: ">f4", -64: ">f8", 16: ">i2", 32: ">i4", 8: "u1"}[bitpix]).tobytes()
+    return gzip.compress(hdr + data + b"\0" * (-len(data) % 2880))
+
+
+def test_batched_stamp_ingest_matches_numpy_decode():
+    """`btsb_ingest_fits_gz` (host threads; no GPU involved): gunzip + FITS parse of a batch of stamps equals the plain
+    gzip + numpy decode the reference's astropy call amounts to (alert_utils.py:141-147), for every pixel type, ragged
+    shapes, NaN / inf pixels, and a batch large enough to use the thread pool; malformed input is an error."""
+    from btsbot_b200 import alert_utils as au
+    g = np.random.default_rng(3)
+    a32 = g.standard_normal((63, 63)).astype(np.float32)
+    a32[5, 7], a32[9, 9] = np.nan, np.inf
+    cases = [(a32, -32, None, None), (g.standard_normal((35, 63)), -64, None, None),
+             ((g.standard_normal((20, 17)) * 1000).astype(np.int16), 16, 2.0, 32768.0),
+             ((g.standard_normal((1, 1)) * 1e6).astype(np.int32), 32, None, None),
+             (np.arange(12, dtype=np.uint8).reshape(3, 4), 8, None, None)]
+    blobs = [_fits_gz(*c) for c in cases] * 40                      # 200 stamps
+    stamps, hw = au.decode_stamps(blobs, threads=4)
+    assert stamps.shape == (200, 63 * 63) and hw.shape == (200, 2)
+    for i, (arr, bitpix, bscale, bzero) in enumerate(cases * 40):
+        h, w = arr.shape
+        assert tuple(hw[i]) == (h, w)
+        ref = arr.astype(np.float64) * (bscale or 1.0) + (bzero or 0.0) if bitpix > 0 else arr
+        assert np.array_equal(stamps[i, :h * w].reshape(h, w), ref.astype(np.float32), equal_nan=True), (i, bitpix)
+    assert au.decode_stamps([])[0].shape == (0, 63 * 63)
+    for bad in (b"not a gzip stream", _fits_gz(np.zeros((64, 63), np.float32)), _fits_gz(a32)[:200]):
+        with pytest.raises(RuntimeError):
+            au.decode_stamps([blobs[0], bad])
+
+
+def test_to_HF_packaging_round_trip(tmp_path, monkeypatch):
+    """to_HF.prep_config / prep_model / config_to_params (to_HF.py:10-43,143-177): a run directory becomes the published
+    layout that `load_HF_model` resolves; the Hugging Face upload itself is out of scope."""
+    import json
+    from btsbot_b200 import to_HF, from_HF
+    cfg = synth.canonical_config("frozen_fusion", "convnext_pico.d1_in1k")
+    run = tmp_path / "run"
+    run.mkdir()
+    with pytest.raises(FileNotFoundError):
+        to_HF.prep_config(str(run))
+    (run / "report.json").write_text(json.dumps({"train_config": cfg, "Training history": {}}))
+    assert to_HF.prep_config(str(run)) == cfg and (run / "train_config.json").is_file()
+    with pytest.raises(FileNotFoundError):
+        to_HF.prep_model(str(run), cfg)
+    sd = synth.to_torch(synth.make_state_dict(cfg, seed=4))
+    torch.save(sd, run / "best_model.pth")
+    monkeypatch.chdir(tmp_path)
+    target = to_HF.package_model(str(run))
+    assert target == from_HF.get_local_model_dir("convnext", True, "randinit") == os.path.join("models", "BTSbot-convnext-pico-randinit-metadata")
+    back = torch.load(os.path.join(target, "pytorch_model.bin"), map_location="cpu")
+    assert set(back) == set(sd) and all(torch.equal(back[k].reshape(-1), sd[k].reshape(-1)) for k in sd)
+    assert to_HF.config_to_params(cfg) == ("convnext", True, "randinit")
+    assert to_HF.config_to_params(synth.canonical_config("MaxViT", "maxvit_tiny_rw_224.sw_in1k")) == ("maxvit", False, "randinit")
+    assert to_HF.config_to_params(dict(synth.canonical_config("ConvNeXt", "convnext_pico.d1_in1k"), pretrained=True)) == ("convnext", False, "imagenet")
+    assert to_HF.get_HF_basemodel("maxvit", "galaxyzoo") == "mwalmsley/baseline-encoder-regression-maxvit_tiny"
+    with pytest.raises(ValueError):
+        to_HF.get_HF_basemodel("resnet", "imagenet")
