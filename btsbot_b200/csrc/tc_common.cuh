@@ -48,8 +48,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// Wait without the nanosleep back-off: try_wait already suspends the thread in hardware, and a 64 ns sleep quantum is a
-// visible fraction of a sub-microsecond pipeline step.  Still bounded: a protocol bug traps instead of hanging the GPU.
+// Wait without the nanosleep back-off: try_wait already suspends the thread in hardware for a short, system-defined
+// interval, and a 64 ns sleep quantum is a visible fraction of a sub-microsecond pipeline step.  Still bounded: a protocol
+// bug traps instead of hanging the GPU.  (Parking the warp with a suspend-time hint -- try_wait ..., 20000 ns, which
+// compiles to TRYWAIT + NANOSLEEP.SYNCS -- removes the polling instructions, ~20 % of everything the fused MLP issues,
+// but wakes later: mlp_fused_80 went from 318 to 352 us, the other kernels did not move; profiles/r02o.  Not kept.)
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
