@@ -25,6 +25,9 @@ STEM_FUSED = os.environ.get("BTSB_STEM_FUSED", "1") != "0"
 #: the wide variants of the fused kernel (C = 256 / 320: single D2 accumulator, G2 split in two UMMAs); BTSB_FUSE_WIDE=0
 #: falls back to the two separate GEMMs for A/B timing
 FUSE_MLP_WIDE = os.environ.get("BTSB_FUSE_WIDE", "1") != "0"
+#: wide fused MLP called IN PLACE (out == res): the update is added to the residual stream by a bulk tensor reduction
+#: instead of load -> add -> store (BTSB_MLP_INPLACE=1; A/B until measured and parity-checked)
+MLP_INPLACE = os.environ.get("BTSB_MLP_INPLACE", "0") != "0"
 #: use the fused fc1->GELU->fc2 kernel where it applies (bf16, C <= 160, 256, 320); tests flip this to cover both paths
 FUSE_MLP = True
 #: head layer 0: contract the F image features on the tensor cores (bf16 features x bf16 weights, fp32 accumulate and
@@ -215,7 +218,8 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
                      flops=2.0 * 49 * M * c + 8.0 * M * c, nbytes=2.0 * es * M * c)
             if capture is not None:
                 capture[f"s{i}b{j}.dwln"] = (y.clone(), h, wd)
-            nxt = torch.empty((M, c), device=dev, dtype=adt)
+            inplace = fused and MLP_INPLACE and c in (256, 320) and capture is None
+            nxt = cur if inplace else torch.empty((M, c), device=dev, dtype=adt)
             if fused:
                 # fc1 -> GELU -> fc2 -> *gamma -> +shortcut in one kernel; bytes: y + res + out (+ L2-resident weights)
                 L.launch(f"mlp_fused_{c}", lib.btsb_convnext_mlp_fused_fwd, _p(y), _p(cur), _p(blk["fc1_w"]),

@@ -13,9 +13,9 @@
 // TMEM buffer.  Replaces the CUDA-core sgemm_kernel (convnext_simt.cu) for the trunk's fc1 / fc2 /
 // downsample GEMMs (timm mlp.fc1, mlp.fc2, downsample.1; MaxViT 1x1 convs / Linears) whenever K % 4 == 0, N % 16 == 0.
 //
-//   warp 0        TMA producer: fp32 tiles A [128 x 32] and W [BN x 32] (128-byte rows, 128B swizzle) into a 3-stage ring
+//   warp 0        TMA producer: fp32 tiles A [128 x 32] and W [BN x 32] (128-byte rows, 128B swizzle) into a 4-slot ring
 //   warps 2..9    splitters: rewrite each landed tile IN PLACE as its hi part and write the lo part to a twin tile at the
-//                 same (swizzled) offsets -- an element-wise pass, so the swizzle never has to be decoded
+//                 same (swizzled) offsets of a 2-slot lo ring -- an element-wise pass, the swizzle is never decoded
 //   warp 1        MMA issuer: per K step of 8 three UMMAs (M128 x N=BN x K8), accumulators double buffered in TMEM
 //   warps 10..17  epilogue: tcgen05.ld -> bias / erf-GELU / SiLU / gamma*(acc+b)+res in fp32 -> 64-byte row pieces
 #include <string.h>
@@ -27,15 +27,17 @@ namespace {
 constexpr int TM = 128;                // rows per tile
 constexpr int TK = 32;                 // fp32 columns per K block (128 bytes)
 constexpr int TBN = 128;               // max tile width
-constexpr int kStagesT = 3;
+constexpr int kStagesT = 4;            // raw (TMA) ring: fp32 A + W tiles, rewritten in place as their hi parts
+constexpr int kLoStages = 2;           // lo ring: the twin tiles exist only between the splitters and the MMAs
 constexpr int kChunkKB = 2;            // K blocks accumulated in TMEM before the sum moves to registers
 constexpr int kATile = TM * 128;       // 16 KB
 constexpr int kWTile = TBN * 128;      // 16 KB
-constexpr int kStageT = 2 * kATile + 2 * kWTile;        // A_hi, A_lo, W_hi, W_lo
+constexpr int kStageT = kATile + kWTile;                // one raw slot: A, W (-> A_hi, W_hi); one lo slot: A_lo, W_lo
 constexpr int kSplitWarps = 8, kEpiWarpsT = 8;
 constexpr int kThreadsT = 64 + 32 * (kSplitWarps + kEpiWarpsT);
 constexpr int kMaxNT = 2560;
-constexpr int kOffBarT = kStagesT * kStageT;
+constexpr int kOffLo = kStagesT * kStageT;
+constexpr int kOffBarT = kOffLo + kLoStages * kStageT;
 constexpr int kOffVecT = kOffBarT + 256;
 constexpr int kSmemT = kOffVecT + 2 * kMaxNT * 4 + 1024;
 static_assert(kSmemT <= 227 * 1024, "shared-memory plan");
@@ -74,12 +76,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sal = smem_dyn + (sbase - smem_u32(smem_dyn));
   const uint32_t bar0 = sbase + kOffBarT;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };                       // TMA bytes landed
-  auto split_bar = [&](int s) { return bar0 + 8u * (kStagesT + s); };         // hi / lo tiles written (kSplitWarps arrivals)
-  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * kStagesT + s); };     // the stage's MMAs retired
-  auto tfull_bar = [&](int s) { return bar0 + 8u * (3 * kStagesT + s); };
-  auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * kStagesT + 2 + s); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + kOffBarT + 8 * (3 * kStagesT + 4));
+  // The TMA ring is deeper than the lo ring: with one 64 KB stage holding all four tiles only three stages fitted and a
+  // single one was ever in flight from L2 (ncu: the MMA warp waited on the split barrier, tensor pipe 35 %)
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };                       // raw slot: TMA bytes landed
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStagesT + s); };         // raw slot: the MMAs reading its hi tiles retired
+  auto split_bar = [&](int l) { return bar0 + 8u * (2 * kStagesT + l); };     // lo slot (and its raw slot's hi rewrite) written
+  auto lo_empty = [&](int l) { return bar0 + 8u * (2 * kStagesT + kLoStages + l); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kStagesT + 2 * kLoStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStagesT + 2 * kLoStages + 2 + s); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + kOffBarT + 8 * (2 * kStagesT + 2 * kLoStages + 4));
   float* bias_s = reinterpret_cast<float*>(sal + kOffVecT);
   float* gamma_s = bias_s + kMaxNT;
 
@@ -96,7 +101,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < kStagesT; ++s) { mbar_init(full_bar(s), 1); mbar_init(split_bar(s), kSplitWarps); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < kStagesT; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int l = 0; l < kLoStages; ++l) { mbar_init(split_bar(l), kSplitWarps); mbar_init(lo_empty(l), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarpsT); }
     fence_barrier_init();
   }
@@ -118,7 +124,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t sa = sbase + stage * kStageT;
           mbar_expect_tx(full_bar(stage), tx_bytes);
           tma_load_2d(sa, &tmA, full_bar(stage), kb * TK, m0);                    // rows / columns past the tensor: zeros
-          tma_load_2d(sa + 2 * kATile, &tmB, full_bar(stage), kb * TK, n0);
+          tma_load_2d(sa + kATile, &tmB, full_bar(stage), kb * TK, n0);
         }
         __syncwarp();
         if (++stage == kStagesT) { stage = 0; phase ^= 1u; }
@@ -127,6 +133,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     int stage = 0; uint32_t phase = 0;
+    int lo = 0; uint32_t lphase = 0;
     uint32_t cidx = 0;                                           // running chunk count: TMEM buffer = cidx & 1
     const uint32_t idesc = idesc_tf32_f32(TM, BN);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -138,12 +145,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tc_fence_after();
         }
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * TBN);
-        mbar_wait_spin(split_bar(stage), phase);
+        mbar_wait_spin(split_bar(lo), lphase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = sbase + stage * kStageT;
-          const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sa + kATile);
-          const uint64_t w_hi = smem_desc_sw128(sa + 2 * kATile), w_lo = smem_desc_sw128(sa + 2 * kATile + kWTile);
+          const uint32_t sa = sbase + stage * kStageT, sl = sbase + kOffLo + lo * kStageT;
+          const uint64_t a_hi = smem_desc_sw128(sa), a_lo = smem_desc_sw128(sl);
+          const uint64_t w_hi = smem_desc_sw128(sa + kATile), w_lo = smem_desc_sw128(sl + kATile);
           const int kmax = (min(TK, K - kb * TK) + 7) / 8;
           for (int kk = 0; kk < kmax; ++kk) {
             // 8 fp32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
@@ -153,26 +160,31 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             umma_tf32(tmem_d, a_hi + o, w_hi + o, idesc, 1u);
           }
           umma_commit(empty_bar(stage));
+          umma_commit(lo_empty(lo));
           if (last) umma_commit(tfull_bar(as));
         }
         __syncwarp();
         if (last) ++cidx;
         if (++stage == kStagesT) { stage = 0; phase ^= 1u; }
+        if (++lo == kLoStages) { lo = 0; lphase ^= 1u; }
       }
     }
   } else if (warp < 2 + kSplitWarps) {
     // ===================== splitters: fp32 tile -> (hi in place, lo twin) =====================
     const int st = (warp - 2) * 32 + lane;                       // 0 .. 255
     int stage = 0; uint32_t phase = 0;
+    int lo = 0; uint32_t lphase = 0;
     const int a_vec = kATile / 16, w_vec = BN * 128 / 16;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait_spin(full_bar(stage), phase);
+        mbar_wait_spin(lo_empty(lo), lphase ^ 1u);             // the MMAs that read this lo slot two K blocks ago retired
         unsigned char* sa = sal + stage * kStageT;
+        unsigned char* sl = sal + kOffLo + lo * kStageT;
         float4* ah = reinterpret_cast<float4*>(sa);
-        float4* al = reinterpret_cast<float4*>(sa + kATile);
-        float4* wh = reinterpret_cast<float4*>(sa + 2 * kATile);
-        float4* wl = reinterpret_cast<float4*>(sa + 2 * kATile + kWTile);
+        float4* al = reinterpret_cast<float4*>(sl);
+        float4* wh = reinterpret_cast<float4*>(sa + kATile);
+        float4* wl = reinterpret_cast<float4*>(sl + kATile);
         // all of this thread's 16-byte pieces are loaded before any is processed (the loop was a chain of dependent
         // LDS -> LOP/FADD -> STS round trips: ncu's top stall of the kernel, with the MMA warp waiting on split_bar)
         constexpr int kPer = kATile / 16 / (kSplitWarps * 32);     // 4 pieces of A and up to 4 of W per thread
@@ -205,8 +217,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         (void)a_vec;
         fence_proxy_async();                                     // generic-proxy writes -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) mbar_arrive(split_bar(stage));
+        if (lane == 0) mbar_arrive(split_bar(lo));
         if (++stage == kStagesT) { stage = 0; phase ^= 1u; }
+        if (++lo == kLoStages) { lo = 0; lphase ^= 1u; }
       }
     }
   } else {

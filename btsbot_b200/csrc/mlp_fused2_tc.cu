@@ -86,6 +86,17 @@ __host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab
   return P;
 }
 
+// Hidden activation: H holds 2 GELU(fc1 + b1) (clamp-free cubic-tanh form, tc_common.cuh gelu_twice2) and the D2 epilogue
+// halves the accumulator inside the FFMA that adds b2 -- power-of-two scalings commute with the bf16 rounding of H, so the
+// result is that of GELU itself.  -DBTSB_GELU_QUINTIC builds the previous form (quintic with clamp, H = GELU) for A/B.
+#ifdef BTSB_GELU_QUINTIC
+__device__ __forceinline__ f32x2_t hidden_act2(f32x2_t x) { return tc::gelu_fast2(x); }
+constexpr float kD2Scale = 1.0f;
+#else
+__device__ __forceinline__ f32x2_t hidden_act2(f32x2_t x) { return tc::gelu_twice2(x); }
+constexpr float kD2Scale = 0.5f;
+#endif
+
 // K-major operand tile descriptor for a block whose rows are `sw` bytes (128 / 64 / 32) with the matching swizzle
 __device__ __forceinline__ uint64_t smem_desc_k(uint32_t saddr, int sw) {
   uint64_t d = 0;
@@ -173,11 +184,14 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       if (tracing && g < (uint32_t)kTraceChunks) trace[((size_t)role * kTraceChunks + g) * kTraceEv + ev] = clock64();
     }
   };
-  constexpr bool TS = EP == 2;
-  static_assert(EP == 0 || EP == 2, "EP");
+  constexpr bool TS = EP == 2 || EP == 4, RED = EP == 4;
+  static_assert(EP == 0 || EP == 2 || EP == 4, "EP");
   static_assert(EP == 0 || !TE, "EP variants belong to the wide (non-staging) kernels");
   constexpr Plan2 P = plan2_for(C, TE, HT, TS);
   static_assert(P.ok, "no shared-memory plan for this C");
+  // EP = 4 (in-place: out == res): the update gamma * (acc + b2) leaves through the slab as a bulk tensor REDUCTION
+  // (global += slab, bf16 add at the L2) -- no residual load at all, so a piece costs one slab round trip instead of a
+  // load -> update -> store chain (the ~15 k-clock drain of EP = 2 holds back the next tile's G2: lesson 9 / 12)
   // wide C (256, 320): one D2 accumulator instead of two (the D2 epilogue of a tile then holds back the first G2 of the
   // next one), and for C > 256 every G2 step is two UMMAs of N = C/2 columns
   constexpr int D2B = (kD2Col + 2 * C + (HT ? 64 : 0) <= 512) ? 2 : 1;
@@ -450,10 +464,10 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
-            v[i] = fmaf(g4.x, __uint_as_float(r[i]) + b4.x, bf16_lo(rr[i / 2]));
-            v[i + 1] = fmaf(g4.y, __uint_as_float(r[i + 1]) + b4.y, bf16_hi(rr[i / 2]));
-            v[i + 2] = fmaf(g4.z, __uint_as_float(r[i + 2]) + b4.z, bf16_lo(rr[i / 2 + 1]));
-            v[i + 3] = fmaf(g4.w, __uint_as_float(r[i + 3]) + b4.w, bf16_hi(rr[i / 2 + 1]));
+            v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), bf16_lo(rr[i / 2]));
+            v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), bf16_hi(rr[i / 2]));
+            v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), bf16_lo(rr[i / 2 + 1]));
+            v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), bf16_hi(rr[i / 2 + 1]));
           }
           uint4 o0, o1;
           o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
@@ -527,10 +541,10 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
-            v[i] = fmaf(g4.x, __uint_as_float(r[i]) + b4.x, bf16_lo(rr[i / 2]));
-            v[i + 1] = fmaf(g4.y, __uint_as_float(r[i + 1]) + b4.y, bf16_hi(rr[i / 2]));
-            v[i + 2] = fmaf(g4.z, __uint_as_float(r[i + 2]) + b4.z, bf16_lo(rr[i / 2 + 1]));
-            v[i + 3] = fmaf(g4.w, __uint_as_float(r[i + 3]) + b4.w, bf16_hi(rr[i / 2 + 1]));
+            v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), bf16_lo(rr[i / 2]));
+            v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), bf16_hi(rr[i / 2]));
+            v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), bf16_lo(rr[i / 2 + 1]));
+            v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), bf16_hi(rr[i / 2 + 1]));
           }
           *p0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
           *p1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
@@ -562,6 +576,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       unsigned char* slab = sal + P.off_slab + ew * 1024;
       const int row0 = tile * FM + q * 32;
       auto slab_load = [&](int gi) {
+        if (RED) return;                                     // in-place reduction: nothing is loaded
         if (lane == 0) {
           tma_store_wait_read();                             // the previous piece's bulk store has drained the slab
           mbar_expect_tx(res_bar(ew), 1024u);
@@ -587,26 +602,33 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           __syncwarp();
           if (lane == 0) mbar_arrive(d2_empty(tb));
         }
-        mbar_wait_spin(res_bar(ew), rph); rph ^= 1u;
-        const uint4 r0 = *p0, r1 = *p1;
-        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        uint32_t rr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (RED) {
+          if (lane == 0) tma_store_wait_read();              // the previous piece's reduction has read the slab
+          __syncwarp();
+        } else {
+          mbar_wait_spin(res_bar(ew), rph); rph ^= 1u;
+          const uint4 r0 = *p0, r1 = *p1;
+          rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+        }
         const int n = gi * 16;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
           const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
-          v[i] = fmaf(g4.x, __uint_as_float(r[i]) + b4.x, bf16_lo(rr[i / 2]));
-          v[i + 1] = fmaf(g4.y, __uint_as_float(r[i + 1]) + b4.y, bf16_hi(rr[i / 2]));
-          v[i + 2] = fmaf(g4.z, __uint_as_float(r[i + 2]) + b4.z, bf16_lo(rr[i / 2 + 1]));
-          v[i + 3] = fmaf(g4.w, __uint_as_float(r[i + 3]) + b4.w, bf16_hi(rr[i / 2 + 1]));
+          v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), bf16_lo(rr[i / 2]));
+          v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), bf16_hi(rr[i / 2]));
+          v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), bf16_lo(rr[i / 2 + 1]));
+          v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), bf16_hi(rr[i / 2 + 1]));
         }
         *p0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
         *p1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tm.o32, slab_addr, gi * 16, row0);   // rows beyond M are clipped by the tensor map
+          if (RED) tma_reduce_add_2d(&tm.o32, slab_addr, gi * 16, row0);   // rows beyond M are clipped by the tensor map
+          else tma_store_2d(&tm.o32, slab_addr, gi * 16, row0);
           tma_store_commit();
         }
         if (gi + 4 < groups2) slab_load(gi + 4);
@@ -642,10 +664,10 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
-        const float2 g0 = unpack_f32x2(gelu_fast2(add_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
-                                                             pack_f32x2(b4.x, b4.y))));
-        const float2 g1 = unpack_f32x2(gelu_fast2(add_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
-                                                             pack_f32x2(b4.z, b4.w))));
+        const float2 g0 = unpack_f32x2(hidden_act2(add_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                                              pack_f32x2(b4.x, b4.y))));
+        const float2 g1 = unpack_f32x2(hidden_act2(add_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
+                                                              pack_f32x2(b4.z, b4.w))));
         o[i / 2] = pack_bf16x2(g0.x, g0.y);
         o[i / 2 + 1] = pack_bf16x2(g1.x, g1.y);
       }
@@ -719,7 +741,7 @@ int mlp_fused2_supported(int C) {
 template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false>
 static int launch2(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res, void* out,
                    int64_t M, cudaStream_t st) {
-  constexpr Plan2 P = plan2_for(C, TE, HT, EP == 2);
+  constexpr Plan2 P = plan2_for(C, TE, HT, EP == 2 || EP == 4);   // must be the kernel's own plan (slabs for EP 2 and 4)
   if constexpr (!TRACE && (C == 80 || C == 160 || C == 320)) {   // the traced variants exist for the bench's three widths
     if (g_mlp_trace != nullptr) return launch2<C, TE, HT, EP, true>(tm, b1, b2, gamma, res, out, M, st);
   }
@@ -756,7 +778,12 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
   if (int e = make_tmap_bf16_2d_sw(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
   if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
-  // wide C: no room for a separate staging tile next to the 80 KB y tile -> per-warp slabs (EP = 2)
+  // wide C: no room for a separate staging tile next to the 80 KB y tile -> per-warp slabs (EP = 2); called in place
+  // (out == res) the update is reduced into the residual stream at the L2 instead (EP = 4)
+  if (res == out) {
+    if (C == 256) return launch2<256, false, true, 4>(tm, b1, b2, gamma, res, out, M, st);
+    if (C == 320) return launch2<320, false, true, 4>(tm, b1, b2, gamma, res, out, M, st);
+  }
   if (C == 256) return launch2<256, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
   if (C == 320) return launch2<320, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
   switch (C) {

@@ -97,6 +97,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(m), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// bulk tensor REDUCTION shared -> global: global[box] += smem[box], element type from the tensor map (bf16 here), performed
+// at the L2; completion tracked like a bulk store
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -250,6 +256,23 @@ __device__ __forceinline__ f32x2_t gelu_fast2(f32x2_t x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a.y));
   const f32x2_t h = mul_f32x2(x, kh);
   return fma3_f32x2(h, pack_f32x2(t0, t1), h);
+}
+
+// 2 x GELU for the fused MLP's hidden activations (the factor 1/2 moves into the D2 epilogue's FFMA, where it is free):
+// 2 GELU(x) = x + x tanh(x (a + b x^2)) with the odd CUBIC fitted (minimax over |x| <= 9) to the erf form: max |error| of
+// GELU itself 2.7e-4 -- above the quintic's 2.5e-5 but below what tanh.approx already contributes (0.5 |x| 2^-11 = 7e-4 at
+// |x| = 3) and a tenth of the bf16 rounding of the value it is stored as.  The cubic is monotone, so the clamp of the
+// quintic form (two unpacked FMNMX per pair) and one FFMA2 go away, and with the halving folded downstream a pair costs
+// 4 packed FMA-pipe instructions + 2 MUFU instead of 8 + 2: the fused MLP's GELU warps are issue-bound (ncu r01m: issue
+// slots 73 %, MUFU 45 %, tensor pipe 28 % at C = 80).
+__device__ __forceinline__ f32x2_t gelu_twice2(f32x2_t x) {
+  const f32x2_t k3 = pack_f32x2(0.03470089f, 0.03470089f), k1 = pack_f32x2(0.80015708f, 0.80015708f);
+  const f32x2_t p = fma3_f32x2(mul_f32x2(x, x), k3, k1);
+  const float2 a = unpack_f32x2(mul_f32x2(p, x));
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a.y));
+  return fma3_f32x2(x, pack_f32x2(t0, t1), x);
 }
 
 // SiLU x * sigmoid(x) == 0.5 x (1 + tanh(x / 2)) for bf16 outputs: one MUFU op

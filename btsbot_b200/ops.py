@@ -75,11 +75,12 @@ def gemm(a, wt, bias, epilogue=L.EPI_BIAS, gamma=None, res=None):
     return out
 
 
-def mlp_fused(y, res, w1, b1, w2, b2, gamma):
-    """res + gamma * (fc2(gelu(fc1(y)+b1))+b2) in one tcgen05 kernel (bf16, C in [64,160])."""
+def mlp_fused(y, res, w1, b1, w2, b2, gamma, inplace=False):
+    """res + gamma * (fc2(gelu(fc1(y)+b1))+b2) in one tcgen05 kernel (bf16, C in [64,160], 256, 320).
+    ``inplace=True`` passes out == res (the wide variants then add the update to ``res`` with a bulk tensor reduction)."""
     _chk(y, res, w1, b1, w2, b2, gamma)
     M, c = y.shape
-    out = torch.empty_like(y)
+    out = res if inplace else torch.empty_like(y)
     L.check(L.lib().btsb_convnext_mlp_fused_fwd(_p(y), _p(res), _p(w1), _p(b1), _p(w2), _p(b2), _p(gamma), _p(out),
                                                 M, c, L.stream_ptr()), "mlp_fused")
     return out

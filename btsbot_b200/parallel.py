@@ -92,10 +92,15 @@ def score_alerts(score_fn, triplets, metadata, batch_size: int = 8192, gather: b
 class AlertScorer:
     """The end-to-end public scoring call: host (numpy / pinned torch) HWC triplets + metadata -> scores.
 
-    Per micro-batch: async H2D copy on a copy stream, K1 (cast + NHWC->NCHW [+ crop/normalise]), model forward,
-    sigmoid epilogue; copies of batch i+1 overlap the kernels of batch i (two streams, two staging buffers)."""
+    Per micro-batch: async H2D copy on a copy stream into one of ``staging_slots`` device staging buffers the scorer owns,
+    K1 (cast + NHWC->NCHW [+ crop/normalise]), model forward, sigmoid epilogue.  The copy of batch i+1 overlaps the kernels
+    of batch i; a slot is overwritten only after the forward that read it has finished (one event per slot), so the host
+    may run any number of calls ahead without the caching allocator ever entering the timed path (a fresh 391 MB
+    ``.to(device)`` per call made the end-to-end rate swing between 0.65 and 1.13 M alerts/s from run to run:
+    ``cudaMalloc`` in the middle of the pipeline whenever the host ran ahead of the events that free the old blocks)."""
 
-    def __init__(self, model, crop_to_size: int = 63, normalize: bool = False, return_scores: bool = True):
+    def __init__(self, model, crop_to_size: int = 63, normalize: bool = False, return_scores: bool = True,
+                 staging_slots: int = 3):
         from . import alert_utils, ops
         self.model, self.crop, self.norm, self.return_scores = model.eval(), crop_to_size, normalize, return_scores
         self._au, self._ops = alert_utils, ops
@@ -103,26 +108,46 @@ class AlertScorer:
         self.meta_only = model._config["model_name"] == "um_nn"
         self.dev = next(model.parameters()).device
         self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.n_slots = max(2, int(staging_slots))
+        self._rings = {}                 # (shape, dtype) -> [next slot, [device buffer, consumed event | None] * n_slots]
 
-    def _to_dev(self, x):
-        t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x
-        return t.to(self.dev, non_blocking=True)
+    def _stage(self, x):
+        """Queue the H2D copy of ``x`` into the next staging slot of its shape on the copy stream; returns the slot."""
+        t = torch.from_numpy(np.ascontiguousarray(x)) if isinstance(x, np.ndarray) else x.contiguous()
+        if t.device == self.dev:
+            return [t, None]
+        key = (tuple(t.shape), t.dtype)
+        ring = self._rings.get(key)
+        if ring is None:
+            if len(self._rings) >= 4:                        # a new batch shape: drop the oldest ring
+                self._rings.pop(next(iter(self._rings)))
+            ring = self._rings[key] = [0, [[torch.empty(t.shape, dtype=t.dtype, device=self.dev), None]
+                                           for _ in range(self.n_slots)]]
+        slot = ring[1][ring[0]]
+        ring[0] = (ring[0] + 1) % self.n_slots
+        if slot[1] is not None:
+            self.copy_stream.wait_event(slot[1])             # the forward that read this slot last has finished
+        slot[0].copy_(t, non_blocking=True)
+        return slot
 
     @torch.no_grad()
     def __call__(self, triplets, metadata=None):
         cur = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.copy_stream):
-            t = None if self.meta_only else self._to_dev(triplets)
-            m = self._to_dev(metadata) if (self.multimodal or self.meta_only) else None
+            ts = None if self.meta_only else self._stage(triplets)
+            ms = self._stage(metadata) if (self.multimodal or self.meta_only) else None
         cur.wait_stream(self.copy_stream)
-        for z in (t, m):
-            if z is not None:
-                z.record_stream(cur)
+        t, m = (None if ts is None else ts[0]), (None if ms is None else ms[0])
         if self.meta_only:
             logits = self.model(input_data=m)
         else:
             x = self._au.triplets_to_model_input(t, self.crop, self.norm)
             logits = self.model(image_input=x, metadata_input=m) if self.multimodal else self.model(input_data=x)
+        for slot in (ts, ms):
+            if slot is not None:
+                if slot[1] is None:
+                    slot[1] = torch.cuda.Event()
+                slot[1].record(cur)
         if not self.return_scores:
             return logits.reshape(-1)
         scores, _ = self._ops.score(logits)

@@ -214,6 +214,31 @@ def test_mlp_fused_tcgen05(cuda_dev, C, M):
     assert err < 4e-2 and (got - ref).abs().mean().item() < 5e-3
 
 
+@pytest.mark.parametrize("C,M", [(320, 1000), (256, 777), (320, 128 * 150 + 5), (80, 300)])
+def test_mlp_fused_in_place(cuda_dev, C, M):
+    """out == res: the wide variants add gamma * (fc2(...) + b2) to the residual rows with a bulk tensor reduction (bf16 add
+    at the L2: the update is rounded to bf16 before the add, one more rounding than the out-of-place kernel); the narrow
+    variants stage the rows and simply overwrite them.  Both must agree with the out-of-place result to bf16 rounding."""
+    from btsbot_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(M, C, generator=g).bfloat16().to(cuda_dev)
+    res = torch.randn(M, C, generator=g).bfloat16().to(cuda_dev)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).bfloat16().to(cuda_dev)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).bfloat16().to(cuda_dev)
+    b1, b2 = (torch.randn(4 * C, generator=g) * 0.1).to(cuda_dev), (torch.randn(C, generator=g) * 0.1).to(cuda_dev)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(cuda_dev)
+    ref = ops.mlp_fused(y, res, w1, b1, w2, b2, gamma).float()
+    buf = res.clone()
+    got = ops.mlp_fused(y, buf, w1, b1, w2, b2, gamma, inplace=True)
+    torch.cuda.synchronize()
+    assert got.data_ptr() == buf.data_ptr()
+    err = (got.float() - ref).abs()
+    print(f"[parity] mlp_fused in place C={C} M={M}: max|in-place - out-of-place| = {err.max().item():.3e}, "
+          f"mean {err.mean().item():.3e}")
+    # two bf16 roundings instead of one: at most ~1.5 ulp of the result (|values| < 8 -> ulp <= 2^-5)
+    assert err.max().item() <= 0.0625 and err.mean().item() < 4e-3
+
+
 @pytest.mark.parametrize("C0,H,W,B", [(80, 63, 63, 37), (64, 63, 63, 5), (128, 20, 36, 3), (16, 8, 8, 700), (96, 31, 47, 9),
                                       (80, 63, 63, 1200)])
 def test_stem_tcgen05(cuda_dev, C0, H, W, B):

@@ -262,3 +262,27 @@ def test_inference_cuda_graph_matches_eager(cuda_dev, golden_logits, golden_batc
             p.mul_(1.01)
     c = _call(graphed, cfg, ti[:40], tm[:40])
     assert not torch.equal(c, _call(eager, cfg, ti[:40], tm[:40]))       # re-packed weights -> new graph
+
+
+@pytest.mark.parametrize("case,precision", [("mm_nano", "bf16"), ("img_nano", "fp32"), ("um_nn", "fp32")])
+def test_alert_scorer_ring_matches_direct_calls(cuda_dev, golden_logits, case, precision):
+    """parallel.AlertScorer (the e2e public call): host HWC triplets (pinned torch and plain numpy) through its staging
+    ring -- more calls in flight than slots, changing batch shapes, no synchronisation in between -- give bitwise the
+    logits of K1 + forward called directly on device-resident inputs."""
+    from btsbot_b200.parallel import AlertScorer
+    cfg, sd, model = _build(case, golden_logits, cuda_dev, precision)
+    n = 96
+    trip, meta = synth.make_triplets(n, start=500), synth.make_metadata(n, start=500)
+    scorer = AlertScorer(model, return_scores=False, staging_slots=2)
+    spans = [(0, 40), (40, 80), (80, 96), (8, 48), (3, 19), (48, 88), (0, 40), (56, 96)]
+    outs = []
+    for k, (lo, hi) in enumerate(spans):                                   # queued back to back, host runs ahead
+        t = trip[lo:hi] if k % 2 else torch.from_numpy(trip[lo:hi].copy()).pin_memory()
+        m = meta[lo:hi] if k % 2 else torch.from_numpy(meta[lo:hi].copy()).pin_memory()
+        outs.append(scorer(t, m if case != "img_nano" else None))
+    torch.cuda.synchronize()
+    for (lo, hi), got in zip(spans, outs):
+        x = btsbot.alert_utils.triplets_to_model_input(torch.from_numpy(trip[lo:hi]).to(cuda_dev))
+        ref = _call(model, cfg, x, torch.from_numpy(meta[lo:hi]).to(cuda_dev)).reshape(-1)
+        assert torch.equal(got, ref), (lo, hi)
+    assert len(scorer._rings) <= 4
