@@ -26,8 +26,13 @@ STEM_FUSED = os.environ.get("BTSB_STEM_FUSED", "1") != "0"
 #: falls back to the two separate GEMMs for A/B timing
 FUSE_MLP_WIDE = os.environ.get("BTSB_FUSE_WIDE", "1") != "0"
 #: wide fused MLP called IN PLACE (out == res): the update is added to the residual stream by a bulk tensor reduction
-#: instead of load -> add -> store (BTSB_MLP_INPLACE=1; A/B until measured and parity-checked)
-MLP_INPLACE = os.environ.get("BTSB_MLP_INPLACE", "0") != "0"
+#: instead of load -> add -> store: 126 -> 117 us per launch at C = 320 (profiles/r02t); BTSB_MLP_INPLACE=0 for A/B
+MLP_INPLACE = os.environ.get("BTSB_MLP_INPLACE", "1") != "0"
+#: bf16 mode: the residual stream of every stage but the last (stem / downsample outputs, block outputs) is stored as
+#: IEEE fp16 instead of bf16 -- same bytes, 8x finer rounding of the tensor that is updated 12-14 times in a row; the
+#: MMA operands stay bf16, the last stage stays bf16 because its rows feed the head GEMM (csrc/common.cuh).
+#: BTSB_XF16=0 restores the all-bf16 stream for A/B.
+XF16 = os.environ.get("BTSB_XF16", "1") != "0"
 #: use the fused fc1->GELU->fc2 kernel where it applies (bf16, C <= 160, 256, 320); tests flip this to cover both paths
 FUSE_MLP = True
 #: head layer 0: contract the F image features on the tensor cores (bf16 features x bf16 weights, fp32 accumulate and
@@ -174,11 +179,22 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
     code, adt = w.code, w.wdt
     h, wd = (H - 4) // 4 + 1, (W - 4) // 4 + 1
     c = w.dims[0]
-    cur = torch.empty((B * h * wd, c), device=dev, dtype=adt)
+    last = len(w.stages) - 1
+    stem_fused = TC_STEM and STEM_FUSED and w.stem_w_tc is not None and c in (64, 80, 96)
+    # fp16 residual stream (bf16 mode, every stage but the last): needs the kernels that know the BF16_XF16 code
+    xf16 = XF16 and code == L.BF16 and stem_fused and last >= 1
+
+    def stream(i):
+        """(dtype code, torch dtype) of stage i's residual stream."""
+        return (L.BF16_XF16, torch.float16) if xf16 and i < last else (code, adt)
+
+    scode, sdt = stream(0)
+    cur = torch.empty((B * h * wd, c), device=dev, dtype=sdt)
     es = cur.element_size()
-    if TC_STEM and STEM_FUSED and w.stem_w_tc is not None and c in (64, 80, 96):
+    if stem_fused:
         L.launch("stem_fused", lib.btsb_stem_fused_fwd, _p(x), B, H, W, _p(w.stem_w_tc), _p(w.stem_b), _p(w.stem_ln_w),
-                 _p(w.stem_ln_b), _p(cur), c, st, flops=2.0 * 48 * c * B * h * wd, nbytes=4.0 * x.numel() + es * cur.numel())
+                 _p(w.stem_ln_b), _p(cur), c, scode, st, flops=2.0 * 48 * c * B * h * wd,
+                 nbytes=4.0 * x.numel() + es * cur.numel())
     elif TC_STEM and w.stem_w_tc is not None:
         patches = torch.empty((B * h * wd, 64), device=dev, dtype=torch.bfloat16)
         L.launch("stem_im2col", lib.btsb_stem_im2col_bf16, _p(x), _p(patches), B, H, W, st,
@@ -200,12 +216,13 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
                 raise ValueError("feature map too small for the 2x2/s2 downsample")
             ho, wo = (h - 2) // 2 + 1, (wd - 2) // 2 + 1
             patches = torch.empty((B * ho * wo, 4 * cin), device=dev, dtype=adt)
-            L.launch("lnpatch", lib.btsb_convnext_lnpatch_fwd, _p(cur), code, B, h, wd, cin, _p(stg["ds_ln_w"]),
+            L.launch("lnpatch", lib.btsb_convnext_lnpatch_fwd, _p(cur), scode, B, h, wd, cin, _p(stg["ds_ln_w"]),
                      _p(stg["ds_ln_b"]), _p(patches), st, flops=8.0 * patches.numel(),
                      nbytes=es * (cur.numel() + patches.numel()))
             h, wd = ho, wo
-            cur = torch.empty((B * h * wd, c), device=dev, dtype=adt)
-            _gemm("gemm_down", patches, stg["ds_w"], stg["ds_b"], None, None, cur, code, L.EPI_BIAS, st)
+            scode, sdt = stream(i)
+            cur = torch.empty((B * h * wd, c), device=dev, dtype=sdt)
+            _gemm("gemm_down", patches, stg["ds_w"], stg["ds_b"], None, None, cur, scode, L.EPI_BIAS, st)
             if capture is not None:
                 capture[f"down{i}"] = (cur, h, wd)
         M = B * h * wd
@@ -213,21 +230,24 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
         fused = FUSE_MLP and code == L.BF16 and c % 16 == 0 and (64 <= c <= 160 or (FUSE_MLP_WIDE and c in (256, 320)))
         hid = None if fused else torch.empty((M, 4 * c), device=dev, dtype=adt)
         for j, blk in enumerate(stg["blocks"]):
-            L.launch(f"dwln_{wd}x{c}", lib.btsb_convnext_dwln_fwd, _p(cur), code, B, h, wd, c, _p(blk["dw_w"]),
+            L.launch(f"dwln_{wd}x{c}", lib.btsb_convnext_dwln_fwd, _p(cur), scode, B, h, wd, c, _p(blk["dw_w"]),
                      _p(blk["dw_b"]), _p(blk["ln_w"]), _p(blk["ln_b"]), _p(y), st,
                      flops=2.0 * 49 * M * c + 8.0 * M * c, nbytes=2.0 * es * M * c)
             if capture is not None:
                 capture[f"s{i}b{j}.dwln"] = (y.clone(), h, wd)
+            # the block updates its input rows in place where the kernel can add to them (wide fused MLP: bulk tensor
+            # reduction); `capture` keeps every block's output, so it takes the out-of-place form
             inplace = fused and MLP_INPLACE and c in (256, 320) and capture is None
-            nxt = cur if inplace else torch.empty((M, c), device=dev, dtype=adt)
+            nxt = cur if inplace else torch.empty((M, c), device=dev, dtype=sdt)
             if fused:
                 # fc1 -> GELU -> fc2 -> *gamma -> +shortcut in one kernel; bytes: y + res + out (+ L2-resident weights)
                 L.launch(f"mlp_fused_{c}", lib.btsb_convnext_mlp_fused_fwd, _p(y), _p(cur), _p(blk["fc1_w"]),
-                         _p(blk["fc1_b"]), _p(blk["fc2_w"]), _p(blk["fc2_b"]), _p(blk["gamma"]), _p(nxt), M, c, st,
+                         _p(blk["fc1_b"]), _p(blk["fc2_w"]), _p(blk["fc2_b"]), _p(blk["gamma"]), _p(nxt), M, c,
+                         L.BF16_XF16 if scode == L.BF16_XF16 else L.BF16, st,
                          flops=16.0 * M * c * c, nbytes=es * (3.0 * M * c + 8.0 * c * c))
             else:
                 _gemm(f"gemm_fc1_{c}", y, blk["fc1_w"], blk["fc1_b"], None, None, hid, code, L.EPI_BIAS_GELU, st)
-                _gemm(f"gemm_fc2_{c}", hid, blk["fc2_w"], blk["fc2_b"], blk["gamma"], cur, nxt, code,
+                _gemm(f"gemm_fc2_{c}", hid, blk["fc2_w"], blk["fc2_b"], blk["gamma"], cur, nxt, scode,
                       L.EPI_SCALE_RES, st)
             cur = nxt
             if capture is not None:

@@ -9,12 +9,14 @@ import ctypes as C
 import os
 import threading
 
-F32, BF16, F64 = 0, 1, 2
+F32, BF16, F64, BF16_XF16 = 0, 1, 2, 3      # BF16_XF16: bf16 compute, the residual-stream tensor of the call in fp16
 ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 EPI_BIAS, EPI_BIAS_GELU, EPI_SCALE_RES, EPI_BIAS_SILU = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbtsbot_b200.so")
+#: the in-tree build; BTSB_LIB names another build of the same sources (A/B timing of a compile-time variant) -- still
+#: this library or nothing, there is no fallback
+LIB_PATH = os.environ.get("BTSB_LIB") or os.path.join(_HERE, "libbtsbot_b200.so")
 
 _lib = None
 _lock = threading.Lock()
@@ -64,9 +66,9 @@ SIGNATURES = {
     "btsb_convnext_poolln_fwd": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, vp]),
     "btsb_gemm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "btsb_stem_im2col_bf16": (i32, [vp, vp, i64, i32, i32, vp]),
-    "btsb_stem_fused_fwd": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp]),
+    "btsb_stem_fused_fwd": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp]),
     "btsb_gemm_ln_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
-    "btsb_convnext_mlp_fused_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp]),
+    "btsb_convnext_mlp_fused_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
     "btsb_meta_head_fwd": (i32, [C.POINTER(HeadParams), i64, vp, vp]),
     "btsb_score_epilogue": (i32, [vp, i64, vp, vp, vp]),
     "btsb_gemm_f32_strided": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, i64, i32, vp]),

@@ -145,7 +145,7 @@ def _attention_block(w: MaxVitWeights, a: dict, cur, B, H, W, c, grid_mode, tag,
     if FUSE_MLP and code == L.BF16 and c % 16 == 0 and (64 <= c <= 160 or c == 256):
         nxt = torch.empty_like(cur)
         L.launch(f"mv_mlp_fused_{c}", lib.btsb_convnext_mlp_fused_fwd, _p(y), _p(cur), _p(a["fc1_w"]), _p(a["fc1_b"]),
-                 _p(a["fc2_w"]), _p(a["fc2_b"]), _p(w.ones(c)), _p(nxt), M, c, st,
+                 _p(a["fc2_w"]), _p(a["fc2_b"]), _p(w.ones(c)), _p(nxt), M, c, L.BF16, st,
                  flops=16.0 * M * c * c, nbytes=es * (3.0 * M * c + 8.0 * c * c))
         cur = nxt
     else:

@@ -1,6 +1,7 @@
 // Shared helpers for the btsbot_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -56,6 +57,7 @@ inline bool first_use_on_device(std::atomic<uint64_t>& mask) {
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ float ldf(const double* p) { return (float)*p; }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
@@ -137,6 +139,51 @@ __device__ __forceinline__ f32x2_t add_f32x2(f32x2_t a, f32x2_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+
+// ---- the residual stream's storage type ------------------------------------------------------------------------------
+// In bf16 mode the tensors between blocks (stem output, block outputs, downsample outputs) can be stored as IEEE fp16
+// instead of bf16 (dtype code BTSB_BF16_XF16): same bytes, 11 instead of 8 significand bits.  The block update is added
+// to this tensor twelve to fourteen times in a row, and its rounding was the largest single contribution to the bf16
+// mode's logit error (CPU emulation rounding at the kernels' points: 1.4e-2 of a 1.4-2.2e-2 total on the worst parity
+// case, 0.7-1.1e-2 with an fp16 or fp32 stream).  MMA operands (LayerNorm outputs, hidden
+// activations, weights) stay bf16.  Stores saturate to the largest finite fp16 instead of overflowing to infinity.
+template <bool XF16>
+__device__ __forceinline__ uint32_t pack_x2(float lo, float hi) {
+  uint32_t r;
+  if constexpr (XF16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool XF16>
+__device__ __forceinline__ float x2_lo(uint32_t v) {
+  if constexpr (XF16) { float f; asm("{.reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, l;}" : "=f"(f) : "r"(v)); return f; }
+  else return __uint_as_float(v << 16);
+}
+template <bool XF16>
+__device__ __forceinline__ float x2_hi(uint32_t v) {
+  if constexpr (XF16) { float f; asm("{.reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, h;}" : "=f"(f) : "r"(v)); return f; }
+  else return __uint_as_float(v & 0xffff0000u);
+}
+template <bool XF16>
+__device__ __forceinline__ f32x2_t x2_to_f32x2(uint32_t v) { return pack_f32x2(x2_lo<XF16>(v), x2_hi<XF16>(v)); }
+// The depthwise-conv kernels are bound by the FMA pipe, where the fp16 -> fp32 conversion instruction (HADD2.F32) also
+// runs: two of them per loaded pixel would add 16 % to that pipe's load.  Instead the 16 bits are moved into fp32 position
+// with ALU-pipe instructions only (sign-extending shift + mask: the fp16 exponent lands in the low five bits of the fp32
+// exponent field), which yields value * 2^-112 EXACTLY -- for fp16 subnormals too, they become fp32 subnormals -- and the
+// conv taps are staged multiplied by 2^112 (kXScale), so every product is the exact one.
+template <bool XF16>
+__device__ __forceinline__ f32x2_t x2_to_f32x2_scaled(uint32_t v) {
+  if constexpr (XF16) {
+    const uint32_t lo = ((uint32_t)((int32_t)(v << 16) >> 3)) & 0x8FFFE000u;
+    const uint32_t hi = ((uint32_t)((int32_t)v >> 3)) & 0x8FFFE000u;
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+  } else {
+    return bf16x2_to_f32x2(v);
+  }
+}
+template <bool XF16> struct XScale { static constexpr float tap = XF16 ? 0x1p112f : 1.0f; };
 
 constexpr float kLnEps = 1e-6f;  // timm LayerNorm2d eps for ConvNeXt
 

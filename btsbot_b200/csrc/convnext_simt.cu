@@ -103,11 +103,11 @@ stem_kernel(const float* __restrict__ x, int64_t B, int H, int W, int ho, int wo
 // =====================================================================================================
 template <int TW> struct DwBounds { static constexpr int kMaxThreads = (TW >= 8) ? 320 : 640; };
 
-template <typename T, int TW>
+template <typename T, int TW, typename TO = T>          // TO != T: fp16 residual-stream rows in, bf16 rows out
 __global__ void __launch_bounds__(DwBounds<TW>::kMaxThreads)
 dwln_kernel(const T* __restrict__ x, int64_t B, int H, int W, int C, int G, const float* __restrict__ wt,
             const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-            T* __restrict__ out) {
+            TO* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int HW = H * W;
   float* conv = reinterpret_cast<float*>(smem_raw);                                  // [G*HW][C] fp32
@@ -176,7 +176,7 @@ dwln_kernel(const T* __restrict__ x, int64_t B, int H, int W, int C, int G, cons
     float q = 0.f;
     for (int k = lane; k < C; k += 32) { const float d = v[k] - mean; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + kLnEps);
-    T* dst = out + (b0 * HW + p) * (int64_t)C;
+    TO* dst = out + (b0 * HW + p) * (int64_t)C;
     for (int k = lane; k < C; k += 32) stf(dst + k, (v[k] - mean) * rstd * __ldg(ln_w + k) + __ldg(ln_b + k));
   }
 }
@@ -184,10 +184,10 @@ dwln_kernel(const T* __restrict__ x, int64_t B, int H, int W, int C, int G, cons
 // =====================================================================================================
 // K5a  LayerNorm2d + 2x2/s2 patch gather: one warp per *used* input pixel.
 // =====================================================================================================
-template <typename T>
+template <typename T, typename TO = T>
 __global__ void __launch_bounds__(256)
 lnpatch_kernel(const T* __restrict__ x, int64_t B, int H, int W, int C, int Ho, int Wo,
-               const float* __restrict__ ln_w, const float* __restrict__ ln_b, T* __restrict__ out) {
+               const float* __restrict__ ln_w, const float* __restrict__ ln_b, TO* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -214,7 +214,7 @@ lnpatch_kernel(const T* __restrict__ x, int64_t B, int H, int W, int C, int Ho, 
     for (int j = 0; j < MAXJ; ++j) if (lane + 32 * j < C) { const float d = v[j] - mean; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) / (float)C + kLnEps);
     const int oy = iy >> 1, dy = iy & 1, ox = ix >> 1, dx = ix & 1;
-    T* dst = out + ((b * Ho + oy) * (int64_t)Wo + ox) * (4 * (int64_t)C) + (dy * 2 + dx) * C;
+    TO* dst = out + ((b * Ho + oy) * (int64_t)Wo + ox) * (4 * (int64_t)C) + (dy * 2 + dx) * C;
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       const int k = lane + 32 * j;
@@ -443,7 +443,7 @@ extern "C" int btsb_convnext_stem_fwd(const float* x, int64_t B, int H, int W, c
   return launch_done("stem");
 }
 
-template <typename T, int TW>
+template <typename T, int TW, typename TO = T>
 static int launch_dwln(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias,
                        const float* ln_w, const float* ln_b, void* out, cudaStream_t st) {
   // threads: multiple of C in [256, 640]
@@ -464,37 +464,37 @@ static int launch_dwln(const void* x, int64_t B, int H, int W, int C, const floa
   if (G > 64) G = 64;
   const size_t smem = (size_t)G * per_img;
   BTSB_REQUIRE(smem <= 227 * 1024, "dwln: map %dx%dx%d needs %zu B of shared memory (> 227 KB)", H, W, C, smem);
-  auto kern = dwln_kernel<T, TW>;
+  auto kern = dwln_kernel<T, TW, TO>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)), "dwln attr");
   const int64_t grid = (B + G - 1) / G;
-  kern<<<(unsigned)grid, threads, smem, st>>>((const T*)x, B, H, W, C, G, w, bias, ln_w, ln_b, (T*)out);
+  kern<<<(unsigned)grid, threads, smem, st>>>((const T*)x, B, H, W, C, G, w, bias, ln_w, ln_b, (TO*)out);
   return launch_done("dwln");
 }
 
-template <typename T>
+template <typename T, typename TO = T>
 static int dispatch_dwln(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias,
                          const float* ln_w, const float* ln_b, void* out, cudaStream_t st) {
-  if (W == 15) return launch_dwln<T, 15>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
-  if (W == 7) return launch_dwln<T, 7>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
-  if (W == 3) return launch_dwln<T, 3>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
-  if (W == 1) return launch_dwln<T, 1>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  if (W == 15) return launch_dwln<T, 15, TO>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  if (W == 7) return launch_dwln<T, 7, TO>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  if (W == 3) return launch_dwln<T, 3, TO>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  if (W == 1) return launch_dwln<T, 1, TO>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
   // any other map width (e.g. the 19 / 9 / 4 / 2 maps of larger "LS" cutouts): 8 outputs per thread while the CTA
   // (a multiple of C threads) fits that variant's register budget, else the 3-output variant (up to 640 threads)
   int r = 1;
   while (C * r < 256) ++r;
-  if (C * r <= DwBounds<8>::kMaxThreads) return launch_dwln<T, 8>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
-  return launch_dwln<T, 3>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  if (C * r <= DwBounds<8>::kMaxThreads) return launch_dwln<T, 8, TO>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+  return launch_dwln<T, 3, TO>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
 }
 
 namespace btsb {
 int dwln_bf16_v2(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
                  const float* ln_b, void* out, cudaStream_t st);
 int dwln_bf16_v3(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
-                 const float* ln_b, void* out, cudaStream_t st);
+                 const float* ln_b, void* out, bool xf16, cudaStream_t st);
 int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
-                    const float* ln_b, void* out, cudaStream_t st);
+                    const float* ln_b, void* out, bool xf16, cudaStream_t st);
 int dwln_bf16_v5(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
-                 const float* ln_b, void* out, cudaStream_t st);
+                 const float* ln_b, void* out, bool xf16, cudaStream_t st);
 int dwln_f32_v3(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
                 const float* ln_b, void* out, cudaStream_t st);
 }
@@ -503,7 +503,7 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
                                       void* stream) {
   if (int e = check_device()) return e;
   BTSB_REQUIRE(B >= 0 && H >= 1 && W >= 1 && C >= 32, "dwln: bad shape");
-  BTSB_REQUIRE(dtype == BTSB_F32 || dtype == BTSB_BF16, "dwln: dtype must be F32 or BF16");
+  BTSB_REQUIRE(dtype == BTSB_F32 || dtype == BTSB_BF16 || dtype == BTSB_BF16_XF16, "dwln: dtype must be F32, BF16 or BF16_XF16");
   if (B == 0) return BTSB_OK;
   BTSB_REQUIRE(x && w && bias && ln_w && ln_b && out, "dwln: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -512,19 +512,21 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
     if (rc != 1) return rc;
     return dispatch_dwln<float>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
   }
+  const bool xf16 = dtype == BTSB_BF16_XF16;       // x: fp16 residual-stream rows; out: bf16 (the fc1 operand) either way
   // each specialised kernel returns 1 when the shape is not its own: small maps -> v5 -> v3 -> v2 -> generic
   {
-    const int rc = dwln_bf16_small(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);   // 3x3 and 1x1 maps
+    const int rc = dwln_bf16_small(x, B, H, W, C, w, bias, ln_w, ln_b, out, xf16, st);   // 3x3 and 1x1 maps
     if (rc != 1) return rc;
   }
   {
-    const int rc = dwln_bf16_v5(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);      // conv and LayerNorm on different warps
+    const int rc = dwln_bf16_v5(x, B, H, W, C, w, bias, ln_w, ln_b, out, xf16, st);      // conv and LayerNorm on different warps
     if (rc != 1) return rc;
   }
   {
-    const int rc = dwln_bf16_v3(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
+    const int rc = dwln_bf16_v3(x, B, H, W, C, w, bias, ln_w, ln_b, out, xf16, st);
     if (rc != 1) return rc;
   }
+  if (xf16) return dispatch_dwln<__half, __nv_bfloat16>(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
   {
     const int rc = dwln_bf16_v2(x, B, H, W, C, w, bias, ln_w, ln_b, out, st);
     if (rc != 1) return rc;
@@ -536,7 +538,7 @@ extern "C" int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H
 // its NV uint4 (8*NV channels, contiguous 16*NV bytes) in registers -- 128-bit loads/stores, thread-local two-pass
 // statistics, only log2(TPP) shuffles.  ~18 warp-instructions per pixel instead of ~200 for the warp-per-pixel kernels
 // above (which were issue-bound at 1.4-1.7 TB/s: profiles/r01c misc.summary).
-template <int NV, int TPP>
+template <int NV, int TPP, bool XF16 = false>          // XF16: x holds IEEE fp16 residual-stream rows (out: bf16)
 __global__ void __launch_bounds__(256)
 lnpatch_tpp_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int W, int Ho, int Wo,
                    const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
@@ -563,7 +565,7 @@ lnpatch_tpp_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int W,
     for (int j = 0; j < NV; ++j) {
       const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s += __uint_as_float(u[k] << 16) + __uint_as_float(u[k] & 0xffff0000u);
+      for (int k = 0; k < 4; ++k) s += x2_lo<XF16>(u[k]) + x2_hi<XF16>(u[k]);
     }
 #pragma unroll
     for (int o = TPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -574,7 +576,7 @@ lnpatch_tpp_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int W,
       const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float d0 = __uint_as_float(u[k] << 16) - mean, d1 = __uint_as_float(u[k] & 0xffff0000u) - mean;
+        const float d0 = x2_lo<XF16>(u[k]) - mean, d1 = x2_hi<XF16>(u[k]) - mean;
         q = fmaf(d0, d0, q); q = fmaf(d1, d1, q);
       }
     }
@@ -594,8 +596,8 @@ lnpatch_tpp_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int H, int W,
       uint32_t o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float lo = (__uint_as_float(u[k] << 16) - mean) * rstd * wv[2 * k] + bb[2 * k];
-        const float hi = (__uint_as_float(u[k] & 0xffff0000u) - mean) * rstd * wv[2 * k + 1] + bb[2 * k + 1];
+        const float lo = (x2_lo<XF16>(u[k]) - mean) * rstd * wv[2 * k] + bb[2 * k];
+        const float hi = (x2_hi<XF16>(u[k]) - mean) * rstd * wv[2 * k + 1] + bb[2 * k + 1];
         __nv_bfloat162 ob = __floats2bfloat162_rn(lo, hi);
         o[k] = *reinterpret_cast<uint32_t*>(&ob);
       }
@@ -666,18 +668,20 @@ static void launch_lnpatch_tpp_f32(const float* xi, int64_t B, int H, int W, int
 
 template <int NV, int TPP>
 static void launch_lnpatch_tpp(const __nv_bfloat16* xi, int64_t B, int H, int W, int Ho, int Wo, const float* ln_w,
-                               const float* ln_b, __nv_bfloat16* xo, cudaStream_t st) {
+                               const float* ln_b, __nv_bfloat16* xo, bool xf16, cudaStream_t st) {
   const int64_t total = B * 4 * (int64_t)Ho * Wo * TPP;
   int64_t grid = (total + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;
-  lnpatch_tpp_kernel<NV, TPP><<<(unsigned)grid, 256, 0, st>>>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo);
+  if (xf16) lnpatch_tpp_kernel<NV, TPP, true><<<(unsigned)grid, 256, 0, st>>>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo);
+  else lnpatch_tpp_kernel<NV, TPP, false><<<(unsigned)grid, 256, 0, st>>>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo);
 }
 
 extern "C" int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, int H, int W, int C,
                                          const float* ln_w, const float* ln_b, void* out, void* stream) {
   if (int e = check_device()) return e;
   BTSB_REQUIRE(B >= 0 && H >= 2 && W >= 2 && C >= 1 && C <= 640, "lnpatch: bad shape (C<=640, H,W>=2)");
-  BTSB_REQUIRE(dtype == BTSB_F32 || dtype == BTSB_BF16, "lnpatch: dtype must be F32 or BF16");
+  BTSB_REQUIRE(dtype == BTSB_F32 || dtype == BTSB_BF16 || dtype == BTSB_BF16_XF16, "lnpatch: dtype must be F32, BF16 or BF16_XF16");
+  const bool xf16 = dtype == BTSB_BF16_XF16;       // x: fp16 residual-stream rows; out (the downsample GEMM operand): bf16
   if (B == 0) return BTSB_OK;
   BTSB_REQUIRE(x && ln_w && ln_b && out, "lnpatch: null pointer");
   const int Ho = (H - 2) / 2 + 1, Wo = (W - 2) / 2 + 1;
@@ -700,13 +704,16 @@ extern "C" int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, in
     const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
     __nv_bfloat16* xo = (__nv_bfloat16*)out;
     switch (C) {
-      case 64: launch_lnpatch_tpp<8, 1>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
-      case 80: launch_lnpatch_tpp<10, 1>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
-      case 128: launch_lnpatch_tpp<8, 2>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
-      case 160: launch_lnpatch_tpp<10, 2>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
-      case 256: launch_lnpatch_tpp<8, 4>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
-      default: launch_lnpatch_tpp<10, 4>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, st); break;
+      case 64: launch_lnpatch_tpp<8, 1>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, xf16, st); break;
+      case 80: launch_lnpatch_tpp<10, 1>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, xf16, st); break;
+      case 128: launch_lnpatch_tpp<8, 2>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, xf16, st); break;
+      case 160: launch_lnpatch_tpp<10, 2>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, xf16, st); break;
+      case 256: launch_lnpatch_tpp<8, 4>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, xf16, st); break;
+      default: launch_lnpatch_tpp<10, 4>(xi, B, H, W, Ho, Wo, ln_w, ln_b, xo, xf16, st); break;
     }
+  } else if (xf16) {
+    lnpatch_kernel<__half, __nv_bfloat16><<<grid, 256, 0, st>>>((const __half*)x, B, H, W, C, Ho, Wo, ln_w, ln_b,
+                                                                 (__nv_bfloat16*)out);
   } else if (C % 2 == 0 && ((uintptr_t)ln_w % 8) == 0 && ((uintptr_t)ln_b % 8) == 0) {
     const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
     __nv_bfloat16* xo = (__nv_bfloat16*)out;

@@ -26,7 +26,7 @@ __device__ __forceinline__ void cp_async16_v3(void* smem_dst, const void* gsrc) 
 // CT > 0: channel count known at compile time (nano 80/160, pico 64/128) -- every shared-memory address becomes an
 // immediate offset, which removes ~1/3 of the issued instructions (integer address arithmetic; profiles/r01c);
 // CT == 0: generic runtime C.
-template <int S, int CT, typename T = __nv_bfloat16>
+template <int S, int CT, typename T = __nv_bfloat16, bool XF16 = false>   // XF16: 2-byte input rows are IEEE fp16 (out: bf16)
 __global__ void __launch_bounds__(kDw3MaxThreads, 1)
 dwln3_kernel(const T* __restrict__ x, int64_t B, int C_rt, int A_rt, int REM_rt, const float* __restrict__ wt,
              const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -77,7 +77,7 @@ dwln3_kernel(const T* __restrict__ x, int64_t B, int C_rt, int A_rt, int REM_rt,
   for (int i = tid; i < NT * NT * C; i += nthr) {
     const int t = i / C, c = i - t * C;
     const int ty = t / NT, tx = t - ty * NT;
-    wsm[i] = __ldg(wt + ((ty + 3 - R) * 7 + (tx + 3 - R)) * C + c);
+    wsm[i] = __ldg(wt + ((ty + 3 - R) * 7 + (tx + 3 - R)) * C + c) * XScale<XF16>::tap;   // fp16 input: common.cuh
   }
   for (int i = tid; i < C; i += nthr) { bsm[i] = __ldg(bias + i); gsm[i] = __ldg(ln_w + i); hsm[i] = __ldg(ln_b + i); }
 
@@ -110,7 +110,7 @@ dwln3_kernel(const T* __restrict__ x, int64_t B, int C_rt, int A_rt, int REM_rt,
         for (int ix = 0; ix < S; ++ix) {
           f32x2_t xin;
           if constexpr (F32) xin = *reinterpret_cast<const f32x2_t*>(im + (size_t)(iy * S + ix) * C);
-          else xin = bf16x2_to_f32x2(*reinterpret_cast<const uint32_t*>(im + (size_t)(iy * S + ix) * C));
+          else xin = x2_to_f32x2_scaled<XF16>(*reinterpret_cast<const uint32_t*>(im + (size_t)(iy * S + ix) * C));
 #pragma unroll
           for (int kx = 0; kx < NT; ++kx) {
             const int t = ix - (kx - R);
@@ -238,7 +238,7 @@ dwln3_kernel(const T* __restrict__ x, int64_t B, int C_rt, int A_rt, int REM_rt,
 
 int num_sms();
 
-template <int S, int CT, typename T = __nv_bfloat16>
+template <int S, int CT, typename T = __nv_bfloat16, bool XF16 = false>
 static int launch_dwln3(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
   constexpr int R = S > 3 ? 3 : S - 1;
@@ -253,7 +253,7 @@ static int launch_dwln3(const void* x, int64_t B, int C, const float* w, const f
   const size_t smem = (size_t)(NT * NT + 3) * C * 4 + (size_t)(sizeof(T) == 4 ? 2 : 1) * S * 32 * ncontrib * 4 +
                       2 * (size_t)HW * C * sizeof(T);
   if (smem > 227 * 1024) return 1;
-  auto kern = dwln3_kernel<S, CT, T>;
+  auto kern = dwln3_kernel<S, CT, T, XF16>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "dwln3 attr");
   const int sms = num_sms();
   // small maps: several CTAs per SM are possible (few warps, little shared memory)
@@ -267,9 +267,17 @@ static int launch_dwln3(const void* x, int64_t B, int C, const float* w, const f
 
 // returns 1 if the shape is not handled here (caller falls back to dwln2 / the generic kernel)
 int dwln_bf16_v3(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
-                 const float* ln_b, void* out, cudaStream_t st) {
+                 const float* ln_b, void* out, bool xf16, cudaStream_t st) {
   if (H != W || C % 16 != 0 || C > 640) return 1;
   if (((uintptr_t)x % 16) != 0 || ((uintptr_t)out % 4) != 0) return 1;
+  using BF = __nv_bfloat16;
+  if (xf16) {                       // fp16 residual stream: the widths that reach this kernel in the nano / pico trunks
+    if (H == 15 && C == 64) return launch_dwln3<15, 64, BF, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    if (H == 7 && C == 128) return launch_dwln3<7, 128, BF, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    if (H == 15) return launch_dwln3<15, 0, BF, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    if (H == 7) return launch_dwln3<7, 0, BF, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    return 1;
+  }
   switch (H) {
     case 15:
       if (C == 80) return launch_dwln3<15, 80>(x, B, C, w, bias, ln_w, ln_b, out, st);

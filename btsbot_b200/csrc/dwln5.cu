@@ -66,7 +66,7 @@ struct Dw5 {
   static_assert(THREADS <= 1024 && (HW * C) % 8 == 0, "shape");
 };
 
-template <int S, int C>
+template <int S, int C, bool XF16>
 __global__ void __launch_bounds__(Dw5<S, C>::THREADS, 1)
 dwln5_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __restrict__ wt, const float* __restrict__ bias,
              const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
@@ -80,7 +80,7 @@ dwln5_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __rest
   const uint32_t bar_full = s_u32(tin + 2 * HW * C), bar_empty = bar_full + 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < 49 * C; i += P::THREADS) wsm[i] = __ldg(wt + i);
+  for (int i = tid; i < 49 * C; i += P::THREADS) wsm[i] = __ldg(wt + i) * XScale<XF16>::tap;   // fp16 input: see common.cuh
   for (int i = tid; i < C; i += P::THREADS) bsm[i] = __ldg(bias + i);
   if (tid == 0) {
     mb_init(bar_full, P::CONV_WARPS);
@@ -133,7 +133,7 @@ dwln5_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __rest
           for (int kx = 0; kx < 7; ++kx) wv[kx] = *reinterpret_cast<const f32x2_t*>(wsm + ((dy + 3) * 7 + kx) * C + 2 * c2);
 #pragma unroll
           for (int ix = 0; ix < S; ++ix) {
-            const f32x2_t xin = bf16x2_to_f32x2(*reinterpret_cast<const uint32_t*>(im + (iy * S + ix) * C));
+            const f32x2_t xin = x2_to_f32x2_scaled<XF16>(*reinterpret_cast<const uint32_t*>(im + (iy * S + ix) * C));
 #pragma unroll
             for (int kx = 0; kx < 7; ++kx) {
               const int t = ix - (kx - 3);
@@ -215,11 +215,11 @@ dwln5_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __rest
 
 int num_sms();
 
-template <int S, int C>
+template <int S, int C, bool XF16>
 static int launch_dwln5(const void* x, int64_t B, const float* w, const float* bias, const float* ln_w, const float* ln_b,
                         void* out, cudaStream_t st) {
   using P = Dw5<S, C>;
-  auto kern = dwln5_kernel<S, C>;
+  auto kern = dwln5_kernel<S, C, XF16>;
   static std::atomic<uint64_t> attr_done{0};
   if (first_use_on_device(attr_done)) {
     BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM), "dwln5 attr");
@@ -232,11 +232,16 @@ static int launch_dwln5(const void* x, int64_t B, const float* w, const float* b
 
 // returns 1 if the shape is not handled here (caller falls back to v3 / v2 / the generic kernel)
 int dwln_bf16_v5(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
-                 const float* ln_b, void* out, cudaStream_t st) {
+                 const float* ln_b, void* out, bool xf16, cudaStream_t st) {
   if (H != W) return 1;
   if (((uintptr_t)x % 16) != 0 || ((uintptr_t)out % 16) != 0) return 1;
-  if (H == 15 && C == 80) return launch_dwln5<15, 80>(x, B, w, bias, ln_w, ln_b, out, st);
-  if (H == 7 && C == 160) return launch_dwln5<7, 160>(x, B, w, bias, ln_w, ln_b, out, st);
+  if (xf16) {
+    if (H == 15 && C == 80) return launch_dwln5<15, 80, true>(x, B, w, bias, ln_w, ln_b, out, st);
+    if (H == 7 && C == 160) return launch_dwln5<7, 160, true>(x, B, w, bias, ln_w, ln_b, out, st);
+    return 1;
+  }
+  if (H == 15 && C == 80) return launch_dwln5<15, 80, false>(x, B, w, bias, ln_w, ln_b, out, st);
+  if (H == 7 && C == 160) return launch_dwln5<7, 160, false>(x, B, w, bias, ln_w, ln_b, out, st);
   // The pico widths (64 / 128) stay on v3 (dwln3.cu).  This kernel is parity-green for them per kernel, and every model
   // moved by < 1e-3 when it was tried -- except the synthetic frozen-fusion / pico case, whose bf16 logit error went from
   // 1.34e-2 (v3's summation order of the LayerNorm statistics) to 2.35e-2, across the 2e-2 bar: the two kernels differ

@@ -21,7 +21,7 @@ namespace btsb {
 // at 2.5 of ~6.5 TB/s); PF = 2 keeps two images per thread in flight for 9 more registers.
 // CPA (opt-in, UNMEASURED, CT > 0 only): the reachable taps -- NT contiguous runs of NT*C floats in the [49][C] tap matrix --
 // are staged with one wave of 16-byte cp.async instead of ~NT*NT*C/T dependent batches of scalar loads per thread.
-template <int S, int CT, int PF, bool CPA = false>
+template <int S, int CT, int PF, bool CPA = false, bool XF16 = false>   // XF16: input rows are IEEE fp16 (out: bf16)
 __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, int C_rt, const float* __restrict__ wt,
                                   const float* __restrict__ bias, const float* __restrict__ ln_w,
                                   const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
@@ -80,7 +80,7 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
       f32x2_t acc[HW], xin[HW];
       const f32x2_t bvp = pack_f32x2(bv.x, bv.y);
 #pragma unroll
-      for (int p = 0; p < HW; ++p) { acc[p] = bvp; xin[p] = bf16x2_to_f32x2(cur[p]); }
+      for (int p = 0; p < HW; ++p) { acc[p] = bvp; xin[p] = x2_to_f32x2<XF16>(cur[p]); }   // HBM / latency-bound: exact cvt
 #pragma unroll
       for (int ty = 0; ty < NT; ++ty) {
 #pragma unroll
@@ -146,7 +146,7 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
 
 int num_sms();
 
-template <int S, int CT, int PF, bool CPA = false>
+template <int S, int CT, int PF, bool CPA = false, bool XF16 = false>
 static int launch_small_pf(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
   constexpr int NT = 2 * (S - 1) + 1;
@@ -155,7 +155,7 @@ static int launch_small_pf(const void* x, int64_t B, int C, const float* w, cons
   const int nw = threads / 32;
   const size_t smem = (size_t)NT * NT * C * 4 + 2 * nw * 32 * 4 + 2 * 16 * 8;
   if (smem > 200 * 1024) return 1;
-  auto kern = dwln_small_kernel<S, CT, PF, CPA>;
+  auto kern = dwln_small_kernel<S, CT, PF, CPA, XF16>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dwln_small attr");
   int per_sm = 1;
   BTSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem), "dwln_small occupancy");
@@ -169,22 +169,31 @@ static int launch_small_pf(const void* x, int64_t B, int C, const float* w, cons
 // cp.async tap staging (compile-time C, 16-byte aligned taps) is the default where it applies: 39 -> 33 us per 8192
 // images at 3x3x320 (profiles/r02a); the two-image prefetch variant (PF = 2) measured slower (37 -> 39 us,
 // profiles/r01n) and is not dispatched.
-template <int S, int CT>
+template <int S, int CT, bool XF16 = false>
 static int launch_small(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
                         const float* ln_b, void* out, cudaStream_t st) {
   if constexpr (CT > 0 && CT % 4 == 0) {
-    if (((uintptr_t)w % 16) == 0) return launch_small_pf<S, CT, 1, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    if (((uintptr_t)w % 16) == 0) return launch_small_pf<S, CT, 1, true, XF16>(x, B, C, w, bias, ln_w, ln_b, out, st);
   }
-  return launch_small_pf<S, CT, 1>(x, B, C, w, bias, ln_w, ln_b, out, st);
+  return launch_small_pf<S, CT, 1, false, XF16>(x, B, C, w, bias, ln_w, ln_b, out, st);
 }
 
 // returns 1 if the shape is not handled here
 int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* w, const float* bias, const float* ln_w,
-                    const float* ln_b, void* out, cudaStream_t st) {
+                    const float* ln_b, void* out, bool xf16, cudaStream_t st) {
   if (H != W || (C & 1) || C > 2048) return 1;
   if (((uintptr_t)x % 4) != 0 || ((uintptr_t)out % 4) != 0 || ((uintptr_t)bias % 8) != 0 || ((uintptr_t)ln_w % 8) != 0 ||
       ((uintptr_t)ln_b % 8) != 0)
     return 1;
+  if (xf16) {
+    if (H == 3) {
+      if (C == 320) return launch_small<3, 320, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+      if (C == 256) return launch_small<3, 256, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+      return launch_small<3, 0, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    }
+    if (H == 1) return launch_small<1, 0, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
+    return 1;
+  }
   if (H == 3) {
     if (C == 320) return launch_small<3, 320>(x, B, C, w, bias, ln_w, ln_b, out, st);
     if (C == 256) return launch_small<3, 256>(x, B, C, w, bias, ln_w, ln_b, out, st);

@@ -86,15 +86,21 @@ __host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab
   return P;
 }
 
-// Hidden activation: H holds 2 GELU(fc1 + b1) (clamp-free cubic-tanh form, tc_common.cuh gelu_twice2) and the D2 epilogue
-// halves the accumulator inside the FFMA that adds b2 -- power-of-two scalings commute with the bf16 rounding of H, so the
-// result is that of GELU itself.  -DBTSB_GELU_QUINTIC builds the previous form (quintic with clamp, H = GELU) for A/B.
-#ifdef BTSB_GELU_QUINTIC
-__device__ __forceinline__ f32x2_t hidden_act2(f32x2_t x) { return tc::gelu_fast2(x); }
-constexpr float kD2Scale = 1.0f;
+// Hidden activation from the fc1 accumulator pair `acc` and the staged bias pair `b` (= kB1Scale * b1).  Both forms leave
+// a power-of-two multiple of GELU in H and the D2 epilogue rescales the accumulator inside the FFMA that adds b2 --
+// power-of-two scalings commute with the bf16 rounding of H, so the result is that of GELU itself.
+//   default            : quintic-tanh GELU (max error 2.5e-5), H = GELU / 4 (tc_common.cuh gelu_quarter_quintic2)
+//   -DBTSB_GELU_CUBIC  : clamp-free cubic-tanh form (max error 2.7e-4), H = 2 GELU (gelu_twice2): 6 instead of 8
+//                        instructions per pair; measured 279 vs 296 us at C = 80 (profiles/r02t) -- see DESIGN.md on why the
+//                        tighter form is the default
+#ifdef BTSB_GELU_CUBIC
+constexpr float kB1Scale = 1.0f, kD2Scale = 0.5f;
+__device__ __forceinline__ f32x2_t hidden_act2(f32x2_t acc, f32x2_t b) { return tc::gelu_twice2(add_f32x2(acc, b)); }
 #else
-__device__ __forceinline__ f32x2_t hidden_act2(f32x2_t x) { return tc::gelu_twice2(x); }
-constexpr float kD2Scale = 0.5f;
+constexpr float kB1Scale = 0.125f, kD2Scale = 4.0f;
+__device__ __forceinline__ f32x2_t hidden_act2(f32x2_t acc, f32x2_t b) {
+  return tc::gelu_quarter_quintic2(fma3_f32x2(acc, pack_f32x2(0.125f, 0.125f), b));
+}
 #endif
 
 // K-major operand tile descriptor for a block whose rows are `sw` bytes (128 / 64 / 32) with the matching swizzle
@@ -168,7 +174,7 @@ struct Maps2 {
 // y tile of the next row tile could only be fetched afterwards (~4 k clocks for 80 KB with every SM at its tile boundary
 // at once).  Removed.  In steady state this kernel streams W1 + W2 (1.6 MB per 128-row tile, 80 KB per ~1800-clock hidden
 // chunk = 45 B/clk/SM, 7.1 TB/s chip-wide) -- it sits on the L2 -> SM bandwidth, not on the tensor pipe.
-template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false>
+template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false, bool XF16 = false>   // XF16: res / out rows are IEEE fp16
 __global__ void __launch_bounds__(kThreads2, 1)   // 19 warps -> 5 on three SMSPs: 96 registers is the hardware ceiling
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
@@ -247,7 +253,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   }
   if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
   float* b1s = reinterpret_cast<float*>(sal + P.off_b1);            // fc1 bias staged once per CTA
-  for (int i = threadIdx.x; i < 4 * C; i += kThreads2) b1s[i] = __ldg(b1 + i);
+  for (int i = threadIdx.x; i < 4 * C; i += kThreads2) b1s[i] = kB1Scale * __ldg(b1 + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -464,16 +470,16 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
-            v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), bf16_lo(rr[i / 2]));
-            v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), bf16_hi(rr[i / 2]));
-            v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), bf16_lo(rr[i / 2 + 1]));
-            v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), bf16_hi(rr[i / 2 + 1]));
+            v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), x2_lo<XF16>(rr[i / 2]));
+            v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), x2_hi<XF16>(rr[i / 2]));
+            v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), x2_lo<XF16>(rr[i / 2 + 1]));
+            v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), x2_hi<XF16>(rr[i / 2 + 1]));
           }
           uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          o0.x = pack_x2<XF16>(v[0], v[1]); o0.y = pack_x2<XF16>(v[2], v[3]);
+          o0.z = pack_x2<XF16>(v[4], v[5]); o0.w = pack_x2<XF16>(v[6], v[7]);
+          o1.x = pack_x2<XF16>(v[8], v[9]); o1.y = pack_x2<XF16>(v[10], v[11]);
+          o1.z = pack_x2<XF16>(v[12], v[13]); o1.w = pack_x2<XF16>(v[14], v[15]);
           uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * C + n);
           op[0] = o0; op[1] = o1;
         }
@@ -541,13 +547,13 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
-            v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), bf16_lo(rr[i / 2]));
-            v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), bf16_hi(rr[i / 2]));
-            v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), bf16_lo(rr[i / 2 + 1]));
-            v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), bf16_hi(rr[i / 2 + 1]));
+            v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), x2_lo<XF16>(rr[i / 2]));
+            v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), x2_hi<XF16>(rr[i / 2]));
+            v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), x2_lo<XF16>(rr[i / 2 + 1]));
+            v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), x2_hi<XF16>(rr[i / 2 + 1]));
           }
-          *p0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-          *p1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+          *p0 = make_uint4(pack_x2<XF16>(v[0], v[1]), pack_x2<XF16>(v[2], v[3]), pack_x2<XF16>(v[4], v[5]), pack_x2<XF16>(v[6], v[7]));
+          *p1 = make_uint4(pack_x2<XF16>(v[8], v[9]), pack_x2<XF16>(v[10], v[11]), pack_x2<XF16>(v[12], v[13]), pack_x2<XF16>(v[14], v[15]));
         }
         off += (uint32_t)(w * 1024); s0 += w;
       }
@@ -617,13 +623,13 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         for (int i = 0; i < 16; i += 4) {
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
           const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
-          v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), bf16_lo(rr[i / 2]));
-          v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), bf16_hi(rr[i / 2]));
-          v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), bf16_lo(rr[i / 2 + 1]));
-          v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), bf16_hi(rr[i / 2 + 1]));
+          v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), x2_lo<XF16>(rr[i / 2]));
+          v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), x2_hi<XF16>(rr[i / 2]));
+          v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), x2_lo<XF16>(rr[i / 2 + 1]));
+          v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), x2_hi<XF16>(rr[i / 2 + 1]));
         }
-        *p0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        *p1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+        *p0 = make_uint4(pack_x2<XF16>(v[0], v[1]), pack_x2<XF16>(v[2], v[3]), pack_x2<XF16>(v[4], v[5]), pack_x2<XF16>(v[6], v[7]));
+        *p1 = make_uint4(pack_x2<XF16>(v[8], v[9]), pack_x2<XF16>(v[10], v[11]), pack_x2<XF16>(v[12], v[13]), pack_x2<XF16>(v[14], v[15]));
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -664,10 +670,10 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
-        const float2 g0 = unpack_f32x2(hidden_act2(add_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
-                                                              pack_f32x2(b4.x, b4.y))));
-        const float2 g1 = unpack_f32x2(hidden_act2(add_f32x2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
-                                                              pack_f32x2(b4.z, b4.w))));
+        const float2 g0 = unpack_f32x2(hidden_act2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                                   pack_f32x2(b4.x, b4.y)));
+        const float2 g1 = unpack_f32x2(hidden_act2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
+                                                   pack_f32x2(b4.z, b4.w)));
         o[i / 2] = pack_bf16x2(g0.x, g0.y);
         o[i / 2 + 1] = pack_bf16x2(g1.x, g1.y);
       }
@@ -738,14 +744,14 @@ int mlp_fused2_supported(int C) {
   return C % 16 == 0 && ((C >= 64 && C <= 160) || C == 256 || C == 320);
 }
 
-template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false>
+template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false, bool XF16 = false>
 static int launch2(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res, void* out,
                    int64_t M, cudaStream_t st) {
   constexpr Plan2 P = plan2_for(C, TE, HT, EP == 2 || EP == 4);   // must be the kernel's own plan (slabs for EP 2 and 4)
-  if constexpr (!TRACE && (C == 80 || C == 160 || C == 320)) {   // the traced variants exist for the bench's three widths
-    if (g_mlp_trace != nullptr) return launch2<C, TE, HT, EP, true>(tm, b1, b2, gamma, res, out, M, st);
+  if constexpr (!TRACE && XF16 && (C == 80 || C == 160 || C == 320)) {   // traced variants: the bench's three widths, fp16 stream
+    if (g_mlp_trace != nullptr) return launch2<C, TE, HT, EP, true, XF16>(tm, b1, b2, gamma, res, out, M, st);
   }
-  auto kern = mlp_fused2_kernel<C, TE, HT, EP, TRACE>;
+  auto kern = mlp_fused2_kernel<C, TE, HT, EP, TRACE, XF16>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
@@ -754,8 +760,35 @@ static int launch2(const Maps2& tm, const float* b1, const float* b2, const floa
 }
 
 
+int make_tmap_f16_2d_sw(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                        uint32_t box_cols, int swizzle_bytes);
+
+template <bool XF16>
+static int mlp_fused2_dispatch(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res,
+                               void* out, int64_t M, int C, cudaStream_t st) {
+  // wide C: no room for a separate staging tile next to the 80 KB y tile -> per-warp slabs (EP = 2); called in place
+  // (out == res) the update is reduced into the residual stream at the L2 instead (EP = 4)
+  if (res == out) {
+    if (C == 256) return launch2<256, false, true, 4, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+    if (C == 320) return launch2<320, false, true, 4, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+  }
+  if (C == 256) return launch2<256, false, true, 2, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+  if (C == 320) return launch2<320, false, true, 2, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+  switch (C) {
+    case 64: return launch2<64, true, true, 0, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+    case 80: return launch2<80, true, true, 0, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+    case 96: return launch2<96, true, true, 0, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+    case 112: return launch2<112, true, true, 0, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+    case 128: return launch2<128, true, true, 0, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+    case 144: return launch2<144, true, true, 0, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+    case 160: return launch2<160, true, true, 0, false, XF16>(tm, b1, b2, gamma, res, out, M, st);
+  }
+  set_error("mlp_fused: C=%d unsupported", C);
+  return BTSB_EINVAL;
+}
+
 int mlp_fused2_launch(const void* y, const void* res, const void* W1, const float* b1, const void* W2, const float* b2,
-                      const float* gamma, void* out, int64_t M, int C, cudaStream_t st) {
+                      const float* gamma, void* out, int64_t M, int C, bool xf16, cudaStream_t st) {
   BTSB_REQUIRE(mlp_fused2_supported(C), "mlp_fused: C=%d unsupported", C);
   const int t32 = (C % 64) >= 32, t16 = (C % 32) >= 16;
   Maps2 tm;
@@ -772,31 +805,16 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
   }
   const int NC = C > 256 ? C / 2 : C;                      // W2 chunk rows per bulk copy / per G2 UMMA
   if (int e = make_tmap_bf16_2d_sw(&tm.w2, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)NC, 64, 128)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.r128, res, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.r64, res, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.r32, res, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
-  if (int e = make_tmap_bf16_2d_sw(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
-  // wide C: no room for a separate staging tile next to the 80 KB y tile -> per-warp slabs (EP = 2); called in place
-  // (out == res) the update is reduced into the residual stream at the L2 instead (EP = 4)
-  if (res == out) {
-    if (C == 256) return launch2<256, false, true, 4>(tm, b1, b2, gamma, res, out, M, st);
-    if (C == 320) return launch2<320, false, true, 4>(tm, b1, b2, gamma, res, out, M, st);
-  }
-  if (C == 256) return launch2<256, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
-  if (C == 320) return launch2<320, false, true, 2>(tm, b1, b2, gamma, res, out, M, st);
-  switch (C) {
-    case 64: return launch2<64, true, true>(tm, b1, b2, gamma, res, out, M, st);
-    case 80: return launch2<80, true, true>(tm, b1, b2, gamma, res, out, M, st);
-    case 96: return launch2<96, true, true>(tm, b1, b2, gamma, res, out, M, st);
-    case 112: return launch2<112, true, true>(tm, b1, b2, gamma, res, out, M, st);
-    case 128: return launch2<128, true, true>(tm, b1, b2, gamma, res, out, M, st);
-    case 144: return launch2<144, true, true>(tm, b1, b2, gamma, res, out, M, st);
-    case 160: return launch2<160, true, true>(tm, b1, b2, gamma, res, out, M, st);
-  }
-  set_error("mlp_fused: C=%d unsupported", C);
-  return BTSB_EINVAL;
+  // residual / output rows: bf16 or (xf16) IEEE fp16 -- the element type matters to the in-place reduction only
+  auto rmap = xf16 ? make_tmap_f16_2d_sw : make_tmap_bf16_2d_sw;
+  if (int e = rmap(&tm.r128, res, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
+  if (int e = rmap(&tm.r64, res, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
+  if (int e = rmap(&tm.r32, res, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
+  if (int e = rmap(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
+  if (int e = rmap(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
+  if (int e = rmap(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
+  if (xf16) return mlp_fused2_dispatch<true>(tm, b1, b2, gamma, res, out, M, C, st);
+  return mlp_fused2_dispatch<false>(tm, b1, b2, gamma, res, out, M, C, st);
 }
 
 }  // namespace btsb
@@ -813,15 +831,16 @@ extern "C" int btsb_debug_mlp_trace(void* buf) {
 // (called at /root/reference/btsbot/architectures.py:132; oracle/convnext_oracle.py block()).
 extern "C" int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const void* W1, const float* b1,
                                            const void* W2, const float* b2, const float* gamma, void* out, int64_t M,
-                                           int C, void* stream) {
+                                           int C, int dtype, void* stream) {
   using namespace btsb;
   if (int e = check_device()) return e;
   BTSB_REQUIRE(M >= 0 && M < (1ll << 31), "mlp_fused: bad M");
+  BTSB_REQUIRE(dtype == BTSB_BF16 || dtype == BTSB_BF16_XF16, "mlp_fused: dtype must be BF16 or BF16_XF16");
   BTSB_REQUIRE(mlp_fused2_supported(C), "mlp_fused: C=%d unsupported (multiple of 16 in [64,160], 256 or 320)", C);
   if (M == 0) return BTSB_OK;
   BTSB_REQUIRE(y && res && W1 && b1 && W2 && b2 && gamma && out, "mlp_fused: null pointer");
   BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)b1 % 16) == 0 &&
                    ((uintptr_t)b2 % 16) == 0 && ((uintptr_t)gamma % 16) == 0,
                "mlp_fused: pointers must be 16-byte aligned");
-  return mlp_fused2_launch(y, res, W1, b1, W2, b2, gamma, out, M, C, (cudaStream_t)stream);
+  return mlp_fused2_launch(y, res, W1, b1, W2, b2, gamma, out, M, C, dtype == BTSB_BF16_XF16, (cudaStream_t)stream);
 }

@@ -37,7 +37,7 @@ constexpr int kSmemS = kOffVecS + 3 * 128 * 4 + 1024;
 // N = C0 at compile time: the epilogue keeps the whole output row (N fp32 accumulators) in registers -> ONE pass over
 // TMEM for mean, variance and normalisation (gemm_tc's runtime-N EPI_LN makes three and was the pacing part: the unfused
 // GEMM took 137 us with TMA-fed operands)
-template <int N>
+template <int N, bool XF16>        // XF16: the output rows open the fp16 residual stream (common.cuh) instead of bf16
 __global__ void __launch_bounds__(kThreadsS, 1)
 stem_fused_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
@@ -188,10 +188,10 @@ stem_fused_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorM
           for (int i = 0; i < 16; ++i)
             v[i] = (__uint_as_float(r[ch][i]) - mean) * rstd * lw_s[ch * 16 + i] + lb_s[ch * 16 + i];
           uint4 o0, o1;
-          o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
-          o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
-          o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
-          o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+          o0.x = pack_x2<XF16>(v[0], v[1]); o0.y = pack_x2<XF16>(v[2], v[3]);
+          o0.z = pack_x2<XF16>(v[4], v[5]); o0.w = pack_x2<XF16>(v[6], v[7]);
+          o1.x = pack_x2<XF16>(v[8], v[9]); o1.y = pack_x2<XF16>(v[10], v[11]);
+          o1.z = pack_x2<XF16>(v[12], v[13]); o1.w = pack_x2<XF16>(v[14], v[15]);
           uint4* op = reinterpret_cast<uint4*>(out + (size_t)row * N + ch * 16);
           op[0] = o0; op[1] = o1;
         }
@@ -203,10 +203,10 @@ stem_fused_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorM
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
-template <int N>
+template <int N, bool XF16>
 static int launch_stem(const float* x, const CUtensorMap& tmW, const float* bias, const float* ln_w, const float* ln_b,
                        void* out, int64_t M, int H, int W, int ho, int wo, cudaStream_t st) {
-  auto kern = stem_fused_kernel<N>;
+  auto kern = stem_fused_kernel<N, XF16>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemS), "stem_fused attr");
   const int tiles = (int)((M + SM_ - 1) / SM_);
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -220,8 +220,9 @@ static int launch_stem(const float* x, const CUtensorMap& tmW, const float* bias
 using namespace btsb;
 
 extern "C" int btsb_stem_fused_fwd(const float* x, int64_t B, int H, int W, const void* w_pad, const float* bias,
-                                   const float* ln_w, const float* ln_b, void* out, int C0, void* stream) {
+                                   const float* ln_w, const float* ln_b, void* out, int C0, int out_dtype, void* stream) {
   if (int e = check_device()) return e;
+  BTSB_REQUIRE(out_dtype == BTSB_BF16 || out_dtype == BTSB_BF16_XF16, "stem_fused: out_dtype must be BF16 or BF16_XF16");
   if (B <= 0) return BTSB_OK;
   BTSB_REQUIRE(x && w_pad && bias && ln_w && ln_b && out && H >= 4 && W >= 4, "stem_fused: bad arguments");
   BTSB_REQUIRE(C0 == 64 || C0 == 80 || C0 == 96, "stem_fused: C0=%d is not instantiated (64, 80, 96); use im2col + gemm_ln", C0);
@@ -232,10 +233,17 @@ extern "C" int btsb_stem_fused_fwd(const float* x, int64_t B, int H, int W, cons
   CUtensorMap tmW;
   if (int e = make_tmap_bf16_2d(&tmW, w_pad, (uint64_t)C0, 64, (uint32_t)C0)) return e;
   cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == BTSB_BF16_XF16) {
+    switch (C0) {
+      case 64: return launch_stem<64, true>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
+      case 80: return launch_stem<80, true>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
+      case 96: return launch_stem<96, true>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
+    }
+  }
   switch (C0) {
-    case 64: return launch_stem<64>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
-    case 80: return launch_stem<80>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
-    case 96: return launch_stem<96>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
+    case 64: return launch_stem<64, false>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
+    case 80: return launch_stem<80, false>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
+    case 96: return launch_stem<96, false>(x, tmW, bias, ln_w, ln_b, out, M, H, W, ho, wo, st);
   }
   set_error("stem_fused: C0=%d is not instantiated (64, 80, 96); use im2col + gemm_ln", C0);
   return BTSB_EINVAL;

@@ -38,6 +38,9 @@ extern "C" {
 #define BTSB_F32 0
 #define BTSB_BF16 1
 #define BTSB_F64 2
+/* bf16 compute (MMA operands, LayerNorm outputs, hidden activations: bf16) with the call's RESIDUAL-STREAM tensor --
+ * named per function below -- stored as IEEE fp16 (same bytes, 11 significand bits; stores saturate). */
+#define BTSB_BF16_XF16 3
 
 /* activation codes (metadata branch / heads) */
 #define BTSB_ACT_NONE 0
@@ -103,14 +106,16 @@ int btsb_convnext_stem_fwd(const float* x, int64_t B, int H, int W, const float*
                            const float* ln_w, const float* ln_b, int C0, void* out, int out_dtype, void* stream);
 
 /* ---- K3: depthwise 7x7 (pad 3) + bias + LayerNorm2d -- timm blocks.j.conv_dw + blocks.j.norm.
- * x, out: [B*H*W, C] dtype F32|BF16 (same for both).  w: [49,C] float32 (k = ky*7+kx), bias/ln_w/ln_b [C].
+ * x, out: [B*H*W, C] dtype F32|BF16 (same for both); BF16_XF16: x is the fp16 residual stream, out (the fc1 operand)
+ * bf16.  w: [49,C] float32 (k = ky*7+kx), bias/ln_w/ln_b [C].
  */
 int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* w,
                            const float* bias, const float* ln_w, const float* ln_b, void* out, void* stream);
 
 /* ---- K5a: downsample prologue -- timm stages.i.downsample.0 LayerNorm2d, emitted directly as the
  * 2x2/s2 patch matrix the conv (downsample.1) consumes as a GEMM.  x: [B*H*W, C]; out: [B*Ho*Wo, 4C] with
- * column (dy*2+dx)*C + c, Ho=(H-2)/2+1 (floor: last odd row/col dropped, as Conv2d does).
+ * column (dy*2+dx)*C + c, Ho=(H-2)/2+1 (floor: last odd row/col dropped, as Conv2d does).  dtype F32|BF16 (both
+ * tensors); BF16_XF16: x is the fp16 residual stream, out (the GEMM operand) bf16.
  */
 int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* ln_w,
                               const float* ln_b, void* out, void* stream);
@@ -125,7 +130,7 @@ int btsb_convnext_poolln_fwd(const void* x, int dtype, int64_t B, int HW, int C,
  * downsample.1.  out[M,N] = epi(A[M,K] . Wt[N,K]^T + bias).  dtype F32: CUDA-core fp32 (the 1e-4 path);
  * dtype BF16: tcgen05/TMEM tensor cores with TMA operand staging, fp32 accumulate, A/Wt/res/out bf16.
  * bias/gamma: [N] float32.  res: [M,N] in `dtype` (EPI_SCALE_RES only).  F32: K % 4 == 0.  BF16: K % 16 == 0,
- * N % 16 == 0, all pointers 16-byte aligned.
+ * N % 16 == 0, all pointers 16-byte aligned.  BF16_XF16: as BF16 with res and out in the fp16 residual stream.
  */
 int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float* gamma, const void* res,
                   void* out, int64_t M, int N, int K, int dtype, int epilogue, void* stream);
@@ -136,9 +141,10 @@ int btsb_gemm_fwd(const void* A, const void* Wt, const float* bias, const float*
  * gemm_ln: out[M,N] = LayerNorm_rows(A[M,K] . Wt[N,K]^T + bias) * ln_w + ln_b, bf16 operands/output, N <= 128. */
 int btsb_stem_im2col_bf16(const float* x, void* patches, int64_t B, int H, int W, void* stream);
 /* the same stem as ONE kernel: the im2col rows are built in shared memory by producer warps straight from the NCHW fp32
- * image (the [M,64] patch matrix never exists in HBM).  w_pad: [C0,64] bf16 (columns 48..63 zero); out [B*h*w, C0] bf16. */
+ * image (the [M,64] patch matrix never exists in HBM).  w_pad: [C0,64] bf16 (columns 48..63 zero); out [B*h*w, C0] bf16
+ * (out_dtype BTSB_BF16) or fp16 (BTSB_BF16_XF16: the rows open the fp16 residual stream). */
 int btsb_stem_fused_fwd(const float* x, int64_t B, int H, int W, const void* w_pad, const float* bias,
-                        const float* ln_w, const float* ln_b, void* out, int C0, void* stream);
+                        const float* ln_w, const float* ln_b, void* out, int C0, int out_dtype, void* stream);
 int btsb_gemm_ln_fwd(const void* A, const void* Wt, const float* bias, const float* ln_w, const float* ln_b,
                      void* out, int64_t M, int N, int K, void* stream);
 
@@ -146,10 +152,12 @@ int btsb_gemm_ln_fwd(const void* A, const void* Wt, const float* bias, const flo
  * TMEM / shared memory (timm blocks.j.mlp + gamma + residual).  BF16 only; C a multiple of 16 in [64,160], 256 or 320
  * (ConvNeXt nano/pico stages 0-2, where the hidden tensor would be 4x the activation traffic).
  * y: dw+LN output [M,C]; res: block input [M,C]; W1 [4C,C], W2 [C,4C] bf16 row-major; b1 [4C], b2/gamma [C] f32.
+ * dtype BTSB_BF16: res / out bf16; BTSB_BF16_XF16: res / out are the fp16 residual stream (y, W1, W2 stay bf16).
+ * out == res (in place) is allowed; C = 256 / 320 then add the update to the rows with a bulk tensor reduction.
  */
 int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const void* W1, const float* b1,
                                 const void* W2, const float* b2, const float* gamma, void* out, int64_t M,
-                                int C, void* stream);
+                                int C, int dtype, void* stream);
 
 /* ---- K6: metadata branch + fusion head in one kernel (architectures.py:146-164,168-170; um_nn 282-290;
  * image-only heads 109-119; frozen_fusion 357-365).

@@ -14,16 +14,17 @@ dev = torch.device("cuda", 0)
 M = B * HW
 g = torch.Generator().manual_seed(0)
 bf = torch.bfloat16
-y = torch.randn(M, C, generator=g).to(bf).to(dev); res = torch.randn(M, C, generator=g).to(bf).to(dev)
+y = torch.randn(M, C, generator=g).to(bf).to(dev); res = torch.randn(M, C, generator=g).to(torch.float16).to(dev)    # the fp16 residual stream
 w1 = (torch.randn(4 * C, C, generator=g) * C ** -0.5).to(bf).to(dev); w2 = (torch.randn(C, 4 * C, generator=g) * (4 * C) ** -0.5).to(bf).to(dev)
 b1 = torch.randn(4 * C, generator=g).to(dev) * 0.1; b2 = torch.randn(C, generator=g).to(dev) * 0.1; gm = torch.randn(C, generator=g).to(dev)
+INPLACE = os.environ.get("BTSB_MLP_INPLACE", "0") != "0"      # out == res: the wide kernels' reduction drain
 for _ in range(3):
-    ops.mlp_fused(y, res, w1, b1, w2, b2, gm)
+    ops.mlp_fused(y, res, w1, b1, w2, b2, gm, inplace=INPLACE)
 torch.cuda.synchronize()
 NR, NG, NE = 17, 64, 8
 buf = torch.zeros(NR * NG * NE, dtype=torch.int64, device=dev)
 L.check(L.lib().btsb_debug_mlp_trace(buf.data_ptr()), "trace on")
-ops.mlp_fused(y, res, w1, b1, w2, b2, gm)
+ops.mlp_fused(y, res, w1, b1, w2, b2, gm, inplace=INPLACE)
 torch.cuda.synchronize()
 L.check(L.lib().btsb_debug_mlp_trace(None), "trace off")
 t = buf.cpu().view(NR, NG, NE)

@@ -46,20 +46,28 @@ def test_stem(cuda_dev, C0, H, W, B, odt):
                                      (64, 15, 15, 3), (128, 7, 7, 5), (256, 3, 3, 5), (512, 1, 1, 5),
                                      (64, 9, 11, 4), (96, 5, 2, 3), (320, 3, 3, 2500), (640, 1, 1, 3000), (48, 3, 3, 40),
                                      (512, 2, 2, 9), (640, 2, 2, 5), (256, 4, 4, 6), (64, 19, 19, 3)])
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
 def test_dwln(cuda_dev, C, H, W, B, dt):
+    """dt float16 = the fp16 residual stream of the bf16 mode: fp16 rows in, bf16 rows out (dtype code BF16_XF16); the
+    inputs include fp16 subnormals and values next to the fp16 maximum (the conv kernels shift the 16 bits into fp32
+    position and fold 2^112 into the taps instead of converting)."""
     from btsbot_b200 import ops
     g = torch.Generator().manual_seed(2)
     x = torch.randn(B, C, H, W, generator=g)
-    if dt == torch.bfloat16:
-        x = x.bfloat16().float()
+    if dt == torch.float16:
+        x.view(-1)[::97] *= 1e-6                      # fp16 subnormals
+        x.view(-1)[5::1013] *= 3e3                    # large magnitudes (|x| up to ~1e4)
+    if dt != torch.float32:
+        x = x.to(dt).float()
     w = torch.randn(C, 1, 7, 7, generator=g) / 7
     b, lw, lb = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
     ref = _ln2d(F.conv2d(x, w, b, padding=3, groups=C), lw, lb)
     got = ops.dwln(_nchw_to_rows(x).to(dt).to(cuda_dev), B, H, W, w.reshape(C, 49).t().contiguous().to(cuda_dev),
                    b.to(cuda_dev), lw.to(cuda_dev), lb.to(cuda_dev))
+    assert got.dtype == (torch.float32 if dt == torch.float32 else torch.bfloat16)
     err = _report(f"dwln C={C} {H}x{W} {dt}", _rows_to_nchw(got.cpu(), B, H, W), ref)
-    assert err < (3e-5 if dt == torch.float32 else 4e-2)
+    # bf16 output rows: half an ulp is 2^-9 of the value (the fp16 case's outliers give LayerNorm outputs up to ~sqrt(C))
+    assert err < (3e-5 if dt == torch.float32 else max(4e-2, 2.0 ** -8 * ref.abs().max().item()))
 
 
 @pytest.mark.parametrize("C,S,B", [(80, 15, 1500), (160, 7, 3000)])
@@ -83,25 +91,29 @@ def test_dwln_warp_specialised_handoff_is_deterministic(cuda_dev, C, S, B):
 
 
 @pytest.mark.parametrize("C,H,W,B", [(80, 15, 15, 5), (160, 7, 7, 9), (320, 3, 3, 11), (64, 15, 15, 2), (256, 4, 6, 3)])
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
 def test_lnpatch_then_gemm_is_downsample(cuda_dev, C, H, W, B, dt):
+    """dt float16: fp16 residual-stream rows in, bf16 patch matrix, bf16 GEMM writing fp16 rows (BF16_XF16)."""
     from btsbot_b200 import ops, _lib as L
     g = torch.Generator().manual_seed(3)
     x = torch.randn(B, C, H, W, generator=g)
-    if dt == torch.bfloat16:
-        x = x.bfloat16().float()
+    if dt != torch.float32:
+        x = x.to(dt).float()
     lw, lb = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
     cout = 2 * C
     w = torch.randn(cout, C, 2, 2, generator=g) / (2 * C ** 0.5)
-    if dt == torch.bfloat16:
+    if dt != torch.float32:
         w = w.bfloat16().float()
     b = torch.randn(cout, generator=g) * 0.1
     ref = F.conv2d(_ln2d(x, lw, lb), w, b, stride=2)
     patches = ops.lnpatch(_nchw_to_rows(x).to(dt).to(cuda_dev), B, H, W, lw.to(cuda_dev), lb.to(cuda_dev))
     ho, wo = ref.shape[2:]
     assert patches.shape == (B * ho * wo, 4 * C)
-    wt = w.permute(0, 2, 3, 1).reshape(cout, 4 * C).contiguous().to(dt).to(cuda_dev)
-    got = ops.gemm(patches, wt, b.to(cuda_dev), L.EPI_BIAS)
+    wdt = torch.float32 if dt == torch.float32 else torch.bfloat16
+    assert patches.dtype == wdt
+    wt = w.permute(0, 2, 3, 1).reshape(cout, 4 * C).contiguous().to(wdt).to(cuda_dev)
+    got = ops.gemm(patches, wt, b.to(cuda_dev), L.EPI_BIAS, out_dtype=dt if dt == torch.float16 else None)
+    assert got.dtype == dt
     err = _report(f"downsample C={C} {H}x{W} {dt}", _rows_to_nchw(got.cpu(), B, ho, wo), ref)
     assert err < (3e-5 if dt == torch.float32 else 5e-2)
 
@@ -147,22 +159,29 @@ def test_gemm_f32(cuda_dev, M, N, K, epi):
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-@pytest.mark.parametrize("epi", [0, 1, 2])
-def test_gemm_bf16_tcgen05(cuda_dev, M, N, K, epi):
+@pytest.mark.parametrize("epi,xdt", [(0, torch.bfloat16), (1, torch.bfloat16), (2, torch.bfloat16), (0, torch.float16),
+                                     (2, torch.float16)])
+def test_gemm_bf16_tcgen05(cuda_dev, M, N, K, epi, xdt):
+    """xdt float16: bf16 operands, res / out in the fp16 residual stream (dtype code BF16_XF16)."""
     from btsbot_b200 import ops
     g = torch.Generator().manual_seed(6)
     a = torch.randn(M, K, generator=g).bfloat16()
     w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
     bias, gamma = torch.randn(N, generator=g) * 0.1, torch.rand(N, generator=g) + 0.5
-    res = torch.randn(M, N, generator=g).bfloat16()
+    res = torch.randn(M, N, generator=g).to(xdt)
     ref = _gemm_ref(a.float(), w.float(), bias, epi, gamma, res.float())
     got = ops.gemm(a.to(cuda_dev), w.to(cuda_dev), bias.to(cuda_dev), epi,
-                   gamma.to(cuda_dev) if epi == 2 else None, res.to(cuda_dev) if epi == 2 else None)
+                   gamma.to(cuda_dev) if epi == 2 else None, res.to(cuda_dev) if epi == 2 else None,
+                   out_dtype=xdt if xdt == torch.float16 else None)
     torch.cuda.synchronize()
+    assert got.dtype == xdt
     got = got.float().cpu()
-    err = _report(f"gemm bf16 {M}x{N}x{K} epi{epi}", got, ref)
-    # exact fp32-accumulated product rounded once to bf16: half an ulp of |value| <= ~8
-    assert err < 3.2e-2 and (got - ref).abs().mean().item() < 4e-3
+    err = _report(f"gemm bf16 {M}x{N}x{K} epi{epi} out {xdt}", got, ref)
+    # exact fp32-accumulated product rounded once to bf16: half an ulp of |value| <= ~8 (fp16: 8 times finer)
+    if xdt == torch.float16:
+        assert err < 4.1e-3 and (got - ref).abs().mean().item() < 5e-4
+    else:
+        assert err < 3.2e-2 and (got - ref).abs().mean().item() < 4e-3
 
 
 def test_gemm_bf16_cta_pair_mode_in_subprocess(cuda_dev):
@@ -193,13 +212,14 @@ def test_gemm_bf16_cta_pair_mode_in_subprocess(cuda_dev):
 
 @pytest.mark.parametrize("C,M", [(80, 1000), (160, 777), (64, 4096), (128, 129), (80, 128 * 300 + 5), (96, 50),
                                  (320, 1000), (256, 777), (320, 128 * 150 + 5), (256, 128 * 149)])
-def test_mlp_fused_tcgen05(cuda_dev, C, M):
+@pytest.mark.parametrize("xdt", [torch.bfloat16, torch.float16])
+def test_mlp_fused_tcgen05(cuda_dev, C, M, xdt):
     """fused fc1->GELU->fc2->*gamma->+res vs fp32 math on the same bf16 operands (hidden rounded to bf16 as the
-    kernel does before the second GEMM)."""
+    kernel does before the second GEMM); res / out bf16 or fp16 (the residual stream, dtype code BF16_XF16)."""
     from btsbot_b200 import ops
     g = torch.Generator().manual_seed(7)
     y = torch.randn(M, C, generator=g).bfloat16()
-    res = torch.randn(M, C, generator=g).bfloat16()
+    res = torch.randn(M, C, generator=g).to(xdt)
     w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).bfloat16()
     w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).bfloat16()
     b1, b2 = torch.randn(4 * C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
@@ -209,20 +229,23 @@ def test_mlp_fused_tcgen05(cuda_dev, C, M):
     got = ops.mlp_fused(y.to(cuda_dev), res.to(cuda_dev), w1.to(cuda_dev), b1.to(cuda_dev), w2.to(cuda_dev),
                         b2.to(cuda_dev), gamma.to(cuda_dev))
     torch.cuda.synchronize()
+    assert got.dtype == xdt
     got = got.float().cpu()
-    err = _report(f"mlp_fused C={C} M={M}", got, ref)
-    assert err < 4e-2 and (got - ref).abs().mean().item() < 5e-3
+    err = _report(f"mlp_fused C={C} M={M} {xdt}", got, ref)
+    # the hidden activation's GELU approximation + its bf16 rounding are common to both; the output rounding is 8x finer in fp16
+    assert err < (2e-2 if xdt == torch.float16 else 4e-2) and (got - ref).abs().mean().item() < (2.5e-3 if xdt == torch.float16 else 5e-3)
 
 
 @pytest.mark.parametrize("C,M", [(320, 1000), (256, 777), (320, 128 * 150 + 5), (80, 300)])
-def test_mlp_fused_in_place(cuda_dev, C, M):
+@pytest.mark.parametrize("xdt", [torch.bfloat16, torch.float16])
+def test_mlp_fused_in_place(cuda_dev, C, M, xdt):
     """out == res: the wide variants add gamma * (fc2(...) + b2) to the residual rows with a bulk tensor reduction (bf16 add
     at the L2: the update is rounded to bf16 before the add, one more rounding than the out-of-place kernel); the narrow
     variants stage the rows and simply overwrite them.  Both must agree with the out-of-place result to bf16 rounding."""
     from btsbot_b200 import ops
     g = torch.Generator().manual_seed(9)
     y = torch.randn(M, C, generator=g).bfloat16().to(cuda_dev)
-    res = torch.randn(M, C, generator=g).bfloat16().to(cuda_dev)
+    res = torch.randn(M, C, generator=g).to(xdt).to(cuda_dev)
     w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).bfloat16().to(cuda_dev)
     w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).bfloat16().to(cuda_dev)
     b1, b2 = (torch.randn(4 * C, generator=g) * 0.1).to(cuda_dev), (torch.randn(C, generator=g) * 0.1).to(cuda_dev)
@@ -233,10 +256,11 @@ def test_mlp_fused_in_place(cuda_dev, C, M):
     torch.cuda.synchronize()
     assert got.data_ptr() == buf.data_ptr()
     err = (got.float() - ref).abs()
-    print(f"[parity] mlp_fused in place C={C} M={M}: max|in-place - out-of-place| = {err.max().item():.3e}, "
+    print(f"[parity] mlp_fused in place C={C} M={M} {xdt}: max|in-place - out-of-place| = {err.max().item():.3e}, "
           f"mean {err.mean().item():.3e}")
-    # two bf16 roundings instead of one: at most ~1.5 ulp of the result (|values| < 8 -> ulp <= 2^-5)
-    assert err.max().item() <= 0.0625 and err.mean().item() < 4e-3
+    # two roundings instead of one: at most ~1.5 ulp of the result (|values| < 8 -> bf16 ulp <= 2^-5, fp16 ulp <= 2^-8)
+    scale = 0.125 if xdt == torch.float16 else 1.0
+    assert err.max().item() <= 0.0625 * scale and err.mean().item() < 4e-3 * scale
 
 
 @pytest.mark.parametrize("C0,H,W,B", [(80, 63, 63, 37), (64, 63, 63, 5), (128, 20, 36, 3), (16, 8, 8, 700), (96, 31, 47, 9),
@@ -267,6 +291,13 @@ def test_stem_tcgen05(cuda_dev, C0, H, W, B):
         # same MMA operands; the LayerNorm statistics are summed in a different order (one pass over the row)
         assert (fused.float().cpu() - got.float().cpu()).abs().max() <= 2 ** -6, (fused.float().cpu() - got.float().cpu()).abs().max()
         assert _report(f"stem fused C0={C0} {H}x{W}", _rows_to_nchw(fused.cpu(), B, h, wd), ref) < 3e-2
+        # ... and as the opening rows of the fp16 residual stream: the same values rounded to fp16 instead of bf16
+        f16 = ops.stem_fused(x.to(cuda_dev), wp.bfloat16().to(cuda_dev), b.to(cuda_dev), lw.to(cuda_dev), lb.to(cuda_dev),
+                             out_dtype=torch.float16)
+        torch.cuda.synchronize()
+        assert f16.dtype == torch.float16
+        assert torch.equal(f16.float().bfloat16(), fused) or (f16.float() - fused.float()).abs().max() <= 2 ** -6
+        assert _report(f"stem fused fp16 rows C0={C0} {H}x{W}", _rows_to_nchw(f16.cpu(), B, h, wd), ref) < 1.2e-2
 
 
 def test_gemm_rejects_bad_arguments(cuda_dev):
