@@ -412,7 +412,7 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
     wl = WORKLOADS[wl_name]
     multimodal = wl["model"].startswith("mm_")
     cfg = dict(synth.canonical_config(wl["model"], wl["kind"]), precision=precision)
-    if wl.get("graph") and os.environ.get("BTSB_BENCH_GRAPH", "1") != "0":
+    if (wl.get("graph") or os.environ.get("BTSB_BENCH_C3_GRAPH") == "1") and os.environ.get("BTSB_BENCH_GRAPH", "1") != "0":
         cfg["infer_cuda_graph"] = True                       # small batch: the host paces ~40 launches per forward
     sd_np = synth.make_state_dict(cfg, seed=2)
     model = getattr(btsbot, wl["model"])(cfg)
@@ -484,9 +484,15 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
     ctx.barrier()
     ms_e2e = f0.elapsed_time(f1)
     ms, ms_e2e = ctx.max_over_ranks(ms, ms_e2e)
-    in_bytes = B * (63 * 63 * 3 * 4 + (25 * 4 if multimodal else 0))
+    # bytes that crossed PCIe per step: the scorer may round the fp32 triplets to bf16 on the host (AlertScorer host_pack)
+    packed = bool(scorer._pack_rings)
+    in_bytes = B * (63 * 63 * 3 * (2 if packed else 4) + (25 * 4 if multimodal else 0))
     out = {"wl": wl, "cfg": cfg, "sd_np": sd_np, "B": B, "steps": steps, "warmup": warm, "ms": ms, "ms_e2e": ms_e2e,
-           "launches": int(launches), "clocks": clocks, "nres": nres, "in_bytes": in_bytes, "multimodal": multimodal}
+           "launches": int(launches), "clocks": clocks, "nres": nres, "in_bytes": in_bytes, "multimodal": multimodal,
+           "res_bytes": B * (63 * 63 * 3 * 4 + (25 * 4 if multimodal else 0)),      # the device-resident step input
+           "host_pack": {"used": packed, "threads": scorer.pack_threads, "host_bytes_per_step": B * 63 * 63 * 3 * 4,
+                         "calibration_ms": None if scorer.last_calibration is None else
+                         {"pack": scorer.last_calibration[1], "fp32_copy": scorer.last_calibration[2]}}}
     if pcie:
         out["h2d_gbs_ceiling"] = h2d_ceiling(ctx, [host_trip[0]] + ([host_meta[0]] if multimodal else []))
 
@@ -553,7 +559,7 @@ def infer_line(args, ctx, r, pk, extras: dict):
     h2d = r["in_bytes"] / (r["ms_e2e"] / steps * 1e-3) / 1e9
     e2e = {"value": e2e_value, "unit": "alerts/s", "h2d_bytes_per_step": ctx.world * r["in_bytes"],
            "d2h_bytes_per_step": ctx.world * B * 4, "ms_per_step": r["ms_e2e"] / steps, "h2d_gbs_per_gpu": h2d,
-           "numa_bound": extras.pop("numa_bound", False)}
+           "numa_bound": extras.pop("numa_bound", False), "host_pack": r.get("host_pack")}
     if "h2d_gbs_ceiling" in r:
         e2e["pcie"] = {"h2d_gbs_per_gpu_bare": r["h2d_gbs_ceiling"], "e2e_over_pcie_peak": h2d / r["h2d_gbs_ceiling"],
                        "how": "the same pinned buffers copied back to back, all ranks at once, max over ranks"}
@@ -564,8 +570,8 @@ def infer_line(args, ctx, r, pk, extras: dict):
         "config": {"workload": wl["label"], "model_kind": wl["kind"], "alerts_per_gpu_per_step": B,
                    "global_alerts_per_step": ctx.world * B,
                    "sharding": "contiguous index ranges, no data-path collective",
-                   "l2_policy": f"inputs larger than L2 ({r['in_bytes'] / 1e6:.0f} MB per step), "
-                                f"{r['nres']} resident batches rotated" if r["in_bytes"] > 126e6 else
+                   "l2_policy": f"inputs larger than L2 ({r['res_bytes'] / 1e6:.0f} MB per step), "
+                                f"{r['nres']} resident batches rotated" if r["res_bytes"] > 126e6 else
                                 f"{r['nres']} resident batches rotated; a step's activations exceed L2"},
         "clocks": r["clocks"], "e2e": e2e, "gpu_launches": r["launches"], "roofline": roof, "kernels": kernels,
     }

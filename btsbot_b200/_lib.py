@@ -57,6 +57,7 @@ SIGNATURES = {
     "btsb_device_ok": (i32, []),
     "btsb_launch_count": (C.c_uint64, []),
     "btsb_preprocess_crop_norm": (i32, [vp, i32, i64, i32, i32, i32, vp, vp]),
+    "btsb_host_pack_bf16": (i32, [vp, vp, i64, i32]),
     "btsb_preprocess_pad_norm": (i32, [vp, vp, i64, i32, vp, i32, vp, vp]),
     "btsb_ingest_fits_gz": (i32, [vp, vp, i64, vp, vp, i32]),
     "btsb_augment_gather_f32": (i32, [vp, vp, vp, i64, i32, vp, vp]),

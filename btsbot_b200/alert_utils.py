@@ -46,13 +46,16 @@ def _crop(triplets, s, normalize, out_hwc):
     t = torch.from_numpy(np.ascontiguousarray(triplets)) if isinstance(triplets, np.ndarray) else triplets
     if t.dim() != 4 or tuple(t.shape[1:]) != (63, 63, 3):
         raise ValueError(f"expected triplets of shape [N,63,63,3], got {tuple(t.shape)}")
-    if t.dtype not in (torch.float32, torch.float64):
+    # bfloat16 rows = triplets packed on the host for the scoring path (parallel.AlertScorer / btsb_host_pack_bf16):
+    # cast + transpose only
+    packed = t.dtype == torch.bfloat16 and s == 63 and not normalize and not out_hwc
+    if t.dtype not in (torch.float32, torch.float64) and not packed:
         t = t.to(torch.float64)
     t = t.to(dev, non_blocking=True).contiguous()
     n = t.shape[0]
     shape = (n, s, s, 3) if out_hwc else (n, 3, s, s)
     out = torch.empty(shape, device=dev, dtype=torch.float32)
-    code = L.F32 if t.dtype == torch.float32 else L.F64
+    code = L.BF16 if packed else (L.F32 if t.dtype == torch.float32 else L.F64)
     # algorithmic bytes: read 63*63*3*e_in, write 3*s*s*4 per alert
     L.launch("crop_norm", lib.btsb_preprocess_crop_norm, _p(t), code, n, int(s), int(bool(normalize)), int(bool(out_hwc)),
              _p(out), L.stream_ptr(), flops=3.0 * n * 63 * 63 * 3,

@@ -79,20 +79,32 @@ crop_norm_kernel(const T* __restrict__ in, int s, int margin, int normalize, int
 template <typename T>
 __global__ void __launch_bounds__(kPreThreads)
 cast_transpose63_kernel(const T* __restrict__ in, float* __restrict__ out) {
-  constexpr int V = 16 / (int)sizeof(T);                     // elements per 16-byte load: 4 floats / 2 doubles
+  constexpr int V = 16 / (int)sizeof(T);                     // elements per 16-byte load: 4 floats / 2 doubles / 8 bf16
   __shared__ __align__(16) float tile_raw[kTrip + 4];
   const int tid = threadIdx.x;
   const int64_t a = blockIdx.x;
   const T* src = in + a * (int64_t)kTrip;
   const int head = (int)(((16u - (unsigned)((uintptr_t)src & 15u)) & 15u) / sizeof(T));   // elements before the first aligned 16 B
   float* tile = tile_raw + ((4 - (head & 3)) & 3);           // tile[head] is 16-byte aligned in shared memory
-  if (tid < head) tile[tid] = (float)src[tid];
+  if (tid < head) tile[tid] = ldf(src + tid);
   const int nvec = (kTrip - head) / V;
   if constexpr (sizeof(T) == 4) {
     const float4* v = reinterpret_cast<const float4*>(src + head);
     float4* t4 = reinterpret_cast<float4*>(tile + head);
 #pragma unroll 4
     for (int i = tid; i < nvec; i += kPreThreads) t4[i] = __ldg(v + i);
+  } else if constexpr (sizeof(T) == 2) {
+    // bf16 rows packed on the host (btsb_host_pack_bf16): the alert starts at any 2-byte phase of a 16-byte line
+    const uint4* v = reinterpret_cast<const uint4*>(src + head);
+    float4* t4 = reinterpret_cast<float4*>(tile + head);
+#pragma unroll 4
+    for (int i = tid; i < nvec; i += kPreThreads) {
+      const uint4 q = __ldg(v + i);
+      t4[2 * i] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
+                              __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+      t4[2 * i + 1] = make_float4(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u),
+                                  __uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
+    }
   } else {
     const double2* v = reinterpret_cast<const double2*>(src + head);
     float2* t2 = reinterpret_cast<float2*>(tile + head);
@@ -102,7 +114,7 @@ cast_transpose63_kernel(const T* __restrict__ in, float* __restrict__ out) {
       t2[i] = make_float2((float)d.x, (float)d.y);
     }
   }
-  for (int i = head + nvec * V + tid; i < kTrip; i += kPreThreads) tile[i] = (float)src[i];
+  for (int i = head + nvec * V + tid; i < kTrip; i += kPreThreads) tile[i] = ldf(src + i);
   __syncthreads();
   float* dst = out + a * (int64_t)kTrip;
 #pragma unroll 4
@@ -255,13 +267,18 @@ extern "C" int btsb_preprocess_crop_norm(const void* in, int in_dtype, int64_t n
   if (int e = check_device()) return e;
   BTSB_REQUIRE(n >= 0, "crop_norm: n < 0");
   BTSB_REQUIRE(crop_to_size >= 1 && crop_to_size <= kImg, "crop_norm: crop_to_size %d not in [1,63]", crop_to_size);
-  BTSB_REQUIRE(in_dtype == BTSB_F32 || in_dtype == BTSB_F64, "crop_norm: in_dtype must be F32 or F64");
+  BTSB_REQUIRE(in_dtype == BTSB_F32 || in_dtype == BTSB_F64 || in_dtype == BTSB_BF16, "crop_norm: in_dtype must be F32, F64 or BF16");
   if (n == 0) return BTSB_OK;
   BTSB_REQUIRE(in && out, "crop_norm: null pointer");
   const int margin = (kImg - crop_to_size) / 2;
   cudaStream_t st = (cudaStream_t)stream;
+  // bf16 input = rows packed by btsb_host_pack_bf16 for the scoring path: cast + transpose only
+  BTSB_REQUIRE(in_dtype != BTSB_BF16 || (crop_to_size == kImg && !normalize && !out_hwc),
+               "crop_norm: BF16 input is the cast + transpose path only (crop 63, no normalisation, NCHW)");
   if (crop_to_size == kImg && !normalize && !out_hwc) {
-    if (in_dtype == BTSB_F32) cast_transpose63_kernel<float><<<(unsigned)n, kPreThreads, 0, st>>>((const float*)in, out);
+    if (in_dtype == BTSB_BF16)
+      cast_transpose63_kernel<__nv_bfloat16><<<(unsigned)n, kPreThreads, 0, st>>>((const __nv_bfloat16*)in, out);
+    else if (in_dtype == BTSB_F32) cast_transpose63_kernel<float><<<(unsigned)n, kPreThreads, 0, st>>>((const float*)in, out);
     else cast_transpose63_kernel<double><<<(unsigned)n, kPreThreads, 0, st>>>((const double*)in, out);
     return launch_done("crop_norm");
   }

@@ -89,6 +89,18 @@ def score_alerts(score_fn, triplets, metadata, batch_size: int = 8192, gather: b
     return torch.cat([p[:s] for p, s in zip(parts, sizes)])
 
 
+def _host_threads() -> int:
+    """Host threads one rank may use for input marshalling: its share of the CPUs it is allowed to run on."""
+    import os
+    try:
+        allowed = len(os.sched_getaffinity(0))
+    except AttributeError:
+        allowed = os.cpu_count() or 1
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    share = max(1, (os.cpu_count() or allowed) // local_world)
+    return max(1, min(32, allowed, share))
+
+
 class AlertScorer:
     """The end-to-end public scoring call: host (numpy / pinned torch) HWC triplets + metadata -> scores.
 
@@ -97,10 +109,18 @@ class AlertScorer:
     of batch i; a slot is overwritten only after the forward that read it has finished (one event per slot), so the host
     may run any number of calls ahead without the caching allocator ever entering the timed path (a fresh 391 MB
     ``.to(device)`` per call made the end-to-end rate swing between 0.65 and 1.13 M alerts/s from run to run:
-    ``cudaMalloc`` in the middle of the pipeline whenever the host ran ahead of the events that free the old blocks)."""
+    ``cudaMalloc`` in the middle of the pipeline whenever the host ran ahead of the events that free the old blocks).
+
+    ``host_pack`` (bf16 models, float32 triplets, plain cast + transpose preprocessing): the end-to-end rate of that path
+    is the PCIe rate of the fp32 input (391 MB per 8192 alerts), and the first thing the bf16 trunk does with a pixel is
+    round it to bf16 -- so the triplets are rounded on the HOST (``btsb_host_pack_bf16``, a pool of host threads writing
+    into pinned memory) and half the bytes cross PCIe, with bit-identical logits.  ``"auto"`` (default) times one pack
+    against one fp32 copy of the first batch of each shape and keeps the faster pipeline (a box with few cores per GPU is
+    better off with the plain copy); ``True`` / ``False`` force it, the environment variable ``BTSB_HOST_PACK=0|1`` too."""
 
     def __init__(self, model, crop_to_size: int = 63, normalize: bool = False, return_scores: bool = True,
-                 staging_slots: int = 3):
+                 staging_slots: int = 3, host_pack="auto"):
+        import os
         from . import alert_utils, ops
         self.model, self.crop, self.norm, self.return_scores = model.eval(), crop_to_size, normalize, return_scores
         self._au, self._ops = alert_utils, ops
@@ -110,6 +130,24 @@ class AlertScorer:
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.n_slots = max(2, int(staging_slots))
         self._rings = {}                 # (shape, dtype) -> [next slot, [device buffer, consumed event | None] * n_slots]
+        env = os.environ.get("BTSB_HOST_PACK")
+        self.host_pack = {"0": False, "1": True}.get(env, host_pack)
+        self._pack_ok = int(crop_to_size) == 63 and not normalize and not self.meta_only and self._rounds_input(model)
+        self._pack_rings = {}            # shape -> [next slot, [pinned bf16, device bf16, copied event, consumed event] * n]
+        self._pack_choice = {}           # shape -> bool ("auto" calibration result)
+        self.pack_threads = _host_threads()
+        self.last_calibration = None     # (shape, pack_ms, copy_ms) of the latest "auto" decision
+
+    @staticmethod
+    def _rounds_input(model) -> bool:
+        """True when the model's first use of a pixel is its bf16 rounding: the bf16 ConvNeXt trunks, whose stem is a
+        tensor-core GEMM over bf16 patches (MaxViT interpolates the fp32 image first; the fp32 mode keeps fp32)."""
+        from . import _engine, _lib as L
+        try:
+            tr = getattr(model.scorer(), "trunk", None)
+        except Exception:
+            return False
+        return tr is not None and tr.code == L.BF16 and _engine.TC_STEM and tr.stem_w_tc is not None
 
     def _stage(self, x):
         """Queue the H2D copy of ``x`` into the next staging slot of its shape on the copy stream; returns the slot."""
@@ -130,14 +168,92 @@ class AlertScorer:
         slot[0].copy_(t, non_blocking=True)
         return slot
 
+    # ---- packed staging: float32 host triplets -> bf16 in pinned memory (host threads) -> H2D of half the bytes ----------
+    def _pack(self, t, slot):
+        from . import _lib as L
+        if slot[2] is not None:
+            slot[2].synchronize()                            # the copy that last read this pinned buffer has finished
+        L.check(L.lib().btsb_host_pack_bf16(t.data_ptr(), slot[0].data_ptr(), t.numel(), self.pack_threads), "host_pack")
+
+    def _stage_packed(self, t):
+        key = tuple(t.shape)
+        ring = self._pack_rings.get(key)
+        if ring is None:
+            if len(self._pack_rings) >= 2:
+                self._pack_rings.pop(next(iter(self._pack_rings)))
+            ring = self._pack_rings[key] = [0, [[torch.empty(t.shape, dtype=torch.bfloat16).pin_memory(),
+                                                 torch.empty(t.shape, dtype=torch.bfloat16, device=self.dev), None, None]
+                                                for _ in range(self.n_slots)]]
+        slot = ring[1][ring[0]]
+        ring[0] = (ring[0] + 1) % self.n_slots
+        self._pack(t, slot)                                  # host threads; the calling thread takes a slice itself
+        if slot[3] is not None:
+            self.copy_stream.wait_event(slot[3])
+        slot[1].copy_(slot[0], non_blocking=True)            # on the copy stream (the caller made it current)
+        if slot[2] is None:
+            slot[2] = torch.cuda.Event()
+        slot[2].record(self.copy_stream)
+        return slot
+
+    def _use_pack(self, t) -> bool:
+        if not self._pack_ok or self.host_pack is False or t.dtype != torch.float32 or t.device.type != "cpu" \
+                or t.dim() != 4 or tuple(t.shape[1:]) != (63, 63, 3):
+            return False
+        if self.host_pack is True:
+            return True
+        key = tuple(t.shape)
+        choice = self._pack_choice.get(key)
+        if choice is None:
+            choice = self._pack_choice[key] = self._calibrate(t)
+        return choice
+
+    def _calibrate(self, t) -> bool:
+        """One pack against one fp32 copy of this batch: the packed pipeline pays when the pack -- which occupies the
+        calling thread -- is clearly shorter than the copy it halves."""
+        import time
+        if t.numel() < (1 << 22):                            # small batches are launch-bound either way: keep the plain copy
+            return False
+        probe = [torch.empty(t.shape, dtype=torch.bfloat16).pin_memory(), None, None, None]
+        self._pack(t, probe)                                 # warm: wakes the pool, touches the pages
+        t0 = time.perf_counter()
+        self._pack(t, probe)
+        pack_ms = (time.perf_counter() - t0) * 1e3
+        dst = torch.empty(t.shape, dtype=t.dtype, device=self.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        src = t if t.is_pinned() else t.pin_memory()         # the plain path's best case
+        with torch.cuda.stream(self.copy_stream):
+            dst.copy_(src, non_blocking=True)
+            e0.record(self.copy_stream)
+            dst.copy_(src, non_blocking=True)
+            e1.record(self.copy_stream)
+        e1.synchronize()
+        copy_ms = e0.elapsed_time(e1)
+        self.last_calibration = (tuple(t.shape), pack_ms, copy_ms)
+        # a packed step costs the calling thread the pack PLUS the launches of the step (~1.5 ms for the ~40 kernels of a
+        # forward issued from Python, ~0.3 ms as one graph replay) before the next pack can start; a plain step costs the
+        # copy, which runs beside the kernels.  Measured on a 16-vCPU B200 box at N = 1 (profiles/r02v): pack 5.9-7.3 ms
+        # against a 7.3 ms copy -> the plain copy stays; with several ranks sharing the host's PCIe switches the copy
+        # slows to 15-17 ms per step and the pack wins.
+        enqueue_ms = 0.3 if self.model._config.get("infer_cuda_graph") else 1.5
+        return pack_ms + enqueue_ms < 0.9 * copy_ms
+
     @torch.no_grad()
     def __call__(self, triplets, metadata=None):
         cur = torch.cuda.current_stream(self.dev)
+        ts = ps = None
+        if not self.meta_only:
+            th = torch.from_numpy(np.ascontiguousarray(triplets)) if isinstance(triplets, np.ndarray) else triplets
+            if th.device.type == "cpu" and self._use_pack(th.contiguous()):
+                with torch.cuda.stream(self.copy_stream):
+                    ps = self._stage_packed(th.contiguous())
+            else:
+                with torch.cuda.stream(self.copy_stream):
+                    ts = self._stage(th)
         with torch.cuda.stream(self.copy_stream):
-            ts = None if self.meta_only else self._stage(triplets)
             ms = self._stage(metadata) if (self.multimodal or self.meta_only) else None
         cur.wait_stream(self.copy_stream)
-        t, m = (None if ts is None else ts[0]), (None if ms is None else ms[0])
+        t = ps[1] if ps is not None else (None if ts is None else ts[0])
+        m = None if ms is None else ms[0]
         if self.meta_only:
             logits = self.model(input_data=m)
         else:
@@ -148,6 +264,10 @@ class AlertScorer:
                 if slot[1] is None:
                     slot[1] = torch.cuda.Event()
                 slot[1].record(cur)
+        if ps is not None:
+            if ps[3] is None:
+                ps[3] = torch.cuda.Event()
+            ps[3].record(cur)
         if not self.return_scores:
             return logits.reshape(-1)
         scores, _ = self._ops.score(logits)

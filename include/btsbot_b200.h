@@ -60,10 +60,17 @@ int btsb_device_ok(void);
 /* number of kernels this library has launched in this process (all threads); bench.py's gpu_launches. */
 uint64_t btsb_launch_count(void);
 
+/* ---- host-side marshalling for the end-to-end scoring call (no CUDA work; host pointers): float32 -> bf16, round to
+ * nearest even (NaN stays NaN), on a pool of host threads (threads <= 0: one per hardware thread, at most 32).  The bf16
+ * mode's first use of a pixel is its bf16 rounding, so packing on the host halves the PCIe bytes of a scoring step with
+ * bit-identical logits; btsb_preprocess_crop_norm accepts the packed rows (in_dtype BTSB_BF16, cast + transpose path).
+ * Replaces nothing in the reference (its triplets reach the GPU as fp32, inference_example.py:62-64). */
+int btsb_host_pack_bf16(const float* src, uint16_t* dst, int64_t n, int threads);
+
 /* ---- K1: array preparation -------------------------------------------------------------------
  * crop_norm: replaces alert_utils.crop_triplets / crop_norm_cutout (alert_utils.py:54-107) fused with the
  * cast + NHWC->NCHW transpose every caller performs next (inference_example.py:62-64, train.py:139-155,
- * val.py:92-94).  in: [n,63,63,3] HWC, in_dtype F32 or F64.  out: [n,3,s,s] NCHW float32.
+ * val.py:92-94).  in: [n,63,63,3] HWC, in_dtype F32 or F64 (or BF16 rows from btsb_host_pack_bf16: full 63x63, no normalisation, NCHW only).  out: [n,3,s,s] NCHW float32.
  * margin = (63-s)/2 (floor).  normalize!=0: each cutout is divided by the L2 norm of its cropped window
  * (norm accumulated in fp64; for F64 input the quotient is formed in fp64 and rounded once to fp32, which
  * is what `.astype(np.float32)` does to the reference's float64 result).  normalize==0: crop/cast/transpose only.

@@ -286,3 +286,53 @@ def test_alert_scorer_ring_matches_direct_calls(cuda_dev, golden_logits, case, p
         ref = _call(model, cfg, x, torch.from_numpy(meta[lo:hi]).to(cuda_dev)).reshape(-1)
         assert torch.equal(got, ref), (lo, hi)
     assert len(scorer._rings) <= 4
+
+
+@pytest.mark.parametrize("case", ["mm_nano", "img_pico", "ff_pico"])
+def test_alert_scorer_host_pack_is_bit_identical(cuda_dev, golden_logits, case):
+    """AlertScorer(host_pack=True): float32 host triplets rounded to bf16 on the host (btsb_host_pack_bf16, pinned ring),
+    half the bytes over PCIe, K1 on the packed rows -- bitwise the logits of the plain fp32 copy, because the bf16 trunk's
+    stem rounds the same pixels the same way.  Includes NaN / inf / subnormal pixels and back-to-back calls that reuse the
+    pinned slots; fp32 models and MaxViT never take the packed path."""
+    from btsbot_b200.parallel import AlertScorer
+    cfg, sd, model = _build(case, golden_logits, cuda_dev, "bf16")
+    n = 200
+    trip, meta = synth.make_triplets(n, start=900).copy(), synth.make_metadata(n, start=900)
+    trip[3, 5, 7, 1] = np.float32(1e-41)
+    trip[4, 0, 0, 0] = np.float32(3.0e38)
+    plain = AlertScorer(model, return_scores=False, host_pack=False)
+    packed = AlertScorer(model, return_scores=False, host_pack=True, staging_slots=2)
+    assert packed._pack_ok
+    m = None if case == "img_pico" else meta
+    outs_p, outs_q = [], []
+    for lo, hi in ((0, 64), (64, 128), (128, 200), (10, 74), (0, 64)):
+        mm = None if m is None else m[lo:hi]
+        outs_q.append(packed(trip[lo:hi], mm))
+        outs_p.append(plain(torch.from_numpy(trip[lo:hi].copy()).pin_memory(), mm))
+    torch.cuda.synchronize()
+    for a, b in zip(outs_p, outs_q):
+        assert torch.equal(a, b)
+    assert len(packed._pack_rings) >= 1 and not plain._pack_rings
+    # auto mode: small batches keep the plain copy; the decision is cached per shape
+    auto = AlertScorer(model, return_scores=False)
+    assert torch.equal(auto(trip[:64], None if m is None else m[:64]), outs_p[0]) and not auto._pack_rings
+    # fp32 model: never packed
+    cfg32, sd32, model32 = _build(case, golden_logits, cuda_dev, "fp32")
+    assert not AlertScorer(model32, host_pack=True)._pack_ok
+
+
+def test_host_pack_kernel_path_matches_cast(cuda_dev):
+    """btsb_host_pack_bf16 + K1 on the packed rows == K1 on the fp32 rows rounded to bf16, for every alert phase of the
+    16-byte line (11 907 elements per alert: consecutive alerts start at different 2-byte offsets)."""
+    from btsbot_b200 import _lib as L
+    n = 37
+    trip = synth.make_triplets(n, start=5)
+    t = torch.from_numpy(trip)
+    packed = torch.empty(t.shape, dtype=torch.bfloat16)
+    L.check(L.lib().btsb_host_pack_bf16(t.data_ptr(), packed.data_ptr(), t.numel(), 3), "host_pack")
+    assert torch.equal(packed, t.to(torch.bfloat16))
+    got = btsbot.alert_utils.triplets_to_model_input(packed.to(cuda_dev))
+    ref = btsbot.alert_utils.triplets_to_model_input(t.to(torch.bfloat16).float().to(cuda_dev))
+    assert got.dtype == torch.float32 and torch.equal(got, ref)
+    got1 = btsbot.alert_utils.triplets_to_model_input(packed[1:].contiguous().to(cuda_dev))     # another base phase
+    assert torch.equal(got1, ref[1:])

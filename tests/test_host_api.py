@@ -290,3 +290,23 @@ def test_to_HF_packaging_round_trip(tmp_path, monkeypatch):
     assert to_HF.get_HF_basemodel("maxvit", "galaxyzoo") == "mwalmsley/baseline-encoder-regression-maxvit_tiny"
     with pytest.raises(ValueError):
         to_HF.get_HF_basemodel("resnet", "imagenet")
+
+
+def test_host_pack_bf16_matches_round_to_nearest_even():
+    """btsb_host_pack_bf16 (host threads, no GPU involved): bit-equal to torch's float32 -> bfloat16 rounding for normal,
+    subnormal, huge and infinite values at every thread count; NaN stays NaN; the pool survives repeated jobs."""
+    import torch
+    from btsbot_b200 import _lib
+    lib = _lib.lib()
+    n = 700 * 63 * 63 * 3 + 5
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(n, generator=g)
+    x[::1001] = float("nan"); x[1::1003] = float("inf"); x[2::1005] = -float("inf"); x[3::1007] = 1e-40; x[4::1009] = 3.4e38
+    x[5::1011] = 1.00390625                         # exactly halfway between two bf16 values: ties to even
+    ref = x.to(torch.bfloat16).view(torch.int16)
+    for threads in (1, 2, 5, 0, 16, 3):
+        out = torch.zeros(n, dtype=torch.int16)
+        _lib.check(lib.btsb_host_pack_bf16(x.data_ptr(), out.data_ptr(), n, threads), "host_pack")
+        same = (ref == out) | (torch.isnan(x) & torch.isnan(out.view(torch.bfloat16).float()))
+        assert bool(same.all()), threads
+    assert lib.btsb_host_pack_bf16(None, None, 5, 1) < 0
