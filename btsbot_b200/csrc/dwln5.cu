@@ -235,18 +235,21 @@ int dwln_bf16_v5(const void* x, int64_t B, int H, int W, int C, const float* w, 
                  const float* ln_b, void* out, bool xf16, cudaStream_t st) {
   if (H != W) return 1;
   if (((uintptr_t)x % 16) != 0 || ((uintptr_t)out % 16) != 0) return 1;
+  // nano (80 / 160) and pico (64 / 128) widths.  Round 1 kept the pico widths on v3 because this kernel's different fp32
+  // summation order of the LayerNorm statistics moved the synthetic frozen-fusion / pico case across the 2e-2 bar
+  // (1.34e-2 -> 2.35e-2): that case sat inside the bf16 noise band, which the fp16 residual stream has since halved
+  // (DESIGN.md lesson 20), so kernels are no longer chosen by which rounding pattern the goldens happen to pass with.
   if (xf16) {
     if (H == 15 && C == 80) return launch_dwln5<15, 80, true>(x, B, w, bias, ln_w, ln_b, out, st);
     if (H == 7 && C == 160) return launch_dwln5<7, 160, true>(x, B, w, bias, ln_w, ln_b, out, st);
+    if (H == 15 && C == 64) return launch_dwln5<15, 64, true>(x, B, w, bias, ln_w, ln_b, out, st);
+    if (H == 7 && C == 128) return launch_dwln5<7, 128, true>(x, B, w, bias, ln_w, ln_b, out, st);
     return 1;
   }
   if (H == 15 && C == 80) return launch_dwln5<15, 80, false>(x, B, w, bias, ln_w, ln_b, out, st);
   if (H == 7 && C == 160) return launch_dwln5<7, 160, false>(x, B, w, bias, ln_w, ln_b, out, st);
-  // The pico widths (64 / 128) stay on v3 (dwln3.cu).  This kernel is parity-green for them per kernel, and every model
-  // moved by < 1e-3 when it was tried -- except the synthetic frozen-fusion / pico case, whose bf16 logit error went from
-  // 1.34e-2 (v3's summation order of the LayerNorm statistics) to 2.35e-2, across the 2e-2 bar: the two kernels differ
-  // only in fp32 summation order, i.e. by an occasional last bf16 bit per activation, which that model's head amplifies.
-  // Its bf16 error is a noise level of ~1.5-2.5e-2, not a kernel defect; the dispatch keeps the order the goldens pass with.
+  if (H == 15 && C == 64) return launch_dwln5<15, 64, false>(x, B, w, bias, ln_w, ln_b, out, st);
+  if (H == 7 && C == 128) return launch_dwln5<7, 128, false>(x, B, w, bias, ln_w, ln_b, out, st);
   return 1;
 }
 

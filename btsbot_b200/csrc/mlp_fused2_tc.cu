@@ -32,6 +32,12 @@ constexpr int NH = 64;             // hidden chunk
 constexpr int kEpiWarps2 = 16;
 constexpr int kG2Warp = 2 + kEpiWarps2;                 // second MMA-issuing warp (G2 stream)
 constexpr int kThreads2 = 64 + kEpiWarps2 * 32 + 32;
+// Narrow kernels (C <= 160, two D2 accumulators): four more warps, one per TMEM lane quarter, do nothing but the D2
+// epilogue.  With the drain on the GELU warps both warp groups left the GELU loop at every tile boundary for ~1.1-1.3 k
+// clocks, and the MUFU pipe -- the resource the C = 80 kernel is on (a warp-wide tanh.approx holds it for 8 clocks; 2560 of
+// a tile's ~4950 clocks busy) -- idled meanwhile (profiles/r02t/mlp_trace_80.txt, DESIGN.md lesson 22).
+constexpr int kD2Warps = 4;
+constexpr int kThreadsDW = kThreads2 + kD2Warps * 32;   // 23 warps: 88 registers per thread
 
 constexpr int kHBytes = FM * 128;  // [128 x 64] bf16
 constexpr int kD2Col = 2 * NH;     // TMEM column of D2 (D1 buffers occupy [0,128))
@@ -44,6 +50,7 @@ struct Plan2 {
   int y_bytes = 0, w1_bytes = 0, w2_bytes = 0;
   int ny = 0, n1 = 0, n2 = 0, resident = 0;
   int off_w1 = 0, off_w2 = 0, off_h = 0, off_stg = 0, off_slab = 0, off_bar = 0, off_b1 = 0, total = 0;
+  int nstg = 1;              // staging tiles (2 for C <= 80: the residual rows of tile t+1 land while tile t drains)
   int slab = 0;              // 1: one 1 KB slab per epilogue warp ([32 rows x 16 columns] bulk tensor copies, wide C)
   int stg = 0;               // 1: residual / output rows move through a [128 x C] bf16 staging tile with bulk tensor copies
   int ht = 0;                // 1: the GELU'd hidden chunk H lives in TMEM (A operand of G2 from TMEM), no shared-memory H tiles
@@ -59,7 +66,7 @@ __host__ __device__ constexpr bool plan2_try(Plan2& P, int ny, int n1, int n2, i
   P.off_w2 = P.off_w1 + n1 * P.w1_bytes;
   P.off_h = P.off_w2 + n2 * P.w2_bytes;
   P.off_stg = P.off_h + (P.ht ? 0 : 2 * kHBytes);
-  P.off_slab = P.off_stg + (P.stg ? P.C * 256 : 0);
+  P.off_slab = P.off_stg + (P.stg ? P.nstg * P.C * 256 : 0);
   P.off_bar = P.off_slab + (P.slab ? kEpiWarps2 * 1024 : 0);
   P.off_b1 = P.off_bar + 1024;
   P.total = P.off_b1 + 4 * P.C * 4 + 1024 /*alignment slack*/;
@@ -68,6 +75,7 @@ __host__ __device__ constexpr bool plan2_try(Plan2& P, int ny, int n1, int n2, i
 
 __host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht, bool slab) {
   P.C = C; P.NJ = (4 * C) / NH; P.stg = te ? 1 : 0; P.ht = ht ? 1 : 0; P.slab = slab ? 1 : 0;
+  P.nstg = (te && C <= 80) ? 2 : 1;         // C = 96 would lose its resident weights to a second tile
   P.nfull = C / 64; P.t32 = (C % 64) >= 32 ? 1 : 0; P.t16 = (C % 32) >= 16 ? 1 : 0;
   P.y_bytes = rup1k(FM * C * 2);
   P.w1_bytes = rup1k(NH * C * 2);
@@ -154,6 +162,20 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+// The C/16 column chunks of a 32-row quarter are staged as slabs of 4 / 2 / 1 chunks (128- / 64- / 32-byte rows, one
+// bulk tensor copy each); chunk gi lives in the slab that starts at chunk s0[gi] and is w[gi] chunks wide.
+struct SlabMap { int s0[16] = {}, w[16] = {}; };
+__host__ __device__ constexpr SlabMap make_slab_map(int groups) {
+  SlabMap m;
+  for (int s0 = 0; s0 < groups;) {
+    const int left = groups - s0;
+    const int w = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+    for (int c = 0; c < w; ++c) { m.s0[s0 + c] = s0; m.w[s0 + c] = w; }
+    s0 += w;
+  }
+  return m;
+}
+
 struct Maps2 {
   CUtensorMap y128, y64, y32;      // [M, C]   boxes [128 rows x 64|32|16 cols], swizzle 128|64|32 B
   CUtensorMap a128, a64, a32;      // W1 [4C, C]: boxes [64 rows x 64|32|16 cols]
@@ -175,7 +197,7 @@ struct Maps2 {
 // at once).  Removed.  In steady state this kernel streams W1 + W2 (1.6 MB per 128-row tile, 80 KB per ~1800-clock hidden
 // chunk = 45 B/clk/SM, 7.1 TB/s chip-wide) -- it sits on the L2 -> SM bandwidth, not on the tensor pipe.
 template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false, bool XF16 = false>   // XF16: res / out rows are IEEE fp16
-__global__ void __launch_bounds__(kThreads2, 1)   // 19 warps -> 5 on three SMSPs: 96 registers is the hardware ceiling
+__global__ void __launch_bounds__(TE ? kThreadsDW : kThreads2, 1)   // 19 warps: 96 registers; 23 (dedicated D2 warps): 88
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
                   __nv_bfloat16* __restrict__ out, int M, long long* __restrict__ trace) {
@@ -191,6 +213,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
     }
   };
   constexpr bool TS = EP == 2 || EP == 4, RED = EP == 4;
+  constexpr bool DW = TE;                     // dedicated D2-epilogue warps (kG2Warp + 1 .. kG2Warp + 4)
   static_assert(EP == 0 || EP == 2 || EP == 4, "EP");
   static_assert(EP == 0 || !TE, "EP variants belong to the wide (non-staging) kernels");
   constexpr Plan2 P = plan2_for(C, TE, HT, TS);
@@ -243,7 +266,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       mbar_init(y_full(i), 1); mbar_init(y_empty(i), 1);
       mbar_init(d1_full(i), 1); mbar_init(d1_empty(i), kEpiWarps2 / 2);
       mbar_init(h_full(i), kEpiWarps2 / 2); mbar_init(h_empty(i), 1);
-      mbar_init(d2_full(i), 1); mbar_init(d2_empty(i), kEpiWarps2);
+      mbar_init(d2_full(i), 1); mbar_init(d2_empty(i), DW ? kD2Warps : kEpiWarps2);
     }
     for (int i = 0; i < kMaxSlots; ++i) {
       mbar_init(w1_full(i), 1); mbar_init(w1_empty(i), 1); mbar_init(w2_full(i), 1); mbar_init(w2_empty(i), 1);
@@ -253,7 +276,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   }
   if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
   float* b1s = reinterpret_cast<float*>(sal + P.off_b1);            // fc1 bias staged once per CTA
-  for (int i = threadIdx.x; i < 4 * C; i += kThreads2) b1s[i] = kB1Scale * __ldg(b1 + i);
+  for (int i = threadIdx.x; i < 4 * C; i += (int)blockDim.x) b1s[i] = kB1Scale * __ldg(b1 + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -411,6 +434,95 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         if (lane == 0) tr(0, n2, 1);
       }
     }
+  } else if (DW && warp > kG2Warp) {
+    // ============================== D2-epilogue warps (narrow kernels only) ==============================
+    // warp = one TMEM lane quarter: 32 rows x all C columns of every tile.  Residual rows arrive by bulk tensor loads into
+    // the quarter's slabs of a staging tile (two tiles for C <= 80: the rows of tile t+1 land while tile t drains), are
+    // updated in place (thread = row) and leave by bulk tensor stores; the TMEM load of chunk gi+1 is in flight during
+    // the arithmetic of chunk gi.
+   if constexpr (DW) {
+    const int q = warp & 3;
+    const int dw = warp - (kG2Warp + 1);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int groups2 = C / 16;
+    constexpr SlabMap SL = make_slab_map(groups2);
+    constexpr int kStgTile = C * 256;                         // [128 rows x C] bf16: four quarters of groups2 KB
+    static_assert(groups2 <= 16, "slab map");
+    auto stg_off = [&](uint32_t tl) { return (uint32_t)(P.off_stg + (int)(tl % (uint32_t)P.nstg) * kStgTile + q * groups2 * 1024); };
+    auto rbar = [&](uint32_t tl) { return res_bar(dw * 2 + (int)(tl % (uint32_t)P.nstg)); };
+    auto res_issue = [&](uint32_t tl) {
+      if (lane == 0) {
+        const int row0 = (int)(blockIdx.x + tl * gridDim.x) * FM + q * 32;
+        tma_store_wait_read();                               // earlier bulk stores have read the slabs being refilled
+        mbar_expect_tx(rbar(tl), (uint32_t)(groups2 * 1024));
+#pragma unroll
+        for (int gi = 0; gi < groups2; ++gi) {
+          if (SL.s0[gi] != gi) continue;                     // first chunk of a slab issues the slab's copy
+          const CUtensorMap* mp = SL.w[gi] == 4 ? &tm.r128 : (SL.w[gi] == 2 ? &tm.r64 : &tm.r32);
+          tma_load_2d(sbase + stg_off(tl) + (uint32_t)(gi * 1024), mp, rbar(tl), gi * 16, row0);
+        }
+      }
+      __syncwarp();
+    };
+    if (nt > 0) res_issue(0);
+    if (P.nstg == 2 && nt > 1) res_issue(1);
+    for (uint32_t tl = 0; tl < nt; ++tl) {
+      const int tb = (int)(tl % (uint32_t)D2B);
+      const int row0 = (int)(blockIdx.x + tl * gridDim.x) * FM + q * 32;
+      unsigned char* stg = sal + stg_off(tl);
+      mbar_wait_spin(d2_full(tb), (tl / (uint32_t)D2B) & 1u);
+      tc_fence_after();
+      uint32_t ra[16], rb[16];
+      tmem_ld16(lane_addr + (uint32_t)(kD2Col + tb * C), ra);
+      mbar_wait_spin(rbar(tl), (tl / (uint32_t)P.nstg) & 1u);
+#pragma unroll
+      for (int gi = 0; gi < groups2; ++gi) {
+        uint32_t (&r)[16] = (gi & 1) ? rb : ra;
+        tmem_ld_wait();
+        if (gi + 1 < groups2) {
+          tmem_ld16(lane_addr + (uint32_t)(kD2Col + tb * C + (gi + 1) * 16), (gi & 1) ? ra : rb);
+        } else {                                             // last D2 read of this warp for this tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d2_empty(tb));
+        }
+        const int sw = SL.w[gi] * 32, c = gi - SL.s0[gi];
+        const int xr = sw == 128 ? (lane & 7) : (sw == 64 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+        unsigned char* rowp = stg + SL.s0[gi] * 1024 + lane * sw;
+        uint4* p0 = reinterpret_cast<uint4*>(rowp + (((2 * c) ^ xr) << 4));
+        uint4* p1 = reinterpret_cast<uint4*>(rowp + (((2 * c + 1) ^ xr) << 4));
+        const uint4 r0 = *p0, r1 = *p1;
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const int n = gi * 16;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(b2 + n + i));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + n + i));
+          v[i] = fmaf(g4.x, fmaf(__uint_as_float(r[i]), kD2Scale, b4.x), x2_lo<XF16>(rr[i / 2]));
+          v[i + 1] = fmaf(g4.y, fmaf(__uint_as_float(r[i + 1]), kD2Scale, b4.y), x2_hi<XF16>(rr[i / 2]));
+          v[i + 2] = fmaf(g4.z, fmaf(__uint_as_float(r[i + 2]), kD2Scale, b4.z), x2_lo<XF16>(rr[i / 2 + 1]));
+          v[i + 3] = fmaf(g4.w, fmaf(__uint_as_float(r[i + 3]), kD2Scale, b4.w), x2_hi<XF16>(rr[i / 2 + 1]));
+        }
+        *p0 = make_uint4(pack_x2<XF16>(v[0], v[1]), pack_x2<XF16>(v[2], v[3]), pack_x2<XF16>(v[4], v[5]), pack_x2<XF16>(v[6], v[7]));
+        *p1 = make_uint4(pack_x2<XF16>(v[8], v[9]), pack_x2<XF16>(v[10], v[11]), pack_x2<XF16>(v[12], v[13]), pack_x2<XF16>(v[14], v[15]));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int gi = 0; gi < groups2; ++gi) {
+          if (SL.s0[gi] != gi) continue;
+          const CUtensorMap* mp = SL.w[gi] == 4 ? &tm.o128 : (SL.w[gi] == 2 ? &tm.o64 : &tm.o32);
+          tma_store_2d(mp, sbase + stg_off(tl) + (uint32_t)(gi * 1024), gi * 16, row0);   // rows beyond M are clipped
+        }
+        tma_store_commit();
+      }
+      __syncwarp();
+      if (tl + (uint32_t)P.nstg < nt) res_issue(tl + (uint32_t)P.nstg);   // refills the slabs just stored from
+    }
+    if (lane == 0) tma_store_wait_all();                     // shared memory must outlive the last bulk store's reads
+   }
   } else {
     // ============================== epilogue warps (2 .. 17) ==============================
     const int q = warp & 3;                 // TMEM lane quarter this warp may touch
@@ -646,7 +758,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
     for (uint32_t g = (uint32_t)grp; g < total; g += 2) {
       const uint32_t tl = g / (uint32_t)NJ; const int j = (int)(g - tl * NJ);
       const uint32_t use = g >> 1;                       // per-buffer use count of D1[grp] / H[grp]
-      if (tl != prev_tl) {
+      if (!DW && tl != prev_tl) {
         // first chunk of this warp in a new tile: the previous tile's D2 epilogue is deferred until after this chunk's
         // GELU so its tail latency (last H hand-off -> G2 -> commit) is hidden; fetch its residual rows now
         if (prev_tl != 0xffffffffu) {
@@ -704,7 +816,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
         if (lane == 0) tr(1 + ew, g, 6);
       }
     }
-    if (nt > 0) {
+    if (!DW && nt > 0) {
       // every group has at least one chunk in every tile (NJ >= 4), so prev_tl is the CTA's last tile here
       const int last = (int)nt - 1;
       if (TE) {
@@ -755,7 +867,7 @@ static int launch2(const Maps2& tm, const float* b1, const float* b2, const floa
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
-  kern<<<grid, kThreads2, P.total, st>>>(tm, b1, b2, gamma, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (int)M, g_mlp_trace);
+  kern<<<grid, TE ? kThreadsDW : kThreads2, P.total, st>>>(tm, b1, b2, gamma, (const __nv_bfloat16*)res, (__nv_bfloat16*)out, (int)M, g_mlp_trace);
   return launch_done("mlp_fused2");
 }
 

@@ -70,7 +70,7 @@ def test_dwln(cuda_dev, C, H, W, B, dt):
     assert err < (3e-5 if dt == torch.float32 else max(4e-2, 2.0 ** -8 * ref.abs().max().item()))
 
 
-@pytest.mark.parametrize("C,S,B", [(80, 15, 1500), (160, 7, 3000)])
+@pytest.mark.parametrize("C,S,B", [(80, 15, 1500), (160, 7, 3000), (64, 15, 1500), (128, 7, 3000)])
 def test_dwln_warp_specialised_handoff_is_deterministic(cuda_dev, C, S, B):
     """dwln5 hands the fp32 conv tile from the conv warps to the LayerNorm warps through two mbarriers (compute-sanitizer's
     racecheck does not model mbarrier phases and flags that hand-off, profiles/r02a_san): a persistent grid with ~10 images
