@@ -485,12 +485,14 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
     ms_e2e = f0.elapsed_time(f1)
     ms, ms_e2e = ctx.max_over_ranks(ms, ms_e2e)
     # bytes that crossed PCIe per step: the scorer may round the fp32 triplets to bf16 on the host (AlertScorer host_pack)
-    packed = bool(scorer._pack_rings)
-    in_bytes = B * (63 * 63 * 3 * (2 if packed else 4) + (25 * 4 if multimodal else 0))
+    # (a fraction of each batch: rows [0, n1) go over as bf16, the rest as fp32)
+    n1 = max((k[1] for k in scorer._pack_rings), default=0)
+    pack_f = n1 / float(B)
+    in_bytes = 63 * 63 * 3 * (2 * n1 + 4 * (B - n1)) + B * (25 * 4 if multimodal else 0)
     out = {"wl": wl, "cfg": cfg, "sd_np": sd_np, "B": B, "steps": steps, "warmup": warm, "ms": ms, "ms_e2e": ms_e2e,
            "launches": int(launches), "clocks": clocks, "nres": nres, "in_bytes": in_bytes, "multimodal": multimodal,
            "res_bytes": B * (63 * 63 * 3 * 4 + (25 * 4 if multimodal else 0)),      # the device-resident step input
-           "host_pack": {"used": packed, "threads": scorer.pack_threads, "host_bytes_per_step": B * 63 * 63 * 3 * 4,
+           "host_pack": {"fraction": pack_f, "threads": scorer.pack_threads, "host_bytes_per_step": B * 63 * 63 * 3 * 4,
                          "calibration_ms": None if scorer.last_calibration is None else
                          {"pack": scorer.last_calibration[1], "fp32_copy": scorer.last_calibration[2]}}}
     if pcie:

@@ -32,15 +32,16 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
-def triplets_to_model_input(triplets, crop_to_size: int = 63, normalize: bool = False) -> torch.Tensor:
+def triplets_to_model_input(triplets, crop_to_size: int = 63, normalize: bool = False, out=None) -> torch.Tensor:
     """``[N,63,63,3]`` HWC float32/float64 (numpy or torch, host or device) -> ``[N,3,s,s]`` float32 CUDA tensor.
 
     ``normalize=False`` is exactly ``astype(float32)`` + ``transpose(0,3,1,2)``; ``normalize=True`` additionally
-    applies ``crop_triplets`` semantics (centre crop with margin ``(63-s)//2`` and per-cutout L2 normalisation)."""
-    return _crop(triplets, crop_to_size, normalize, out_hwc=False)
+    applies ``crop_triplets`` semantics (centre crop with margin ``(63-s)//2`` and per-cutout L2 normalisation).
+    ``out``: an existing contiguous ``[N,3,s,s]`` float32 CUDA tensor (e.g. a slice of a batch) to write into."""
+    return _crop(triplets, crop_to_size, normalize, out_hwc=False, out=out)
 
 
-def _crop(triplets, s, normalize, out_hwc):
+def _crop(triplets, s, normalize, out_hwc, out=None):
     lib = L.lib()
     dev = _dev()
     t = torch.from_numpy(np.ascontiguousarray(triplets)) if isinstance(triplets, np.ndarray) else triplets
@@ -54,7 +55,12 @@ def _crop(triplets, s, normalize, out_hwc):
     t = t.to(dev, non_blocking=True).contiguous()
     n = t.shape[0]
     shape = (n, s, s, 3) if out_hwc else (n, 3, s, s)
-    out = torch.empty(shape, device=dev, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(shape, device=dev, dtype=torch.float32)
+    elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != t.device:
+        raise ValueError(f"out must be a contiguous float32 tensor of shape {shape} on {t.device}")
+    if n == 0:
+        return out
     code = L.BF16 if packed else (L.F32 if t.dtype == torch.float32 else L.F64)
     # algorithmic bytes: read 63*63*3*e_in, write 3*s*s*4 per alert
     L.launch("crop_norm", lib.btsb_preprocess_crop_norm, _p(t), code, n, int(s), int(bool(normalize)), int(bool(out_hwc)),

@@ -111,12 +111,14 @@ class AlertScorer:
     ``.to(device)`` per call made the end-to-end rate swing between 0.65 and 1.13 M alerts/s from run to run:
     ``cudaMalloc`` in the middle of the pipeline whenever the host ran ahead of the events that free the old blocks).
 
-    ``host_pack`` (bf16 models, float32 triplets, plain cast + transpose preprocessing): the end-to-end rate of that path
-    is the PCIe rate of the fp32 input (391 MB per 8192 alerts), and the first thing the bf16 trunk does with a pixel is
-    round it to bf16 -- so the triplets are rounded on the HOST (``btsb_host_pack_bf16``, a pool of host threads writing
-    into pinned memory) and half the bytes cross PCIe, with bit-identical logits.  ``"auto"`` (default) times one pack
-    against one fp32 copy of the first batch of each shape and keeps the faster pipeline (a box with few cores per GPU is
-    better off with the plain copy); ``True`` / ``False`` force it, the environment variable ``BTSB_HOST_PACK=0|1`` too."""
+    ``host_pack`` (bf16 ConvNeXt models, float32 triplets, plain cast + transpose preprocessing): the end-to-end rate of
+    that path is the PCIe rate of the fp32 input (391 MB per 8192 alerts), and the first thing the bf16 trunk does with a
+    pixel is round it to bf16 -- so the scorer can round a FRACTION f of each batch on the host (``btsb_host_pack_bf16``: a
+    pool of host threads writing into pinned memory) while the DMA engine is already moving the other, untouched fp32
+    part; the packed part follows with half its bytes, K1 runs once per part, and the logits are bit-identical.
+    ``"auto"`` (default) times one pack and one fp32 copy of the first batch of each shape and picks the f that balances
+    the host threads against the PCIe link (0 = plain copy when the host cannot keep up: few cores per GPU, small batches);
+    ``True`` / ``False`` / a float in [0, 1] force it, the environment variable ``BTSB_HOST_PACK`` (0, 1 or a fraction) too."""
 
     def __init__(self, model, crop_to_size: int = 63, normalize: bool = False, return_scores: bool = True,
                  staging_slots: int = 3, host_pack="auto"):
@@ -131,12 +133,18 @@ class AlertScorer:
         self.n_slots = max(2, int(staging_slots))
         self._rings = {}                 # (shape, dtype) -> [next slot, [device buffer, consumed event | None] * n_slots]
         env = os.environ.get("BTSB_HOST_PACK")
-        self.host_pack = {"0": False, "1": True}.get(env, host_pack)
+        if env is not None:
+            host_pack = float(env)
+        if host_pack is True:
+            host_pack = 1.0
+        elif host_pack is False:
+            host_pack = 0.0
+        self.host_pack = host_pack       # "auto" or the packed fraction f
         self._pack_ok = int(crop_to_size) == 63 and not normalize and not self.meta_only and self._rounds_input(model)
-        self._pack_rings = {}            # shape -> [next slot, [pinned bf16, device bf16, copied event, consumed event] * n]
-        self._pack_choice = {}           # shape -> bool ("auto" calibration result)
+        self._pack_rings = {}            # (shape, n1) -> [next slot, [pinned bf16, dev bf16, dev f32, copied ev, consumed ev] * n]
+        self._pack_choice = {}           # shape -> packed fraction f ("auto" calibration result)
         self.pack_threads = _host_threads()
-        self.last_calibration = None     # (shape, pack_ms, copy_ms) of the latest "auto" decision
+        self.last_calibration = None     # (shape, pack_ms, copy_ms, f) of the latest "auto" decision
 
     @staticmethod
     def _rounds_input(model) -> bool:
@@ -168,56 +176,65 @@ class AlertScorer:
         slot[0].copy_(t, non_blocking=True)
         return slot
 
-    # ---- packed staging: float32 host triplets -> bf16 in pinned memory (host threads) -> H2D of half the bytes ----------
-    def _pack(self, t, slot):
+    # ---- split staging: rows [0, n1) rounded to bf16 on the host, rows [n1, B) copied as they are ----------------------
+    def _pack(self, t, pinned):
         from . import _lib as L
-        if slot[2] is not None:
-            slot[2].synchronize()                            # the copy that last read this pinned buffer has finished
-        L.check(L.lib().btsb_host_pack_bf16(t.data_ptr(), slot[0].data_ptr(), t.numel(), self.pack_threads), "host_pack")
+        L.check(L.lib().btsb_host_pack_bf16(t.data_ptr(), pinned.data_ptr(), t.numel(), self.pack_threads), "host_pack")
 
-    def _stage_packed(self, t):
-        key = tuple(t.shape)
+    def _stage_split(self, t, f):
+        B = t.shape[0]
+        n1 = min(B, max(1, int(round(f * B))))
+        key = (tuple(t.shape), n1)
         ring = self._pack_rings.get(key)
         if ring is None:
             if len(self._pack_rings) >= 2:
                 self._pack_rings.pop(next(iter(self._pack_rings)))
-            ring = self._pack_rings[key] = [0, [[torch.empty(t.shape, dtype=torch.bfloat16).pin_memory(),
-                                                 torch.empty(t.shape, dtype=torch.bfloat16, device=self.dev), None, None]
-                                                for _ in range(self.n_slots)]]
+            tail = tuple(t.shape[1:])
+            ring = self._pack_rings[key] = [0, [[torch.empty((n1,) + tail, dtype=torch.bfloat16).pin_memory(),
+                                                 torch.empty((n1,) + tail, dtype=torch.bfloat16, device=self.dev),
+                                                 torch.empty((B - n1,) + tail, dtype=torch.float32, device=self.dev),
+                                                 None, None] for _ in range(self.n_slots)]]
         slot = ring[1][ring[0]]
         ring[0] = (ring[0] + 1) % self.n_slots
-        self._pack(t, slot)                                  # host threads; the calling thread takes a slice itself
+        if slot[4] is not None:
+            self.copy_stream.wait_event(slot[4])             # the forward that read this slot's device buffers has finished
+        if n1 < B:
+            slot[2].copy_(t[n1:], non_blocking=True)         # the DMA engine starts on the fp32 part right away ...
         if slot[3] is not None:
-            self.copy_stream.wait_event(slot[3])
-        slot[1].copy_(slot[0], non_blocking=True)            # on the copy stream (the caller made it current)
-        if slot[2] is None:
-            slot[2] = torch.cuda.Event()
-        slot[2].record(self.copy_stream)
-        return slot
+            slot[3].synchronize()                            # (the copy that last read this pinned buffer has finished)
+        self._pack(t[:n1], slot[0])                          # ... while the host threads round the other part
+        slot[1].copy_(slot[0], non_blocking=True)
+        if slot[3] is None:
+            slot[3] = torch.cuda.Event()
+        slot[3].record(self.copy_stream)
+        return slot, n1
 
-    def _use_pack(self, t) -> bool:
-        if not self._pack_ok or self.host_pack is False or t.dtype != torch.float32 or t.device.type != "cpu" \
-                or t.dim() != 4 or tuple(t.shape[1:]) != (63, 63, 3):
-            return False
-        if self.host_pack is True:
-            return True
+    def _packed_fraction(self, t) -> float:
+        if not self._pack_ok or t.dtype != torch.float32 or t.device.type != "cpu" or t.dim() != 4 \
+                or tuple(t.shape[1:]) != (63, 63, 3) or t.shape[0] == 0:
+            return 0.0
+        if self.host_pack != "auto":
+            return float(self.host_pack)
         key = tuple(t.shape)
-        choice = self._pack_choice.get(key)
-        if choice is None:
-            choice = self._pack_choice[key] = self._calibrate(t)
-        return choice
+        f = self._pack_choice.get(key)
+        if f is None:
+            f = self._pack_choice[key] = self._calibrate(t)
+        return f
 
-    def _calibrate(self, t) -> bool:
-        """One pack against one fp32 copy of this batch: the packed pipeline pays when the pack -- which occupies the
-        calling thread -- is clearly shorter than the copy it halves."""
+    def _calibrate(self, t) -> float:
+        """One pack against one fp32 copy of this batch.  With a fraction f packed, a step occupies the calling thread
+        for f * pack + the launches of the step, and the PCIe link for (1 - f/2) * copy; f balances the two, capped so that
+        the pack is no longer than the fp32 part's copy it runs beside (else the link idles waiting for the pack)."""
         import time
         if t.numel() < (1 << 22):                            # small batches are launch-bound either way: keep the plain copy
-            return False
-        probe = [torch.empty(t.shape, dtype=torch.bfloat16).pin_memory(), None, None, None]
+            return 0.0
+        probe = torch.empty(t.shape, dtype=torch.bfloat16).pin_memory()
         self._pack(t, probe)                                 # warm: wakes the pool, touches the pages
-        t0 = time.perf_counter()
-        self._pack(t, probe)
-        pack_ms = (time.perf_counter() - t0) * 1e3
+        pack_ms = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            self._pack(t, probe)
+            pack_ms = min(pack_ms, (time.perf_counter() - t0) * 1e3)
         dst = torch.empty(t.shape, dtype=t.dtype, device=self.dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         src = t if t.is_pinned() else t.pin_memory()         # the plain path's best case
@@ -228,36 +245,49 @@ class AlertScorer:
             e1.record(self.copy_stream)
         e1.synchronize()
         copy_ms = e0.elapsed_time(e1)
-        self.last_calibration = (tuple(t.shape), pack_ms, copy_ms)
-        # a packed step costs the calling thread the pack PLUS the launches of the step (~1.5 ms for the ~40 kernels of a
-        # forward issued from Python, ~0.3 ms as one graph replay) before the next pack can start; a plain step costs the
-        # copy, which runs beside the kernels.  Measured on a 16-vCPU B200 box at N = 1 (profiles/r02v): pack 5.9-7.3 ms
-        # against a 7.3 ms copy -> the plain copy stays; with several ranks sharing the host's PCIe switches the copy
-        # slows to 15-17 ms per step and the pack wins.
+        # launches of a step on the calling thread: ~1.5 ms for the ~40 kernels of a forward issued from Python, ~0.3 ms
+        # as one graph replay
         enqueue_ms = 0.3 if self.model._config.get("infer_cuda_graph") else 1.5
-        return pack_ms + enqueue_ms < 0.9 * copy_ms
+        # balance thread and link; keep the pack within the link work queued beside it (the previous batch's bf16 part +
+        # this batch's fp32 part), and never beyond 0.65: measured on a 16-vCPU B200 box (profiles/r02z, 8192 alerts per
+        # step, pack 4.9-6.9 ms, copy 7.1-7.3 ms) the step takes 7.25 / 6.13 / 5.56 / 5.15 / 5.75 / 5.96 / 6.34 ms at
+        # f = 0 / 0.35 / 0.5 / 0.65 / 0.7 / 0.8 / 1.0
+        f = (copy_ms - enqueue_ms) / (pack_ms + 0.5 * copy_ms)
+        f = max(0.0, min(f, copy_ms / (pack_ms + 0.5 * copy_ms), 0.65))
+        period = max(f * pack_ms + enqueue_ms, (1.0 - 0.5 * f) * copy_ms)
+        if period > 0.9 * copy_ms:                           # not worth the host threads
+            f = 0.0
+        self.last_calibration = (tuple(t.shape), pack_ms, copy_ms, f)
+        return f
 
     @torch.no_grad()
     def __call__(self, triplets, metadata=None):
         cur = torch.cuda.current_stream(self.dev)
         ts = ps = None
+        n1 = 0
         if not self.meta_only:
             th = torch.from_numpy(np.ascontiguousarray(triplets)) if isinstance(triplets, np.ndarray) else triplets
-            if th.device.type == "cpu" and self._use_pack(th.contiguous()):
-                with torch.cuda.stream(self.copy_stream):
-                    ps = self._stage_packed(th.contiguous())
-            else:
-                with torch.cuda.stream(self.copy_stream):
+            f = self._packed_fraction(th.contiguous()) if th.device.type == "cpu" else 0.0
+            with torch.cuda.stream(self.copy_stream):
+                if f > 0.0:
+                    ps, n1 = self._stage_split(th.contiguous(), f)
+                else:
                     ts = self._stage(th)
         with torch.cuda.stream(self.copy_stream):
             ms = self._stage(metadata) if (self.multimodal or self.meta_only) else None
         cur.wait_stream(self.copy_stream)
-        t = ps[1] if ps is not None else (None if ts is None else ts[0])
         m = None if ms is None else ms[0]
         if self.meta_only:
             logits = self.model(input_data=m)
         else:
-            x = self._au.triplets_to_model_input(t, self.crop, self.norm)
+            if ps is not None:                               # K1 once per part, into one [B,3,63,63] tensor
+                B = n1 + ps[2].shape[0]
+                x = torch.empty((B, 3, 63, 63), device=self.dev, dtype=torch.float32)
+                self._au.triplets_to_model_input(ps[1], self.crop, self.norm, out=x[:n1])
+                if n1 < B:
+                    self._au.triplets_to_model_input(ps[2], self.crop, self.norm, out=x[n1:])
+            else:
+                x = self._au.triplets_to_model_input(ts[0], self.crop, self.norm)
             logits = self.model(image_input=x, metadata_input=m) if self.multimodal else self.model(input_data=x)
         for slot in (ts, ms):
             if slot is not None:
@@ -265,9 +295,9 @@ class AlertScorer:
                     slot[1] = torch.cuda.Event()
                 slot[1].record(cur)
         if ps is not None:
-            if ps[3] is None:
-                ps[3] = torch.cuda.Event()
-            ps[3].record(cur)
+            if ps[4] is None:
+                ps[4] = torch.cuda.Event()
+            ps[4].record(cur)
         if not self.return_scores:
             return logits.reshape(-1)
         scores, _ = self._ops.score(logits)

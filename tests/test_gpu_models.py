@@ -302,17 +302,19 @@ def test_alert_scorer_host_pack_is_bit_identical(cuda_dev, golden_logits, case):
     trip[4, 0, 0, 0] = np.float32(3.0e38)
     plain = AlertScorer(model, return_scores=False, host_pack=False)
     packed = AlertScorer(model, return_scores=False, host_pack=True, staging_slots=2)
-    assert packed._pack_ok
+    split = AlertScorer(model, return_scores=False, host_pack=0.4)        # 40 % of each batch packed, the rest as fp32
+    assert packed._pack_ok and split._pack_ok
     m = None if case == "img_pico" else meta
-    outs_p, outs_q = [], []
-    for lo, hi in ((0, 64), (64, 128), (128, 200), (10, 74), (0, 64)):
+    outs_p, outs_q, outs_s = [], [], []
+    for lo, hi in ((0, 64), (64, 128), (128, 200), (10, 74), (0, 64), (5, 6)):
         mm = None if m is None else m[lo:hi]
         outs_q.append(packed(trip[lo:hi], mm))
+        outs_s.append(split(torch.from_numpy(trip[lo:hi].copy()).pin_memory(), mm))
         outs_p.append(plain(torch.from_numpy(trip[lo:hi].copy()).pin_memory(), mm))
     torch.cuda.synchronize()
-    for a, b in zip(outs_p, outs_q):
-        assert torch.equal(a, b)
-    assert len(packed._pack_rings) >= 1 and not plain._pack_rings
+    for a, b, c in zip(outs_p, outs_q, outs_s):
+        assert torch.equal(a, b) and torch.equal(a, c)
+    assert len(packed._pack_rings) >= 1 and len(split._pack_rings) >= 1 and not plain._pack_rings
     # auto mode: small batches keep the plain copy; the decision is cached per shape
     auto = AlertScorer(model, return_scores=False)
     assert torch.equal(auto(trip[:64], None if m is None else m[:64]), outs_p[0]) and not auto._pack_rings
