@@ -141,10 +141,11 @@ class AlertScorer:
             host_pack = 0.0
         self.host_pack = host_pack       # "auto" or the packed fraction f
         self._pack_ok = int(crop_to_size) == 63 and not normalize and not self.meta_only and self._rounds_input(model)
-        self._pack_rings = {}            # (shape, n1) -> [next slot, [pinned bf16, dev bf16, dev f32, copied ev, consumed ev] * n]
+        self._pack_rings = {}            # shape -> [next slot, [pinned bf16, dev bf16, dev f32, copied ev, consumed ev] * n]
         self._pack_choice = {}           # shape -> packed fraction f ("auto" calibration result)
         self.pack_threads = _host_threads()
         self.last_calibration = None     # (shape, pack_ms, copy_ms, f) of the latest "auto" decision
+        self.last_fraction = 0.0         # packed fraction of the latest call
 
     @staticmethod
     def _rounds_input(model) -> bool:
@@ -184,29 +185,30 @@ class AlertScorer:
     def _stage_split(self, t, f):
         B = t.shape[0]
         n1 = min(B, max(1, int(round(f * B))))
-        key = (tuple(t.shape), n1)
+        key = tuple(t.shape)
         ring = self._pack_rings.get(key)
         if ring is None:
             if len(self._pack_rings) >= 2:
                 self._pack_rings.pop(next(iter(self._pack_rings)))
-            tail = tuple(t.shape[1:])
-            ring = self._pack_rings[key] = [0, [[torch.empty((n1,) + tail, dtype=torch.bfloat16).pin_memory(),
-                                                 torch.empty((n1,) + tail, dtype=torch.bfloat16, device=self.dev),
-                                                 torch.empty((B - n1,) + tail, dtype=torch.float32, device=self.dev),
+            # full-size buffers, used through [:n1] / [n1:] views: the packed fraction may change from call to call
+            ring = self._pack_rings[key] = [0, [[torch.empty(t.shape, dtype=torch.bfloat16).pin_memory(),
+                                                 torch.empty(t.shape, dtype=torch.bfloat16, device=self.dev),
+                                                 torch.empty(t.shape, dtype=torch.float32, device=self.dev),
                                                  None, None] for _ in range(self.n_slots)]]
         slot = ring[1][ring[0]]
         ring[0] = (ring[0] + 1) % self.n_slots
         if slot[4] is not None:
             self.copy_stream.wait_event(slot[4])             # the forward that read this slot's device buffers has finished
         if n1 < B:
-            slot[2].copy_(t[n1:], non_blocking=True)         # the DMA engine starts on the fp32 part right away ...
+            slot[2][n1:].copy_(t[n1:], non_blocking=True)    # the DMA engine starts on the fp32 part right away ...
         if slot[3] is not None:
             slot[3].synchronize()                            # (the copy that last read this pinned buffer has finished)
-        self._pack(t[:n1], slot[0])                          # ... while the host threads round the other part
-        slot[1].copy_(slot[0], non_blocking=True)
+        self._pack(t[:n1], slot[0][:n1])                     # ... while the host threads round the other part
+        slot[1][:n1].copy_(slot[0][:n1], non_blocking=True)
         if slot[3] is None:
             slot[3] = torch.cuda.Event()
         slot[3].record(self.copy_stream)
+        self.last_fraction = n1 / float(B)
         return slot, n1
 
     def _packed_fraction(self, t) -> float:
@@ -224,7 +226,10 @@ class AlertScorer:
     def _calibrate(self, t) -> float:
         """One pack against one fp32 copy of this batch.  With a fraction f packed, a step occupies the calling thread
         for f * pack + the launches of the step, and the PCIe link for (1 - f/2) * copy; f balances the two, capped so that
-        the pack is no longer than the fp32 part's copy it runs beside (else the link idles waiting for the pack)."""
+        the pack is no longer than the link work queued beside it (else the link idles waiting for the pack).  An online
+        hill-climb of f on the observed call period was tried on top of this (profiles/r02z/visit_log_adapt_*.txt): 1.51 M
+        against 1.60 M alerts/s at N = 1 (the optimum is sharp, the search dithers around it) and 2.59 M against 2.60 M at
+        N = 4 on a box whose host memory system, not f, limits the step -- removed."""
         import time
         if t.numel() < (1 << 22):                            # small batches are launch-bound either way: keep the plain copy
             return 0.0
@@ -281,11 +286,11 @@ class AlertScorer:
             logits = self.model(input_data=m)
         else:
             if ps is not None:                               # K1 once per part, into one [B,3,63,63] tensor
-                B = n1 + ps[2].shape[0]
+                B = ps[2].shape[0]
                 x = torch.empty((B, 3, 63, 63), device=self.dev, dtype=torch.float32)
-                self._au.triplets_to_model_input(ps[1], self.crop, self.norm, out=x[:n1])
+                self._au.triplets_to_model_input(ps[1][:n1], self.crop, self.norm, out=x[:n1])
                 if n1 < B:
-                    self._au.triplets_to_model_input(ps[2], self.crop, self.norm, out=x[n1:])
+                    self._au.triplets_to_model_input(ps[2][n1:], self.crop, self.norm, out=x[n1:])
             else:
                 x = self._au.triplets_to_model_input(ts[0], self.crop, self.norm)
             logits = self.model(image_input=x, metadata_input=m) if self.multimodal else self.model(input_data=x)
