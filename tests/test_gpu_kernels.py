@@ -317,3 +317,64 @@ def test_score_epilogue(cuda_dev):
     assert (s.cpu() - torch.sigmoid(lg)).abs().max() < 1e-6
     ref_lab = (torch.sigmoid(lg) > 0.5).to(torch.uint8)
     assert torch.equal(lab.cpu(), ref_lab)
+
+
+def test_fp16_residual_stream_saturates_instead_of_overflowing(cuda_dev):
+    """BTSB_BF16_XF16 stores (GEMM epilogue, fused-MLP epilogue out of place and in place): a value beyond the fp16 range
+    becomes +-65504, never inf / NaN -- a checkpoint with an outlier channel degrades gracefully instead of poisoning the
+    LayerNorm that reads the row next."""
+    from btsbot_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(13)
+    M, K, N = 300, 64, 64
+    a = torch.randn(M, K, generator=g).bfloat16().to(cuda_dev)
+    w = (torch.randn(N, K, generator=g) / 8).bfloat16().to(cuda_dev)
+    bias = torch.zeros(N)
+    bias[3], bias[7] = 1.0e5, -2.0e5
+    out = ops.gemm(a, w, bias.to(cuda_dev), L.EPI_BIAS, out_dtype=torch.float16)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert (out[:, 3] == 65504).all() and (out[:, 7] == -65504).all()
+    C = 80
+    y = torch.randn(M, C, generator=g).bfloat16().to(cuda_dev)
+    res = torch.randn(M, C, generator=g).half()
+    res[:, 5] = 65000.0
+    res = res.to(cuda_dev)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).bfloat16().to(cuda_dev)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).bfloat16().to(cuda_dev)
+    b1 = torch.zeros(4 * C).to(cuda_dev)
+    b2 = torch.zeros(C)
+    b2[5] = 2000.0
+    gamma = torch.ones(C).to(cuda_dev)
+    got = ops.mlp_fused(y, res, w1, b1, w2, b2.to(cuda_dev), gamma)
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all() and (got[:, 5] == 65504).all()
+
+
+@pytest.mark.parametrize("C,H,W,B", [(80, 15, 15, 37), (64, 15, 15, 5), (80, 9, 11, 3), (64, 2, 2, 700), (80, 15, 15, 1200)])
+@pytest.mark.parametrize("xdt,odt", [(torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16),
+                                     (torch.float16, torch.bfloat16)])
+def test_down_fused_tcgen05(cuda_dev, C, H, W, B, xdt, odt):
+    """One-kernel downsample (LayerNorm2d + 2x2/s2 conv + bias, A operand built in shared memory) vs fp32 LN + conv on the
+    same rounded operands, and vs the two-kernel path (lnpatch + GEMM) it replaces: same bf16 patches into the same MMA."""
+    from btsbot_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, C, H, W, generator=g).to(xdt).float()
+    lw, lb = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    cout = 2 * C
+    w = (torch.randn(cout, C, 2, 2, generator=g) / (2 * C ** 0.5)).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(_ln2d(x, lw, lb), w, b, stride=2)
+    ho, wo = ref.shape[2:]
+    rows = _nchw_to_rows(x).to(xdt).to(cuda_dev)
+    wt = w.permute(0, 2, 3, 1).reshape(cout, 4 * C).contiguous().bfloat16().to(cuda_dev)
+    got = ops.down_fused(rows, B, H, W, lw.to(cuda_dev), lb.to(cuda_dev), wt, b.to(cuda_dev), out_dtype=odt)
+    torch.cuda.synchronize()
+    assert got.shape == (B * ho * wo, cout) and got.dtype == odt
+    err = _report(f"down_fused C={C} {H}x{W} {xdt}->{odt}", _rows_to_nchw(got.cpu(), B, ho, wo), ref)
+    assert err < 5e-2
+    patches = ops.lnpatch(rows, B, H, W, lw.to(cuda_dev), lb.to(cuda_dev))
+    two = ops.gemm(patches, wt, b.to(cuda_dev), L.EPI_BIAS, out_dtype=odt if odt == torch.float16 else None)
+    torch.cuda.synchronize()
+    d = (two.float() - got.float()).abs().max().item()
+    print(f"[parity] down_fused vs lnpatch + gemm: max|d|={d:.3e}")
+    assert d <= (2 ** -8 if odt == torch.float16 else 2 ** -5)      # LayerNorm statistics are summed in a different order
