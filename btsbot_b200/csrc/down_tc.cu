@@ -4,11 +4,11 @@
 // lnpatch + gemm_down moved the LayerNorm'ed 2x2 patch matrix through HBM: per 8192 alerts 295 MB of rows in, 257 MB of
 // patches out and in again, 128 MB of rows out (125 + 65 us).  Here the A operand of the GEMM is built in shared memory by
 // eight producer warps straight from the residual-stream rows (the stem kernel's scheme, stem_tc.cu):
-//   warps 10-17  producers : thread = (output pixel p of a 128-row tile, dx); for dy = 0, 1 it loads the Cin channels of
-//                            input pixel (2 oy + dy, 2 ox + dx) (Cin / 8 16-byte loads; the two threads of an output pixel
-//                            read 2 Cin contiguous elements), LayerNorms them in registers (two-pass variance) and stores
-//                            the bf16 result as Cin / 8 16-byte chunks of row p at K offset (dy 2 + dx) Cin in the
-//                            128B-swizzled K-major layout UMMA reads; fence.proxy.async + one mbarrier arrival per warp
+//   warps 10-25  producers : thread = one input pixel (output pixel p of a 128-row tile, dy, dx): it loads the Cin channels
+//                            of pixel (2 oy + dy, 2 ox + dx) (Cin / 8 16-byte loads), LayerNorms them in registers
+//                            (two-pass variance, packed-pair arithmetic) and stores the bf16 result as Cin / 8 16-byte
+//                            chunks of row p at K offset (dy 2 + dx) Cin in the 128B-swizzled K-major layout UMMA reads;
+//                            fence.proxy.async + one mbarrier arrival per warp
 //   warp 0       streams the weight matrix [N x 4 Cin] as [N x 64] K blocks through a 3-slot ring (TMA, L2-resident)
 //   warp 1       MMA issuer: 4 Cin / 16 tcgen05.mma (M128 x N x K16) per tile into one of two TMEM accumulators
 //   warps 2-9    epilogue: thread = output row: tcgen05.ld -> + bias -> bf16 / fp16 rows (the residual stream) to global
@@ -26,8 +26,8 @@ int num_sms();
 namespace {
 constexpr int DM = 128;                  // output pixels per tile
 constexpr int kWSlots = 3;
-constexpr int kEpiD = 8, kProdD = 8;
-constexpr int kThreadsD = (2 + kEpiD + kProdD) * 32;          // 576
+constexpr int kEpiD = 8, kProdD = 16;
+constexpr int kThreadsD = (2 + kEpiD + kProdD) * 32;          // 832 -> 72 registers per thread
 
 template <int CIN, int N>
 struct DsPlan {
@@ -57,7 +57,7 @@ down_fused_kernel(const uint16_t* __restrict__ x, const __grid_constant__ CUtens
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sal = smem_dyn + (sbase - smem_u32(smem_dyn));
   const uint32_t bar0 = sbase + P::kOffBar;
-  auto a_full = [&](int s) { return bar0 + 8u * s; };                       // 2, count 2 * kProdD (two dy passes per warp)
+  auto a_full = [&](int s) { return bar0 + 8u * s; };                       // 2, count kProdD (one arrival per producer warp)
   auto a_empty = [&](int s) { return bar0 + 8u * (2 + s); };                // 2, count 1 (commit)
   auto w_full = [&](int s) { return bar0 + 8u * (4 + s); };                 // kWSlots
   auto w_empty = [&](int s) { return bar0 + 8u * (4 + kWSlots + s); };      // kWSlots
@@ -65,18 +65,18 @@ down_fused_kernel(const uint16_t* __restrict__ x, const __grid_constant__ CUtens
   auto tempty_bar = [&](int s) { return bar0 + 8u * (6 + 2 * kWSlots + s); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sal + P::kOffBar + 8 * (8 + 2 * kWSlots));
   float* bias_s = reinterpret_cast<float*>(sal + P::kOffVec);
-  float* lw_s = bias_s + N;
-  float* lb_s = lw_s + CIN;
+  float4* lwb_s = reinterpret_cast<float4*>(bias_s + N);      // per channel pair: (ln_w[2i], ln_w[2i+1], ln_b[2i], ln_b[2i+1])
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int num_tiles = (M + DM - 1) / DM;
   for (int i = threadIdx.x; i < N; i += kThreadsD) bias_s[i] = __ldg(bias + i);
-  for (int i = threadIdx.x; i < CIN; i += kThreadsD) { lw_s[i] = __ldg(ln_w + i); lb_s[i] = __ldg(ln_b + i); }
+  for (int i = threadIdx.x; i < CIN / 2; i += kThreadsD)
+    lwb_s[i] = make_float4(__ldg(ln_w + 2 * i), __ldg(ln_w + 2 * i + 1), __ldg(ln_b + 2 * i), __ldg(ln_b + 2 * i + 1));
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(a_full(s), 2 * kProdD); mbar_init(a_empty(s), 1);
+      mbar_init(a_full(s), kProdD); mbar_init(a_empty(s), 1);
       mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4);
     }
     for (int s = 0; s < kWSlots; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
@@ -130,73 +130,72 @@ down_fused_kernel(const uint16_t* __restrict__ x, const __grid_constant__ CUtens
       }
     }
   } else if (warp >= 2 + kEpiD) {
-    // ===================== A producers: thread = (output pixel, dx), two input pixels (dy = 0, 1) each =================
-    const int pt = (warp - 2 - kEpiD) * 32 + lane;             // 0 .. 255
-    const int p = pt >> 1, dx = pt & 1;                        // row of the tile, horizontal position in the 2x2 patch
+    // ===================== A producers: thread = one input pixel (output pixel p, dy, dx) of a 128-row tile ==============
+    // 16 warps x 32 = the 512 input pixels of a tile: one batch of Cin / 8 16-byte loads per thread and tile (the four
+    // threads of an output pixel read two runs of 2 Cin contiguous elements), packed-pair arithmetic (FADD2 / FFMA2)
+    const int pt = (warp - 2 - kEpiD) * 32 + lane;             // 0 .. 511
+    const int p = pt >> 2, dy = (pt >> 1) & 1, dx = pt & 1;
     const int hw = ho * wo;
     constexpr float invC = 1.0f / (float)CIN;
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt & 1; const uint32_t aphase = (uint32_t)(lt >> 1) & 1u;
       const int m = tile * DM + p;
-      int b = 0, oy = 0, ox = 0;
-      if (m < M) { b = m / hw; const int r = m - b * hw; oy = r / wo; ox = r - oy * wo; }
-      bool waited = false;
-#pragma unroll 1
-      for (int dy = 0; dy < 2; ++dy) {
-        uint4 v[NCH];
-        if (m < M) {
-          const uint4* src = reinterpret_cast<const uint4*>(x + (((size_t)b * H + (2 * oy + dy)) * W + (2 * ox + dx)) * CIN);
+      uint4 v[NCH];
+      if (m < M) {
+        const int b = m / hw, r = m - b * hw;
+        const int oy = r / wo, ox = r - oy * wo;
+        const uint4* src = reinterpret_cast<const uint4*>(x + (((size_t)b * H + (2 * oy + dy)) * W + (2 * ox + dx)) * CIN);
 #pragma unroll
-          for (int j = 0; j < NCH; ++j) v[j] = __ldg(src + j);
-        } else {
+        for (int j = 0; j < NCH; ++j) v[j] = __ldg(src + j);
+      } else {
 #pragma unroll
-          for (int j = 0; j < NCH; ++j) v[j] = make_uint4(0, 0, 0, 0);
-        }
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) s += x2_lo<XF16IN>(u[k]) + x2_hi<XF16IN>(u[k]);
-        }
-        const float mean = s * invC;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float d0 = x2_lo<XF16IN>(u[k]) - mean, d1 = x2_hi<XF16IN>(u[k]) - mean;
-            q = fmaf(d0, d0, q); q = fmaf(d1, d1, q);
-          }
-        }
-        const float rstd = rsqrtf(q * invC + kLnEps);
-        if (!waited) {                                         // the MMAs that read this A buffer two tiles ago have retired
-          mbar_wait_spin(a_empty(ab), aphase ^ 1u);
-          waited = true;
-        }
-        unsigned char* tileA = sal + ab * P::kATile;
-        const int c0 = (dy * 2 + dx) * NCH;                    // first 16-byte chunk of this segment in the K = 4 Cin row
-#pragma unroll
-        for (int j = 0; j < NCH; ++j) {
-          const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-          uint32_t o[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int ch = 8 * j + 2 * k;
-            const float lo = (x2_lo<XF16IN>(u[k]) - mean) * rstd * lw_s[ch] + lb_s[ch];
-            const float hi = (x2_hi<XF16IN>(u[k]) - mean) * rstd * lw_s[ch + 1] + lb_s[ch + 1];
-            o[k] = m < M ? pack_bf16x2(lo, hi) : 0u;
-          }
-          const int c = c0 + j;                                // chunk index in the row: block c >> 3, chunk c & 7 of it
-          unsigned char* rowp = tileA + (c >> 3) * P::kABlock + (p >> 3) * 1024 + (p & 7) * 128;
-          *reinterpret_cast<uint4*>(rowp + (((c & 7) ^ (p & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        fence_proxy_async();                                   // generic-proxy stores -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full(ab));
+        for (int j = 0; j < NCH; ++j) v[j] = make_uint4(0, 0, 0, 0);
       }
+      f32x2_t s2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s2 = add_f32x2(s2, x2_to_f32x2<XF16IN>(u[k]));
+      }
+      const float2 ss = unpack_f32x2(s2);
+      const float mean = (ss.x + ss.y) * invC;
+      const f32x2_t nm2 = pack_f32x2(-mean, -mean);
+      f32x2_t q2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const f32x2_t d = add_f32x2(x2_to_f32x2<XF16IN>(u[k]), nm2);
+          q2 = fma3_f32x2(d, d, q2);
+        }
+      }
+      const float2 qq = unpack_f32x2(q2);
+      const float rstd = rsqrtf((qq.x + qq.y) * invC + kLnEps);
+      const f32x2_t r2 = pack_f32x2(rstd, rstd), nmr2 = pack_f32x2(-mean * rstd, -mean * rstd);
+      mbar_wait_spin(a_empty(ab), aphase ^ 1u);                // the MMAs that read this A buffer two tiles ago have retired
+      unsigned char* tileA = sal + ab * P::kATile;
+      const int c0 = (dy * 2 + dx) * NCH;                      // first 16-byte chunk of this segment in the K = 4 Cin row
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const uint32_t u[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 wb = lwb_s[4 * j + k];
+          const f32x2_t y = fma3_f32x2(x2_to_f32x2<XF16IN>(u[k]), r2, nmr2);            // (x - mean) * rstd
+          const float2 z = unpack_f32x2(fma3_f32x2(y, pack_f32x2(wb.x, wb.y), pack_f32x2(wb.z, wb.w)));
+          o[k] = m < M ? pack_bf16x2(z.x, z.y) : 0u;
+        }
+        const int c = c0 + j;                                  // chunk index in the row: block c >> 3, chunk c & 7 of it
+        unsigned char* rowp = tileA + (c >> 3) * P::kABlock + (p >> 3) * 1024 + (p & 7) * 128;
+        *reinterpret_cast<uint4*>(rowp + (((c & 7) ^ (p & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async();                                     // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(ab));
     }
   } else {
     // ===================== epilogue: thread = one output row =====================
