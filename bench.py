@@ -900,12 +900,7 @@ def library_kernel_table(dev, B: int, dims=(80, 160, 320, 640), maps=(15, 7, 3, 
             xn = F.layer_norm(x, (ci,), g, b, 1e-6).permute(0, 3, 1, 2)
             tl.append(_time_cuda(lambda: F.layer_norm(x, (ci,), g, b, 1e-6), reps))
             tg.append(_time_cuda(lambda: F.conv2d(xn, wd, bd, stride=2), reps))
-        # the first transition is one kernel here (down_fused); lnpatch / gemm_down rows average the launches that remain
-        from btsbot_b200 import _engine
-        first_fused = _engine.DOWN_FUSED and (dims[0], dims[1]) in ((80, 160), (64, 128))
-        t["down_fused"] = tl[0] + tg[0]
-        rest = slice(1, None) if first_fused else slice(0, None)
-        t["lnpatch"], t["gemm_down"] = sum(tl[rest]) / len(tl[rest]), sum(tg[rest]) / len(tg[rest])
+        t["lnpatch"], t["gemm_down"] = sum(tl) / len(tl), sum(tg) / len(tg)
         # metadata branch + fusion head (BatchNorm1d eval, 2 + 3 Linears, GELU), fp32 as the reference runs it
         m = torch.randn(B, 25, device=dev)
         feat = torch.randn(B, dims[-1], device=dev)

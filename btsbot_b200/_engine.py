@@ -28,9 +28,6 @@ FUSE_MLP_WIDE = os.environ.get("BTSB_FUSE_WIDE", "1") != "0"
 #: wide fused MLP called IN PLACE (out == res): the update is added to the residual stream by a bulk tensor reduction
 #: instead of load -> add -> store: 126 -> 117 us per launch at C = 320 (profiles/r02t); BTSB_MLP_INPLACE=0 for A/B
 MLP_INPLACE = os.environ.get("BTSB_MLP_INPLACE", "1") != "0"
-#: first downsample of the nano / pico trunks (LayerNorm2d + 2x2/s2 conv) as one tcgen05 kernel whose A operand is built in
-#: shared memory (csrc/down_tc.cu); BTSB_DOWN_FUSED=0 keeps the LayerNorm-patch kernel + GEMM for A/B
-DOWN_FUSED = os.environ.get("BTSB_DOWN_FUSED", "1") != "0"
 #: bf16 mode: the residual stream of every stage but the last (stem / downsample outputs, block outputs) is stored as
 #: IEEE fp16 instead of bf16 -- same bytes, 8x finer rounding of the tensor that is updated 12-14 times in a row; the
 #: MMA operands stay bf16, the last stage stays bf16 because its rows feed the head GEMM (csrc/common.cuh).
@@ -218,24 +215,14 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
             if h < 2 or wd < 2:
                 raise ValueError("feature map too small for the 2x2/s2 downsample")
             ho, wo = (h - 2) // 2 + 1, (wd - 2) // 2 + 1
-            if DOWN_FUSED and code == L.BF16 and (cin, c) in ((80, 160), (64, 128)):
-                # LayerNorm2d + 2x2/s2 conv + bias in one kernel: the patch matrix never exists in HBM
-                ncode, ndt = stream(i)
-                nxt = torch.empty((B * ho * wo, c), device=dev, dtype=ndt)
-                L.launch("down_fused", lib.btsb_convnext_down_fused_fwd, _p(cur), scode, B, h, wd, cin,
-                         _p(stg["ds_ln_w"]), _p(stg["ds_ln_b"]), _p(stg["ds_w"]), _p(stg["ds_b"]), c, _p(nxt), ncode, st,
-                         flops=2.0 * 4 * cin * c * B * ho * wo + 8.0 * 4 * cin * B * ho * wo,
-                         nbytes=es * (cur.numel() + nxt.numel() + 4.0 * cin * c))
-                h, wd, scode, sdt, cur = ho, wo, ncode, ndt, nxt
-            else:
-                patches = torch.empty((B * ho * wo, 4 * cin), device=dev, dtype=adt)
-                L.launch("lnpatch", lib.btsb_convnext_lnpatch_fwd, _p(cur), scode, B, h, wd, cin, _p(stg["ds_ln_w"]),
-                         _p(stg["ds_ln_b"]), _p(patches), st, flops=8.0 * patches.numel(),
-                         nbytes=es * (cur.numel() + patches.numel()))
-                h, wd = ho, wo
-                scode, sdt = stream(i)
-                cur = torch.empty((B * h * wd, c), device=dev, dtype=sdt)
-                _gemm("gemm_down", patches, stg["ds_w"], stg["ds_b"], None, None, cur, scode, L.EPI_BIAS, st)
+            patches = torch.empty((B * ho * wo, 4 * cin), device=dev, dtype=adt)
+            L.launch("lnpatch", lib.btsb_convnext_lnpatch_fwd, _p(cur), scode, B, h, wd, cin, _p(stg["ds_ln_w"]),
+                     _p(stg["ds_ln_b"]), _p(patches), st, flops=8.0 * patches.numel(),
+                     nbytes=es * (cur.numel() + patches.numel()))
+            h, wd = ho, wo
+            scode, sdt = stream(i)
+            cur = torch.empty((B * h * wd, c), device=dev, dtype=sdt)
+            _gemm("gemm_down", patches, stg["ds_w"], stg["ds_b"], None, None, cur, scode, L.EPI_BIAS, st)
             if capture is not None:
                 capture[f"down{i}"] = (cur, h, wd)
         M = B * h * wd

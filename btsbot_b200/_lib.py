@@ -64,7 +64,6 @@ SIGNATURES = {
     "btsb_convnext_stem_fwd": (i32, [vp, i64, i32, i32, vp, vp, vp, vp, i32, vp, i32, vp]),
     "btsb_convnext_dwln_fwd": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
     "btsb_convnext_lnpatch_fwd": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp]),
-    "btsb_convnext_down_fused_fwd": (i32, [vp, i32, i64, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32, vp]),
     "btsb_convnext_poolln_fwd": (i32, [vp, i32, i64, i32, i32, vp, vp, vp, vp]),
     "btsb_gemm_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]),
     "btsb_stem_im2col_bf16": (i32, [vp, vp, i64, i32, i32, vp]),

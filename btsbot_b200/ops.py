@@ -57,19 +57,6 @@ def lnpatch(x, B, H, W, ln_w, ln_b):
     return out
 
 
-def down_fused(x, B, H, W, ln_w, ln_b, wt, bias, out_dtype=None):
-    """LayerNorm2d + Conv2d(k2, s2) + bias in one tcgen05 kernel: x rows [B*H*W, Cin] bf16 | fp16 (residual stream),
-    wt [N, 4Cin] bf16 in the lnpatch column order -> rows [B*Ho*Wo, N] (``out_dtype`` bf16 | fp16, default x's)."""
-    _chk(x, ln_w, ln_b, wt, bias)
-    cin, n = x.shape[1], wt.shape[0]
-    ho, wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
-    out_dtype = out_dtype or x.dtype
-    out = torch.empty((B * ho * wo, n), device=x.device, dtype=out_dtype)
-    L.check(L.lib().btsb_convnext_down_fused_fwd(_p(x), _CODE[x.dtype], B, H, W, cin, _p(ln_w), _p(ln_b), _p(wt), _p(bias),
-                                                 n, _p(out), _CODE[out_dtype], L.stream_ptr()), "down_fused")
-    return out
-
-
 def poolln(x, B, HW, ln_w=None, ln_b=None):
     _chk(x, ln_w, ln_b)
     out = torch.empty((B, x.shape[1]), device=x.device, dtype=torch.float32)

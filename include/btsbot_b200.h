@@ -127,15 +127,6 @@ int btsb_convnext_dwln_fwd(const void* x, int dtype, int64_t B, int H, int W, in
 int btsb_convnext_lnpatch_fwd(const void* x, int dtype, int64_t B, int H, int W, int C, const float* ln_w,
                               const float* ln_b, void* out, void* stream);
 
-/* ---- K5 fused (bf16): downsample.0 LayerNorm2d + downsample.1 Conv2d(Cin, N, k2, s2) + bias in ONE tcgen05 kernel; the A
- * operand (LayerNorm'ed 2x2 patches) is built in shared memory from the rows, so the [M, 4Cin] patch matrix never crosses
- * HBM.  x: [B*H*W, Cin] rows, in_dtype BF16 or BF16_XF16 (fp16 residual stream); Wt: [N, 4Cin] bf16, column
- * (dy*2+dx)*Cin + c; out: [B*Ho*Wo, N] rows in out_dtype (BF16 | BF16_XF16).  (Cin, N) = (80, 160) or (64, 128): the first
- * downsample of the nano / pico trunks, where the patch matrix is 257 MB per 8192 alerts; other shapes: lnpatch + gemm. */
-int btsb_convnext_down_fused_fwd(const void* x, int in_dtype, int64_t B, int H, int W, int Cin, const float* ln_w,
-                                 const float* ln_b, const void* Wt, const float* bias, int N, void* out, int out_dtype,
-                                 void* stream);
-
 /* ---- head prologue: global average pool + LayerNorm2d + flatten (architectures.py:109-113,136-141,
  * 309-313).  x: [B*HW, C] dtype F32|BF16 -> out [B, C] float32.  ln_w==NULL: pool only.
  */

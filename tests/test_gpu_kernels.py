@@ -348,33 +348,3 @@ def test_fp16_residual_stream_saturates_instead_of_overflowing(cuda_dev):
     got = ops.mlp_fused(y, res, w1, b1, w2, b2.to(cuda_dev), gamma)
     torch.cuda.synchronize()
     assert torch.isfinite(got.float()).all() and (got[:, 5] == 65504).all()
-
-
-@pytest.mark.parametrize("C,H,W,B", [(80, 15, 15, 37), (64, 15, 15, 5), (80, 9, 11, 3), (64, 2, 2, 700), (80, 15, 15, 1200)])
-@pytest.mark.parametrize("xdt,odt", [(torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16),
-                                     (torch.float16, torch.bfloat16)])
-def test_down_fused_tcgen05(cuda_dev, C, H, W, B, xdt, odt):
-    """One-kernel downsample (LayerNorm2d + 2x2/s2 conv + bias, A operand built in shared memory) vs fp32 LN + conv on the
-    same rounded operands, and vs the two-kernel path (lnpatch + GEMM) it replaces: same bf16 patches into the same MMA."""
-    from btsbot_b200 import ops, _lib as L
-    g = torch.Generator().manual_seed(17)
-    x = torch.randn(B, C, H, W, generator=g).to(xdt).float()
-    lw, lb = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
-    cout = 2 * C
-    w = (torch.randn(cout, C, 2, 2, generator=g) / (2 * C ** 0.5)).bfloat16().float()
-    b = torch.randn(cout, generator=g) * 0.1
-    ref = F.conv2d(_ln2d(x, lw, lb), w, b, stride=2)
-    ho, wo = ref.shape[2:]
-    rows = _nchw_to_rows(x).to(xdt).to(cuda_dev)
-    wt = w.permute(0, 2, 3, 1).reshape(cout, 4 * C).contiguous().bfloat16().to(cuda_dev)
-    got = ops.down_fused(rows, B, H, W, lw.to(cuda_dev), lb.to(cuda_dev), wt, b.to(cuda_dev), out_dtype=odt)
-    torch.cuda.synchronize()
-    assert got.shape == (B * ho * wo, cout) and got.dtype == odt
-    err = _report(f"down_fused C={C} {H}x{W} {xdt}->{odt}", _rows_to_nchw(got.cpu(), B, ho, wo), ref)
-    assert err < 5e-2
-    patches = ops.lnpatch(rows, B, H, W, lw.to(cuda_dev), lb.to(cuda_dev))
-    two = ops.gemm(patches, wt, b.to(cuda_dev), L.EPI_BIAS, out_dtype=odt if odt == torch.float16 else None)
-    torch.cuda.synchronize()
-    d = (two.float() - got.float()).abs().max().item()
-    print(f"[parity] down_fused vs lnpatch + gemm: max|d|={d:.3e}")
-    assert d <= (2 ** -8 if odt == torch.float16 else 2 ** -5)      # LayerNorm statistics are summed in a different order
