@@ -166,51 +166,10 @@ __device__ __forceinline__ float x2_hi(uint32_t v) {
 }
 template <bool XF16>
 __device__ __forceinline__ f32x2_t x2_to_f32x2(uint32_t v) { return pack_f32x2(x2_lo<XF16>(v), x2_hi<XF16>(v)); }
-// The depthwise-conv kernels are bound by the FMA pipe, where the fp16 -> fp32 conversion instruction (HADD2.F32) also
-// runs: two of them per loaded pixel would add 16 % to that pipe's load.  Instead the 16 bits are moved into fp32 position
-// with ALU-pipe instructions only (sign-extending shift + mask: the fp16 exponent lands in the low five bits of the fp32
-// exponent field), which yields value * 2^-112 EXACTLY -- for fp16 subnormals too, they become fp32 subnormals -- and the
-// conv taps are staged multiplied by 2^112 (kXScale), so every product is the exact one.
-// BTSB_XCVT selects how the conv kernels turn an fp16 pair into fp32 (A/B builds; the default is what measured fastest):
-//   0  both halves by ALU shifts (5 ALU instructions per pair, both taps of a channel pair scaled by 2^112)
-//   1  both halves by cvt (2 HADD2.F32 per pair on the FMA pipe, taps unscaled)
-//   2  low half by cvt, high half by ALU shift (1 + 2 instructions; only the odd channel's taps scaled)
-#ifndef BTSB_XCVT
-#define BTSB_XCVT 0
-#endif
-template <bool XF16>
-__device__ __forceinline__ f32x2_t x2_to_f32x2_scaled(uint32_t v) {
-  if constexpr (XF16) {
-#if BTSB_XCVT == 1
-    return x2_to_f32x2<true>(v);
-#elif BTSB_XCVT == 2
-    const uint32_t hi = ((uint32_t)((int32_t)v >> 3)) & 0x8FFFE000u;
-    f32x2_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(__float_as_uint(x2_lo<true>(v))), "r"(hi));
-    return r;
-#else
-    const uint32_t lo = ((uint32_t)((int32_t)(v << 16) >> 3)) & 0x8FFFE000u;
-    const uint32_t hi = ((uint32_t)((int32_t)v >> 3)) & 0x8FFFE000u;
-    f32x2_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-    return r;
-#endif
-  } else {
-    return bf16x2_to_f32x2(v);
-  }
-}
-// factor the conv taps of channel c are staged with (c even = low half of its pair, c odd = high half)
-template <bool XF16>
-__device__ __forceinline__ float x_tap_scale(int c) {
-  if constexpr (!XF16) return 1.0f;
-#if BTSB_XCVT == 1
-  return 1.0f;
-#elif BTSB_XCVT == 2
-  return (c & 1) ? 0x1p112f : 1.0f;
-#else
-  return 0x1p112f;
-#endif
-}
+// (The depthwise-conv kernels convert with the same two cvt per pair.  An ALU-only alternative -- shift the 16 bits into
+// fp32 position, which yields value * 2^-112 exactly, and fold 2^112 into the taps -- was built on the assumption that
+// HADD2.F32 would load the FMA pipe those kernels are bound by; measured, the cvt form is the faster one: dwln_15x80
+// 360 vs 391 us, dwln_7x160 156 vs 184 us, a mixed form 370 / 165 (profiles/r02cv).)
 
 constexpr float kLnEps = 1e-6f;  // timm LayerNorm2d eps for ConvNeXt
 

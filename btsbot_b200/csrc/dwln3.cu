@@ -77,7 +77,7 @@ dwln3_kernel(const T* __restrict__ x, int64_t B, int C_rt, int A_rt, int REM_rt,
   for (int i = tid; i < NT * NT * C; i += nthr) {
     const int t = i / C, c = i - t * C;
     const int ty = t / NT, tx = t - ty * NT;
-    wsm[i] = __ldg(wt + ((ty + 3 - R) * 7 + (tx + 3 - R)) * C + c) * x_tap_scale<XF16>(c);   // fp16 input: common.cuh
+    wsm[i] = __ldg(wt + ((ty + 3 - R) * 7 + (tx + 3 - R)) * C + c);   // fp16 input: common.cuh
   }
   for (int i = tid; i < C; i += nthr) { bsm[i] = __ldg(bias + i); gsm[i] = __ldg(ln_w + i); hsm[i] = __ldg(ln_b + i); }
 
@@ -110,7 +110,7 @@ dwln3_kernel(const T* __restrict__ x, int64_t B, int C_rt, int A_rt, int REM_rt,
         for (int ix = 0; ix < S; ++ix) {
           f32x2_t xin;
           if constexpr (F32) xin = *reinterpret_cast<const f32x2_t*>(im + (size_t)(iy * S + ix) * C);
-          else xin = x2_to_f32x2_scaled<XF16>(*reinterpret_cast<const uint32_t*>(im + (size_t)(iy * S + ix) * C));
+          else xin = x2_to_f32x2<XF16>(*reinterpret_cast<const uint32_t*>(im + (size_t)(iy * S + ix) * C));
 #pragma unroll
           for (int kx = 0; kx < NT; ++kx) {
             const int t = ix - (kx - R);

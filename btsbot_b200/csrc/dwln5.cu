@@ -80,7 +80,7 @@ dwln5_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __rest
   const uint32_t bar_full = s_u32(tin + 2 * HW * C), bar_empty = bar_full + 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  for (int i = tid; i < 49 * C; i += P::THREADS) wsm[i] = __ldg(wt + i) * x_tap_scale<XF16>(i);   // fp16 input: see common.cuh
+  for (int i = tid; i < 49 * C; i += P::THREADS) wsm[i] = __ldg(wt + i);   // fp16 input: see common.cuh
   for (int i = tid; i < C; i += P::THREADS) bsm[i] = __ldg(bias + i);
   if (tid == 0) {
     mb_init(bar_full, P::CONV_WARPS);
@@ -133,7 +133,7 @@ dwln5_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __rest
           for (int kx = 0; kx < 7; ++kx) wv[kx] = *reinterpret_cast<const f32x2_t*>(wsm + ((dy + 3) * 7 + kx) * C + 2 * c2);
 #pragma unroll
           for (int ix = 0; ix < S; ++ix) {
-            const f32x2_t xin = x2_to_f32x2_scaled<XF16>(*reinterpret_cast<const uint32_t*>(im + (iy * S + ix) * C));
+            const f32x2_t xin = x2_to_f32x2<XF16>(*reinterpret_cast<const uint32_t*>(im + (iy * S + ix) * C));
 #pragma unroll
             for (int kx = 0; kx < 7; ++kx) {
               const int t = ix - (kx - 3);

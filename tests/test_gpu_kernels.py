@@ -49,8 +49,7 @@ def test_stem(cuda_dev, C0, H, W, B, odt):
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
 def test_dwln(cuda_dev, C, H, W, B, dt):
     """dt float16 = the fp16 residual stream of the bf16 mode: fp16 rows in, bf16 rows out (dtype code BF16_XF16); the
-    inputs include fp16 subnormals and values next to the fp16 maximum (the conv kernels shift the 16 bits into fp32
-    position and fold 2^112 into the taps instead of converting)."""
+    inputs include fp16 subnormals and large magnitudes."""
     from btsbot_b200 import ops
     g = torch.Generator().manual_seed(2)
     x = torch.randn(B, C, H, W, generator=g)
