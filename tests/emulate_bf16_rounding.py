@@ -1,10 +1,10 @@
 """CPU emulation of the bf16 mode's rounding points on the oracle (DESIGN.md lesson 20):
-    python scripts/emulate_bf16_rounding.py [case]      (case: a key of tests/cases.MODEL_CASES, default ff_pico)
+    python tests/emulate_bf16_rounding.py [case]      (case: a key of tests/cases.MODEL_CASES, default ff_pico)
 Prints the max logit error against the fp32 oracle with each rounding (input, weights, residual stream, LayerNorm outputs,
 hidden activations) switched on alone, all but one, all (eight draws with a 1e-6 jitter before every rounding), and with the
 residual stream in bf16 / fp16 / fp32 (all stages or some).  Test infrastructure: imports oracle/."""
 import os, sys, numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # tests/ -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from btsbot_b200 import synth
 from oracle import convnext_oracle as O
