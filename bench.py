@@ -473,11 +473,13 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
     def e2e_step(i):
         lg = scorer(host_trip[i % nres], host_meta[i % nres] if multimodal else None)
         out_host.copy_(lg.view(-1, 1), non_blocking=True)
-    # warm-up of the e2e pipeline: the scorer calibrates its host-packing fraction on the first call; every staging slot
-    # is used once before the timed region
-    for i in range(4):
+    # warm-up of the e2e pipeline: the scorer calibrates its host-packing fraction on the first call and, if the split looks
+    # worthwhile, A/Bs it against the plain copy over its next twelve calls (AlertScorer._probe_record); the decision is
+    # taken on the first timed call at the latest (all warm-up work has completed by then)
+    for i in range(16 if scorer._pack_ok else 4):
         e2e_step(i)
     ctx.barrier()
+    torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
     for i in range(steps):
@@ -496,7 +498,8 @@ def bench_infer(ctx, wl_name: str, precision: str, B: int, steps: int, warmup: i
            "res_bytes": B * (63 * 63 * 3 * 4 + (25 * 4 if multimodal else 0)),      # the device-resident step input
            "host_pack": {"fraction": pack_f, "threads": scorer.pack_threads, "host_bytes_per_step": B * 63 * 63 * 3 * 4,
                          "calibration_ms": None if scorer.last_calibration is None else
-                         {"pack": scorer.last_calibration[1], "fp32_copy": scorer.last_calibration[2]}}}
+                         {"pack": scorer.last_calibration[1], "fp32_copy": scorer.last_calibration[2]},
+                         "probe": scorer.last_probe}}
     if pcie:
         out["h2d_gbs_ceiling"] = h2d_ceiling(ctx, [host_trip[0]] + ([host_meta[0]] if multimodal else []))
 

@@ -338,3 +338,28 @@ def test_host_pack_kernel_path_matches_cast(cuda_dev):
     assert got.dtype == torch.float32 and torch.equal(got, ref)
     got1 = btsbot.alert_utils.triplets_to_model_input(packed[1:].contiguous().to(cuda_dev))     # another base phase
     assert torch.equal(got1, ref[1:])
+
+
+def test_alert_scorer_probe_decides_between_plain_and_split(cuda_dev, golden_logits):
+    """"auto" mode after a calibration that favours the split: six calls plain, six calls split, then the decision from the
+    measured completion periods -- whichever way it goes, every call returns the logits of the plain path bitwise."""
+    from btsbot_b200.parallel import AlertScorer
+    cfg, sd, model = _build("mm_nano", golden_logits, cuda_dev, "bf16")
+    n = 96
+    trip = torch.from_numpy(synth.make_triplets(n, start=300)).pin_memory()
+    meta = synth.make_metadata(n, start=300)
+    ref = AlertScorer(model, return_scores=False, host_pack=False)(trip, meta).clone()
+    sc = AlertScorer(model, return_scores=False)                       # auto
+    key = tuple(trip.shape)
+    sc._pack_choice[key] = 0.5                                          # as if the calibration had chosen f = 0.5
+    sc._probe[key] = {"f": 0.5, "calls": 0, "events": [], "dt": ([], [])}
+    fractions = []
+    for k in range(14):
+        assert torch.equal(sc(trip, meta), ref)
+        fractions.append(sc.last_fraction)
+        if k == 12:
+            torch.cuda.synchronize()
+    assert fractions[:6] == [0.0] * 6 and fractions[6:12] == [0.5] * 6
+    assert sc.last_probe is not None and not sc._probe
+    assert sc._pack_choice[key] in (0.0, 0.5) and sc.last_probe["kept"] == (sc._pack_choice[key] == 0.5)
+    assert fractions[13] == sc._pack_choice[key]
