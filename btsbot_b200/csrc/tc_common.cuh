@@ -241,8 +241,9 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // Two GELUs per call on packed fp32 pairs (sm_100 FMUL2 / FFMA2): the scalar form issues 9-10 instructions per
 // element and is issue-bound at 10.1 clk per warp-element and SMSP, just above the MUFU floor of 8.1
 // (profiles/r01d_micro_gelu.txt); packed, the FMA-pipe part is 3 instructions per element.
-// (Evaluating both tanh with one tanh.approx.f16x2 was tried: the two cvt it needs made the fused MLP 9 % SLOWER --
-// 346 vs 317 us at C = 80 -- and the fp16 argument rounding broke the 2e-2 logit bar of one model; not kept.)
+// (Evaluating both tanh with one tanh.approx.f16x2 was tried twice: round 1 346 vs 317 us at C = 80; again after the D2
+// epilogue left the GELU warps and the MUFU pipe read 65 % busy: 280 vs 247 us (profiles/r02h2) -- the pack and the two cvt
+// cost more issue slots than the second MUFU costs pipe time.  Not kept.)
 __device__ __forceinline__ f32x2_t gelu_fast2(f32x2_t x) {
   const f32x2_t k5 = pack_f32x2(-3.5151679e-4f, -3.5151679e-4f), k3 = pack_f32x2(0.037005646f, 0.037005646f);
   const f32x2_t k1 = pack_f32x2(0.7975078843f, 0.7975078843f), kh = pack_f32x2(0.5f, 0.5f);
