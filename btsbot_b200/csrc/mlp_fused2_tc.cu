@@ -96,19 +96,21 @@ __host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab
 
 // Hidden activation from the fc1 accumulator pair `acc` and the staged bias pair `b` (= kB1Scale * b1).  Both forms leave
 // a power-of-two multiple of GELU in H and the D2 epilogue rescales the accumulator inside the FFMA that adds b2 --
-// power-of-two scalings commute with the bf16 rounding of H, so the result is that of GELU itself.
-//   default            : quintic-tanh GELU (max error 2.5e-5), H = GELU / 4 (tc_common.cuh gelu_quarter_quintic2)
-//   -DBTSB_GELU_CUBIC  : clamp-free cubic-tanh form (max error 2.7e-4), H = 2 GELU (gelu_twice2): 6 instead of 8
-//                        instructions per pair; measured 279 vs 296 us at C = 80 (profiles/r02t) -- see DESIGN.md on why the
-//                        tighter form is the default
-#ifdef BTSB_GELU_CUBIC
-constexpr float kB1Scale = 1.0f, kD2Scale = 0.5f;
-__device__ __forceinline__ f32x2_t hidden_act2(f32x2_t acc, f32x2_t b) { return tc::gelu_twice2(add_f32x2(acc, b)); }
-#else
+// power-of-two scalings commute with the bf16 rounding of H, so the result is that of the GELU form itself.
+//   default              : clamp-free cubic-tanh form (max error 2.7e-4 against 0.5 |x| 2^-11 = 7e-4 of tanh.approx itself),
+//                          H = 2 GELU (tc_common.cuh gelu_twice2): 136 FMA / MUFU / convert instructions per 32 elements
+//   -DBTSB_GELU_QUINTIC  : quintic-tanh form (max error 2.5e-5), H = GELU / 4 (gelu_quarter_quintic2): 160 instructions
+// The GELU warps are issue-bound once the D2 epilogue has its own warps (ncu r02y: issue slots 71 %, top stall
+// not-selected), so the instruction count is what counts: 228 vs 251 us at C = 80, 175 vs 182 us at C = 160
+// (profiles/r02cu); the bf16 logit errors of the two builds differ by noise (3.1-9.2e-3 vs 3.4-12.0e-3 over the cases).
+#ifdef BTSB_GELU_QUINTIC
 constexpr float kB1Scale = 0.125f, kD2Scale = 4.0f;
 __device__ __forceinline__ f32x2_t hidden_act2(f32x2_t acc, f32x2_t b) {
   return tc::gelu_quarter_quintic2(fma3_f32x2(acc, pack_f32x2(0.125f, 0.125f), b));
 }
+#else
+constexpr float kB1Scale = 1.0f, kD2Scale = 0.5f;
+__device__ __forceinline__ f32x2_t hidden_act2(f32x2_t acc, f32x2_t b) { return tc::gelu_twice2(add_f32x2(acc, b)); }
 #endif
 
 // K-major operand tile descriptor for a block whose rows are `sw` bytes (128 / 64 / 32) with the matching swizzle
