@@ -594,7 +594,8 @@ def compact(r, ctx):
     return {"workload": r["wl"]["label"], "alerts_per_gpu_per_step": r["B"], "value": tot / (r["ms"] * 1e-3),
             "unit": "alerts/s", "ms_per_step": r["ms"] / r["steps"], "steps": r["steps"], "n_gpus": ctx.world,
             "e2e": {"value": tot / (r["ms_e2e"] * 1e-3), "unit": "alerts/s", "h2d_bytes_per_step": ctx.world * r["in_bytes"],
-                    "d2h_bytes_per_step": ctx.world * r["B"] * 4}, "gpu_launches": r["launches"], "clocks": r["clocks"]}
+                    "d2h_bytes_per_step": ctx.world * r["B"] * 4, "host_pack": r.get("host_pack")},
+            "gpu_launches": r["launches"], "clocks": r["clocks"]}
 
 
 # ----------------------------------------------------------------------------------------------------------
