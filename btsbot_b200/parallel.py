@@ -118,7 +118,8 @@ class AlertScorer:
     part; the packed part follows with half its bytes, K1 runs once per part, and the logits are bit-identical.
     ``"auto"`` (default) times one pack and one fp32 copy of the first batch of each shape and picks the f that balances
     the host threads against the PCIe link (0 = plain copy when the host cannot keep up: few cores per GPU, small batches),
-    then lets the pipeline decide: six calls plain, six calls split, the shorter measured period stays;
+    then lets the pipeline decide: six calls plain, six calls split, the shorter measured period stays (single-rank jobs
+    only: ranks sharing a host interfere in ways a per-rank measurement does not see);
     ``True`` / ``False`` / a float in [0, 1] force it, the environment variable ``BTSB_HOST_PACK`` (0, 1 or a fraction) too."""
 
     def __init__(self, model, crop_to_size: int = 63, normalize: bool = False, return_scores: bool = True,
@@ -145,6 +146,7 @@ class AlertScorer:
         self._pack_rings = {}            # shape -> [next slot, [pinned bf16, dev bf16, dev f32, copied ev, consumed ev] * n]
         self._pack_choice = {}           # shape -> packed fraction f ("auto" calibration result)
         self.pack_threads = _host_threads()
+        self._multi_rank = int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1
         self.last_calibration = None     # (shape, pack_ms, copy_ms, f) of the latest "auto" decision
         self.last_fraction = 0.0         # packed fraction of the latest call
         self._probe = {}                 # shape -> state of the plain-vs-split A/B of the first calls ("auto" mode)
@@ -220,6 +222,12 @@ class AlertScorer:
             return 0.0
         if self.host_pack != "auto":
             return float(self.host_pack)
+        if self._multi_rank:
+            # several ranks on one host share its memory system, and their packs and copies drift in and out of phase:
+            # the per-rank probe read 5.0 ms (split) against 7.0 ms (plain) at N = 2 while the job's max-over-ranks step
+            # was 7.8 ms against 7.3 ms plain (profiles/r02n2); N = 4 gained 9 % on one box, N = 8 with four threads per
+            # rank lost.  "auto" therefore packs in single-rank jobs only; a fraction can still be forced.
+            return 0.0
         key = tuple(t.shape)
         f = self._pack_choice.get(key)
         if f is None:
