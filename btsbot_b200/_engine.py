@@ -28,8 +28,6 @@ FUSE_MLP_WIDE = os.environ.get("BTSB_FUSE_WIDE", "1") != "0"
 #: wide fused MLP called IN PLACE (out == res): the update is added to the residual stream by a bulk tensor reduction
 #: instead of load -> add -> store: 126 -> 117 us per launch at C = 320 (profiles/r02t); BTSB_MLP_INPLACE=0 for A/B
 MLP_INPLACE = os.environ.get("BTSB_MLP_INPLACE", "1") != "0"
-#: fused MLP at C = 64 / 80: fc1's bias folded into the GEMM (BTSB_FOLD_BIAS=0 keeps the bias add in the GELU warps, A/B)
-FOLD_BIAS = os.environ.get("BTSB_FOLD_BIAS", "1") != "0"
 #: bf16 mode: the residual stream of every stage but the last (stem / downsample outputs, block outputs) is stored as
 #: IEEE fp16 instead of bf16 -- same bytes, 8x finer rounding of the tensor that is updated 12-14 times in a row; the
 #: MMA operands stay bf16, the last stage stays bf16 because its rows feed the head GEMM (csrc/common.cuh).
@@ -112,19 +110,6 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
-def fold_bias(w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """``[N, K]`` weights + ``[N]`` bias -> ``[N, K + 16]`` bf16 with the bias in two extra columns as
-    ``bf16(b)`` and ``bf16(b - bf16(b))`` (14 zero columns after them): the fused MLP's bias-folded fc1 operand, which the
-    kernel multiplies with a constant block of ones (``btsb_convnext_mlp_fused_fwd`` with ``b1 = NULL``)."""
-    n, k = w.shape
-    out = torch.zeros((n, k + 16), device=w.device, dtype=torch.bfloat16)
-    out[:, :k] = w.to(torch.bfloat16)
-    hi = b.float().to(torch.bfloat16)
-    out[:, k] = hi
-    out[:, k + 1] = (b.float() - hi.float()).to(torch.bfloat16)
-    return out.contiguous()
-
-
 class TrunkWeights:
     """Kernel-ready copy of a timm-keyed ConvNeXt trunk (keys: SURVEY.md section 8b)."""
 
@@ -162,8 +147,6 @@ class TrunkWeights:
                     ln_w=_f32c(g(q + "norm.weight")), ln_b=_f32c(g(q + "norm.bias")),
                     fc1_w=g(q + "mlp.fc1.weight").detach().reshape(4 * c, c).to(wdt).contiguous(),
                     fc1_b=_f32c(g(q + "mlp.fc1.bias")),
-                    fc1_wx=fold_bias(g(q + "mlp.fc1.weight").detach().reshape(4 * c, c), g(q + "mlp.fc1.bias").detach())
-                    if code == L.BF16 and c in (64, 80) else None,
                     fc2_w=g(q + "mlp.fc2.weight").detach().reshape(c, 4 * c).to(wdt).contiguous(),
                     fc2_b=_f32c(g(q + "mlp.fc2.bias")),
                     gamma=_f32c(g(q + "gamma")),
@@ -258,11 +241,8 @@ def trunk_forward(w: TrunkWeights, x: torch.Tensor, capture: dict | None = None)
             nxt = cur if inplace else torch.empty((M, c), device=dev, dtype=sdt)
             if fused:
                 # fc1 -> GELU -> fc2 -> *gamma -> +shortcut in one kernel; bytes: y + res + out (+ L2-resident weights)
-                # C = 64 / 80 on the fp16 stream: fc1's bias rides in the GEMM (bias-folded weights, b1 = NULL)
-                bfold = FOLD_BIAS and scode == L.BF16_XF16 and blk.get("fc1_wx") is not None
-                L.launch(f"mlp_fused_{c}", lib.btsb_convnext_mlp_fused_fwd, _p(y), _p(cur),
-                         _p(blk["fc1_wx"] if bfold else blk["fc1_w"]), None if bfold else _p(blk["fc1_b"]),
-                         _p(blk["fc2_w"]), _p(blk["fc2_b"]), _p(blk["gamma"]), _p(nxt), M, c,
+                L.launch(f"mlp_fused_{c}", lib.btsb_convnext_mlp_fused_fwd, _p(y), _p(cur), _p(blk["fc1_w"]),
+                         _p(blk["fc1_b"]), _p(blk["fc2_w"]), _p(blk["fc2_b"]), _p(blk["gamma"]), _p(nxt), M, c,
                          L.BF16_XF16 if scode == L.BF16_XF16 else L.BF16, st,
                          flops=16.0 * M * c * c, nbytes=es * (3.0 * M * c + 8.0 * c * c))
             else:

@@ -50,14 +50,13 @@ struct Plan2 {
   int y_bytes = 0, w1_bytes = 0, w2_bytes = 0;
   int ny = 0, n1 = 0, n2 = 0, resident = 0;
   int off_w1 = 0, off_w2 = 0, off_h = 0, off_stg = 0, off_slab = 0, off_bar = 0, off_b1 = 0, total = 0;
-  int bf = 0;                // 1: fc1's bias rides in an extra 16-column K block (y: constant ones, W1: b1 as hi + lo bf16)
   int nstg = 1;              // staging tiles (2 for C <= 80: the residual rows of tile t+1 land while tile t drains)
   int slab = 0;              // 1: one 1 KB slab per epilogue warp ([32 rows x 16 columns] bulk tensor copies, wide C)
   int stg = 0;               // 1: residual / output rows move through a [128 x C] bf16 staging tile with bulk tensor copies
   int ht = 0;                // 1: the GELU'd hidden chunk H lives in TMEM (A operand of G2 from TMEM), no shared-memory H tiles
   bool ok = false;
 };
-__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab = false, bool bf = false);
+__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab = false);
 
 __host__ __device__ constexpr int rup1k(int x) { return (x + 1023) & ~1023; }
 
@@ -74,13 +73,12 @@ __host__ __device__ constexpr bool plan2_try(Plan2& P, int ny, int n1, int n2, i
   return P.total <= kSmemMax && n1 <= kMaxSlots && n2 <= kMaxSlots;
 }
 
-__host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht, bool slab, bool bf) {
+__host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht, bool slab) {
   P.C = C; P.NJ = (4 * C) / NH; P.stg = te ? 1 : 0; P.ht = ht ? 1 : 0; P.slab = slab ? 1 : 0;
   P.nstg = (te && C <= 80) ? 2 : 1;         // C = 96 would lose its resident weights to a second tile
   P.nfull = C / 64; P.t32 = (C % 64) >= 32 ? 1 : 0; P.t16 = (C % 32) >= 16 ? 1 : 0;
-  P.bf = bf ? 1 : 0;
-  P.y_bytes = rup1k(FM * (C + (bf ? 16 : 0)) * 2);
-  P.w1_bytes = rup1k(NH * (C + (bf ? 16 : 0)) * 2);
+  P.y_bytes = rup1k(FM * C * 2);
+  P.w1_bytes = rup1k(NH * C * 2);
   P.w2_bytes = rup1k(C * 128);
   if (plan2_try(P, 2, P.NJ, P.NJ, 1)) return true;      // everything resident, y double buffered
   if (plan2_try(P, 2, 3, 4, 0)) return true;
@@ -90,9 +88,9 @@ __host__ __device__ constexpr bool make_plan2(Plan2& P, int C, bool te, bool ht,
   return plan2_try(P, 1, 2, 1, 0);                      // C = 320: 80 KB y tile, 40 KB weight chunks
 }
 
-__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab, bool bf) {
+__host__ __device__ constexpr Plan2 plan2_for(int C, bool te, bool ht, bool slab) {
   Plan2 P;
-  P.ok = make_plan2(P, C, te, ht, slab, bf);
+  P.ok = make_plan2(P, C, te, ht, slab);
   return P;
 }
 
@@ -114,14 +112,6 @@ __device__ __forceinline__ f32x2_t hidden_act2(f32x2_t acc, f32x2_t b) {
 constexpr float kB1Scale = 1.0f, kD2Scale = 0.5f;
 __device__ __forceinline__ f32x2_t hidden_act2(f32x2_t acc, f32x2_t b) { return tc::gelu_twice2(add_f32x2(acc, b)); }
 #endif
-// bias already in the accumulator (BF kernels)
-__device__ __forceinline__ f32x2_t hidden_act2_nb(f32x2_t acc) {
-#ifdef BTSB_GELU_QUINTIC
-  return tc::gelu_quarter_quintic2(mul_f32x2(acc, pack_f32x2(0.125f, 0.125f)));
-#else
-  return tc::gelu_twice2(acc);
-#endif
-}
 
 // K-major operand tile descriptor for a block whose rows are `sw` bytes (128 / 64 / 32) with the matching swizzle
 __device__ __forceinline__ uint64_t smem_desc_k(uint32_t saddr, int sw) {
@@ -191,7 +181,6 @@ __host__ __device__ constexpr SlabMap make_slab_map(int groups) {
 struct Maps2 {
   CUtensorMap y128, y64, y32;      // [M, C]   boxes [128 rows x 64|32|16 cols], swizzle 128|64|32 B
   CUtensorMap a128, a64, a32;      // W1 [4C, C]: boxes [64 rows x 64|32|16 cols]
-  CUtensorMap ab;                  // bias-folded W1 [4C, C + 16]: box [64 rows x 16 cols] at column C (swizzle 32 B)
   CUtensorMap w2;                  // W2 [C, 4C]: box [C rows x 64 cols], swizzle 128 B
   CUtensorMap r128, r64, r32;      // res [M, C]: boxes [32 rows x 64|32|16 cols] (bulk loads into the staging tile)
   CUtensorMap o128, o64, o32;      // out [M, C]: same boxes (bulk stores from the staging tile)
@@ -209,9 +198,7 @@ struct Maps2 {
 // y tile of the next row tile could only be fetched afterwards (~4 k clocks for 80 KB with every SM at its tile boundary
 // at once).  Removed.  In steady state this kernel streams W1 + W2 (1.6 MB per 128-row tile, 80 KB per ~1800-clock hidden
 // chunk = 45 B/clk/SM, 7.1 TB/s chip-wide) -- it sits on the L2 -> SM bandwidth, not on the tensor pipe.
-// BF: fc1's bias is folded into G1 (W1 carries 16 more columns: b1 as hi + lo bf16 parts, the y tile a constant block of
-// ones) -- the GELU warps are issue-bound and the bias add was one of their 8.5 instructions per element pair
-template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false, bool XF16 = false, bool BF = false>   // XF16: fp16 res / out rows
+template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false, bool XF16 = false>   // XF16: res / out rows are IEEE fp16
 __global__ void __launch_bounds__(TE ? kThreadsDW : kThreads2, 1)   // 19 warps: 96 registers; 23 (dedicated D2 warps): 88
 mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1, const float* __restrict__ b2,
                   const float* __restrict__ gamma, const __nv_bfloat16* __restrict__ res,
@@ -231,11 +218,8 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   constexpr bool DW = TE;                     // dedicated D2-epilogue warps (kG2Warp + 1 .. kG2Warp + 4)
   static_assert(EP == 0 || EP == 2 || EP == 4, "EP");
   static_assert(EP == 0 || !TE, "EP variants belong to the wide (non-staging) kernels");
-  constexpr Plan2 P = plan2_for(C, TE, HT, TS, BF);
+  constexpr Plan2 P = plan2_for(C, TE, HT, TS);
   static_assert(P.ok, "no shared-memory plan for this C");
-  static_assert(!BF || TE, "bias folding belongs to the narrow kernels");
-  constexpr int kYBias = P.nfull * FM * 128 + P.t32 * FM * 64 + P.t16 * FM * 32;     // offset of the ones block in a y buffer
-  constexpr int kWBias = P.nfull * NH * 128 + P.t32 * NH * 64 + P.t16 * NH * 32;     // offset of the bias block in a W1 slot
   // EP = 4 (in-place: out == res): the update gamma * (acc + b2) leaves through the slab as a bulk tensor REDUCTION
   // (global += slab, bf16 add at the L2) -- no residual load at all, so a piece costs one slab round trip instead of a
   // load -> update -> store chain (the ~15 k-clock drain of EP = 2 holds back the next tile's G2: lesson 9 / 12)
@@ -294,18 +278,7 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
   }
   if (warp == 1) { tmem_alloc(smem_u32((const void*)tmem_slot), 512); tmem_relinquish(); }
   float* b1s = reinterpret_cast<float*>(sal + P.off_b1);            // fc1 bias staged once per CTA
-  if constexpr (!BF) {
-    for (int i = threadIdx.x; i < 4 * C; i += (int)blockDim.x) b1s[i] = kB1Scale * __ldg(b1 + i);
-  } else {
-    // the constant K block of every y buffer: row r = (1, 1, 0, ..., 0) in the 32-byte-swizzled K-major layout (columns
-    // 0 and 1 meet the hi and lo parts of b1 in W1's extra block); TMA never writes here
-    for (int i = threadIdx.x; i < P.ny * FM * 2; i += (int)blockDim.x) {
-      const int yb = i / (FM * 2), r = (i >> 1) % FM, c = i & 1;
-      const uint4 v = c == 0 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(sal + yb * P.y_bytes + kYBias + r * 32 + ((c ^ ((r >> 2) & 1)) << 4)) = v;
-    }
-    fence_proxy_async();
-  }
+  for (int i = threadIdx.x; i < 4 * C; i += (int)blockDim.x) b1s[i] = kB1Scale * __ldg(b1 + i);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -334,13 +307,12 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       if (!P.resident || t1 == 0) {
         mbar_wait_spin(w1_empty(s1), ph1 ^ 1u);
         if (elect_one()) {
-          mbar_expect_tx(w1_full(s1), (uint32_t)(NH * (C + (BF ? 16 : 0)) * 2));
+          mbar_expect_tx(w1_full(s1), (uint32_t)(NH * C * 2));
           const uint32_t dst = sbase + P.off_w1 + s1 * P.w1_bytes;
 #pragma unroll
           for (int kb = 0; kb < P.nfull; ++kb) tma_load_2d(dst + kb * NH * 128, &tm.a128, w1_full(s1), kb * 64, j1 * NH);
           if (P.t32) tma_load_2d(dst + P.nfull * NH * 128, &tm.a64, w1_full(s1), P.nfull * 64, j1 * NH);
           if (P.t16) tma_load_2d(dst + P.nfull * NH * 128 + P.t32 * NH * 64, &tm.a32, w1_full(s1), P.nfull * 64 + P.t32 * 32, j1 * NH);
-          if (BF) tma_load_2d(dst + kWBias, &tm.ab, w1_full(s1), C, j1 * NH);
         }
         __syncwarp();
       }
@@ -392,8 +364,6 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
           for (int kk = 0; kk < sw / 32; ++kk)
             umma_bf16(dcol, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc1, (kb | kk) != 0 ? 1u : 0u);
         }
-        if constexpr (BF)        // + b1: ones block of the y tile x (b1_hi, b1_lo) block of the W1 chunk, one K = 16 step
-          umma_bf16(dcol, smem_desc_k(ya + kYBias, 32), smem_desc_k(wa + kWBias, 32), idesc1, 1u);
         umma_commit(d1_full(b1i));
         if (!P.resident) umma_commit(w1_empty(s1));
         if (j1 == NJ - 1) umma_commit(y_empty(yb));                // y tile no longer needed once these retire
@@ -813,15 +783,11 @@ mlp_fused2_kernel(const __grid_constant__ Maps2 tm, const float* __restrict__ b1
       uint32_t o[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        float2 g0, g1;
-        if constexpr (BF) {                                  // the accumulator already holds fc1 + b1
-          g0 = unpack_f32x2(hidden_act2_nb(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]))));
-          g1 = unpack_f32x2(hidden_act2_nb(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]))));
-        } else {
-          const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
-          g0 = unpack_f32x2(hidden_act2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), pack_f32x2(b4.x, b4.y)));
-          g1 = unpack_f32x2(hidden_act2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), pack_f32x2(b4.z, b4.w)));
-        }
+        const float4 b4 = *reinterpret_cast<const float4*>(b1s + hcol + i);
+        const float2 g0 = unpack_f32x2(hidden_act2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                                   pack_f32x2(b4.x, b4.y)));
+        const float2 g1 = unpack_f32x2(hidden_act2(pack_f32x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
+                                                   pack_f32x2(b4.z, b4.w)));
         o[i / 2] = pack_bf16x2(g0.x, g0.y);
         o[i / 2 + 1] = pack_bf16x2(g1.x, g1.y);
       }
@@ -892,14 +858,14 @@ int mlp_fused2_supported(int C) {
   return C % 16 == 0 && ((C >= 64 && C <= 160) || C == 256 || C == 320);
 }
 
-template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false, bool XF16 = false, bool BF = false>
+template <int C, bool TE, bool HT, int EP = 0, bool TRACE = false, bool XF16 = false>
 static int launch2(const Maps2& tm, const float* b1, const float* b2, const float* gamma, const void* res, void* out,
                    int64_t M, cudaStream_t st) {
-  constexpr Plan2 P = plan2_for(C, TE, HT, EP == 2 || EP == 4, BF);   // must be the kernel's own plan
+  constexpr Plan2 P = plan2_for(C, TE, HT, EP == 2 || EP == 4);   // must be the kernel's own plan (slabs for EP 2 and 4)
   if constexpr (!TRACE && XF16 && (C == 80 || C == 160 || C == 320)) {   // traced variants: the bench's three widths, fp16 stream
-    if (g_mlp_trace != nullptr) return launch2<C, TE, HT, EP, true, XF16, BF>(tm, b1, b2, gamma, res, out, M, st);
+    if (g_mlp_trace != nullptr) return launch2<C, TE, HT, EP, true, XF16>(tm, b1, b2, gamma, res, out, M, st);
   }
-  auto kern = mlp_fused2_kernel<C, TE, HT, EP, TRACE, XF16, BF>;
+  auto kern = mlp_fused2_kernel<C, TE, HT, EP, TRACE, XF16>;
   BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax), "mlp_fused2 attr");
   const int m_tiles = (int)((M + FM - 1) / FM);
   const int grid = min(m_tiles, num_sms());
@@ -935,32 +901,21 @@ static int mlp_fused2_dispatch(const Maps2& tm, const float* b1, const float* b2
   return BTSB_EINVAL;
 }
 
-int make_tmap_bf16_2d_pitch(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
-                            uint32_t box_cols, int swizzle_bytes, uint64_t pitch_elems);
-
 int mlp_fused2_launch(const void* y, const void* res, const void* W1, const float* b1, const void* W2, const float* b2,
                       const float* gamma, void* out, int64_t M, int C, bool xf16, cudaStream_t st) {
   BTSB_REQUIRE(mlp_fused2_supported(C), "mlp_fused: C=%d unsupported", C);
-  // b1 == NULL: bias-folded weights -- W1 is [4C, C + 16] bf16 whose last 16 columns are (bf16(b1), bf16(b1 - bf16(b1)),
-  // 0 x 14); the kernel multiplies them with a constant block of ones (fp16-stream kernels of C = 64 / 80 only)
-  const bool bf = b1 == nullptr;
-  BTSB_REQUIRE(!bf || (xf16 && (C == 64 || C == 80)), "mlp_fused: bias-folded weights (b1 = NULL) need C = 64 / 80 and BF16_XF16");
-  const uint64_t w1_pitch = (uint64_t)(C + (bf ? 16 : 0));
   const int t32 = (C % 64) >= 32, t16 = (C % 32) >= 16;
   Maps2 tm;
   memset(&tm, 0, sizeof(tm));
   if (int e = make_tmap_bf16_2d_sw(&tm.y128, y, (uint64_t)M, (uint64_t)C, FM, 64, 128)) return e;
-  if (int e = make_tmap_bf16_2d_pitch(&tm.a128, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 64, 128, w1_pitch)) return e;
+  if (int e = make_tmap_bf16_2d_sw(&tm.a128, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 64, 128)) return e;
   if (t32) {
     if (int e = make_tmap_bf16_2d_sw(&tm.y64, y, (uint64_t)M, (uint64_t)C, FM, 32, 64)) return e;
-    if (int e = make_tmap_bf16_2d_pitch(&tm.a64, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 32, 64, w1_pitch)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.a64, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 32, 64)) return e;
   }
   if (t16) {
     if (int e = make_tmap_bf16_2d_sw(&tm.y32, y, (uint64_t)M, (uint64_t)C, FM, 16, 32)) return e;
-    if (int e = make_tmap_bf16_2d_pitch(&tm.a32, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 16, 32, w1_pitch)) return e;
-  }
-  if (bf) {
-    if (int e = make_tmap_bf16_2d_pitch(&tm.ab, W1, (uint64_t)(4 * C), w1_pitch, NH, 16, 32, w1_pitch)) return e;
+    if (int e = make_tmap_bf16_2d_sw(&tm.a32, W1, (uint64_t)(4 * C), (uint64_t)C, NH, 16, 32)) return e;
   }
   const int NC = C > 256 ? C / 2 : C;                      // W2 chunk rows per bulk copy / per G2 UMMA
   if (int e = make_tmap_bf16_2d_sw(&tm.w2, W2, (uint64_t)C, (uint64_t)(4 * C), (uint32_t)NC, 64, 128)) return e;
@@ -972,10 +927,6 @@ int mlp_fused2_launch(const void* y, const void* res, const void* W1, const floa
   if (int e = rmap(&tm.o128, out, (uint64_t)M, (uint64_t)C, 32, 64, 128)) return e;
   if (int e = rmap(&tm.o64, out, (uint64_t)M, (uint64_t)C, 32, 32, 64)) return e;
   if (int e = rmap(&tm.o32, out, (uint64_t)M, (uint64_t)C, 32, 16, 32)) return e;
-  if (bf) {
-    if (C == 64) return launch2<64, true, true, 0, false, true, true>(tm, b1, b2, gamma, res, out, M, st);
-    return launch2<80, true, true, 0, false, true, true>(tm, b1, b2, gamma, res, out, M, st);
-  }
   if (xf16) return mlp_fused2_dispatch<true>(tm, b1, b2, gamma, res, out, M, C, st);
   return mlp_fused2_dispatch<false>(tm, b1, b2, gamma, res, out, M, C, st);
 }
@@ -1001,7 +952,7 @@ extern "C" int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const
   BTSB_REQUIRE(dtype == BTSB_BF16 || dtype == BTSB_BF16_XF16, "mlp_fused: dtype must be BF16 or BF16_XF16");
   BTSB_REQUIRE(mlp_fused2_supported(C), "mlp_fused: C=%d unsupported (multiple of 16 in [64,160], 256 or 320)", C);
   if (M == 0) return BTSB_OK;
-  BTSB_REQUIRE(y && res && W1 && W2 && b2 && gamma && out, "mlp_fused: null pointer");      // b1 == NULL: bias-folded W1
+  BTSB_REQUIRE(y && res && W1 && b1 && W2 && b2 && gamma && out, "mlp_fused: null pointer");
   BTSB_REQUIRE(((uintptr_t)res % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)b1 % 16) == 0 &&
                    ((uintptr_t)b2 % 16) == 0 && ((uintptr_t)gamma % 16) == 0,
                "mlp_fused: pointers must be 16-byte aligned");

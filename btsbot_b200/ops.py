@@ -80,18 +80,15 @@ def gemm(a, wt, bias, epilogue=L.EPI_BIAS, gamma=None, res=None, out_dtype=None)
     return out
 
 
-def mlp_fused(y, res, w1, b1, w2, b2, gamma, inplace=False, fold_bias=False):
+def mlp_fused(y, res, w1, b1, w2, b2, gamma, inplace=False):
     """res + gamma * (fc2(gelu(fc1(y)+b1))+b2) in one tcgen05 kernel (bf16, C in [64,160], 256, 320); ``res`` bf16 or
     fp16 (the residual stream), the result has its dtype.
     ``inplace=True`` passes out == res (the wide variants then add the update to ``res`` with a bulk tensor reduction)."""
     _chk(y, res, w1, b1, w2, b2, gamma)
     M, c = y.shape
     out = res if inplace else torch.empty_like(res)
-    if fold_bias:                                    # fc1's bias inside the GEMM (C = 64 / 80, fp16 residual stream)
-        from ._engine import fold_bias as _fold
-        w1, b1 = _fold(w1, b1), None
-    L.check(L.lib().btsb_convnext_mlp_fused_fwd(_p(y), _p(res), _p(w1), _p(b1) if b1 is not None else None, _p(w2), _p(b2),
-                                                _p(gamma), _p(out), M, c, _CODE[res.dtype], L.stream_ptr()), "mlp_fused")
+    L.check(L.lib().btsb_convnext_mlp_fused_fwd(_p(y), _p(res), _p(w1), _p(b1), _p(w2), _p(b2), _p(gamma), _p(out),
+                                                M, c, _CODE[res.dtype], L.stream_ptr()), "mlp_fused")
     return out
 
 

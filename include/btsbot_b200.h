@@ -161,9 +161,6 @@ int btsb_gemm_ln_fwd(const void* A, const void* Wt, const float* bias, const flo
  * y: dw+LN output [M,C]; res: block input [M,C]; W1 [4C,C], W2 [C,4C] bf16 row-major; b1 [4C], b2/gamma [C] f32.
  * dtype BTSB_BF16: res / out bf16; BTSB_BF16_XF16: res / out are the fp16 residual stream (y, W1, W2 stay bf16).
  * out == res (in place) is allowed; C = 256 / 320 then add the update to the rows with a bulk tensor reduction.
- * b1 == NULL (C = 64 / 80 with BTSB_BF16_XF16): W1 is the bias-folded matrix [4C, C + 16] bf16 whose last 16 columns are
- * (bf16(b1), bf16(b1 - bf16(b1)), 0 x 14); the kernel multiplies them with a constant block of ones, so the GELU warps
- * skip the bias add.
  */
 int btsb_convnext_mlp_fused_fwd(const void* y, const void* res, const void* W1, const float* b1,
                                 const void* W2, const float* b2, const float* gamma, void* out, int64_t M,

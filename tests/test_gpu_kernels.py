@@ -347,30 +347,3 @@ def test_fp16_residual_stream_saturates_instead_of_overflowing(cuda_dev):
     got = ops.mlp_fused(y, res, w1, b1, w2, b2.to(cuda_dev), gamma)
     torch.cuda.synchronize()
     assert torch.isfinite(got.float()).all() and (got[:, 5] == 65504).all()
-
-
-@pytest.mark.parametrize("C,M", [(80, 1000), (64, 4096), (80, 128 * 300 + 5), (64, 50)])
-def test_mlp_fused_bias_folded(cuda_dev, C, M):
-    """fc1's bias inside the GEMM (W1 with 16 extra columns: b1 as hi + lo bf16 parts, multiplied with a constant block of
-    ones; C = 64 / 80, fp16 residual stream): same result as the kernel that adds the bias in its GELU warps -- the bias
-    reaches the fp32 accumulator within 2^-17 relative -- and as the fp64 reference."""
-    from btsbot_b200 import ops
-    g = torch.Generator().manual_seed(21)
-    y = torch.randn(M, C, generator=g).bfloat16()
-    res = torch.randn(M, C, generator=g).half()
-    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).bfloat16()
-    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).bfloat16()
-    b1, b2 = torch.randn(4 * C, generator=g) * 0.7, torch.randn(C, generator=g) * 0.1
-    gamma = torch.rand(C, generator=g) + 0.5
-    hid = F.gelu(y.double() @ w1.double().t() + b1.double()).float().bfloat16()
-    ref = (res.double() + gamma.double() * (hid.double() @ w2.double().t() + b2.double())).float()
-    args = [t.to(cuda_dev) for t in (y, res, w1, b1, w2, b2, gamma)]
-    plain = ops.mlp_fused(*args).float().cpu()
-    folded = ops.mlp_fused(*args, fold_bias=True).float().cpu()
-    torch.cuda.synchronize()
-    err = _report(f"mlp_fused bias-folded C={C} M={M}", folded, ref)
-    d = (folded - plain).abs()
-    print(f"[parity] bias-folded vs bias in the GELU warps: max {d.max().item():.3e}, mean {d.mean().item():.3e}")
-    assert err < 2e-2 and (folded - ref).abs().mean().item() < 2.5e-3
-    # a hidden value may round to the neighbouring bf16 where the two bias paths differ in the last fp32 bits
-    assert d.max().item() < 1.6e-2 and d.mean().item() < 2e-4
