@@ -79,6 +79,8 @@ TENSOR_FAMILIES = ("gemm", "mlp_fused", "mv_expand", "mv_project", "mv_qkv", "mv
                    "mv_shortcut", "mv_attn_tc", "t_wgrad_tc")
 
 #: kernel family -> stem of its `ncu --set full` summary under profiles/<visit>/ (scripts/ncu_summary.py output)
+#: fraction of the 49 taps that fall inside the map: what the conv kernels actually multiply
+FP32_VALID_TAPS = {"dwln_15": 38.4 / 49.0, "dwln_7": 27.9 / 49.0}
 NCU_SUMMARY = {"mlp_fused_320": "mlp2_320", "mlp_fused_80": "mlp2_80", "mlp_fused_160": "mlp2_160",
                "dwln_15x80": "dwln15", "gemm_fc1_640": "fc1_640", "gemm_fc2_640": "fc2_640"}
 
@@ -95,6 +97,13 @@ def add_roofline_fractions(kernels: dict, pk: dict, precision: str) -> None:
     for name, k in kernels.items():
         k["bound"] = kernel_bound(name, precision)
         k["frac"] = k["tflops"] / pk["tf_sust"] if k["bound"] == "tensor" else k["gbs"] / pk["hbm"]
+        # dw7x7 + LN on the 15^2 / 7^2 maps: SURVEY.md files it under HBM (kept in `bound` / `frac`), but on B200 the kernel
+        # sits on the FP32 FMA pipe (ncu: top stall math-pipe throttle): also report the valid-tap FMA rate against the
+        # nominal pipe peak (SMs x 128 FMA/clk x SM clock; the measured FFMA2 ceiling of this access pattern is 0.77 of it)
+        ratio = FP32_VALID_TAPS.get(name.split("x")[0])
+        if ratio is not None and k.get("tflops"):
+            peak = pk.get("sms", 148) * 128 * 2 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+            k["fp32_pipe"] = {"tflops_valid_taps": k["tflops"] * ratio, "peak": peak, "frac": k["tflops"] * ratio / peak}
 
 
 def ncu_traffic(kernel: str, batch: int):
