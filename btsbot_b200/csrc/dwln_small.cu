@@ -144,7 +144,127 @@ __global__ void dwln_small_kernel(const __nv_bfloat16* __restrict__ x, int64_t B
   }
 }
 
+// ---- 3x3 maps, one WARP per image (C = 64 * NP: nano 320, pico 256) --------------------------------------------------
+// The kernel above gives one channel pair to a thread and an image to a CTA, so the LayerNorm statistics cross warps:
+// two CTA barriers and a shared-memory hop per image, and ~420 of each thread's ~500 instructions per image are not FFMA2
+// (loads, conversions, the statistics tree, the LayerNorm application) -- it runs at 55 % of its issue floor.  Here a lane
+// owns NP channel pairs of the image (pairs lane, lane + 32, ...), keeps all NP x 9 accumulators in registers, and the
+// statistics of the 9 pixels need one 31-shuffle tree per IMAGE instead of per warp: no barrier, no shared-memory hop.
+template <int C, bool XF16>
+__global__ void __launch_bounds__(128)
+dwln_w3_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __restrict__ wt, const float* __restrict__ bias,
+               const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
+  constexpr int NP = C / 64, C2 = C / 2, HW = 9, NT = 5;
+  extern __shared__ __align__(16) unsigned char sm[];
+  float* wsm = reinterpret_cast<float*>(sm);                 // [25][C] reachable taps
+  float* bsm = wsm + NT * NT * C;                            // conv bias, LN weight, LN bias: [3][C]
+  const int tid = threadIdx.x, lane = tid & 31;
+  {
+    constexpr int kRun = NT * C / 4;                         // 16-byte granules per tap row (5 taps x C floats, contiguous)
+    for (int i = tid; i < NT * kRun; i += 128) {
+      const int ty = i / kRun, k = i - ty * kRun;
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(wsm + ty * NT * C + 4 * k);
+      const float* g = wt + ((ty + 1) * 7 + 1) * C + 4 * k;  // taps (ty + 1, 1 .. 5) of the 7x7 kernel
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int i = tid; i < C; i += 128) { bsm[i] = __ldg(bias + i); bsm[C + i] = __ldg(ln_w + i); bsm[2 * C + i] = __ldg(ln_b + i); }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t gw = (int64_t)blockIdx.x * 4 + (tid >> 5), nwarps = (int64_t)gridDim.x * 4;
+  constexpr float invC = 1.0f / (float)C;
+  for (int64_t img = gw; img < B; img += nwarps) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + img * (int64_t)HW * C);
+    f32x2_t acc[NP][HW];
+    uint32_t xr[HW];
+#pragma unroll
+    for (int p = 0; p < HW; ++p) xr[p] = __ldg(src + p * C2 + lane);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int pair = lane + 32 * j;
+      f32x2_t xin[HW];
+#pragma unroll
+      for (int p = 0; p < HW; ++p) xin[p] = x2_to_f32x2<XF16>(xr[p]);
+      if (j + 1 < NP) {                                      // the next pair's pixels are in flight during this pair's FMAs
+#pragma unroll
+        for (int p = 0; p < HW; ++p) xr[p] = __ldg(src + p * C2 + pair + 32);
+      }
+      const f32x2_t bv = *reinterpret_cast<const f32x2_t*>(bsm + 2 * pair);
+#pragma unroll
+      for (int p = 0; p < HW; ++p) acc[j][p] = bv;
+#pragma unroll
+      for (int ty = 0; ty < NT; ++ty) {
+#pragma unroll
+        for (int tx = 0; tx < NT; ++tx) {
+          const f32x2_t w = *reinterpret_cast<const f32x2_t*>(wsm + (ty * NT + tx) * C + 2 * pair);
+          const int dy = ty - 2, dx = tx - 2;                // input = output + (dy, dx)
+#pragma unroll
+          for (int oy = 0; oy < 3; ++oy) {
+#pragma unroll
+            for (int ox = 0; ox < 3; ++ox) {
+              const int iy = oy + dy, ix = ox + dx;
+              if (iy >= 0 && iy < 3 && ix >= 0 && ix < 3) fma_f32x2(acc[j][oy * 3 + ox], w, xin[iy * 3 + ix]);
+            }
+          }
+        }
+      }
+    }
+    // ---- per-pixel statistics over the C channels: lane-local partial sums, one recursive-halving tree per image ----
+    float red[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) red[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+#pragma unroll
+      for (int p = 0; p < HW; ++p) {
+        const float2 a = unpack_f32x2(acc[j][p]);
+        red[p] += a.x + a.y;
+        red[16 + p] = fmaf(a.x, a.x, fmaf(a.y, a.y, red[16 + p]));
+      }
+    }
+    seg_reduce32<32>(red, lane);                             // lane l now holds the total of value l in red[0]
+    float mean[HW], rstd[HW];
+#pragma unroll
+    for (int p = 0; p < HW; ++p) {
+      const float s = __shfl_sync(0xffffffffu, red[0], p), q = __shfl_sync(0xffffffffu, red[0], 16 + p);
+      mean[p] = s * invC;
+      rstd[p] = rsqrtf(fmaxf(q * invC - mean[p] * mean[p], 0.f) + kLnEps);
+    }
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + img * (int64_t)HW * C);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const int pair = lane + 32 * j;
+      const float2 gwv = *reinterpret_cast<const float2*>(bsm + C + 2 * pair);
+      const float2 gbv = *reinterpret_cast<const float2*>(bsm + 2 * C + 2 * pair);
+#pragma unroll
+      for (int p = 0; p < HW; ++p) {
+        const float2 a = unpack_f32x2(acc[j][p]);
+        const __nv_bfloat162 o = __floats2bfloat162_rn((a.x - mean[p]) * rstd[p] * gwv.x + gbv.x,
+                                                       (a.y - mean[p]) * rstd[p] * gwv.y + gbv.y);
+        dst[p * C2 + pair] = *reinterpret_cast<const uint32_t*>(&o);
+      }
+    }
+  }
+}
+
 int num_sms();
+
+template <int C, bool XF16>
+static int launch_w3(const void* x, int64_t B, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+                     void* out, cudaStream_t st) {
+  const size_t smem = (size_t)(25 + 3) * C * 4;
+  auto kern = dwln_w3_kernel<C, XF16>;
+  BTSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "dwln_w3 attr");
+  int per_sm = 1;
+  BTSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem), "dwln_w3 occupancy");
+  if (per_sm < 1) per_sm = 1;
+  const int64_t cap = (int64_t)num_sms() * per_sm, need = (B + 3) / 4;
+  const int grid = (int)(need < cap ? need : cap);
+  kern<<<grid, 128, smem, st>>>((const __nv_bfloat16*)x, B, w, bias, ln_w, ln_b, (__nv_bfloat16*)out);
+  return launch_done("dwln_w3");
+}
+
 
 template <int S, int CT, int PF, bool CPA = false, bool XF16 = false>
 static int launch_small_pf(const void* x, int64_t B, int C, const float* w, const float* bias, const float* ln_w,
@@ -185,6 +305,14 @@ int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* 
   if (((uintptr_t)x % 4) != 0 || ((uintptr_t)out % 4) != 0 || ((uintptr_t)bias % 8) != 0 || ((uintptr_t)ln_w % 8) != 0 ||
       ((uintptr_t)ln_b % 8) != 0)
     return 1;
+  // 3x3 maps at the nano / pico widths: one warp per image (BTSB_DWLN_W3=0 keeps the thread-per-pair kernel for A/B)
+  static const bool w3 = !(getenv("BTSB_DWLN_W3") && atoi(getenv("BTSB_DWLN_W3")) == 0);
+  if (w3 && H == 3 && (C == 320 || C == 256) && ((uintptr_t)w % 16) == 0) {
+    if (C == 320) return xf16 ? launch_w3<320, true>(x, B, w, bias, ln_w, ln_b, out, st)
+                              : launch_w3<320, false>(x, B, w, bias, ln_w, ln_b, out, st);
+    return xf16 ? launch_w3<256, true>(x, B, w, bias, ln_w, ln_b, out, st)
+                : launch_w3<256, false>(x, B, w, bias, ln_w, ln_b, out, st);
+  }
   if (xf16) {
     if (H == 3) {
       if (C == 320) return launch_small<3, 320, true>(x, B, C, w, bias, ln_w, ln_b, out, st);
