@@ -248,7 +248,62 @@ dwln_w3_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __re
   }
 }
 
+// 1x1 maps (last stage): the 7x7 depthwise conv sees one pixel, i.e. y = LN(w_centre * x + b); a warp per image,
+// C / 64 channel pairs per lane, two warp reductions for the statistics -- no shared memory at all.
+template <int C, bool XF16>
+__global__ void __launch_bounds__(256)
+dwln_w1_kernel(const __nv_bfloat16* __restrict__ x, int64_t B, const float* __restrict__ wt, const float* __restrict__ bias,
+               const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out) {
+  constexpr int NP = C / 64, C2 = C / 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  f32x2_t w[NP], bv[NP];
+  float2 gwv[NP], gbv[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    const int pair = lane + 32 * j;
+    w[j] = *reinterpret_cast<const f32x2_t*>(wt + 24 * C + 2 * pair);        // centre tap (ky = kx = 3) of the [49][C] matrix
+    bv[j] = *reinterpret_cast<const f32x2_t*>(bias + 2 * pair);
+    gwv[j] = *reinterpret_cast<const float2*>(ln_w + 2 * pair);
+    gbv[j] = *reinterpret_cast<const float2*>(ln_b + 2 * pair);
+  }
+  constexpr float invC = 1.0f / (float)C;
+  for (int64_t img = gw; img < B; img += nwarps) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x + img * (int64_t)C);
+    float2 a[NP];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      f32x2_t acc = bv[j];
+      fma_f32x2(acc, w[j], x2_to_f32x2<XF16>(__ldg(src + lane + 32 * j)));
+      a[j] = unpack_f32x2(acc);
+      s += a[j].x + a[j].y;
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { const float d0 = a[j].x - mean, d1 = a[j].y - mean; q = fmaf(d0, d0, fmaf(d1, d1, q)); }
+    const float rstd = rsqrtf(warp_sum(q) * invC + kLnEps);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + img * (int64_t)C);
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const __nv_bfloat162 o = __floats2bfloat162_rn((a[j].x - mean) * rstd * gwv[j].x + gbv[j].x,
+                                                     (a[j].y - mean) * rstd * gwv[j].y + gbv[j].y);
+      dst[lane + 32 * j] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+  }
+}
+
 int num_sms();
+
+template <int C, bool XF16>
+static int launch_w1(const void* x, int64_t B, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+                     void* out, cudaStream_t st) {
+  const int64_t cap = (int64_t)num_sms() * 8, need = (B + 7) / 8;
+  const int grid = (int)(need < cap ? need : cap);
+  dwln_w1_kernel<C, XF16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, B, w, bias, ln_w, ln_b, (__nv_bfloat16*)out);
+  return launch_done("dwln_w1");
+}
 
 template <int C, bool XF16>
 static int launch_w3(const void* x, int64_t B, const float* w, const float* bias, const float* ln_w, const float* ln_b,
@@ -312,6 +367,12 @@ int dwln_bf16_small(const void* x, int64_t B, int H, int W, int C, const float* 
                               : launch_w3<320, false>(x, B, w, bias, ln_w, ln_b, out, st);
     return xf16 ? launch_w3<256, true>(x, B, w, bias, ln_w, ln_b, out, st)
                 : launch_w3<256, false>(x, B, w, bias, ln_w, ln_b, out, st);
+  }
+  if (w3 && H == 1 && (C == 640 || C == 512) && ((uintptr_t)w % 8) == 0) {
+    if (C == 640) return xf16 ? launch_w1<640, true>(x, B, w, bias, ln_w, ln_b, out, st)
+                              : launch_w1<640, false>(x, B, w, bias, ln_w, ln_b, out, st);
+    return xf16 ? launch_w1<512, true>(x, B, w, bias, ln_w, ln_b, out, st)
+                : launch_w1<512, false>(x, B, w, bias, ln_w, ln_b, out, st);
   }
   if (xf16) {
     if (H == 3) {

@@ -6,5 +6,5 @@ timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_models.py 
 for v in w3 small; do
   if [ $v = w3 ]; then envs="BTSB_X=0"; else envs="BTSB_DWLN_W3=0"; fi
   env $envs BTSB_HOST_PACK=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > $OUT/bench_c3_$v.log 2>$OUT/bench_c3_$v.err; echo "bench $v rc=$?"; tail -n 2 $OUT/bench_c3_$v.err
-  python scripts/show_bench.py $OUT/bench_c3_$v.log 2>/dev/null | cut -c1-150 | grep -E "value|dwln_3"
+  python scripts/show_bench.py $OUT/bench_c3_$v.log 2>/dev/null | cut -c1-150 | grep -E "value|dwln_3|dwln_1"
 done
